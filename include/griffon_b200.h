@@ -1,0 +1,226 @@
+/*
+ * griffon_b200.h -- C-ABI of the B200-native Griffon hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the
+ * reference's Cython class `PyCombustionKernels` / module functions `py_btddod_*`
+ * (reference: src/spitfire/griffon/griffon.pyx) or the C++ method behind it
+ * (src/spitfire/griffon/include/combustion_kernels.h, btddod_matrix_kernels.h).
+ * The citation next to each declaration names the interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *  - all functions return int: 0 = ok, <0 = argument / state / CUDA error
+ *    (text via gb_last_error()), >0 reserved. Nothing throws.
+ *  - `*_batch` entry points take DEVICE pointers and a cudaStream_t passed as
+ *    void* (NULL = default stream); they are asynchronous w.r.t. the host.
+ *  - `*_host` entry points take HOST pointers, stage through device buffers
+ *    owned by the handle, run the same kernels and copy back; synchronous.
+ *  - single-state methods of the reference are `*_host` calls with n = 1.
+ *  - layouts are the reference's: reactor state [T, Y_0..Y_{ns-2}] per state
+ *    (AoS, stride ns), Jacobian ns x ns column-major per state, flamelet state
+ *    [nzi][ns], flamelet Jacobian in BTDDOD storage (nzi col-major ns x ns
+ *    blocks, then (nzi-1)*ns sub-diagonal, then (nzi-1)*ns super-diagonal).
+ *  - there is NO CPU fallback: if no CUDA device is usable every compute entry
+ *    point returns GB_ERR_CUDA.
+ */
+#ifndef GRIFFON_B200_H
+#define GRIFFON_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_OK 0
+#define GB_ERR_ARG (-1)
+#define GB_ERR_STATE (-2)
+#define GB_ERR_CUDA (-3)
+#define GB_ERR_UNSUPPORTED (-4)
+
+/* reaction types, as RateType in combustion_kernels.h:60-67 */
+#define GB_RXN_SIMPLE 1
+#define GB_RXN_THIRD_BODY 2
+#define GB_RXN_LINDEMANN 3
+#define GB_RXN_TROE 4
+
+typedef struct gb_mech gb_mech; /* opaque; owns host tables + device copies (CombustionKernels*, griffon.pyx:220-229) */
+
+const char *gb_last_error(void);
+/* number of usable CUDA devices (0 if none), never fails */
+int gb_cuda_device_count(void);
+
+/* ---- mechanism construction: replaces the 18 `mechanism_*` setters ------------------------------------- */
+gb_mech *gb_mech_create(void);                                  /* griffon.pyx:225 __cinit__            */
+void gb_mech_destroy(gb_mech *m);                               /* griffon.pyx:228 __dealloc__          */
+int gb_mech_set_ref_pressure(gb_mech *m, double p_ref);         /* chemistry_setup.cpp:64               */
+int gb_mech_set_ref_temperature(gb_mech *m, double T_ref);      /* chemistry_setup.cpp:74               */
+int gb_mech_set_gas_constant(gb_mech *m, double Ru);            /* chemistry_setup.cpp:69               */
+int gb_mech_set_element_mw(gb_mech *m, const char *element, double mw); /* one entry of mechanism_set_element_mw_map, :21 */
+int gb_mech_add_element(gb_mech *m, const char *element);       /* chemistry_setup.cpp:26               */
+int gb_mech_add_species(gb_mech *m, const char *name, int n_atoms, const char *const *atom_names,
+                        const double *atom_counts);             /* chemistry_setup.cpp:36               */
+int gb_mech_resize_heat_capacity_data(gb_mech *m);              /* chemistry_setup.cpp:79               */
+int gb_mech_add_const_cp(gb_mech *m, const char *species, double Tmin, double Tmax, double T0, double h0,
+                         double s0, double cp);                 /* chemistry_setup.cpp:89               */
+int gb_mech_add_nasa7_cp(gb_mech *m, const char *species, double Tmin, double Tmid, double Tmax,
+                         const double *low7, const double *high7); /* chemistry_setup.cpp:102           */
+int gb_mech_add_nasa9_cp(gb_mech *m, const char *species, double Tmin, double Tmax, int n_coeffs,
+                         const double *coeffs);                 /* chemistry_setup.cpp:132 (NASA9: GB_ERR_UNSUPPORTED at finalize) */
+/* One generic adder covers mechanism_add_reaction_{simple,three_body,Lindemann,Troe}[_with_special_orders]
+ * (chemistry_setup.cpp:156-345). Unused groups are passed with n = 0 / NULL. Ea is Ea/Ru (K), as the
+ * reference's Python passes it (mechanism.py:185). troe4 = [A, T3, T1, T2] zero padded (griffon.pyx:410-416). */
+int gb_mech_add_reaction(gb_mech *m, int type, int reversible,
+                         int n_reactants, const char *const *reactant_names, const int *reactant_stoich,
+                         int n_products, const char *const *product_names, const int *product_stoich,
+                         double fwd_A, double fwd_b, double fwd_Ea_over_R,
+                         int n_eff, const char *const *eff_names, const double *eff_values, double default_eff,
+                         double flf_A, double flf_b, double flf_Ea_over_R, const double *troe4,
+                         int n_orders, const char *const *order_names, const double *order_values);
+int gb_mech_n_species(const gb_mech *m);
+int gb_mech_n_reactions(const gb_mech *m);
+int gb_mech_molecular_weights(const gb_mech *m, double *out_mw /* [ns] host */);
+/* packs the tables and uploads them to the current CUDA device (done lazily by every compute call) */
+int gb_mech_commit(gb_mech *m);
+
+/* ---- thermodynamics (griffon.pyx:684-758; thermodynamics_kernels.cpp) ----------------------------------- */
+/* what: selects the quantity; T[n], y[n*ns] (full mass-fraction vectors), out sized per `what`.             */
+#define GB_THERMO_MMW 0          /* mixture_molecular_weight(y)          out[n]    combustion_kernels.h:381 */
+#define GB_THERMO_DENSITY 1      /* ideal_gas_density(p=aux,T,y)         out[n]    thermodynamics_kernels.cpp:29 */
+#define GB_THERMO_PRESSURE 2     /* ideal_gas_pressure(rho=aux,T,y)      out[n]    thermodynamics_kernels.cpp:37 */
+#define GB_THERMO_CP_MIX 3       /* cp_mix(T,y)                          out[n]    :133 */
+#define GB_THERMO_CV_MIX 4       /* cv_mix(T,y)                          out[n]    :149 */
+#define GB_THERMO_H_MIX 5        /* enthalpy_mix(T,y)                    out[n]    :366 */
+#define GB_THERMO_E_MIX 6        /* energy_mix(T,y)                      out[n]    :375 */
+#define GB_THERMO_CP_SPECIES 7   /* species_cp(T)                        out[n*ns] :143 */
+#define GB_THERMO_CV_SPECIES 8   /* species_cv(T)                        out[n*ns] :156 */
+#define GB_THERMO_H_SPECIES 9    /* species_enthalpies(T)                out[n*ns] :262 */
+#define GB_THERMO_E_SPECIES 10   /* species_energies(T)                  out[n*ns] :353 */
+#define GB_THERMO_DCPDT_SPECIES 11 /* dcpdT_species(T,y)                 out[n*ns] :183 */
+#define GB_THERMO_MOLE_FRACTIONS 12 /* mole_fractions(y)                 out[n*ns] :17  */
+int gb_thermo_batch(gb_mech *m, int what, int n, const double *aux /* [n] or NULL */, const double *T,
+                    const double *y, double *out, void *stream);
+int gb_thermo_host(gb_mech *m, int what, int n, const double *aux, const double *T, const double *y, double *out);
+
+/* ---- kinetics (griffon.pyx:763-783; chemistry_kernels.cpp:35-483) ---------------------------------------- */
+/* production_rates(T, rho, y, out_w): y full [n*ns], out_w [n*ns] */
+int gb_production_rates_batch(gb_mech *m, int n, const double *T, const double *rho, const double *y,
+                              double *out_w, void *stream);
+int gb_production_rates_host(gb_mech *m, int n, const double *T, const double *rho, const double *y, double *out_w);
+/* prod_rates_primitive_sensitivities(rho, T, y, option, out[(ns+1)^2]) col-major, ld ns+1 per state */
+int gb_prod_rates_sens_batch(gb_mech *m, int n, const double *rho, const double *T, const double *y,
+                             int rates_sensitivity_option, double *out_sens, void *stream);
+int gb_prod_rates_sens_host(gb_mech *m, int n, const double *rho, const double *T, const double *y,
+                            int rates_sensitivity_option, double *out_sens);
+
+/* ---- isobaric reactor (griffon.pyx:788-824; isobaric_reactor_kernels.cpp:170-343) ------------------------ */
+typedef struct gb_reactor_params {
+  double pressure;            /* Pa, shared by the batch                                         */
+  double inflow_temperature;  /* T_in                                                            */
+  const double *inflow_y;     /* [ns] full inflow mass fractions; only read when open != 0       */
+  double tau;                 /* mixing time                                                     */
+  double fluid_temperature;   /* T_inf  (convection)                                             */
+  double surf_temperature;    /* T_surf (radiation)                                              */
+  double h_conv;
+  double eps_rad;
+  double surface_area_over_volume;
+  int heat_transfer_option;   /* 0 adiabatic, 1 isothermal, 2 diathermal (:206-218)              */
+  int open;                   /* bool                                                            */
+} gb_reactor_params;
+/* state [n*ns] = [T, Y_0..Y_{ns-2}] per state; out_rhs [n*ns]. inflow_y is a DEVICE pointer for _batch. */
+int gb_reactor_rhs_isobaric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                  double *out_rhs, void *stream);
+int gb_reactor_rhs_isobaric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                 double *out_rhs);
+/* out_jac [n*ns*ns], per state column-major (row i, col j at i + j*ns). rates_sensitivity_option 0 (dense),
+ * 2 (sparse) give identical results; 1 (no-TBAF, inexact) is mapped to exact. sensitivity_transform_option 0. */
+int gb_reactor_jac_isobaric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                  int rates_sensitivity_option, int sensitivity_transform_option,
+                                  double *out_rhs, double *out_jac, void *stream);
+int gb_reactor_jac_isobaric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                 int rates_sensitivity_option, int sensitivity_transform_option, double *out_rhs,
+                                 double *out_jac);
+
+/* ---- flamelet (griffon.pyx:556-679; flamelet_kernels.cpp:31-90, 1039-1409) -------------------------------- */
+/* Host-side setup helpers (cold; run once per Flamelet) */
+int gb_flamelet_stencils(const gb_mech *m, const double *dz, int nzi, const double *dissipation_rate,
+                         const double *inv_lewis, double *out_cmajor, double *out_csub, double *out_csup,
+                         double *out_mcoeff, double *out_ncoeff);
+int gb_flamelet_jac_indices(const gb_mech *m, int nzi, int *out_rows, int *out_cols);
+
+typedef struct gb_flamelet_params {
+  int nzi;                    /* interior grid points                                                        */
+  double pressure;
+  const double *oxy_state;    /* [ns]  = [T, Y_0..Y_{ns-2}] of the oxidizer stream (Z=0 boundary)            */
+  const double *fuel_state;   /* [ns]  fuel stream (Z=1 boundary)                                            */
+  int adiabatic;              /* bool                                                                        */
+  const double *T_convection; /* per flamelet [nzi]; the four heat-loss arrays are read only if !adiabatic   */
+  const double *h_convection;
+  const double *T_radiation;
+  const double *h_radiation;
+  const double *cmajor;       /* per flamelet [nzi*ns]                                                       */
+  const double *csub;
+  const double *csup;
+  const double *mcoeff;       /* per flamelet [nzi]                                                          */
+  const double *ncoeff;
+  const double *chi;          /* per flamelet [nzi+2] full-grid dissipation rate, indexed chi[i] as the
+                                 reference does (flamelet_kernels.cpp:1175)               */
+  int include_enthalpy_flux;
+  int include_variable_cp;
+  int use_scaled_heat_loss;
+  /* strides (in doubles) between consecutive flamelets of a batch for each per-flamelet array; 0 = shared   */
+  long stride_heat;           /* T_convection,h_convection,T_radiation,h_radiation                           */
+  long stride_coeff;          /* cmajor,csub,csup                                                            */
+  long stride_mn;             /* mcoeff,ncoeff                                                               */
+  long stride_chi;            /* chi                                                                         */
+} gb_flamelet_params;
+/* state, out_rhs: [F][nzi*ns] */
+int gb_flamelet_rhs_batch(gb_mech *m, int n_flamelets, const double *state, const gb_flamelet_params *prm,
+                          double *out_rhs, void *stream);
+int gb_flamelet_rhs_host(gb_mech *m, int n_flamelets, const double *state, const gb_flamelet_params *prm,
+                         double *out_rhs);
+/* out_jac: [F][ns*(nzi*ns + 2*(nzi-1))] BTDDOD; written completely (no need to pre-zero, unlike the reference
+ * which accumulates into the off-diagonals, flamelet_kernels.cpp:1386-1394). out_expeig [F][nzi*ns] is written
+ * only if compute_eigenvalues (max(Re(lambda)) - diffterm clipped at 0, per point). */
+int gb_flamelet_jacobian_batch(gb_mech *m, int n_flamelets, const double *state, const gb_flamelet_params *prm,
+                               int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
+                               int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
+                               double *out_jac, void *stream);
+int gb_flamelet_jacobian_host(gb_mech *m, int n_flamelets, const double *state, const gb_flamelet_params *prm,
+                              int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
+                              int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
+                              double *out_jac);
+
+/* ---- BTDDOD block-Thomas (griffon.pyx:1006-1113; btddod_matrix_kernels.cpp:19-165, 429-465) --------------- */
+/* Batched over n_systems independent matrices stored back to back (stride = block_size*(num_blocks*block_size
+ * + 2*(num_blocks-1)) doubles for matrices, num_blocks*block_size^2 for l_values, num_blocks*block_size for
+ * pivots / vectors). Pivots are LAPACK-style 1-based row indices (dgetrf semantics). */
+int gb_btddod_full_factorize_batch(int n_systems, double *d_factors, int num_blocks, int block_size,
+                                   double *out_l_values, int *out_d_pivots, void *stream);
+int gb_btddod_full_solve_batch(int n_systems, const double *d_factors, const double *l_values, const int *d_pivots,
+                               const double *rhs, int num_blocks, int block_size, double *out_solution,
+                               void *stream);
+int gb_btddod_full_matvec_batch(int n_systems, const double *matrix, const double *vec, int num_blocks,
+                                int block_size, double *out_matvec, void *stream);
+/* A <- matrix_scale*A + diag_scale*diag(diagonal) */
+int gb_btddod_scale_and_add_diagonal_batch(int n_systems, double *matrix, double matrix_scale,
+                                           const double *diagonal, double diag_scale, int num_blocks,
+                                           int block_size, void *stream);
+int gb_btddod_full_factorize_host(int n_systems, double *d_factors, int num_blocks, int block_size,
+                                  double *out_l_values, int *out_d_pivots);
+int gb_btddod_full_solve_host(int n_systems, const double *d_factors, const double *l_values, const int *d_pivots,
+                              const double *rhs, int num_blocks, int block_size, double *out_solution);
+int gb_btddod_full_matvec_host(int n_systems, const double *matrix, const double *vec, int num_blocks,
+                               int block_size, double *out_matvec);
+int gb_btddod_scale_and_add_diagonal_host(int n_systems, double *matrix, double matrix_scale,
+                                          const double *diagonal, double diag_scale, int num_blocks,
+                                          int block_size);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------ */
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long gb_kernel_launch_count(void);
+/* name of the build (arch, flags), for logs */
+const char *gb_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIFFON_B200_H */

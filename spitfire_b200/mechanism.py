@@ -1,0 +1,173 @@
+"""
+Chemical mechanism loading and stream mixing, Cantera-free.
+
+Host-side mirror of the reference's `spitfire.chemistry.mechanism` (reference:
+src/spitfire/chemistry/mechanism.py:52-757): same class name, constructor arguments, properties and methods,
+same `mech_data` dictionary (so pickles interoperate), but the mechanism is read by `_yaml_ingest` instead of a
+`cantera.Solution`, and streams are `spitfire_b200.streams.Stream` objects (duck-typing `cantera.Quantity`)
+whose thermodynamics is evaluated by Griffon's NASA7 kernels.
+"""
+from numpy import sum, array, abs  # noqa: F401  (names kept as in the reference module)
+import numpy as np
+
+from spitfire_b200._yaml_ingest import extract_yaml_mechanism_data, GAS_CONSTANT, MechanismIngestError  # noqa: F401
+
+
+def populate_griffon_mechanism_data(griffon, mech_data, ct_element_mw_map, elem_list, ref_temperature, ref_pressure,
+                                    spec_name_list, spec_dict, reac_list, transport_model,
+                                    gas_constant=GAS_CONSTANT):
+    """Feed a Griffon-like object (anything with the 18 `mechanism_*` setters) and fill `mech_data`.
+
+    Follows mechanism.py:122-258 call for call, so the same routine drives the product binding and (in tests) the
+    oracle bindings."""
+    griffon.mechanism_set_ref_pressure(ref_pressure)
+    mech_data['ref_pressure'] = ref_pressure
+    griffon.mechanism_set_ref_temperature(ref_temperature)
+    mech_data['ref_temperature'] = ref_temperature
+    griffon.mechanism_set_gas_constant(gas_constant)
+    mech_data['gas_constant'] = gas_constant
+
+    griffon.mechanism_set_element_mw_map(ct_element_mw_map)
+    mech_data['element_mw_map'] = ct_element_mw_map
+
+    for e in elem_list:
+        griffon.mechanism_add_element(e)
+        mech_data['elements'].append(e)
+
+    for s in spec_name_list:
+        griffon.mechanism_add_species(s, spec_dict[s]['atoms'])
+        mech_data['species'][s] = dict()
+        mech_data['species'][s]['atom_map'] = spec_dict[s]['atoms']
+
+    griffon.mechanism_resize_heat_capacity_data()
+
+    for s in spec_dict:
+        cp = spec_dict[s]['heat-capacity']
+        if cp['type'] == 'constant':
+            griffon.mechanism_add_const_cp(s, cp['Tmin'], cp['Tmax'], cp['T0'], cp['h0'], cp['s0'], cp['cp'])
+            mech_data['species'][s]['cp'] = ('constant', cp['Tmin'], cp['Tmax'], cp['T0'], cp['h0'], cp['s0'],
+                                             cp['cp'])
+        elif cp['type'] == 'NASA7':
+            lo, hi = np.asarray(cp['low-coeffs']).tolist(), np.asarray(cp['high-coeffs']).tolist()
+            griffon.mechanism_add_nasa7_cp(s, cp['Tmin'], cp['Tmid'], cp['Tmax'], lo, hi)
+            mech_data['species'][s]['cp'] = ('NASA7', cp['Tmin'], cp['Tmid'], cp['Tmax'], lo, hi)
+        elif cp['type'] == 'NASA9':
+            c = np.asarray(cp['coeffs']).tolist()
+            griffon.mechanism_add_nasa9_cp(s, cp['Tmin'], cp['Tmax'], c)
+            mech_data['species'][s]['cp'] = ('NASA9', cp['Tmin'], cp['Tmax'], c)
+        if transport_model is not None and 'transport-data' in spec_dict[s]:
+            mech_data['species'][s]['transport-data'] = dict(spec_dict[s]['transport-data'])
+
+    mech_data['transport-model'] = transport_model
+
+    R = gas_constant
+    for rx in reac_list:
+        t = rx['type']
+        special = 'orders' in rx
+        if t == 'simple':
+            if special:
+                griffon.mechanism_add_reaction_simple_with_special_orders(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['A'], rx['b'], rx['Ea'] / R, rx['orders'])
+                mech_data['reactions'].append(('simple-special', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['A'], rx['b'], rx['Ea'], rx['orders']))
+            else:
+                griffon.mechanism_add_reaction_simple(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['A'], rx['b'], rx['Ea'] / R)
+                mech_data['reactions'].append(('simple', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['A'], rx['b'], rx['Ea']))
+        elif t == 'three-body':
+            if special:
+                griffon.mechanism_add_reaction_three_body_with_special_orders(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['A'], rx['b'], rx['Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'], rx['orders'])
+                mech_data['reactions'].append(('three-body-special', rx['reactants'], rx['products'],
+                                               rx['reversible'], rx['A'], rx['b'], rx['Ea'], rx['efficiencies'],
+                                               rx['default-eff'], rx['orders']))
+            else:
+                griffon.mechanism_add_reaction_three_body(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['A'], rx['b'], rx['Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'])
+                mech_data['reactions'].append(('three-body', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['A'], rx['b'], rx['Ea'], rx['efficiencies'], rx['default-eff']))
+        elif t == 'Lindemann':
+            if special:
+                griffon.mechanism_add_reaction_Lindemann_with_special_orders(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'] / R, rx['orders'])
+                mech_data['reactions'].append(('Lindemann-special', rx['reactants'], rx['products'],
+                                               rx['reversible'], rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'],
+                                               rx['efficiencies'], rx['default-eff'], rx['flf-A'], rx['flf-b'],
+                                               rx['flf-Ea'], rx['orders']))
+            else:
+                griffon.mechanism_add_reaction_Lindemann(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'] / R)
+                mech_data['reactions'].append(('Lindemann', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'], rx['efficiencies'],
+                                               rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea']))
+        elif t == 'Troe':
+            troe = np.asarray(rx['Troe-params']).tolist()
+            if special:
+                griffon.mechanism_add_reaction_Troe_with_special_orders(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'] / R, troe,
+                    rx['orders'])
+                mech_data['reactions'].append(('Troe-special', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'], rx['efficiencies'],
+                                               rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'], troe,
+                                               rx['orders']))
+            else:
+                griffon.mechanism_add_reaction_Troe(
+                    rx['reactants'], rx['products'], rx['reversible'], rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'] / R,
+                    rx['efficiencies'], rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'] / R, troe)
+                mech_data['reactions'].append(('Troe', rx['reactants'], rx['products'], rx['reversible'],
+                                               rx['fwd-A'], rx['fwd-b'], rx['fwd-Ea'], rx['efficiencies'],
+                                               rx['default-eff'], rx['flf-A'], rx['flf-b'], rx['flf-Ea'], troe))
+        else:
+            raise ValueError(f'unknown reaction type {t}')
+
+
+def mech_data_to_extracted(gdata):
+    """Invert `mech_data` (the pickled form, mechanism.py:108-115) back into the extraction tuple.
+
+    The reference rebuilds a cantera.Solution from it (`_build_cantera_solution`, mechanism.py:260-373); no
+    Cantera is needed here because `mech_data` already holds everything Griffon is fed."""
+    spec_name_list = list(gdata['species'].keys())
+    spec_dict = dict()
+    for s in spec_name_list:
+        spec = gdata['species'][s]
+        cp = spec['cp']
+        if cp[0] == 'constant':
+            hc = dict(zip(('Tmin', 'Tmax', 'T0', 'h0', 's0', 'cp'), cp[1:]))
+            hc['type'] = 'constant'
+        elif cp[0] == 'NASA7':
+            hc = dict({'type': 'NASA7', 'Tmin': cp[1], 'Tmid': cp[2], 'Tmax': cp[3],
+                       'low-coeffs': np.array(cp[4]), 'high-coeffs': np.array(cp[5])})
+        elif cp[0] == 'NASA9':
+            hc = dict({'type': 'NASA9', 'Tmin': cp[1], 'Tmax': cp[2], 'coeffs': np.array(cp[3])})
+        else:
+            raise ValueError(f'unknown cp type {cp[0]}')
+        spec_dict[s] = dict({'atoms': spec['atom_map'], 'heat-capacity': hc})
+        if 'transport-data' in spec:
+            spec_dict[s]['transport-data'] = spec['transport-data']
+    reac_list = list()
+    for rxn in gdata['reactions']:
+        t = rxn[0]
+        base = t.replace('-special', '')
+        d = dict({'type': base, 'reactants': rxn[1], 'products': rxn[2], 'reversible': rxn[3]})
+        if base in ('simple', 'three-body'):
+            d['A'], d['b'], d['Ea'] = rxn[4:7]
+            if base == 'three-body':
+                d['efficiencies'], d['default-eff'] = rxn[7], rxn[8]
+        else:
+            d['fwd-A'], d['fwd-b'], d['fwd-Ea'] = rxn[4:7]
+            d['efficiencies'], d['default-eff'] = rxn[7], rxn[8]
+            d['flf-A'], d['flf-b'], d['flf-Ea'] = rxn[9:12]
+            if base == 'Troe':
+                d['Troe-params'] = np.array(rxn[12])
+        if 'special' in t:
+            d['orders'] = rxn[-1]
+        reac_list.append(d)
+    return (gdata['element_mw_map'], list(gdata['elements']), gdata['ref_temperature'], gdata['ref_pressure'],
+            spec_name_list, spec_dict, reac_list, gdata.get('transport-model', None)), gdata.get('gas_constant',
+                                                                                                GAS_CONSTANT)
