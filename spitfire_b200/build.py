@@ -1,0 +1,63 @@
+"""
+Builds spitfire_b200/libgriffon_b200.so (the C-ABI library of include/griffon_b200.h) with nvcc for sm_100a.
+
+    python -m spitfire_b200.build [--force] [--parity]
+
+nvcc cross-compiles without a GPU. The library links the CUDA runtime statically and has no torch / Python
+dependency. `--parity` builds with --fmad=false (no FMA contraction), used to quantify how much of the GPU-vs-CPU
+difference is contraction and how much is libm.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libgriffon_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def stale(target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    deps = sources() + glob.glob(os.path.join(CSRC, '*.h')) + glob.glob(os.path.join(CSRC, '*.cuh')) + \
+        [os.path.join(os.path.dirname(HERE), 'include', 'griffon_b200.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, parity=False, out=LIB, verbose=True):
+    if not force and not stale(out):
+        return out
+    flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+             '--shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default',
+             '-Xptxas', '-v', '--expt-relaxed-constexpr']
+    tag = ' -O3'
+    if parity:
+        flags += ['--fmad=false']
+        tag += ' --fmad=false'
+    flags += ['-DGB_FLAGS="%s"' % tag]
+    cmd = [NVCC] + flags + ['-o', out] + sources()
+    if verbose:
+        print(' '.join(cmd), flush=True)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = res.stdout
+    with open(os.path.join(HERE, 'build.log'), 'w') as f:
+        f.write(log)
+    if res.returncode != 0:
+        print(log)
+        raise RuntimeError('nvcc failed')
+    if verbose:
+        for line in log.splitlines():
+            if 'registers' in line or 'error' in line or 'warning' in line.lower() and 'ptxas' not in line:
+                print(line)
+    return out
+
+
+if __name__ == '__main__':
+    build(force='--force' in sys.argv, parity='--parity' in sys.argv)

@@ -1,0 +1,631 @@
+// gb_api.cu -- C-ABI compute entry points (include/griffon_b200.h): argument checks, lazy mechanism commit,
+// kernel launches, and the *_host variants that stage host buffers through device scratch owned by the handle.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/griffon_b200.h"
+#include "gb_kernels.cuh"
+#include "gb_mech.h"
+
+using namespace gb;
+
+#define GB_STR2(x) #x
+#define GB_STR(x) GB_STR2(x)
+#ifndef GB_FLAGS
+#define GB_FLAGS ""
+#endif
+
+namespace
+{
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  cudaGetLastError();
+  return GB_ERR_CUDA;
+}
+
+int ready(gb_mech *m)
+{
+  if (!m)
+  {
+    set_error("null mechanism handle");
+    return GB_ERR_ARG;
+  }
+  return commit(m->h);
+}
+
+// device scratch slot k of at least `bytes` bytes
+int scratch(gb_mech *m, int k, size_t bytes, void **out)
+{
+  HostMech &h = m->h;
+  if (h.d_scratch_bytes[k] < bytes)
+  {
+    if (h.d_scratch[k])
+      cudaFree(h.d_scratch[k]);
+    h.d_scratch[k] = nullptr;
+    h.d_scratch_bytes[k] = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&h.d_scratch[k], want);
+    if (e != cudaSuccess)
+      return cuda_fail(e, "scratch allocation");
+    h.d_scratch_bytes[k] = want;
+  }
+  *out = h.d_scratch[k];
+  return GB_OK;
+}
+
+#define CK(call)                         \
+  do                                     \
+  {                                      \
+    cudaError_t e__ = (call);            \
+    if (e__ != cudaSuccess)              \
+      return cuda_fail(e__, #call);      \
+  } while (0)
+#define RC(call)            \
+  do                        \
+  {                         \
+    int rc__ = (call);      \
+    if (rc__ != GB_OK)      \
+      return rc__;          \
+  } while (0)
+
+ReactorDev reactor_dev(const gb_reactor_params *p, const double *d_yin)
+{
+  ReactorDev r;
+  r.p = p->pressure;
+  r.T_in = p->inflow_temperature;
+  r.tau = p->tau;
+  r.T_inf = p->fluid_temperature;
+  r.T_surf = p->surf_temperature;
+  r.h_conv = p->h_conv;
+  r.eps_rad = p->eps_rad;
+  r.SoV = p->surface_area_over_volume;
+  r.y_in = d_yin;
+  r.heat_option = p->heat_transfer_option;
+  r.open = p->open ? 1 : 0;
+  return r;
+}
+
+int check_reactor(const gb_mech *m, int n, const void *state, const gb_reactor_params *p, const void *out)
+{
+  (void)m;
+  if (n < 0 || (n > 0 && (!state || !out)) || !p)
+  {
+    set_error("bad reactor arguments");
+    return GB_ERR_ARG;
+  }
+  if (p->heat_transfer_option < 0 || p->heat_transfer_option > 2)
+  {
+    set_error("heat_transfer_option must be 0, 1 or 2");
+    return GB_ERR_ARG;
+  }
+  if (p->open && !p->inflow_y)
+  {
+    set_error("open reactor needs inflow_y");
+    return GB_ERR_ARG;
+  }
+  return GB_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+  long gb_kernel_launch_count(void) { return kernel_launch_count(); }
+  const char *gb_build_info(void) { return "griffon_b200 sm_100a fp64, nvcc " GB_STR(__CUDACC_VER_MAJOR__) "." GB_STR(__CUDACC_VER_MINOR__) GB_FLAGS; }
+
+  // ---- thermo ----------------------------------------------------------------------------------------------------
+  int gb_thermo_batch(gb_mech *m, int what, int n, const double *aux, const double *T, const double *y, double *out,
+                      void *stream)
+  {
+    RC(ready(m));
+    if (what < 0 || what > 12 || n < 0 || !out)
+    {
+      set_error("bad thermo arguments");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    CK(launch_thermo(m->h.dm, what, n, aux, T, y, out, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_thermo_host(gb_mech *m, int what, int n, const double *aux, const double *T, const double *y, double *out)
+  {
+    RC(ready(m));
+    if (what < 0 || what > 12 || n < 0 || !out)
+    {
+      set_error("bad thermo arguments");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    const bool per_species = what >= 7;
+    void *d_aux = nullptr, *d_T = nullptr, *d_y = nullptr, *d_out = nullptr;
+    RC(scratch(m, 0, sizeof(double) * n, &d_aux));
+    RC(scratch(m, 1, sizeof(double) * n, &d_T));
+    RC(scratch(m, 2, sizeof(double) * n * ns, &d_y));
+    RC(scratch(m, 3, sizeof(double) * n * (per_species ? ns : 1), &d_out));
+    if (aux)
+      CK(cudaMemcpy(d_aux, aux, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (T)
+      CK(cudaMemcpy(d_T, T, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (y)
+      CK(cudaMemcpy(d_y, y, sizeof(double) * n * ns, cudaMemcpyHostToDevice));
+    CK(launch_thermo(m->h.dm, what, n, aux ? (double *)d_aux : nullptr, T ? (double *)d_T : nullptr,
+                     y ? (double *)d_y : nullptr, (double *)d_out, 0));
+    CK(cudaMemcpy(out, d_out, sizeof(double) * n * (per_species ? ns : 1), cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  // ---- kinetics --------------------------------------------------------------------------------------------------
+  int gb_production_rates_batch(gb_mech *m, int n, const double *T, const double *rho, const double *y, double *out_w,
+                                void *stream)
+  {
+    RC(ready(m));
+    if (n < 0 || (n > 0 && (!T || !rho || !y || !out_w)))
+    {
+      set_error("bad production_rates arguments");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_PRODRATES;
+    a.n = n;
+    a.in_T = T, a.in_rho = rho, a.in_y = y;
+    a.out0 = out_w;
+    CK(launch_rates(a, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_production_rates_host(gb_mech *m, int n, const double *T, const double *rho, const double *y, double *out_w)
+  {
+    RC(ready(m));
+    if (n <= 0)
+      return n == 0 ? GB_OK : GB_ERR_ARG;
+    const int ns = m->h.dm.ns;
+    void *d_T, *d_rho, *d_y, *d_w;
+    RC(scratch(m, 0, sizeof(double) * n, &d_T));
+    RC(scratch(m, 1, sizeof(double) * n, &d_rho));
+    RC(scratch(m, 2, sizeof(double) * n * ns, &d_y));
+    RC(scratch(m, 3, sizeof(double) * n * ns, &d_w));
+    CK(cudaMemcpy(d_T, T, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_rho, rho, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_y, y, sizeof(double) * n * ns, cudaMemcpyHostToDevice));
+    RC(gb_production_rates_batch(m, n, (double *)d_T, (double *)d_rho, (double *)d_y, (double *)d_w, nullptr));
+    CK(cudaMemcpy(out_w, d_w, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  int gb_prod_rates_sens_batch(gb_mech *m, int n, const double *rho, const double *T, const double *y,
+                               int rates_sensitivity_option, double *out_sens, void *stream)
+  {
+    RC(ready(m));
+    if (n < 0 || (n > 0 && (!T || !rho || !y || !out_sens)) || rates_sensitivity_option < 0 ||
+        rates_sensitivity_option > 2)
+    {
+      set_error("bad prod_rates_sens arguments");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_SENS;
+    a.n = n;
+    a.in_T = T, a.in_rho = rho, a.in_y = y;
+    a.out1 = out_sens;
+    CK(launch_jac(a, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_prod_rates_sens_host(gb_mech *m, int n, const double *rho, const double *T, const double *y,
+                              int rates_sensitivity_option, double *out_sens)
+  {
+    RC(ready(m));
+    if (n <= 0)
+      return n == 0 ? GB_OK : GB_ERR_ARG;
+    const int ns = m->h.dm.ns;
+    const size_t so = (size_t)(ns + 1) * (ns + 1);
+    void *d_T, *d_rho, *d_y, *d_s;
+    RC(scratch(m, 0, sizeof(double) * n, &d_T));
+    RC(scratch(m, 1, sizeof(double) * n, &d_rho));
+    RC(scratch(m, 2, sizeof(double) * n * ns, &d_y));
+    RC(scratch(m, 3, sizeof(double) * n * so, &d_s));
+    CK(cudaMemcpy(d_T, T, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_rho, rho, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_y, y, sizeof(double) * n * ns, cudaMemcpyHostToDevice));
+    RC(gb_prod_rates_sens_batch(m, n, (double *)d_rho, (double *)d_T, (double *)d_y, rates_sensitivity_option,
+                                (double *)d_s, nullptr));
+    CK(cudaMemcpy(out_sens, d_s, sizeof(double) * n * so, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  // ---- isobaric reactor ----------------------------------------------------------------------------------------
+  int gb_reactor_rhs_isobaric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                    double *out_rhs, void *stream)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_REACTOR_RHS;
+    a.n = n;
+    a.in_state = state;
+    a.p = prm->pressure;
+    a.out0 = out_rhs;
+    a.rx = reactor_dev(prm, prm->inflow_y);
+    CK(launch_rates(a, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_reactor_jac_isobaric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                    int rates_sensitivity_option, int sensitivity_transform_option, double *out_rhs,
+                                    double *out_jac, void *stream)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n > 0 && !out_jac)
+    {
+      set_error("out_jac is null");
+      return GB_ERR_ARG;
+    }
+    if (rates_sensitivity_option < 0 || rates_sensitivity_option > 2 || sensitivity_transform_option != 0)
+    {
+      set_error("rates_sensitivity_option must be 0..2 and sensitivity_transform_option 0");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_REACTOR_JAC;
+    a.n = n;
+    a.in_state = state;
+    a.p = prm->pressure;
+    a.out0 = out_rhs;
+    a.out1 = out_jac;
+    a.rx = reactor_dev(prm, prm->inflow_y);
+    CK(launch_jac(a, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  static int stage_reactor(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                           gb_reactor_params *dprm, double **d_state)
+  {
+    const int ns = m->h.dm.ns;
+    void *p_state, *p_yin;
+    RC(scratch(m, 0, sizeof(double) * n * ns, &p_state));
+    RC(scratch(m, 1, sizeof(double) * ns, &p_yin));
+    CK(cudaMemcpy(p_state, state, sizeof(double) * n * ns, cudaMemcpyHostToDevice));
+    *dprm = *prm;
+    if (prm->open)
+    {
+      CK(cudaMemcpy(p_yin, prm->inflow_y, sizeof(double) * ns, cudaMemcpyHostToDevice));
+      dprm->inflow_y = (const double *)p_yin;
+    }
+    else
+      dprm->inflow_y = nullptr;
+    *d_state = (double *)p_state;
+    return GB_OK;
+  }
+
+  int gb_reactor_rhs_isobaric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                   double *out_rhs)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    gb_reactor_params dprm;
+    double *d_state;
+    RC(stage_reactor(m, n, state, prm, &dprm, &d_state));
+    void *d_rhs;
+    RC(scratch(m, 2, sizeof(double) * n * ns, &d_rhs));
+    RC(gb_reactor_rhs_isobaric_batch(m, n, d_state, &dprm, (double *)d_rhs, nullptr));
+    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  int gb_reactor_jac_isobaric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                   int rates_sensitivity_option, int sensitivity_transform_option, double *out_rhs,
+                                   double *out_jac)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    gb_reactor_params dprm;
+    double *d_state;
+    RC(stage_reactor(m, n, state, prm, &dprm, &d_state));
+    void *d_rhs, *d_jac;
+    RC(scratch(m, 2, sizeof(double) * n * ns, &d_rhs));
+    RC(scratch(m, 3, sizeof(double) * (size_t)n * ns * ns, &d_jac));
+    RC(gb_reactor_jac_isobaric_batch(m, n, d_state, &dprm, rates_sensitivity_option, sensitivity_transform_option,
+                                     (double *)d_rhs, (double *)d_jac, nullptr));
+    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * ns * ns, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+}
+
+// ---- flamelet ------------------------------------------------------------------------------------------------------
+namespace
+{
+
+int check_flamelet(int F, const void *state, const gb_flamelet_params *p, const void *out)
+{
+  if (F < 0 || !p || (F > 0 && (!state || !out)))
+  {
+    set_error("bad flamelet arguments");
+    return GB_ERR_ARG;
+  }
+  if (p->nzi < 2)
+  {
+    set_error("a flamelet needs at least two interior grid points");
+    return GB_ERR_ARG;
+  }
+  if (!p->oxy_state || !p->fuel_state || !p->cmajor || !p->csub || !p->csup || !p->mcoeff || !p->ncoeff || !p->chi)
+  {
+    set_error("flamelet parameter arrays must not be null");
+    return GB_ERR_ARG;
+  }
+  if (!p->adiabatic && (!p->T_convection || !p->h_convection || !p->T_radiation || !p->h_radiation))
+  {
+    set_error("non-adiabatic flamelets need the four heat-loss arrays");
+    return GB_ERR_ARG;
+  }
+  return GB_OK;
+}
+
+// fills the device-side flamelet descriptor and runs the pre-pass (cp grid, max T, boundary cp)
+int flamelet_dev(gb_mech *m, int F, const double *d_state, const gb_flamelet_params *p, FlameletDev *fl,
+                 cudaStream_t s)
+{
+  fl->nzi = p->nzi;
+  fl->oxy = p->oxy_state, fl->fuel = p->fuel_state;
+  fl->adiabatic = p->adiabatic ? 1 : 0;
+  fl->T_conv = p->T_convection, fl->h_conv = p->h_convection, fl->T_rad = p->T_radiation, fl->h_rad = p->h_radiation;
+  fl->cmajor = p->cmajor, fl->csub = p->csub, fl->csup = p->csup;
+  fl->mcoeff = p->mcoeff, fl->ncoeff = p->ncoeff, fl->chi = p->chi;
+  fl->stride_heat = p->stride_heat, fl->stride_coeff = p->stride_coeff, fl->stride_mn = p->stride_mn;
+  fl->stride_chi = p->stride_chi;
+  fl->include_enthalpy_flux = p->include_enthalpy_flux ? 1 : 0;
+  fl->include_variable_cp = p->include_variable_cp ? 1 : 0;
+  fl->use_scaled_heat_loss = p->use_scaled_heat_loss ? 1 : 0;
+  fl->scale_and_offset = 0;
+  fl->prefactor = 1.;
+  void *cpg, *mt, *bc;
+  RC(scratch(m, 4, sizeof(double) * (size_t)F * p->nzi, &cpg));
+  RC(scratch(m, 5, sizeof(double) * (size_t)F, &mt));
+  RC(scratch(m, 6, sizeof(double) * 2, &bc));
+  fl->cp_grid = (const double *)cpg, fl->maxT = (const double *)mt, fl->cp_bc = (const double *)bc;
+  CK(launch_flamelet_prepass(m->h.dm, F, d_state, *fl, (double *)cpg, (double *)mt, (double *)bc, s));
+  return GB_OK;
+}
+
+// temporary device copies of the host flamelet arrays for the *_host entry points
+struct FlameletStage
+{
+  std::vector<void *> bufs;
+  gb_flamelet_params dp;
+  ~FlameletStage()
+  {
+    for (void *b : bufs)
+      cudaFree(b);
+  }
+  int put(const double *h, size_t n, const double **out)
+  {
+    *out = nullptr;
+    if (!h)
+      return GB_OK;
+    void *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * (n ? n : 1)));
+    bufs.push_back(d);
+    CK(cudaMemcpy(d, h, sizeof(double) * n, cudaMemcpyHostToDevice));
+    *out = (const double *)d;
+    return GB_OK;
+  }
+  int stage(int ns, int F, const gb_flamelet_params *p)
+  {
+    dp = *p;
+    const size_t nzi = p->nzi;
+    const size_t nh = p->stride_heat ? (size_t)(F - 1) * p->stride_heat + nzi : nzi;
+    const size_t nc = p->stride_coeff ? (size_t)(F - 1) * p->stride_coeff + nzi * ns : nzi * ns;
+    const size_t nm = p->stride_mn ? (size_t)(F - 1) * p->stride_mn + nzi : nzi;
+    const size_t nx = p->stride_chi ? (size_t)(F - 1) * p->stride_chi + nzi + 2 : nzi + 2;
+    RC(put(p->oxy_state, ns, &dp.oxy_state));
+    RC(put(p->fuel_state, ns, &dp.fuel_state));
+    if (!p->adiabatic)
+    {
+      RC(put(p->T_convection, nh, &dp.T_convection));
+      RC(put(p->h_convection, nh, &dp.h_convection));
+      RC(put(p->T_radiation, nh, &dp.T_radiation));
+      RC(put(p->h_radiation, nh, &dp.h_radiation));
+    }
+    RC(put(p->cmajor, nc, &dp.cmajor));
+    RC(put(p->csub, nc, &dp.csub));
+    RC(put(p->csup, nc, &dp.csup));
+    RC(put(p->mcoeff, nm, &dp.mcoeff));
+    RC(put(p->ncoeff, nm, &dp.ncoeff));
+    RC(put(p->chi, nx, &dp.chi));
+    return GB_OK;
+  }
+};
+
+} // namespace
+
+extern "C"
+{
+
+  // flamelet_stencils, flamelet_kernels.cpp:31-48 (host, once per Flamelet)
+  int gb_flamelet_stencils(const gb_mech *m, const double *dz, int nzi, const double *chi, const double *inv_lewis,
+                           double *cmajor, double *csub, double *csup, double *mcoeff, double *ncoeff)
+  {
+    if (!m || !dz || !chi || !inv_lewis || !cmajor || !csub || !csup || !mcoeff || !ncoeff || nzi < 1)
+    {
+      set_error("bad flamelet_stencils arguments");
+      return GB_ERR_ARG;
+    }
+    const int ns = (int)m->h.species.size();
+    for (int i = 0; i < nzi; ++i)
+    {
+      const double dzt = dz[i] + dz[i + 1];
+      for (int l = 0; l < ns; ++l)
+      {
+        cmajor[i * ns + l] = -chi[1 + i] / (dz[i] * dz[i + 1]) * inv_lewis[l];
+        csub[i * ns + l] = chi[1 + i] / (dzt * dz[i]) * inv_lewis[l];
+        csup[i * ns + l] = chi[1 + i] / (dzt * dz[i + 1]) * inv_lewis[l];
+      }
+      ncoeff[i] = 1 / (dz[i] + dz[i + 1]);
+      mcoeff[i] = -ncoeff[i];
+    }
+    return GB_OK;
+  }
+
+  // flamelet_jac_indices, flamelet_kernels.cpp:50-90: COO indices of the BTDDOD storage
+  int gb_flamelet_jac_indices(const gb_mech *m, int nzi, int *rows, int *cols)
+  {
+    if (!m || !rows || !cols || nzi < 1)
+    {
+      set_error("bad flamelet_jac_indices arguments");
+      return GB_ERR_ARG;
+    }
+    const int ns = (int)m->h.species.size();
+    size_t idx = 0;
+    for (int iz = 0; iz < nzi; ++iz)
+      for (int iq = 0; iq < ns; ++iq)
+        for (int jq = 0; jq < ns; ++jq, ++idx)
+        {
+          rows[idx] = iz * ns + jq;
+          cols[idx] = iz * ns + iq;
+        }
+    for (int iz = 1; iz < nzi; ++iz)
+      for (int iq = 0; iq < ns; ++iq, ++idx)
+      {
+        rows[idx] = iz * ns + iq;
+        cols[idx] = iz * ns + iq - ns;
+      }
+    for (int iz = 0; iz < nzi - 1; ++iz)
+      for (int iq = 0; iq < ns; ++iq, ++idx)
+      {
+        rows[idx] = iz * ns + iq;
+        cols[idx] = iz * ns + iq + ns;
+      }
+    return GB_OK;
+  }
+
+  int gb_flamelet_rhs_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm, double *out_rhs,
+                            void *stream)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, state, prm, out_rhs));
+    if (F == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_FLAMELET_RHS;
+    a.n = F * prm->nzi;
+    a.in_state = state;
+    a.p = prm->pressure;
+    a.out0 = out_rhs;
+    RC(flamelet_dev(m, F, state, prm, &a.fl, (cudaStream_t)stream));
+    CK(launch_rates(a, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_flamelet_jacobian_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
+                                 int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
+                                 int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
+                                 double *out_jac, void *stream)
+  {
+    (void)diffterm, (void)out_expeig;
+    RC(ready(m));
+    RC(check_flamelet(F, state, prm, out_jac));
+    if (compute_eigenvalues)
+    {
+      set_error("compute_eigenvalues (PsiTC eigenvalue bound) is not implemented on the device yet");
+      return GB_ERR_UNSUPPORTED;
+    }
+    if (rates_sensitivity_option < 0 || rates_sensitivity_option > 2 || sensitivity_transform_option != 0)
+    {
+      set_error("rates_sensitivity_option must be 0..2 and sensitivity_transform_option 0");
+      return GB_ERR_ARG;
+    }
+    if (F == 0)
+      return GB_OK;
+    ChemArgs a{};
+    a.dm = m->h.dm;
+    a.mode = MODE_FLAMELET_JAC;
+    a.n = F * prm->nzi;
+    a.in_state = state;
+    a.p = prm->pressure;
+    a.out1 = out_jac;
+    RC(flamelet_dev(m, F, state, prm, &a.fl, (cudaStream_t)stream));
+    a.fl.scale_and_offset = scale_and_offset ? 1 : 0;
+    a.fl.prefactor = prefactor;
+    CK(launch_jac(a, (cudaStream_t)stream));
+    CK(launch_flamelet_offdiag(m->h.dm, F, a.fl, out_jac, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_flamelet_rhs_host(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm, double *out_rhs)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, state, prm, out_rhs));
+    if (F == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    const size_t nv = (size_t)F * prm->nzi * ns;
+    FlameletStage st;
+    RC(st.stage(ns, F, prm));
+    void *d_state, *d_rhs;
+    RC(scratch(m, 0, sizeof(double) * nv, &d_state));
+    RC(scratch(m, 2, sizeof(double) * nv, &d_rhs));
+    CK(cudaMemcpy(d_state, state, sizeof(double) * nv, cudaMemcpyHostToDevice));
+    RC(gb_flamelet_rhs_batch(m, F, (double *)d_state, &st.dp, (double *)d_rhs, nullptr));
+    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * nv, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  int gb_flamelet_jacobian_host(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
+                                int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
+                                int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
+                                double *out_jac)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, state, prm, out_jac));
+    if (F == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    const size_t nv = (size_t)F * prm->nzi * ns;
+    const size_t nj = (size_t)F * ns * ((size_t)prm->nzi * ns + 2 * (prm->nzi - 1));
+    FlameletStage st;
+    RC(st.stage(ns, F, prm));
+    void *d_state, *d_jac, *d_eig;
+    RC(scratch(m, 0, sizeof(double) * nv, &d_state));
+    RC(scratch(m, 3, sizeof(double) * nj, &d_jac));
+    RC(scratch(m, 2, sizeof(double) * nv, &d_eig));
+    CK(cudaMemcpy(d_state, state, sizeof(double) * nv, cudaMemcpyHostToDevice));
+    RC(gb_flamelet_jacobian_batch(m, F, (double *)d_state, &st.dp, compute_eigenvalues, diffterm, scale_and_offset,
+                                  prefactor, rates_sensitivity_option, sensitivity_transform_option, (double *)d_eig,
+                                  (double *)d_jac, nullptr));
+    CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * nj, cudaMemcpyDeviceToHost));
+    if (compute_eigenvalues && out_expeig)
+      CK(cudaMemcpy(out_expeig, d_eig, sizeof(double) * nv, cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+}

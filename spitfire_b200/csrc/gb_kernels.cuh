@@ -1,0 +1,73 @@
+// gb_kernels.cuh -- launch interface of the chemistry kernels (implemented in gb_kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gb_mech.h"
+
+namespace gb
+{
+
+enum ChemMode : int
+{
+  MODE_PRODRATES = 0,    // in: T[n], rho[n], y[n][ns]            out0: w[n][ns]
+  MODE_REACTOR_RHS = 1,  // in: state[n][ns]                      out0: rhs[n][ns]
+  MODE_FLAMELET_RHS = 2, // in: state[F][nzi][ns]                 out0: rhs[F][nzi][ns]
+  MODE_SENS = 3,         // in: rho[n], T[n], y[n][ns]            out1: wsens[n][(ns+1)^2]
+  MODE_REACTOR_JAC = 4,  // in: state[n][ns]                      out0: rhs[n][ns], out1: jac[n][ns*ns]
+  MODE_FLAMELET_JAC = 5  // in: state[F][nzi][ns]                 out1: BTDDOD jac per flamelet
+};
+
+struct ReactorDev
+{
+  double p, T_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV;
+  const double *y_in; // device [ns] or null
+  int heat_option, open;
+};
+
+struct FlameletDev
+{
+  int nzi;
+  const double *oxy, *fuel;                 // device [ns]
+  int adiabatic;
+  const double *T_conv, *h_conv, *T_rad, *h_rad; // device, per flamelet [nzi]
+  const double *cmajor, *csub, *csup;       // device, per flamelet [nzi*ns]
+  const double *mcoeff, *ncoeff;            // device, per flamelet [nzi]
+  const double *chi;                        // device, per flamelet [nzi+2]
+  long stride_heat, stride_coeff, stride_mn, stride_chi;
+  int include_enthalpy_flux, include_variable_cp, use_scaled_heat_loss;
+  // work arrays produced by the pre-pass (flamelet_prepass): cp at every interior point and at both streams
+  const double *cp_grid;                    // [F][nzi]
+  const double *maxT;                       // [F]
+  double cp_oxy, cp_fuel;                   // filled on device: read through cp_bc
+  const double *cp_bc;                      // [2] = {cp(oxy), cp(fuel)}
+  // jacobian extras
+  int scale_and_offset;
+  double prefactor;
+};
+
+struct ChemArgs
+{
+  DeviceMech dm;
+  int mode;
+  int n;           // number of thermochemical states (for flamelets F*nzi)
+  const double *in_T, *in_rho, *in_y, *in_state;
+  double p;        // pressure for state-based modes
+  double *out0, *out1;
+  ReactorDev rx;
+  FlameletDev fl;
+  int G;           // states per CTA tile
+  int GS;          // smem stride per index (G padded to odd)
+};
+
+// launches; return cudaError_t of the launch
+cudaError_t launch_rates(const ChemArgs &a, cudaStream_t s);
+cudaError_t launch_jac(const ChemArgs &a, cudaStream_t s);
+cudaError_t launch_thermo(const DeviceMech &dm, int what, int n, const double *aux, const double *T, const double *y,
+                          double *out, cudaStream_t s);
+// flamelet pre-pass: cp_grid[F][nzi], maxT[F], cp_bc[2]
+cudaError_t launch_flamelet_prepass(const DeviceMech &dm, int F, const double *state, const FlameletDev &fl,
+                                    double *cp_grid, double *maxT, double *cp_bc, cudaStream_t s);
+cudaError_t launch_flamelet_offdiag(const DeviceMech &dm, int F, const FlameletDev &fl, double *out_jac, cudaStream_t s);
+long kernel_launch_count();
+
+} // namespace gb

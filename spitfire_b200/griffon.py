@@ -1,0 +1,304 @@
+"""
+Python binding of the B200 Griffon library -- the drop-in for `spitfire.griffon.griffon`.
+
+`PyCombustionKernels` keeps the method names and positional argument orders of the reference's Cython class
+(reference: src/spitfire/griffon/griffon.pyx:220-987); the `py_btddod_*` module functions mirror griffon.pyx:1006-1113.
+Every single-state method is a batch-of-one call of the CUDA path (`gb_*_host` in include/griffon_b200.h): outputs are
+preallocated by the caller and filled in place, exactly as in the reference. New `*_batch` methods expose the batched
+device entry points; they accept torch CUDA tensors (zero-copy, asynchronous on the current torch stream) or numpy
+arrays (staged through the library's device scratch, synchronous).
+
+There is no CPU fallback: if the shared library or a CUDA device is missing, calls raise `GriffonB200Error`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from spitfire_b200._cabi import MechanismSetters, declare_mech_abi, dptr, iptr, c_double_p, c_int_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libgriffon_b200.so')
+_lib = None
+
+
+class GriffonB200Error(RuntimeError):
+    pass
+
+
+class ReactorParams(C.Structure):
+    """gb_reactor_params of include/griffon_b200.h"""
+    _fields_ = [('pressure', C.c_double), ('inflow_temperature', C.c_double), ('inflow_y', c_double_p),
+                ('tau', C.c_double), ('fluid_temperature', C.c_double), ('surf_temperature', C.c_double),
+                ('h_conv', C.c_double), ('eps_rad', C.c_double), ('surface_area_over_volume', C.c_double),
+                ('heat_transfer_option', C.c_int), ('open', C.c_int)]
+
+
+class FlameletParams(C.Structure):
+    """gb_flamelet_params of include/griffon_b200.h"""
+    _fields_ = [('nzi', C.c_int), ('pressure', C.c_double), ('oxy_state', c_double_p), ('fuel_state', c_double_p),
+                ('adiabatic', C.c_int), ('T_convection', c_double_p), ('h_convection', c_double_p),
+                ('T_radiation', c_double_p), ('h_radiation', c_double_p), ('cmajor', c_double_p),
+                ('csub', c_double_p), ('csup', c_double_p), ('mcoeff', c_double_p), ('ncoeff', c_double_p),
+                ('chi', c_double_p), ('include_enthalpy_flux', C.c_int), ('include_variable_cp', C.c_int),
+                ('use_scaled_heat_loss', C.c_int), ('stride_heat', C.c_long), ('stride_coeff', C.c_long),
+                ('stride_mn', C.c_long), ('stride_chi', C.c_long)]
+
+
+def load_library():
+    """dlopen the in-tree CUDA library and declare the C-ABI; raises GriffonB200Error if it is not built"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GriffonB200Error(f'{LIB_PATH} is not built; run `python -m spitfire_b200.build` (needs nvcc). '
+                               'The B200 Griffon path has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    declare_mech_abi(lib, 'gb_')
+    P, D, I, L = C.c_void_p, C.c_double, C.c_int, C.c_long
+    dp, ip = c_double_p, c_int_p
+    V = C.c_void_p  # raw device/host address
+
+    def sig(name, restype, argtypes):
+        f = getattr(lib, name)
+        f.restype, f.argtypes = restype, argtypes
+
+    sig('gb_last_error', C.c_char_p, [])
+    sig('gb_cuda_device_count', I, [])
+    sig('gb_mech_commit', I, [P])
+    sig('gb_kernel_launch_count', L, [])
+    sig('gb_build_info', C.c_char_p, [])
+    sig('gb_thermo_batch', I, [P, I, I, V, V, V, V, V])
+    sig('gb_thermo_host', I, [P, I, I, V, V, V, V])
+    sig('gb_production_rates_batch', I, [P, I, V, V, V, V, V])
+    sig('gb_production_rates_host', I, [P, I, V, V, V, V])
+    sig('gb_prod_rates_sens_batch', I, [P, I, V, V, V, I, V, V])
+    sig('gb_prod_rates_sens_host', I, [P, I, V, V, V, I, V])
+    RP = C.POINTER(ReactorParams)
+    sig('gb_reactor_rhs_isobaric_batch', I, [P, I, V, RP, V, V])
+    sig('gb_reactor_rhs_isobaric_host', I, [P, I, V, RP, V])
+    sig('gb_reactor_jac_isobaric_batch', I, [P, I, V, RP, I, I, V, V, V])
+    sig('gb_reactor_jac_isobaric_host', I, [P, I, V, RP, I, I, V, V])
+    sig('gb_flamelet_stencils', I, [P, dp, I, dp, dp, dp, dp, dp, dp, dp])
+    sig('gb_flamelet_jac_indices', I, [P, I, ip, ip])
+    FP = C.POINTER(FlameletParams)
+    sig('gb_flamelet_rhs_batch', I, [P, I, V, FP, V, V])
+    sig('gb_flamelet_rhs_host', I, [P, I, V, FP, V])
+    sig('gb_flamelet_jacobian_batch', I, [P, I, V, FP, I, D, I, D, I, I, V, V, V])
+    sig('gb_flamelet_jacobian_host', I, [P, I, V, FP, I, D, I, D, I, I, V, V])
+    sig('gb_btddod_full_factorize_batch', I, [I, V, I, I, V, V, V])
+    sig('gb_btddod_full_solve_batch', I, [I, V, V, V, V, I, I, V, V])
+    sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
+    sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
+    sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
+    sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
+    sig('gb_btddod_full_matvec_host', I, [I, V, V, I, I, V])
+    sig('gb_btddod_scale_and_add_diagonal_host', I, [I, V, D, V, D, I, I])
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load_library().gb_last_error()
+        raise GriffonB200Error(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
+
+
+def kernel_launch_count():
+    return load_library().gb_kernel_launch_count()
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith('torch')
+
+
+def _addr(x, dtype=np.float64):
+    """raw address of a numpy array (host) or torch tensor (host or device), with layout checks"""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        want = {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+        if x.dtype != want or not x.is_contiguous():
+            raise TypeError(f'expected a contiguous {want} tensor')
+        return C.c_void_p(x.data_ptr())
+    if not isinstance(x, np.ndarray) or x.dtype != dtype or not x.flags['C_CONTIGUOUS']:
+        raise TypeError(f'expected a C-contiguous {np.dtype(dtype).name} ndarray')
+    return C.c_void_p(x.ctypes.data)
+
+
+def _on_device(*xs):
+    flags = [(_is_torch(x) and x.is_cuda) for x in xs if x is not None]
+    if any(flags) and not all(flags):
+        raise TypeError('mixing device tensors and host arrays in one call')
+    return bool(flags) and all(flags)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PyCombustionKernels(MechanismSetters):
+    _prefix = 'gb_'
+
+    def __init__(self):
+        self._lib = load_library()
+        self._h = C.c_void_p(self._lib.gb_mech_create())
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.gb_mech_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        check(rc, what)
+
+    def commit(self):
+        """pack and upload the mechanism tables to the current CUDA device (also done lazily by every call)"""
+        check(self._lib.gb_mech_commit(self._h), 'mech_commit')
+
+    # ---- thermodynamics (griffon.pyx:684-758) -------------------------------------------------------------------
+    def _thermo1(self, what, T=None, y=None, aux=None, per_species=False):
+        ns = self.n_species
+        Ta = None if T is None else np.array([T], dtype=np.float64)
+        aa = None if aux is None else np.array([aux], dtype=np.float64)
+        out = np.zeros(ns if per_species else 1)
+        check(self._lib.gb_thermo_host(self._h, what, 1, _addr(aa), _addr(Ta), _addr(y), _addr(out)), 'thermo')
+        return out
+
+    def mixture_molecular_weight(self, y):
+        return float(self._thermo1(0, None, y)[0])
+
+    def ideal_gas_density(self, p, T, y):
+        return float(self._thermo1(1, T, y, aux=p)[0])
+
+    def ideal_gas_pressure(self, rho, T, y):
+        return float(self._thermo1(2, T, y, aux=rho)[0])
+
+    def cp_mix(self, T, y):
+        return float(self._thermo1(3, T, y)[0])
+
+    def cv_mix(self, T, y):
+        return float(self._thermo1(4, T, y)[0])
+
+    def enthalpy_mix(self, T, y):
+        return float(self._thermo1(5, T, y)[0])
+
+    def energy_mix(self, T, y):
+        return float(self._thermo1(6, T, y)[0])
+
+    def species_cp(self, T, out):
+        out[:] = self._thermo1(7, T, None, per_species=True)
+
+    def species_cv(self, T, out):
+        out[:] = self._thermo1(8, T, None, per_species=True)
+
+    def species_enthalpies(self, T, out):
+        out[:] = self._thermo1(9, T, None, per_species=True)
+
+    def species_energies(self, T, out):
+        out[:] = self._thermo1(10, T, None, per_species=True)
+
+    def dcpdT_species(self, T, y, out):
+        out[:] = self._thermo1(11, T, y, per_species=True)
+
+    def mole_fractions(self, y, x):
+        x[:] = self._thermo1(12, None, y, per_species=True)
+
+    def thermo_batch(self, what, T, y, out, aux=None):
+        """batched thermodynamic helper; `what` is one of the GB_THERMO_* codes of include/griffon_b200.h"""
+        n = out.shape[0]
+        if _on_device(T, y, out, aux):
+            check(self._lib.gb_thermo_batch(self._h, what, n, _addr(aux), _addr(T), _addr(y), _addr(out), _stream()),
+                  'thermo_batch')
+        else:
+            check(self._lib.gb_thermo_host(self._h, what, n, _addr(aux), _addr(T), _addr(y), _addr(out)), 'thermo')
+
+    # ---- kinetics (griffon.pyx:763-783) ---------------------------------------------------------------------------
+    def production_rates(self, T, rho, y, out_w):
+        """positional (T, rho, y, out): what every reference caller passes (griffon.pyx:763-768)"""
+        Ta, ra = np.array([T], dtype=np.float64), np.array([rho], dtype=np.float64)
+        check(self._lib.gb_production_rates_host(self._h, 1, _addr(Ta), _addr(ra), _addr(y), _addr(out_w)),
+              'production_rates')
+
+    def prod_rates_primitive_sensitivities(self, rho, T, y, option, out):
+        Ta, ra = np.array([T], dtype=np.float64), np.array([rho], dtype=np.float64)
+        check(self._lib.gb_prod_rates_sens_host(self._h, 1, _addr(ra), _addr(Ta), _addr(y), int(option), _addr(out)),
+              'prod_rates_primitive_sensitivities')
+
+    def production_rates_batch(self, T, rho, y, out_w):
+        n = T.shape[0]
+        if _on_device(T, rho, y, out_w):
+            check(self._lib.gb_production_rates_batch(self._h, n, _addr(T), _addr(rho), _addr(y), _addr(out_w),
+                                                      _stream()), 'production_rates_batch')
+        else:
+            check(self._lib.gb_production_rates_host(self._h, n, _addr(T), _addr(rho), _addr(y), _addr(out_w)),
+                  'production_rates')
+
+    def prod_rates_sens_batch(self, rho, T, y, option, out):
+        n = T.shape[0]
+        if _on_device(T, rho, y, out):
+            check(self._lib.gb_prod_rates_sens_batch(self._h, n, _addr(rho), _addr(T), _addr(y), int(option),
+                                                     _addr(out), _stream()), 'prod_rates_sens_batch')
+        else:
+            check(self._lib.gb_prod_rates_sens_host(self._h, n, _addr(rho), _addr(T), _addr(y), int(option),
+                                                    _addr(out)), 'prod_rates_sens')
+
+    # ---- isobaric reactor (griffon.pyx:788-824) -------------------------------------------------------------------
+    @staticmethod
+    def _reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_):
+        prm = ReactorParams()
+        prm.pressure, prm.inflow_temperature, prm.tau = float(p), float(T_in), float(tau)
+        prm.fluid_temperature, prm.surf_temperature = float(T_inf), float(T_surf)
+        prm.h_conv, prm.eps_rad, prm.surface_area_over_volume = float(h_conv), float(eps_rad), float(SoV)
+        prm.heat_transfer_option, prm.open = int(heat_option), int(bool(open_))
+        # closed reactors pass a length-1 dummy y_in (reactors.py:226); it is never dereferenced
+        a = _addr(y_in) if open_ else None
+        prm.inflow_y = C.cast(a, c_double_p) if a is not None else None
+        return prm
+
+    def reactor_rhs_isobaric(self, state, p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_,
+                             out_rhs):
+        prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        check(self._lib.gb_reactor_rhs_isobaric_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)),
+              'reactor_rhs_isobaric')
+
+    def reactor_jac_isobaric(self, state, p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_,
+                             rates_sens_option, sens_transform_option, out_rhs, out_jac):
+        prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        check(self._lib.gb_reactor_jac_isobaric_host(self._h, 1, _addr(state), C.byref(prm), int(rates_sens_option),
+                                                     int(sens_transform_option), _addr(out_rhs), _addr(out_jac)),
+              'reactor_jac_isobaric')
+
+    def reactor_rhs_isobaric_batch(self, state, p, out_rhs, T_in=0., y_in=None, tau=0., T_inf=0., T_surf=0.,
+                                   h_conv=0., eps_rad=0., SoV=0., heat_option=0, open_=False):
+        """state [n, ns] -> out_rhs [n, ns]; torch CUDA tensors (async) or numpy arrays (sync, host<->device inside)"""
+        n = state.shape[0]
+        prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        if _on_device(state, out_rhs):
+            check(self._lib.gb_reactor_rhs_isobaric_batch(self._h, n, _addr(state), C.byref(prm), _addr(out_rhs),
+                                                          _stream()), 'reactor_rhs_isobaric_batch')
+        else:
+            check(self._lib.gb_reactor_rhs_isobaric_host(self._h, n, _addr(state), C.byref(prm), _addr(out_rhs)),
+                  'reactor_rhs_isobaric')
+
+    def reactor_jac_isobaric_batch(self, state, p, out_rhs, out_jac, T_in=0., y_in=None, tau=0., T_inf=0., T_surf=0.,
+                                   h_conv=0., eps_rad=0., SoV=0., heat_option=0, open_=False, rates_sens_option=0,
+                                   sens_transform_option=0):
+        """state [n, ns] -> out_rhs [n, ns], out_jac [n, ns*ns] (column-major ns x ns per state)"""
+        n = state.shape[0]
+        prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        if _on_device(state, out_rhs, out_jac):
+            check(self._lib.gb_reactor_jac_isobaric_batch(self._h, n, _addr(state), C.byref(prm),
+                                                          int(rates_sens_option), int(sens_transform_option),
+                                                          _addr(out_rhs), _addr(out_jac), _stream()),
+                  'reactor_jac_isobaric_batch')
+        else:
+            check(self._lib.gb_reactor_jac_isobaric_host(self._h, n, _addr(state), C.byref(prm),
+                                                         int(rates_sens_option), int(sens_transform_option),
+                                                         _addr(out_rhs), _addr(out_jac)), 'reactor_jac_isobaric')

@@ -171,3 +171,137 @@ def mech_data_to_extracted(gdata):
     return (gdata['element_mw_map'], list(gdata['elements']), gdata['ref_temperature'], gdata['ref_pressure'],
             spec_name_list, spec_dict, reac_list, gdata.get('transport-model', None)), gdata.get('gas_constant',
                                                                                                 GAS_CONSTANT)
+
+
+class ChemicalMechanismSpec(object):
+    """A class that loads chemical mechanisms and mixes streams (mirror of mechanism.py:52-757, Cantera-free).
+
+    **Constructor**: specify a chemical mechanism file in cantera YAML format
+
+    Parameters
+    ----------
+    cantera_input : str
+        a cantera YAML file describing the thermochemistry
+    group_name : str
+        the phase to use
+    mech_data : dict
+        (extension) a `mech_data` dictionary as pickled by the reference (`ChemicalMechanismSpec.mech_data`); when
+        given, the file arguments are ignored. This is what `__setstate__` uses instead of rebuilding a
+        cantera.Solution (mechanism.py:111-113).
+    griffon_factory : callable
+        (extension, used by tests) builds the Griffon-like object to populate; defaults to the CUDA
+        `spitfire_b200.griffon.PyCombustionKernels`.
+    """
+
+    def __init__(self, cantera_input=None, group_name='gas', cantera_solution=None, cantera_xml=None, mech_data=None,
+                 griffon_factory=None):
+        if cantera_xml is not None:
+            cantera_input = cantera_input if cantera_input is not None else cantera_xml
+            print('Deprecation warning: the "cantera_xml" input argument to ChemicalMechanismSpec is deprecated and '
+                  'will be removed.\nUse the "cantera_input" argument instead.')
+        if cantera_solution is not None:
+            raise NotImplementedError('spitfire_b200 reads mechanisms without Cantera; pass a YAML file or mech_data')
+        self._mech_file_path = cantera_input if cantera_input is not None else 'cantera-input-not-given'
+        self._group_name = group_name if group_name is not None else 'cantera-group-not-given'
+
+        self._mech_data = dict()
+        self._mech_data['ref_pressure'] = None
+        self._mech_data['ref_temperature'] = None
+        self._mech_data['elements'] = list()
+        self._mech_data['species'] = dict()
+        self._mech_data['reactions'] = list()
+        self._mech_data['transport-model'] = None
+
+        self._element_stoichiometry = {'O': -1.0, 'H': 0.5, 'C': 2.0, 'Al': 1.5, 'U': 1.0, 'Ar': 0.0, 'N': 0.0,
+                                       'He': 0.0}
+        if griffon_factory is None:
+            from spitfire_b200.griffon import PyCombustionKernels
+            griffon_factory = PyCombustionKernels
+        self._griffon_factory = griffon_factory
+        self._griffon = griffon_factory()
+        if mech_data is not None:
+            extracted, gas_constant = mech_data_to_extracted(mech_data)
+        else:
+            extracted, gas_constant = extract_yaml_mechanism_data(cantera_input, group_name), GAS_CONSTANT
+        populate_griffon_mechanism_data(self._griffon, self._mech_data, *extracted, gas_constant=gas_constant)
+        self._species_names = list(extracted[4])
+        self._species_index = {s: i for i, s in enumerate(self._species_names)}
+        self._element_names = list(extracted[1])
+        self._atom_maps = [dict(extracted[5][s]['atoms']) for s in self._species_names]
+        mw_map = extracted[0]
+        self._molecular_weights = array([sum([mw_map[a] * n for a, n in sorted(am.items())])
+                                         for am in self._atom_maps])
+        self._gas_constant = gas_constant
+
+    @property
+    def mech_data(self):
+        return self._mech_data
+
+    @property
+    def element_stoichiometry(self):
+        return self._element_stoichiometry
+
+    @element_stoichiometry.setter
+    def element_stoichiometry(self, custom_stoichiometry):
+        if custom_stoichiometry is not None:
+            self._element_stoichiometry = custom_stoichiometry
+
+    def __getstate__(self):
+        return dict({'mech_data': self._mech_data, 'element_stoichiometry': self._element_stoichiometry})
+
+    def __setstate__(self, state):
+        self.__init__(mech_data=state['mech_data'])
+        if 'element_stoichiometry' in state:
+            self._element_stoichiometry = state['element_stoichiometry']
+
+    @property
+    def griffon(self):
+        """Obtain this mechanism's griffon PyCombustionKernels object"""
+        return self._griffon
+
+    @property
+    def mech_file_path(self):
+        return self._mech_file_path
+
+    @property
+    def group_name(self):
+        return self._group_name
+
+    @property
+    def n_species(self):
+        return len(self._species_names)
+
+    @property
+    def n_reactions(self):
+        return len(self._mech_data['reactions'])
+
+    @property
+    def species_names(self):
+        return list(self._species_names)
+
+    @property
+    def element_names(self):
+        return list(self._element_names)
+
+    @property
+    def gas_constant(self):
+        return self._gas_constant
+
+    def species_index(self, name):
+        return self._species_index[name]
+
+    @property
+    def molecular_weights(self):
+        return array(self._molecular_weights)
+
+    def molecular_weight(self, ni):
+        if isinstance(ni, str):
+            return self._molecular_weights[self._species_index[ni]]
+        elif isinstance(ni, (int, np.integer)):
+            return self._molecular_weights[ni]
+        else:
+            raise TypeError('ChemicalMechanismSpec.molecular_weight(ni) takes a string or integer, given ' + str(ni))
+
+    def n_atoms(self, species, element):
+        k = species if isinstance(species, (int, np.integer)) else self._species_index[species]
+        return self._atom_maps[k].get(element, 0.0)
