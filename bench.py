@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200 Griffon hot path (contract in the task statement).
+
+Metric (BASELINE.json): batched isobaric-reactor RHS + analytical Jacobian, thermochemical states per second, on
+BASELINE config 3: GRI-3.0 methane/air (53 species, 325 reactions), 1,048,576 synthetic states per GPU
+(spitfire_b200.synthetic, seed 20241017), p = 1 atm, closed adiabatic reactor. One "step" = one pass of
+`reactor_jac_isobaric_batch` (which returns both the RHS and the Jacobian, like the reference's
+`reactor_jac_isobaric`) over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--states S] [--mech NAME]
+
+  default arm      : `value` = device-resident throughput (inputs in HBM, CUDA-event timed, max over ranks);
+                     `e2e`   = same metric through the host-buffer C-ABI entry point (pinned host memory in, results
+                               copied back to the host every step);
+                     `roofline` for k_jac against the measured HBM peak; `cpu_baseline` = the reference's CPU path on
+                     this box's host cores (bounded sample).
+  --impl reference : the reference's own CPU implementation (oracle/_ref when present, else the oracle port) on all
+                     host cores, bounded sample per step.
+Under torchrun (N > 1) every rank owns its own batch (weak scaling, no collective in the data path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np  # noqa: E402
+
+METRIC = 'reactor RHS+Jacobian states/sec (GRI-3.0)'
+UNIT = 'states/s'
+PRESSURE = 101325.
+
+
+def load_mech_data(name):
+    with open(os.path.join(ROOT, 'tests', 'golden', 'mech', name + '.json')) as f:
+        return json.load(f)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---- CPU arm (the only place bench.py executes oracle/) ------------------------------------------------------------
+def _cpu_worker(args):
+    kind, mech_name, fuel, lo, n, reps = args
+    from oracle.oracle import OracleKernels
+    from spitfire_b200.mechanism import ChemicalMechanismSpec
+    from spitfire_b200.synthetic import synthetic_states
+    m = ChemicalMechanismSpec(mech_data=load_mech_data(mech_name), griffon_factory=lambda: OracleKernels(kind))
+    ns = m.n_species
+    state, _ = synthetic_states(m.species_names, lo + n, fuel)
+    state = np.ascontiguousarray(state[lo:lo + n])
+    rhs, jac = np.zeros((n, ns)), np.zeros((n, ns * ns))
+    m.griffon.reactor_jac_isobaric_many(state[:8], PRESSURE, 0, rhs[:8], jac[:8])  # touch
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        m.griffon.reactor_jac_isobaric_many(state, PRESSURE, 0, rhs, jac)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+class CpuArm(object):
+    """the reference's single-state `reactor_jac_isobaric` looped over a sample of the workload on every host core
+    (one process per core, like the reference's own multiprocessing mode, tabulation.py:542-556)"""
+
+    def __init__(self, mech_name, fuel, per_core_states):
+        from oracle import oracle
+        self.kind = 'reference' if oracle.available('reference') else 'port'
+        self.mech_name, self.fuel = mech_name, fuel
+        self.cores = host_cores()
+        self.per_core = per_core_states
+        import multiprocessing as mp
+        self.pool = mp.get_context('fork').Pool(self.cores)
+
+    def run(self, reps):
+        """returns the list over `reps` of wall seconds for cores*per_core states (all cores busy concurrently)"""
+        jobs = [(self.kind, self.mech_name, self.fuel, c * self.per_core, self.per_core, reps)
+                for c in range(self.cores)]
+        t0 = time.perf_counter()
+        per_worker = self.pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+        # per repetition the slowest worker bounds the throughput
+        step_times = [max(w[k] for w in per_worker) for k in range(reps)]
+        return step_times, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    @property
+    def sample(self):
+        return (f'{self.cores * self.per_core} states of the workload per step ({self.per_core} per core), single-state '
+                f'reactor_jac_isobaric looped in C, one process per core')
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    arm = CpuArm(args.mech, args.fuel, args.cpu_states_per_core)
+    step_times, _ = arm.run(args.warmup + args.steps)
+    arm.close()
+    timed = step_times[args.warmup:]
+    n = arm.cores * arm.per_core
+    ms = 1e3 * float(np.mean(timed))
+    value = n / (ms * 1e-3)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, n_states=n),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm -------------------------------------------------------------------------------------------------------
+def workload_config(args, n_states):
+    return {'workload': f'BASELINE config 3: GRI-3.0 methane/air batched isobaric reactor RHS+analytical Jacobian '
+                        f'({args.mech}, closed adiabatic, 1 atm)',
+            'mechanism': args.mech, 'states_per_gpu': n_states, 'seed': 20241017,
+            'l2': 'inputs_and_outputs_larger_than_L2',
+            'parallelism': f'independent state shards x{args.gpus}, no data-path collective'}
+
+
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(smax)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic_per_launch(mech, n_states):
+    """dram bytes of one k_jac launch from the committed ncu capture (profiles/roofline_traffic.json), scaled to the
+    launch size; None if no capture has been committed"""
+    p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(mech)
+    if not e:
+        return None
+    return float(e['dram_bytes']) / float(e['states']) * n_states
+
+
+def run_gpu_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    # CPU baseline first, before any CUDA context exists in this process (fork-safe); rank 0 at N=1 only
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            arm = CpuArm(args.mech, args.fuel, args.cpu_states_per_core)
+            st, _ = arm.run(2)
+            arm.close()
+            n_cpu = arm.cores * arm.per_core
+            cpu_baseline = {'value': n_cpu / st[-1], 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind,
+                            'sample': arm.sample}
+        except Exception as e:  # the checker is optional for the measurement itself
+            cpu_baseline = {'value': None, 'unit': UNIT, 'cores': host_cores(), 'kind': 'unavailable',
+                            'sample': f'failed: {e}'}
+
+    import torch
+    import torch.distributed as dist
+    from spitfire_b200 import griffon
+    from spitfire_b200.mechanism import ChemicalMechanismSpec
+    from spitfire_b200.synthetic import synthetic_states
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    mech = ChemicalMechanismSpec(mech_data=load_mech_data(args.mech))
+    g, ns = mech.griffon, mech.n_species
+    n = args.states
+    # every rank owns a different slice of the seeded sequence
+    state_np, _ = synthetic_states(mech.species_names, n, args.fuel, seed=20241017 + rank)
+    d_state = torch.from_numpy(state_np).cuda()
+    d_rhs = torch.empty((n, ns), dtype=torch.float64, device='cuda')
+    d_jac = torch.empty((n, ns * ns), dtype=torch.float64, device='cuda')
+
+    def step():
+        g.reactor_jac_isobaric_batch(d_state, PRESSURE, d_rhs, d_jac)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = griffon.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    launches = griffon.kernel_launch_count() - launches0
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.stop()
+
+    # ---- end to end through the host-buffer entry point: pinned host state in, rhs + jac back to the host ----------
+    e2e_states = min(n, args.e2e_states)
+    h_state = torch.from_numpy(state_np[:e2e_states]).pin_memory()
+    h_rhs = torch.empty((e2e_states, ns), dtype=torch.float64).pin_memory()
+    h_jac = torch.empty((e2e_states, ns * ns), dtype=torch.float64).pin_memory()
+    hs, hr, hj = h_state.numpy(), h_rhs.numpy(), h_jac.numpy()
+    g.reactor_jac_isobaric_batch(hs, PRESSURE, hr, hj)
+    barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.reactor_jac_isobaric_batch(hs, PRESSURE, hr, hj)  # synchronous: returns when the results are on the host
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    check = float(hr[0, 0])  # read of the step's result on the host
+
+    t_ms = torch.tensor([total_ms / args.steps, e2e_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step, e2e_ms = float(t_ms[0]), float(t_ms[1])
+    if rank == 0:
+        value = world * n / (ms_per_step * 1e-3)
+        peak, peak_src = measured_hbm_peak()
+        bytes_per_state = 8 * (ns * ns + 2 * ns)  # ns in, ns + ns^2 out
+        kernel_ms = float(np.mean(step_ms))
+        achieved = bytes_per_state * n / (kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, n),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': ncu_traffic_per_launch(args.mech, n), 'kernel': 'k_jac',
+                         'algorithmic_bytes_per_launch': bytes_per_state * n, 'kernel_ms': kernel_ms,
+                         'peak_source': peak_src},
+            'cpu_baseline': cpu_baseline,
+            'e2e': {'value': world * e2e_states / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(8 * e2e_states * ns),
+                    'd2h_bytes_per_step': int(8 * e2e_states * (ns + ns * ns)),
+                    'states_per_step': e2e_states, 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+                    'api': 'PyCombustionKernels.reactor_jac_isobaric_batch(numpy) -> gb_reactor_jac_isobaric_host',
+                    'result_check': check},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'build': load_build_info(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_build_info():
+    from spitfire_b200 import griffon
+    return griffon.load_library().gb_build_info().decode()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--mech', default='methane-gri30')
+    ap.add_argument('--fuel', default=None)
+    ap.add_argument('--states', type=int, default=1 << 20)
+    ap.add_argument('--e2e-states', type=int, default=1 << 18)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--cpu-states-per-core', type=int, default=2048)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.fuel is None:
+        args.fuel = 'H2' if args.mech.startswith('h2') else 'CH4'
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1765,6 +1765,25 @@ void go_reactor_jac_isobaric(const go_mech *m, const double *state, double p, do
   free(P);
 }
 
+void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rates_sens_option,
+                                  double *out_rhs, double *out_jac)
+{
+  const int ns = m->ns;
+  const double dummy = 0.;
+  for (int i = 0; i < n; ++i)
+    go_reactor_jac_isobaric(m, state + (size_t)i * ns, p, 0., &dummy, 0., 0., 0., 0., 0., 0., 0, 0, rates_sens_option,
+                            0, out_rhs + (size_t)i * ns, out_jac + (size_t)i * ns * ns);
+}
+
+void go_reactor_rhs_isobaric_many(const go_mech *m, int n, const double *state, double p, double *out_rhs)
+{
+  const int ns = m->ns;
+  const double dummy = 0.;
+  for (int i = 0; i < n; ++i)
+    go_reactor_rhs_isobaric(m, state + (size_t)i * ns, p, 0., &dummy, 0., 0., 0., 0., 0., 0., 0, 0,
+                            out_rhs + (size_t)i * ns);
+}
+
 /* ----------------------------------------------------------------------------------------------------------------
  * flamelet -- flamelet_kernels.cpp
  * -------------------------------------------------------------------------------------------------------------- */

@@ -76,6 +76,12 @@ void go_reactor_jac_isobaric(const go_mech *m, const double *state, double p, do
                              int heat_option, int open, int rates_sens_option, int sens_transform_option,
                              double *out_rhs, double *out_jac);
 
+/* convenience for timing the CPU path without Python overhead: a plain loop of the single-state call over n states
+ * (state [n][ns], out_rhs [n][ns], out_jac [n][ns*ns]); closed adiabatic reactor */
+void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rates_sens_option,
+                                  double *out_rhs, double *out_jac);
+void go_reactor_rhs_isobaric_many(const go_mech *m, int n, const double *state, double p, double *out_rhs);
+
 /* flamelet (argument order of the C++ methods: T_conv, h_conv, T_rad, h_rad) */
 void go_flamelet_stencils(const go_mech *m, const double *dz, int nzi, const double *chi, const double *inv_lewis,
                           double *out_cmajor, double *out_csub, double *out_csup, double *out_mcoeff,

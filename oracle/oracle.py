@@ -54,6 +54,8 @@ def _load(kind):
     sig('go_prod_rates_primitive_sensitivities', None, [P, D, D, dp, I, dp])
     sig('go_reactor_rhs_isobaric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, dp])
     sig('go_reactor_jac_isobaric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, I, I, dp, dp])
+    sig('go_reactor_jac_isobaric_many', None, [P, I, dp, D, I, dp, dp])
+    sig('go_reactor_rhs_isobaric_many', None, [P, I, dp, D, dp])
     sig('go_flamelet_stencils', None, [P, dp, I, dp, dp, dp, dp, dp, dp, dp])
     sig('go_flamelet_jac_indices', None, [P, I, ip, ip])
     sig('go_flamelet_rhs', None, [P, dp, D, dp, dp, I, dp, dp, dp, dp, I, dp, dp, dp, dp, dp, dp, I, I, I, dp])
@@ -146,6 +148,14 @@ class OracleKernels(MechanismSetters):
         self._lib.go_reactor_jac_isobaric(self._h, dptr(state), p, T_in, dptr(y_in), tau, T_inf, T_surf, h_conv,
                                           eps_rad, SoV, int(heat_option), int(bool(open_)), int(rates_sens_option),
                                           int(sens_transform_option), dptr(out_rhs), dptr(out_jac))
+
+    def reactor_jac_isobaric_many(self, state, p, rates_sens_option, out_rhs, out_jac):
+        """plain C loop of the single-state call over state[n, ns] (ctypes releases the GIL: thread-parallel)"""
+        self._lib.go_reactor_jac_isobaric_many(self._h, state.shape[0], dptr(state), p, int(rates_sens_option),
+                                               dptr(out_rhs), dptr(out_jac))
+
+    def reactor_rhs_isobaric_many(self, state, p, out_rhs):
+        self._lib.go_reactor_rhs_isobaric_many(self._h, state.shape[0], dptr(state), p, dptr(out_rhs))
 
     # flamelet -- griffon.pyx:556-679 (Python order: T_conv, T_rad, h_conv, h_rad)
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):

@@ -259,6 +259,24 @@ extern "C"
                                rso, sto, out_rhs, out_jac);
   }
 
+  void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rso, double *out_rhs,
+                                    double *out_jac)
+  {
+    const int ns = (int)m->mw.size();
+    const double dummy = 0.;
+    for (int i = 0; i < n; ++i)
+      m->ck.reactor_jac_isobaric(state + (size_t)i * ns, p, 0., &dummy, 0., 0., 0., 0., 0., 0., 0, false, rso, 0,
+                                 out_rhs + (size_t)i * ns, out_jac + (size_t)i * ns * ns);
+  }
+  void go_reactor_rhs_isobaric_many(const go_mech *m, int n, const double *state, double p, double *out_rhs)
+  {
+    const int ns = (int)m->mw.size();
+    const double dummy = 0.;
+    for (int i = 0; i < n; ++i)
+      m->ck.reactor_rhs_isobaric(state + (size_t)i * ns, p, 0., &dummy, 0., 0., 0., 0., 0., 0., 0, false,
+                                 out_rhs + (size_t)i * ns);
+  }
+
   void go_flamelet_stencils(const go_mech *m, const double *dz, int nzi, const double *chi, const double *inv_lewis,
                             double *cmajor, double *csub, double *csup, double *mcoeff, double *ncoeff)
   {

@@ -302,3 +302,120 @@ class PyCombustionKernels(MechanismSetters):
             check(self._lib.gb_reactor_jac_isobaric_host(self._h, n, _addr(state), C.byref(prm),
                                                          int(rates_sens_option), int(sens_transform_option),
                                                          _addr(out_rhs), _addr(out_jac)), 'reactor_jac_isobaric')
+
+    # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
+    def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):
+        check(self._lib.gb_flamelet_stencils(self._h, dptr(dz), int(nzi), dptr(chi), dptr(inv_lewis),
+                                             dptr(out_cmajor), dptr(out_csub), dptr(out_csup), dptr(out_mcoeff),
+                                             dptr(out_ncoeff)), 'flamelet_stencils')
+
+    def flamelet_jac_indices(self, nzi, out_rows, out_cols):
+        check(self._lib.gb_flamelet_jac_indices(self._h, int(nzi), iptr(out_rows), iptr(out_cols)),
+              'flamelet_jac_indices')
+
+    @staticmethod
+    def _flamelet_params(p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup, mcoeff,
+                         ncoeff, chi, include_enthalpy_flux, include_variable_cp, use_scaled_heat_loss,
+                         strides=(0, 0, 0, 0)):
+        prm = FlameletParams()
+        prm.nzi, prm.pressure = int(nzi), float(p)
+
+        def P(x):
+            a = _addr(x)
+            return C.cast(a, c_double_p) if a is not None else None
+
+        prm.oxy_state, prm.fuel_state = P(oxy), P(fuel)
+        prm.adiabatic = int(bool(adiabatic))
+        if not adiabatic:
+            prm.T_convection, prm.h_convection = P(T_conv), P(h_conv)
+            prm.T_radiation, prm.h_radiation = P(T_rad), P(h_rad)
+        prm.cmajor, prm.csub, prm.csup = P(cmajor), P(csub), P(csup)
+        prm.mcoeff, prm.ncoeff, prm.chi = P(mcoeff), P(ncoeff), P(chi)
+        prm.include_enthalpy_flux = int(bool(include_enthalpy_flux))
+        prm.include_variable_cp = int(bool(include_variable_cp))
+        prm.use_scaled_heat_loss = int(bool(use_scaled_heat_loss))
+        prm.stride_heat, prm.stride_coeff, prm.stride_mn, prm.stride_chi = [int(s) for s in strides]
+        return prm
+
+    def flamelet_rhs(self, state, p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
+                     mcoeff, ncoeff, chi, include_enthalpy_flux, include_variable_cp, use_scaled_heat_loss, out_rhs):
+        """Python argument order (T_conv, T_rad, h_conv, h_rad) as in griffon.pyx:580-620"""
+        prm = self._flamelet_params(p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
+                                    mcoeff, ncoeff, chi, include_enthalpy_flux, include_variable_cp,
+                                    use_scaled_heat_loss)
+        check(self._lib.gb_flamelet_rhs_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)), 'flamelet_rhs')
+
+    def flamelet_jacobian(self, state, p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
+                          mcoeff, ncoeff, chi, compute_eigenvalues, diffterm, scale_and_offset, prefactor,
+                          rates_sens_option, sens_transform_option, include_enthalpy_flux, include_variable_cp,
+                          use_scaled_heat_loss, out_expeig, out_jac):
+        prm = self._flamelet_params(p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
+                                    mcoeff, ncoeff, chi, include_enthalpy_flux, include_variable_cp,
+                                    use_scaled_heat_loss)
+        check(self._lib.gb_flamelet_jacobian_host(self._h, 1, _addr(state), C.byref(prm),
+                                                  int(bool(compute_eigenvalues)), float(diffterm),
+                                                  int(bool(scale_and_offset)), float(prefactor),
+                                                  int(rates_sens_option), int(sens_transform_option),
+                                                  _addr(out_expeig), _addr(out_jac)), 'flamelet_jacobian')
+
+    def flamelet_rhs_batch(self, n_flamelets, state, prm, out_rhs):
+        """state/out [F, nzi*ns]; prm from `_flamelet_params` with arrays living where `state` lives"""
+        if _on_device(state, out_rhs):
+            check(self._lib.gb_flamelet_rhs_batch(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+                                                  _addr(out_rhs), _stream()), 'flamelet_rhs_batch')
+        else:
+            check(self._lib.gb_flamelet_rhs_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+                                                 _addr(out_rhs)), 'flamelet_rhs')
+
+    def flamelet_jacobian_batch(self, n_flamelets, state, prm, out_jac, compute_eigenvalues=False, diffterm=0.,
+                                scale_and_offset=False, prefactor=1., rates_sens_option=0, sens_transform_option=0,
+                                out_expeig=None):
+        if _on_device(state, out_jac):
+            check(self._lib.gb_flamelet_jacobian_batch(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+                                                       int(bool(compute_eigenvalues)), float(diffterm),
+                                                       int(bool(scale_and_offset)), float(prefactor),
+                                                       int(rates_sens_option), int(sens_transform_option),
+                                                       _addr(out_expeig), _addr(out_jac), _stream()),
+                  'flamelet_jacobian_batch')
+        else:
+            check(self._lib.gb_flamelet_jacobian_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+                                                      int(bool(compute_eigenvalues)), float(diffterm),
+                                                      int(bool(scale_and_offset)), float(prefactor),
+                                                      int(rates_sens_option), int(sens_transform_option),
+                                                      _addr(out_expeig), _addr(out_jac)), 'flamelet_jacobian')
+
+
+# ---- BTDDOD module functions (griffon.pyx:1006-1113) --------------------------------------------------------------
+def _bt(name_batch, name_host, on_dev, *args):
+    lib = load_library()
+    if on_dev:
+        check(getattr(lib, name_batch)(*args, _stream()), name_batch)
+    else:
+        check(getattr(lib, name_host)(*args), name_host)
+
+
+def py_btddod_full_factorize(out_d_factors, num_blocks, block_size, out_l_values, out_d_pivots, n_systems=1):
+    _bt('gb_btddod_full_factorize_batch', 'gb_btddod_full_factorize_host',
+        _on_device(out_d_factors, out_l_values, out_d_pivots),
+        int(n_systems), _addr(out_d_factors), int(num_blocks), int(block_size), _addr(out_l_values),
+        _addr(out_d_pivots, np.int32))
+
+
+def py_btddod_full_solve(d_factors, l_values, d_pivots, rhs, num_blocks, block_size, out_solution, n_systems=1):
+    _bt('gb_btddod_full_solve_batch', 'gb_btddod_full_solve_host',
+        _on_device(d_factors, l_values, d_pivots, rhs, out_solution),
+        int(n_systems), _addr(d_factors), _addr(l_values), _addr(d_pivots, np.int32), _addr(rhs), int(num_blocks),
+        int(block_size), _addr(out_solution))
+
+
+def py_btddod_full_matvec(matrix_values, vec, num_blocks, block_size, out_matvec, n_systems=1):
+    _bt('gb_btddod_full_matvec_batch', 'gb_btddod_full_matvec_host', _on_device(matrix_values, vec, out_matvec),
+        int(n_systems), _addr(matrix_values), _addr(vec), int(num_blocks), int(block_size), _addr(out_matvec))
+
+
+def py_btddod_scale_and_add_diagonal(in_out_matrix_values, matrix_scale, diagonal, diag_scale, num_blocks, block_size,
+                                     n_systems=1):
+    _bt('gb_btddod_scale_and_add_diagonal_batch', 'gb_btddod_scale_and_add_diagonal_host',
+        _on_device(in_out_matrix_values, diagonal),
+        int(n_systems), _addr(in_out_matrix_values), float(matrix_scale), _addr(diagonal), float(diag_scale),
+        int(num_blocks), int(block_size))
