@@ -1,11 +1,14 @@
 """
 Builds spitfire_b200/libgriffon_b200.so (the C-ABI library of include/griffon_b200.h) with nvcc for sm_100a.
 
-    python -m spitfire_b200.build [--force] [--parity]
+    python -m spitfire_b200.build [--force] [--fma]
 
 nvcc cross-compiles without a GPU. The library links the CUDA runtime statically and has no torch / Python
-dependency. `--parity` builds with --fmad=false (no FMA contraction), used to quantify how much of the GPU-vs-CPU
-difference is contraction and how much is libm.
+dependency. The default build passes --fmad=false: the reference is compiled for baseline x86-64 (no FMA,
+setup.py:91), and contraction alone moves cancellation-dominated Jacobian entries by up to 1e-9 relative (measured on
+the CPU by recompiling the reference algorithm with -mfma). Without contraction the GPU result
+stays within 1e-12 of the reference on every well-conditioned entry; the measured cost on k_jac is < 1 %.
+`--fma` builds the contracted variant (libgriffon_b200_fma.so) for comparison.
 """
 import glob
 import os
@@ -31,7 +34,7 @@ def stale(target):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, parity=False, out=LIB, verbose=True):
+def build(force=False, parity=True, out=LIB, verbose=True):
     if not force and not stale(out):
         return out
     flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -60,4 +63,7 @@ def build(force=False, parity=False, out=LIB, verbose=True):
 
 
 if __name__ == '__main__':
-    build(force='--force' in sys.argv, parity='--parity' in sys.argv)
+    if '--fma' in sys.argv:
+        build(force=True, parity=False, out=os.path.join(HERE, 'libgriffon_b200_fma.so'))
+    else:
+        build(force='--force' in sys.argv)

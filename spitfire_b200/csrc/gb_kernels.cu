@@ -750,24 +750,271 @@ __device__ __forceinline__ void jac_reaction(const DeviceMech &dm, int r, int g,
   rec[4 * GS] = b;
 }
 
+// ---- staged (shared-memory) parameter access ---------------------------------------------------------------------
+__device__ __forceinline__ double as_double(unsigned long long u) { return __longlong_as_double((long long)u); }
+
+// Reaction phase, fast path: identical arithmetic to jac_reaction() but every parameter comes from the chunk's
+// parameter blob staged in shared memory (format: gb_mech.cu commit(), "per-chunk staged images").
+__device__ __forceinline__ void jac_reaction_staged(const DeviceMech &dm, const unsigned long long *P, int g, int GS,
+                                                    const double *sc, const double *sy, const double *sg,
+                                                    const double *sdb, double *srec_g)
+{
+  const unsigned long long w0 = P[0], w1 = P[1];
+  const int f = (int)(unsigned int)w0;
+  double *rec = srec_g + (size_t)(unsigned int)(w0 >> 32) * GS;
+  const int nrc = (int)(w1 & 255), npd = (int)((w1 >> 8) & 255), nn = (int)((w1 >> 16) & 255),
+            ntb = (int)((w1 >> 24) & 255), nslots = (int)((w1 >> 32) & 255);
+  const int sum_stoich = (int)(signed char)((w1 >> 40) & 255), sum_rc = (int)((w1 >> 48) & 255),
+            sum_pd = (int)((w1 >> 56) & 255);
+  const int type = f_type(f);
+  const unsigned long long *Prc = P + (type == RT_SIMPLE ? 5 : 13);
+  const unsigned long long *Ppd = Prc + 2 * nrc;
+  const unsigned long long *Pnet = Ppd + 2 * npd;
+  const unsigned long long *Ptb = Pnet + nn;
+
+  const int ns = dm.ns, last = ns - 1;
+  const double T = SM(sc, Tile::S_T, g), invT = SM(sc, Tile::S_INVT, g), logT = SM(sc, Tile::S_LOGT, g);
+  const double rho = SM(sc, Tile::S_RHO, g);
+  const double invM = 1. / SM(sc, Tile::S_MMW, g);
+  const double ct = rho * invM;
+  const double invRu = 1. / dm.Ru;
+  for (int k = 0; k < nslots; ++k)
+    rec[(5 + k) * GS] = 0.;
+
+  const double kfb = as_double(P[3]), kfE = as_double(P[4]);
+  const double kf = rate_constant(f_kform(f), as_double(P[2]), kfb, kfE, T, invT, logT);
+  const double kf_sens = invT * (kfb + kfE * invT);
+  double cR = 0.;
+
+#define SP_IDX(Q, i) ((int)(Q[2 * (i)] & 0xffff))
+#define SP_ST(Q, i) ((int)((Q[2 * (i)] >> 16) & 255))
+#define SP_SLOT(Q, i) ((int)(signed char)((Q[2 * (i)] >> 24) & 255))
+#define SP_INVMW(Q, i) as_double(Q[2 * (i) + 1])
+#define SP_CONC(Q, i) (SM(sy, SP_IDX(Q, i), g) * rho * SP_INVMW(Q, i))
+
+  // product of concentrations (except position skip) continuing v, and the derivative wrt position `which`
+  auto mult = [&](double v, const unsigned long long *Q, int n, int skip, bool seq, bool use_pow) {
+    for (int i = 0; i < n; ++i)
+    {
+      if (i == skip)
+        continue;
+      const double c = SP_CONC(Q, i);
+      const int nu = SP_ST(Q, i);
+      if (seq)
+      {
+        for (int k = 0; k < nu; ++k)
+          v *= c;
+      }
+      else if (nu == 1)
+        v *= c;
+      else if (nu == 2)
+        v *= c * c;
+      else if (nu == 3)
+        v *= c * c * c;
+      else if (use_pow)
+        v *= pow(c, (double)nu);
+    }
+    return v;
+  };
+  auto deriv = [&](double a, const unsigned long long *Q, int n, int which, bool seq, bool use_pow) {
+    const int nu = SP_ST(Q, which);
+    if (nu > 1)
+    {
+      const double c = SP_CONC(Q, which);
+      if (nu == 2)
+        a = a * 2. * c;
+      else if (nu == 3)
+        a = a * 3. * c * c;
+      else
+        a = use_pow ? a * (double)nu * pow(c, (double)(nu - 1)) : 0.;
+    }
+    return mult(a, Q, n, which, seq, use_pow);
+  };
+
+  const bool fseq = (f & F_FWD_SPECIAL) != 0, rseq = (f & F_REV_SPECIAL) != 0;
+  double Rnet = mult(kf, Prc, nrc, -1, fseq, false);
+  double dRnetdrho = Rnet / ct * invM * sum_rc;
+  double dRnetdT = Rnet * kf_sens;
+  for (int i = 0; i < nrc; ++i)
+  {
+    const double d = deriv(kf * rho * SP_INVMW(Prc, i), Prc, nrc, i, fseq, false);
+    if (SP_IDX(Prc, i) == last)
+      cR -= d;
+    else
+      rec[(5 + SP_SLOT(Prc, i)) * GS] = d;
+  }
+  if (f & F_REVERSIBLE)
+  {
+    double gs, ds;
+    {
+      const int i0 = (int)(Pnet[0] & 0xffff), s0 = (int)(signed char)((Pnet[0] >> 16) & 255);
+      gs = s0 * SM(sg, i0, g);
+      ds = s0 * SM(sdb, i0, g);
+    }
+    for (int i = 1; i < nn; ++i)
+    {
+      const int ii = (int)(Pnet[i] & 0xffff), si = (int)(signed char)((Pnet[i] >> 16) & 255);
+      gs = gs + si * SM(sg, ii, g);
+      ds = ds + si * SM(sdb, ii, g);
+    }
+    const double Kc = exp(-(sum_stoich * SM(sc, Tile::S_AUX7, g) - invT * invRu * (gs)));
+    const double dKc = -ds;
+    const double kr = kf / Kc;
+    const double Rr = mult(kr, Ppd, npd, -1, rseq, false);
+    Rnet -= Rr;
+    dRnetdrho -= Rr / ct * invM * sum_pd;
+    dRnetdT -= Rr * (kf_sens - dKc);
+    for (int i = 0; i < npd; ++i)
+    {
+      const double d = deriv(kr * rho * SP_INVMW(Ppd, i), Ppd, npd, i, rseq, true);
+      if (SP_IDX(Ppd, i) == last)
+        cR += d;
+      else
+        rec[(5 + SP_SLOT(Ppd, i)) * GS] -= d;
+    }
+  }
+
+  double Ctbaf = 1., dCdrho = 0., dCdT = 0., coef = 0.;
+  const double base = (type != RT_SIMPLE) ? as_double(P[5]) : 0.;
+  if (type != RT_SIMPLE)
+  {
+    double M = base * ct;
+    double dMdrho = base * invM;
+    for (int i = 0; i < ntb; ++i)
+    {
+      const double e = as_double(Ptb[2 * i + 1]) * SM(sy, (int)(Ptb[2 * i] & 0xffff), g);
+      M = M + rho * e;
+      dMdrho += e;
+    }
+    if (type == RT_THIRD_BODY)
+    {
+      Ctbaf = M;
+      dCdrho = dMdrho;
+      coef = rho;
+    }
+    else
+    {
+      const double kpb = as_double(P[7]), kpE = as_double(P[8]);
+      const double kp_over_kf = as_double(P[6]) * exp(kpb * logT - kpE * invT) / kf;
+      const double kp_sens = invT * (kpb + kpE * invT);
+      const double pr = kp_over_kf * M;
+      double nsTmp;
+      if (type == RT_LINDEMANN)
+      {
+        Ctbaf = pr / (1. + pr);
+        dCdT = Ctbaf / (1. + pr) * (kp_sens - kf_sens);
+        nsTmp = kp_over_kf / ((1. + pr) * (1. + pr));
+      }
+      else
+      {
+        const double tr0 = as_double(P[9]), tr1 = as_double(P[10]), tr2 = as_double(P[11]), tr3 = as_double(P[12]);
+        const int tb = f_troe(f);
+        double fCent = 0., dfCentdT = 0.;
+        if (tb & TROE_T3)
+        {
+          const double t1exp = exp(-T / tr1);
+          fCent = (1 - tr0) * t1exp;
+          dfCentdT = (tr0 - 1) / tr1 * t1exp;
+        }
+        if (tb & TROE_T1)
+        {
+          const double t2exp = exp(-T / tr2);
+          fCent = (tb & TROE_T3) ? fCent + tr0 * t2exp : tr0 * t2exp;
+          dfCentdT = (tb & TROE_T3) ? dfCentdT - tr0 / tr2 * t2exp : -tr0 / tr2 * t2exp;
+        }
+        if (tb & TROE_T2)
+        {
+          const double t3exp = exp(-invT * tr3);
+          const bool any = (tb & (TROE_T3 | TROE_T1)) != 0;
+          fCent = any ? fCent + t3exp : t3exp;
+          dfCentdT = any ? dfCentdT + t3exp * tr3 * invT * invT : t3exp * tr3 * invT * invT;
+        }
+        const double log10pr = log10(fmax(pr, 1.e-300));
+        const double log10fcent = log10(fmax(fCent, 1.e-300));
+        const double logfcent = log(fmax(fCent, 1.e-300));
+        const double ln10 = log(10.);
+        const double aTroe = log10pr - 0.67 * log10fcent - 0.4;
+        const double bTroe = -0.14 * log10pr - 1.1762 * log10fcent + 0.806;
+        const double gTroe = 1 / (1 + (aTroe / bTroe) * (aTroe / bTroe));
+        const double fTroe = pow(fCent, gTroe);
+        Ctbaf = fTroe * pr / (1 + pr);
+        const double dfTroedT =
+            fTroe * (gTroe / fCent * dfCentdT +
+                     logfcent * (-2.0 * gTroe * gTroe / ln10 * aTroe / (bTroe * bTroe * bTroe) *
+                                 ((bTroe + 0.14 * aTroe) * (kp_sens - kf_sens) -
+                                  (0.67 * bTroe - 1.1762 * aTroe) * dfCentdT / fCent)));
+        dCdT = 1. / (1. + 1. / pr) * dfTroedT + fTroe * pr / ((1. + pr) * (1. + pr)) * (kp_sens - kf_sens);
+        nsTmp = kp_over_kf * (-2.0 / (1. + pr) * fTroe * logfcent * gTroe * gTroe / ln10 * aTroe /
+                                  (bTroe * bTroe * bTroe) * (bTroe + 0.14 * aTroe) +
+                              fTroe / ((1. + pr) * (1 + pr)));
+      }
+      dCdrho = nsTmp * dMdrho;
+      coef = nsTmp * rho;
+    }
+  }
+  rec[0] = Rnet * Ctbaf;
+  rec[GS] = dRnetdrho * Ctbaf + dCdrho * Rnet;
+  rec[2 * GS] = dRnetdT * Ctbaf + dCdT * Rnet;
+  double b = cR * Ctbaf;
+  if (type != RT_SIMPLE)
+  {
+    for (int k = 0; k < nslots; ++k)
+      rec[(5 + k) * GS] *= Ctbaf;
+    for (int i = 0; i < ntb; ++i)
+    {
+      const double e = coef * as_double(Ptb[2 * i + 1]);
+      const int slot = (int)(signed char)((Ptb[2 * i] >> 24) & 255);
+      if (slot >= 0)
+        rec[(5 + slot) * GS] += e * Rnet;
+      else
+        b -= e * Rnet;
+    }
+    rec[3 * GS] = coef * base * Rnet;
+  }
+  else
+    rec[3 * GS] = 0.;
+  rec[4 * GS] = b;
+#undef SP_IDX
+#undef SP_ST
+#undef SP_SLOT
+#undef SP_INVMW
+#undef SP_CONC
+}
+
+// 16-byte asynchronous global->shared copies (LDGSTS) of a [words] x 8-byte image, spread over the CTA
+__device__ __forceinline__ void stage_async(void *dst_smem, const void *src_gmem, int bytes)
+{
+  const unsigned base = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const char *src = (const char *)src_gmem;
+  for (int o = threadIdx.x * 16; o < bytes; o += blockDim.x * 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(base + o), "l"(src + o) : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const DeviceMech &dm = a.dm;
   const int ns = dm.ns, G = a.G, GS = a.GS;
   const int nsm1 = ns - 1;
-  double *sc = smem;                   // [NSC][GS]
+  const int ncolx = nsm1 + 5; // extended row: Y_0..Y_{ns-2}, w, dw/drho, dw/dT, A, B
+  // staged images first (16-byte aligned), then the per-state working set
+  unsigned long long *sprm = (unsigned long long *)smem;                    // [max_prm_words]
+  unsigned long long *ssegs = sprm + dm.max_prm_words;                      // [max_segs]
+  unsigned int *sitems = (unsigned int *)(ssegs + dm.max_segs);             // [max_items]
+  double *sc = (double *)(sitems + dm.max_items);                           // [NSC][GS]
   double *sy = sc + Tile::NSC * GS;    // [ns][GS]
   double *sg = sy + ns * GS;           // Gibbs
   double *sdb = sg + ns * GS;          // dB/dT
   double *sh = sdb + ns * GS;          // enthalpies
   double *scp = sh + ns * GS;          // species cp
-  double *sdcp = scp + ns * GS;        // species dcp/dT (only its y-weighted sum is needed; kept for clarity)
-  double *srow = sdcp + ns * GS;       // [5][ns][GS]: w, dw/drho, dw/dT, A, B
-  double *sprho = srow + 5 * ns * GS;  // [ns][GS] primitive-Jacobian rho column P[:,rho]
+  double *sdcp = scp + ns * GS;        // species dcp/dT
+  double *sprho = sdcp + ns * GS;      // [ns][GS] primitive-Jacobian rho column P[:,rho]
   double *strow = sprho + ns * GS;     // [ns+1][GS] T-row of the primitive Jacobian (cols rho, T, Y_k)
   double *srec = strow + (ns + 1) * GS; // [rec_cap][GS]
-  double *sJ = srec + dm.rec_cap * GS; // [ns-1 cols][ns rows][GS] sparse part of dw_i/dY_k
+  double *sJ = srec + dm.rec_cap * GS; // [ncolx][ns][GS] extended rows of dw_i/d(Y_k | w,rho,T,A,B)
+  double *srow = sJ + (size_t)nsm1 * ns * GS; // alias: [5][ns][GS] = columns ns-1..ns+3 of sJ
 
   const int ntiles = (a.n + G - 1) / G;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
@@ -775,14 +1022,21 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     const int tile0 = tile * G;
     const int gcount = min(G, a.n - tile0);
     __syncthreads();
+    // stage chunk 0's parameters and gather schedule while the tile is loaded
+    stage_async(sprm, dm.cprm + dm.cprm_off[0], 8 * (dm.cprm_off[1] - dm.cprm_off[0]));
+    stage_async(ssegs, dm.csegs + dm.cseg_off[0], 8 * (dm.cseg_off[1] - dm.cseg_off[0]));
+    stage_async(sitems, dm.citems + dm.citem_off[0], 4 * (dm.citem_off[1] - dm.citem_off[0]));
+    stage_commit();
     load_tile<true>(a, tile0, gcount, sc, sy);
-    for (int e = threadIdx.x; e < nsm1 * ns * GS; e += blockDim.x)
+    for (int e = threadIdx.x; e < ncolx * ns * GS; e += blockDim.x)
       sJ[e] = 0.;
-    for (int e = threadIdx.x; e < 5 * ns * GS; e += blockDim.x)
-      srow[e] = 0.;
     __syncthreads();
     if (threadIdx.x < gcount)
+    {
       state_scalars(a, threadIdx.x, sc, sy);
+      const int g = threadIdx.x;
+      SM(sc, Tile::S_AUX7, g) = log(dm.p_ref * SM(sc, Tile::S_INVT, g) * (1. / dm.Ru)); // log(p0/(R T)), :535
+    }
     __syncthreads();
     for (int item = threadIdx.x; item < gcount * ns; item += blockDim.x)
     {
@@ -795,10 +1049,11 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       SM(scp, i, g) = t.cp;
       SM(sdcp, i, g) = t.dcp;
     }
+    stage_wait_all();
     __syncthreads();
-    if (threadIdx.x < gcount)
+    if (threadIdx.x >= blockDim.x - gcount)
     { // cp and dcp/dT of the mixture in species order (thermodynamics_kernels.cpp:45-131, 183-260)
-      const int g = threadIdx.x;
+      const int g = blockDim.x - 1 - threadIdx.x;
       double cp = 0., dcp = 0.;
       for (int i = 0; i < ns; ++i)
       {
@@ -814,48 +1069,68 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     for (int c = 0; c < dm.n_chunks; ++c)
     {
       const int r0 = dm.chunk_rxn[c], nrc = dm.chunk_rxn[c + 1] - r0;
-      // reaction phase
-      for (int item = threadIdx.x; item < gcount * nrc; item += blockDim.x)
+      // reaction phase: parameters from the staged blob
       {
-        const int rr = item / gcount, g = item - rr * gcount;
-        const int r = r0 + rr;
-        jac_reaction(dm, r, g, GS, sc, sy, sg, sdb, srec + (size_t)dm.rec_off[r] * GS + g);
-      }
-      __syncthreads();
-      // row phase: rates_sensitivities_exact.cpp:1014-1026 gathered by row, reactions ascending
-      for (int item = threadIdx.x; item < gcount * ns; item += blockDim.x)
-      {
-        const int io = item / gcount, g = item - io * gcount;
-        const int i = dm.row_order[io];
-        const int p0 = dm.row_off[c * ns + i], p1 = dm.row_off[c * ns + i + 1];
-        if (p0 == p1)
-          continue;
-        double w = SM(srow, i, g), wr = SM(srow, ns + i, g), wt = SM(srow, 2 * ns + i, g),
-               A = SM(srow, 3 * ns + i, g), B = SM(srow, 4 * ns + i, g);
-        for (int p = p0; p < p1; ++p)
+        const unsigned int *offs = (const unsigned int *)sprm;
+        for (int item = threadIdx.x; item < gcount * nrc; item += blockDim.x)
         {
-          const int r = dm.row_rxn[p];
-          const double fac = dm.row_fac[p];
-          const double *rec = srec + (size_t)dm.rec_off[r] * GS + g;
-          w += fac * rec[0];
-          wr += fac * rec[GS];
-          wt += fac * rec[2 * GS];
-          A += fac * rec[3 * GS];
-          B += fac * rec[4 * GS];
-          const int s0 = dm.slot_off[r], nsl = dm.slot_off[r + 1] - s0;
-          for (int k = 0; k < nsl; ++k)
-          {
-            const int col = dm.slot_species[s0 + k];
-            SM(sJ, col * ns + i, g) += fac * rec[(5 + k) * GS];
-          }
+          const int rr = item / gcount, g = item - rr * gcount;
+          const unsigned long long *P = sprm + offs[rr];
+          if (((int)(unsigned int)P[0]) & F_HAS_ORDERS)
+            jac_reaction(dm, r0 + rr, g, GS, sc, sy, sg, sdb, srec + (size_t)dm.rec_off[r0 + rr] * GS + g);
+          else
+            jac_reaction_staged(dm, P, g, GS, sc, sy, sg, sdb, srec + g);
         }
-        SM(srow, i, g) = w;
-        SM(srow, ns + i, g) = wr;
-        SM(srow, 2 * ns + i, g) = wt;
-        SM(srow, 3 * ns + i, g) = A;
-        SM(srow, 4 * ns + i, g) = B;
       }
+      stage_wait_all(); // this chunk's gather schedule (issued one phase ago) has landed
       __syncthreads();
+      // the parameter buffer is free: prefetch the next chunk's parameters under the gather phase
+      if (c + 1 < dm.n_chunks)
+      {
+        stage_async(sprm, dm.cprm + dm.cprm_off[c + 1], 8 * (dm.cprm_off[c + 2] - dm.cprm_off[c + 1]));
+        stage_commit();
+      }
+      // gather phase: balanced segments of (row, column)-sorted items; every entry is summed in reaction order in a
+      // register and added to its shared-memory slot once per chunk (rates_sensitivities_exact.cpp:1014-1026)
+      {
+        const int nseg = dm.cseg_off[c + 1] - dm.cseg_off[c];
+        for (int item = threadIdx.x; item < gcount * nseg; item += blockDim.x)
+        {
+          const int sidx = item / gcount, g = item - sidx * gcount;
+          const unsigned long long sd = ssegs[sidx];
+          const int row = (int)(sd & 0xffff), cnt = (int)((sd >> 16) & 0xffff);
+          if (cnt == 0)
+            continue;
+          const unsigned int *it = sitems + (unsigned int)(sd >> 32);
+          const double negmw = -dm.mw[row];
+          const double *recg = srec + g;
+          unsigned int u = it[0];
+          int col = (int)((u >> 16) & 0xfff);
+          double acc = 0.;
+          for (int k = 0; k < cnt; ++k)
+          {
+            u = it[k];
+            const int ck = (int)((u >> 16) & 0xfff);
+            if (ck != col)
+            {
+              SM(sJ, col * ns + row, g) += acc;
+              acc = 0.;
+              col = ck;
+            }
+            const int nu = ((int)u) >> 28; // sign-extended 4-bit stoichiometric coefficient
+            acc += ((double)nu * negmw) * recg[(size_t)(u & 0xffff) * GS];
+          }
+          SM(sJ, col * ns + row, g) += acc;
+        }
+      }
+      stage_wait_all(); // next chunk's parameters have landed
+      __syncthreads();
+      if (c + 1 < dm.n_chunks)
+      { // the schedule buffers are free: prefetch the next chunk's schedule under its reaction phase
+        stage_async(ssegs, dm.csegs + dm.cseg_off[c + 1], 8 * (dm.cseg_off[c + 2] - dm.cseg_off[c + 1]));
+        stage_async(sitems, dm.citems + dm.citem_off[c + 1], 4 * (dm.citem_off[c + 2] - dm.citem_off[c + 1]));
+        stage_commit();
+      }
     }
 
     if (a.mode == MODE_SENS)
@@ -1327,7 +1602,8 @@ static size_t rates_smem(const DeviceMech &dm, int GS)
 static size_t jac_smem(const DeviceMech &dm, int GS)
 {
   const size_t ns = dm.ns;
-  return sizeof(double) * (size_t)GS * (Tile::NSC + 7 * ns + 5 * ns + ns + (ns + 1) + dm.rec_cap + (ns - 1) * ns);
+  return 8 * (size_t)dm.max_prm_words + 8 * (size_t)dm.max_segs + 4 * (size_t)dm.max_items +
+         sizeof(double) * (size_t)GS * (Tile::NSC + 6 * ns + ns + (ns + 1) + dm.rec_cap + (ns - 1 + 5) * ns);
 }
 
 static int env_int(const char *name, int dflt)

@@ -331,6 +331,178 @@ int commit(HostMech &m)
   std::stable_sort(row_order.begin(), row_order.end(),
                    [&](short a, short b) { return row_total[a] > row_total[b]; });
 
+  // ---- per-chunk staged images (parameters, gather items, balanced segments) ---------------------------------
+  std::vector<unsigned long long> cprm, csegs;
+  std::vector<unsigned int> citems;
+  std::vector<int> cprm_off(1, 0), citem_off(1, 0), cseg_off(1, 0);
+  int max_prm_words = 2, max_items = 4, max_segs = 2;
+  int seg_target = 12;
+  if (const char *e = std::getenv("GB_SEGMENT_ITEMS"))
+    seg_target = std::max(1, std::atoi(e));
+  auto dbits = [](double v) {
+    unsigned long long u;
+    std::memcpy(&u, &v, 8);
+    return u;
+  };
+  for (int c = 0; c < n_chunks; ++c)
+  {
+    const int r0 = chunk_rxn[c], r1 = chunk_rxn[c + 1], nrc_ = r1 - r0;
+    const size_t base = cprm.size();
+    const int hdr_words = (nrc_ + 1) / 2;
+    cprm.resize(base + hdr_words, 0ull);
+    std::vector<unsigned int> offs(nrc_, 0u);
+    for (int r = r0; r < r1; ++r)
+    {
+      const HostReaction &x = m.reactions[r];
+      offs[r - r0] = (unsigned int)(cprm.size() - base);
+      const int ntb_ = (int)x.tb_idx.size();
+      const int nsl = slot_off[r + 1] - slot_off[r];
+      cprm.push_back((unsigned long long)(unsigned int)flags[r] | ((unsigned long long)(unsigned int)rec_off[r] << 32));
+      unsigned long long w1 = 0;
+      w1 |= (unsigned long long)(x.n_rc & 255);
+      w1 |= (unsigned long long)(x.n_pd & 255) << 8;
+      w1 |= (unsigned long long)(x.n_net & 255) << 16;
+      w1 |= (unsigned long long)(ntb_ & 255) << 24;
+      w1 |= (unsigned long long)(nsl & 255) << 32;
+      w1 |= (unsigned long long)((unsigned char)(signed char)x.sum_stoich) << 40;
+      w1 |= (unsigned long long)(x.sum_rc & 255) << 48;
+      w1 |= (unsigned long long)(x.sum_pd & 255) << 56;
+      cprm.push_back(w1);
+      cprm.push_back(dbits(x.kf[0]));
+      cprm.push_back(dbits(x.kf[1]));
+      cprm.push_back(dbits(x.kf[2]));
+      if (x.type != RT_SIMPLE)
+      {
+        cprm.push_back(dbits(x.base_eff));
+        for (int k = 0; k < 3; ++k)
+          cprm.push_back(dbits(x.kp[k]));
+        for (int k = 0; k < 4; ++k)
+          cprm.push_back(dbits(x.troe[k]));
+      }
+      for (int i = 0; i < x.n_rc; ++i)
+      {
+        const unsigned long long w = (unsigned long long)(unsigned short)x.rc_idx[i] |
+                                     ((unsigned long long)(unsigned char)x.rc_st[i] << 16) |
+                                     ((unsigned long long)(unsigned char)rc_slot[NSR * (size_t)r + i] << 24);
+        cprm.push_back(w);
+        cprm.push_back(dbits(m.invmw[x.rc_idx[i]]));
+      }
+      for (int i = 0; i < x.n_pd; ++i)
+      {
+        const unsigned long long w = (unsigned long long)(unsigned short)x.pd_idx[i] |
+                                     ((unsigned long long)(unsigned char)x.pd_st[i] << 16) |
+                                     ((unsigned long long)(unsigned char)pd_slot[NSR * (size_t)r + i] << 24);
+        cprm.push_back(w);
+        cprm.push_back(dbits(m.invmw[x.pd_idx[i]]));
+      }
+      for (int i = 0; i < x.n_net; ++i)
+        cprm.push_back((unsigned long long)(unsigned short)x.net_idx[i] |
+                       ((unsigned long long)(unsigned char)(signed char)x.net_st[i] << 16));
+      for (int j = 0; j < ntb_; ++j)
+      {
+        cprm.push_back((unsigned long long)(unsigned short)x.tb_idx[j] |
+                       ((unsigned long long)(unsigned char)tb_slot[tb_off[r] + j] << 24));
+        cprm.push_back(dbits(x.tb_eff[j]));
+      }
+      if (x.n_rc > 255 || ntb_ > 255 || nsl > 120 || std::abs(x.sum_stoich) > 127)
+      {
+        set_error("reaction too large for the packed parameter format");
+        return GB_ERR_UNSUPPORTED;
+      }
+    }
+    std::memcpy(&cprm[base], offs.data(), sizeof(unsigned int) * nrc_);
+    if ((cprm.size() - base) & 1)
+      cprm.push_back(0ull);
+    cprm_off.push_back((int)cprm.size());
+    max_prm_words = std::max(max_prm_words, (int)(cprm.size() - base));
+
+    // gather items of the chunk, by row then column then reaction
+    struct Item
+    {
+      int row, col, r, rec, nu;
+    };
+    std::vector<Item> items;
+    for (int r = r0; r < r1; ++r)
+    {
+      const HostReaction &x = m.reactions[r];
+      const int nsl = slot_off[r + 1] - slot_off[r];
+      bool last_involved = false;
+      for (int i = 0; i < x.n_rc; ++i)
+        last_involved |= (x.rc_idx[i] == last && !x.has_orders);
+      for (int i = 0; i < x.n_pd; ++i)
+        last_involved |= (x.pd_idx[i] == last && x.reversible && !x.has_orders);
+      for (int i = 0; i < x.n_sp; ++i)
+        last_involved |= (x.sp_idx[i] == last);
+      for (size_t j = 0; j < x.tb_idx.size(); ++j)
+        last_involved |= (x.tb_idx[j] == last);
+      for (int k = 0; k < x.n_net; ++k)
+      {
+        const int row = x.net_idx[k], nu = x.net_st[k];
+        if (nu < -8 || nu > 7)
+        {
+          set_error("net stoichiometric coefficient outside [-8, 7]");
+          return GB_ERR_UNSUPPORTED;
+        }
+        for (int q = 0; q < nsl; ++q)
+          items.push_back({row, (int)slot_species[slot_off[r] + q], r, rec_off[r] + 5 + q, nu});
+        for (int q = 0; q < 3; ++q)
+          items.push_back({row, ns - 1 + q, r, rec_off[r] + q, nu});
+        if (x.type != RT_SIMPLE)
+          items.push_back({row, ns - 1 + 3, r, rec_off[r] + 3, nu});
+        if (last_involved)
+          items.push_back({row, ns - 1 + 4, r, rec_off[r] + 4, nu});
+      }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+      if (a.row != b.row)
+        return a.row < b.row;
+      if (a.col != b.col)
+        return a.col < b.col;
+      return a.r < b.r;
+    });
+    const size_t ibase = citems.size(), sbase = csegs.size();
+    size_t k = 0;
+    while (k < items.size())
+    {
+      // grow the segment entry by entry (an entry = run of equal (row, col)) up to ~seg_target items, within one row
+      const size_t begin = k;
+      const int row = items[k].row;
+      while (k < items.size() && items[k].row == row)
+      {
+        size_t e = k;
+        while (e < items.size() && items[e].row == row && items[e].col == items[k].col)
+          ++e;
+        if (k > begin && (int)(e - begin) > seg_target)
+          break;
+        k = e;
+      }
+      if (k - begin > 65535 || begin > 0xffffffffull)
+      {
+        set_error("gather segment too long");
+        return GB_ERR_UNSUPPORTED;
+      }
+      csegs.push_back((unsigned long long)(unsigned short)row | ((unsigned long long)(k - begin) << 16) |
+                      ((unsigned long long)begin << 32));
+    }
+    for (const Item &it : items)
+    {
+      if (it.rec > 65535 || it.col > 4095)
+      {
+        set_error("record offset / column outside the packed item format");
+        return GB_ERR_UNSUPPORTED;
+      }
+      citems.push_back((unsigned int)it.rec | ((unsigned int)it.col << 16) | ((unsigned int)(it.nu & 15) << 28));
+    }
+    while ((citems.size() - ibase) & 3)
+      citems.push_back(0u);
+    if ((csegs.size() - sbase) & 1)
+      csegs.push_back(0ull); // count 0: no-op segment
+    citem_off.push_back((int)citems.size());
+    cseg_off.push_back((int)csegs.size());
+    max_items = std::max(max_items, (int)(citems.size() - ibase));
+    max_segs = std::max(max_segs, (int)(csegs.size() - sbase));
+  }
+
   std::vector<double> cpc = m.cpc;
   Blob b;
   const size_t o_mw = b.add(m.mw), o_invmw = b.add(m.invmw), o_tmin = b.add(m.tmin), o_tmax = b.add(m.tmax);
@@ -348,6 +520,8 @@ int commit(HostMech &m)
   const size_t o_chunk = b.add(chunk_rxn), o_recoff = b.add(rec_off);
   const size_t o_rowoff = b.add(row_off), o_rowrxn = b.add(row_rxn), o_rowfac = b.add(row_fac),
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
+  const size_t o_cprm = b.add(cprm), o_cprmoff = b.add(cprm_off), o_citems = b.add(citems),
+               o_citemoff = b.add(citem_off), o_csegs = b.add(csegs), o_csegoff = b.add(cseg_off);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -387,6 +561,10 @@ int commit(HostMech &m)
   d.row_off = at<int>(base, o_rowoff), d.row_rxn = at<int>(base, o_rowrxn);
   d.row_fac = at<double>(base, o_rowfac), d.row_stmw = at<double>(base, o_rowstmw);
   d.row_order = at<short>(base, o_roworder);
+  d.cprm = at<unsigned long long>(base, o_cprm), d.cprm_off = at<int>(base, o_cprmoff);
+  d.citems = at<unsigned int>(base, o_citems), d.citem_off = at<int>(base, o_citemoff);
+  d.csegs = at<unsigned long long>(base, o_csegs), d.cseg_off = at<int>(base, o_csegoff);
+  d.max_prm_words = max_prm_words, d.max_items = max_items, d.max_segs = max_segs;
   m.committed = true;
   return GB_OK;
 }

@@ -97,7 +97,21 @@ struct DeviceMech
   const double *row_stmw;                          // nu*MW, for production_rates' `w -= nu*MW*(k-kr)`
   // row processing order (heaviest first) for load balance
   const short *row_order;                          // [ns]
-  // rates-only records (production_rates / rhs path): one double per reaction, all reactions in one chunk
+  // ---- per-chunk images staged into shared memory by k_jac (cp.async), see gb_mech.cu pack_chunks() ----
+  // parameter blob of chunk c: 8-byte words cprm[cprm_off[c] .. cprm_off[c+1]); it starts with one 32-bit word offset
+  // per reaction of the chunk (padded to a whole number of 8-byte words), followed by the reactions' packed records
+  const unsigned long long *cprm;
+  const int *cprm_off;                             // [n_chunks+1], even (16-byte aligned chunks)
+  // gather items of chunk c, sorted by (row, column, reaction): rec(16) | col(12) << 16 | (nu & 15) << 28, where rec
+  // is the record slot (in doubles, relative to the chunk's record base), col the column of the extended row
+  // (0..ns-2: Y_k, ns-1..ns+3: w, dw/drho, dw/dT, A, B) and nu the net stoichiometric coefficient (factor -nu*MW_row)
+  const unsigned int *citems;
+  const int *citem_off;                            // [n_chunks+1], multiples of 4
+  // balanced segments of chunk c: row(16) | count(16) << 16 | begin(32) << 32 (begin relative to the chunk's items);
+  // a segment never splits a (row, column) entry
+  const unsigned long long *csegs;
+  const int *cseg_off;                             // [n_chunks+1], even
+  int max_prm_words, max_items, max_segs;
 };
 
 struct HostMech

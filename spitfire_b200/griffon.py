@@ -18,7 +18,7 @@ import numpy as np
 from spitfire_b200._cabi import MechanismSetters, declare_mech_abi, dptr, iptr, c_double_p, c_int_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgriffon_b200.so')
+LIB_PATH = os.environ.get('GRIFFON_B200_LIB', os.path.join(HERE, 'libgriffon_b200.so'))
 _lib = None
 
 

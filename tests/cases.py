@@ -116,18 +116,26 @@ def assemble_dense(A, nzi, ns):
     return M
 
 
-def error_stats(a, ref, per_state_axis=None):
-    """returns dict(strict_max, strict_p999, strict_median, scaled_max) where scaled = |d|/(|ref| + 1e-3*max|ref|)
-    with the max taken per state (rows of a 2-D array) or over the whole array"""
+def error_stats(a, ref):
+    """error measures between a computed array and its reference; 2-D arrays are [state, entries] and every state is
+    scaled by its own max|ref| (1-D arrays by the global max):
+      strict_*   : |d|/|ref| over entries with ref != 0 (inf where ref == 0 != a)
+      big_max    : max |d|/|ref| over the "well-conditioned" entries |ref| >= 1e-3 * scale
+      scaled_max : max |d| / (|ref| + 1e-3 * scale) over all entries"""
     a, ref = np.asarray(a), np.asarray(ref)
     d = np.abs(a - ref)
     if a.ndim == 2:
-        scale = np.max(np.abs(ref), axis=1, keepdims=True)
+        scale = np.max(np.abs(ref), axis=1, keepdims=True) * np.ones_like(ref)
     else:
-        scale = np.max(np.abs(ref)) if ref.size else 0.
+        scale = (np.max(np.abs(ref)) if ref.size else 0.) * np.ones_like(ref)
     with np.errstate(all='ignore'):
         strict = np.where(np.abs(ref) > 0, d / np.abs(ref), np.where(d == 0, 0., np.inf))
         scaled = np.where(d == 0, 0., d / (np.abs(ref) + 1e-3 * scale))
-    return dict(strict_max=float(np.max(strict)), strict_p999=float(np.quantile(strict, 0.999)),
-                strict_median=float(np.median(strict)), scaled_max=float(np.max(scaled)),
+    big = (np.abs(ref) >= 1e-3 * scale) & (np.abs(ref) > 0)
+    finite = strict[np.isfinite(strict)]
+    return dict(strict_max=float(np.max(strict)) if strict.size else 0.,
+                strict_p999=float(np.quantile(finite, 0.999)) if finite.size else 0.,
+                strict_median=float(np.median(strict)) if strict.size else 0.,
+                big_max=float(np.max(strict[big])) if big.any() else 0.,
+                scaled_max=float(np.max(scaled)) if scaled.size else 0.,
                 nan=int(np.isnan(a).sum()))
