@@ -8,6 +8,31 @@
 namespace gb
 {
 
+struct Tile
+{
+  // scalars per state, [NSC][GS]
+  enum
+  {
+    S_T = 0,
+    S_LOGT,
+    S_INVT,
+    S_RHO,
+    S_MMW,
+    S_CP,
+    S_CPSENST,
+    S_P,
+    S_AUX0,
+    S_AUX1,
+    S_AUX2,
+    S_AUX3,
+    S_AUX4,
+    S_AUX5,
+    S_AUX6,
+    S_AUX7,
+    NSC
+  };
+};
+
 __device__ __forceinline__ int f_type(int f) { return f & F_TYPE_MASK; }
 __device__ __forceinline__ int f_kform(int f) { return (f >> F_KFORM_SHIFT) & 7; }
 __device__ __forceinline__ int f_troe(int f) { return (f >> F_TROE_SHIFT) & 7; }

@@ -503,6 +503,13 @@ int commit(HostMech &m)
     max_segs = std::max(max_segs, (int)(csegs.size() - sbase));
   }
 
+  JacPlanHost jp;
+  {
+    const int rc = build_jac_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, jp);
+    if (rc != GB_OK)
+      return rc;
+  }
+
   std::vector<double> cpc = m.cpc;
   Blob b;
   const size_t o_mw = b.add(m.mw), o_invmw = b.add(m.invmw), o_tmin = b.add(m.tmin), o_tmax = b.add(m.tmax);
@@ -522,6 +529,9 @@ int commit(HostMech &m)
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
   const size_t o_cprm = b.add(cprm), o_cprmoff = b.add(cprm_off), o_citems = b.add(citems),
                o_citemoff = b.add(citem_off), o_csegs = b.add(csegs), o_csegoff = b.add(cseg_off);
+
+  const size_t o_jpprm = b.add(jp.prm), o_jpoff = b.add(jp.prm_off), o_jpstream = b.add(jp.stream),
+               o_jptstart = b.add(jp.tstart), o_jpfix = b.add(jp.fix), o_jpemap = b.add(jp.emap);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -565,6 +575,12 @@ int commit(HostMech &m)
   d.citems = at<unsigned int>(base, o_citems), d.citem_off = at<int>(base, o_citemoff);
   d.csegs = at<unsigned long long>(base, o_csegs), d.cseg_off = at<int>(base, o_csegoff);
   d.max_prm_words = max_prm_words, d.max_items = max_items, d.max_segs = max_segs;
+  d.jp_prm = at<unsigned long long>(base, o_jpprm), d.jp_prm_off = at<int>(base, o_jpoff);
+  d.jp_stream = at<unsigned int>(base, o_jpstream), d.jp_tstart = at<int>(base, o_jptstart);
+  d.jp_fix = at<int>(base, o_jpfix);
+  d.jp_emap = at<unsigned short>(base, o_jpemap);
+  d.jp_threads = jp.threads, d.jp_rec_total = jp.rec_total, d.jp_nslots = jp.nslots, d.jp_rbase = jp.rbase;
+  d.jp_tbase = jp.tbase, d.jp_sbase = jp.sbase, d.jp_nfix = (int)jp.fix.size() / 3;
   m.committed = true;
   return GB_OK;
 }

@@ -112,6 +112,25 @@ struct DeviceMech
   const unsigned long long *csegs;
   const int *cseg_off;                             // [n_chunks+1], even
   int max_prm_words, max_items, max_segs;
+  // ---- Jacobian plan (gb_plan.cu), consumed by k_jac (gb_jac.cu) ----
+  const unsigned long long *jp_prm; // packed parameters of all reactions
+  const int *jp_prm_off;            // [nr] word offset of reaction r in jp_prm
+  const unsigned int *jp_stream;    // gather stream: header {slot:20, count:11, product:1} followed by `count` items
+  const int *jp_tstart;             // [jp_threads+1] stream range of every CTA thread
+  const int *jp_fix;                // [3*jp_nfix] (dest slot, first extra slot, number of extra parts)
+  const unsigned short *jp_emap;    // [ns*(ns-1)] logical R entry k*ns+i -> compact slot, 0xffff = structurally zero
+  int jp_threads, jp_rec_total, jp_nslots, jp_rbase, jp_tbase, jp_sbase, jp_nfix;
+};
+
+constexpr int JP_REC_HDR = 6; // record = {q, dq/drho, dq/dT, a, b, H, dq/dY_slot...}
+
+struct JacPlanHost
+{
+  std::vector<unsigned long long> prm;
+  std::vector<int> prm_off, tstart, fix;
+  std::vector<unsigned int> stream;
+  std::vector<unsigned short> emap;
+  int threads = 512, rec_total = 0, nslots = 0, rbase = 0, tbase = 0, sbase = 0;
 };
 
 struct HostMech
@@ -140,6 +159,11 @@ struct HostMech
   void *d_scratch[8] = {nullptr};
   size_t d_scratch_bytes[8] = {0};
 };
+
+int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
+                   const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
+                   const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
+                   const std::vector<int> &tb_off, JacPlanHost &out);
 
 // returns 0 or a negative GB_ERR_* code; message in gb::last_error
 int finalize_reaction(const HostMech &m, HostReaction &x);

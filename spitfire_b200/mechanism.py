@@ -305,3 +305,97 @@ class ChemicalMechanismSpec(object):
     def n_atoms(self, species, element):
         k = species if isinstance(species, (int, np.integer)) else self._species_index[species]
         return self._atom_maps[k].get(element, 0.0)
+
+    # ---- streams (mechanism.py:602-757), Cantera-free -------------------------------------------------------------------
+    def stream(self, properties=None, values=None, stp_air=False):
+        """Build a mixture of species with certain properties, e.g. stream('TPX', (300., 101325., 'O2:1, N2:3.76')),
+        stream('TPY', ...), stream('HPY', ...), stream('X', 'H2:1') or stream(stp_air=True)
+        (3.74 mol N2 per mol O2 at 300 K and one atmosphere, mechanism.py:618-622)."""
+        from spitfire_b200.streams import Stream
+        q = Stream(self)
+        if stp_air:
+            if properties is not None or values is not None:
+                print('Warning in building a stream of air at standard conditions!'
+                      'The properties and values arguments will be ignored because stp_air=True was set.')
+            q.TPX = 300., 101325., 'o2:1 n2:3.74'
+        else:
+            if properties is None:
+                raise ValueError('ChemicalMechanismSpec.stream() was called improperly.\n'
+                                 'There are two ways to build streams:\n'
+                                 ' 1)  stream(stp_air=True)\n'
+                                 ' 2)  stream(properties, values), e.g. stream(\'X\', \'O2:1, N2:1\')\n'
+                                 '     or stream(\'TPY\', (300., 101325., \'O2:1, N2:1\'))\n')
+            if values is None:
+                raise ValueError('ChemicalMechanismSpec.stream() expects two arguments '
+                                 'if properties are set in the construction')
+            if not hasattr(type(q), properties) or not isinstance(getattr(type(q), properties), property):
+                raise ValueError(f'unsupported stream property set "{properties}"')
+            setattr(q, properties, values)
+        return q
+
+    def copy_stream(self, stream):
+        """Make a duplicate of a stream - use this to avoid inadvertently modifying a stream by reference."""
+        from spitfire_b200.streams import Stream
+        q = Stream(self)
+        q.TPX = stream.TPX
+        return q
+
+    @staticmethod
+    def mix_streams(streams, basis, constant='HP'):
+        """Mix a number of streams by mass/mole and at constant HP (default), TP or UV (mechanism.py:651-677)"""
+        q_list = []
+        for stream, amount in streams:
+            if basis == 'mass':
+                stream.mass = amount
+            elif basis == 'mole':
+                stream.moles = amount
+            stream.constant = constant
+            q_list.append(stream)
+        mix = q_list[0]
+        for q in q_list[1:]:
+            mix = mix + q
+        return mix if len(q_list) > 1 else mix.copy()
+
+    def _get_atoms_in_stream(self, stream, atom_names):
+        atom_amounts = {atom: 0 for atom in atom_names}
+        X = stream.X
+        for i, species in enumerate(self._species_names):
+            for atom in atom_names:
+                atom_amounts[atom] += X[i] * self.n_atoms(i, atom)
+        return atom_amounts
+
+    def stoich_molar_fuel_to_oxy_ratio(self, fuel_stream, oxy_stream):
+        """molar ratio of fuel to oxidizer at stoichiometric conditions (mechanism.py:696-713)"""
+        present = self._element_names
+        for atom in present:
+            if atom not in self._element_stoichiometry:
+                raise KeyError(f'Error computing stoichiometric fuel/oxidizer ratio. Atom "{atom}" is not present in '
+                               f'the element stoichiometry map, {self._element_stoichiometry}. All atoms must be '
+                               f'included in the stoichiometry map. Atoms present in your mechanism are {present}.')
+        atom_names = [a for a in self._element_stoichiometry.keys() if a in present]
+        fuel_atoms = self._get_atoms_in_stream(fuel_stream, atom_names)
+        oxy_atoms = self._get_atoms_in_stream(oxy_stream, atom_names)
+        return -sum([self._element_stoichiometry[a] * oxy_atoms[a] for a in atom_names]) / \
+            sum([self._element_stoichiometry[a] * fuel_atoms[a] for a in atom_names])
+
+    def stoich_mass_fuel_to_oxy_ratio(self, fuel_stream, oxy_stream):
+        mf = fuel_stream.mean_molecular_weight
+        mx = oxy_stream.mean_molecular_weight
+        return mf / mx * self.stoich_molar_fuel_to_oxy_ratio(fuel_stream, oxy_stream)
+
+    def stoich_mixture_fraction(self, fuel_stream, oxy_stream):
+        """mixture fraction at stoichiometric conditions (mechanism.py:715-722)"""
+        eta = self.stoich_mass_fuel_to_oxy_ratio(fuel_stream, oxy_stream)
+        return eta / (1. + eta)
+
+    def mix_for_equivalence_ratio(self, phi, fuel, oxy):
+        """Mix a stream of fuel and oxidizer such that the mixture has a specified equivalence ratio (mole basis)"""
+        from spitfire_b200.streams import Stream
+        r_st = self.stoich_molar_fuel_to_oxy_ratio(fuel, oxy)
+        X = phi * r_st * fuel.X + oxy.X
+        q = Stream(self)
+        q.TPX = oxy.T, oxy.P, X / np.sum(X)
+        return q
+
+    def mix_for_normalized_equivalence_ratio(self, normalized_phi, fuel, oxy):
+        return self.mix_for_equivalence_ratio(normalized_phi / (1. - normalized_phi), fuel, oxy)
