@@ -4,18 +4,20 @@
 // + transform_isobaric_primitive_jacobian (isobaric_reactor_kernels.cpp:58-168, 221-343) and the per-point part of
 // flamelet_jacobian (flamelet_kernels.cpp:1254-1408) for batches of states.
 //
-// A CTA owns a tile of G states ("state blocking": every thread does its unit of work for all G states, so mechanism
-// data is decoded once per tile and each thread carries G independent dependency chains). Phases, separated by
-// __syncthreads():
-//   load    : coalesced read of the G state vectors
-//   thermo  : thread per species -> cp_i, h_i, dcp_i/dT, Gibbs, dB_i/dT; meanwhile one warp does the order-sensitive
-//             per-state sums (Y_ns = 1 - sum, mixture weight) sequentially as the reference does
-//   react   : thread per reaction -> record {q, dq/drho, dq/dT, a, b, H, dq/dY_slot...} in shared memory
-//   gather  : thread per balanced range of the static plan stream (gb_plan.cu): every destination is summed in a
-//             register in ascending reaction order and stored once -- no atomics, no read-modify-write
-//   fix/row : split destinations are recombined; per-row and per-state quantities of chem_jac_isobaric are formed
-//   output  : the ns x ns block is transformed to (T, Y) variables and streamed to HBM, lanes along the contiguous
-//             (column-major) dimension, G fully coalesced stores per thread
+// A CTA owns a tile of G states whose working set lives in shared memory with the state index fastest ([row][g]).
+// Phases, separated by __syncthreads() (the static schedule is built on the host, gb_plan.cu):
+//   load     : coalesced read of the G state vectors
+//   thermo   : thread per (species, state) -> cp_i, h_i, dcp_i/dT, Gibbs, dB_i/dT; two groups of G threads do the
+//              order-sensitive sums (Y_ns = 1 - sum, mixture weight) sequentially as the reference does
+//   conc     : thread per (species, state) -> concentrations; per-state scalars
+//   react    : warp per reaction group, lane = state + G * reaction-in-group -> reaction records in shared memory
+//   gather   : lane per destination part, G accumulators in registers, items in ascending reaction order; the sums
+//              stay in registers until every warp is done reading records, then overwrite the record region
+//   fix      : split destinations are recombined in part order
+//   rows/cols: per-row constants of the output transform, column sums for the temperature row (species order)
+//   T-row    : final temperature-row values
+//   output   : J = c1_row * R + u_col * c2_row + c3_row streamed to HBM, lanes along the contiguous (column-major)
+//              dimension, G coalesced stores per thread and entry
 // HBM traffic is the algorithmic minimum: ns doubles in, ns + ns^2 doubles out per state.
 #include <cuda_runtime.h>
 
@@ -32,23 +34,117 @@ namespace gb
 extern std::atomic<long> g_jac_launches;
 std::atomic<long> g_jac_launches{0};
 
+// per-state scalars of the tile, [JP_NSC][G]
+enum JScalar : int
+{
+  J_T = 0,
+  J_LOGT,
+  J_INVT,
+  J_RHO,
+  J_MMW,
+  J_INVM,  // 1/mmw
+  J_CT,    // rho/mmw
+  J_IRHO,  // 1/rho
+  J_DRHOF, // (1/ct)*(1/mmw): d(prod C)/drho = R * sum_nu * J_DRHOF
+  J_LPRT,  // log(p_ref/(Ru T))
+  J_CP,
+  J_DCP,
+  J_DPART, // partial sum of Y_i/M_i over i < ns-1
+  J_M0,    // open reactor: inflow enthalpy term
+  J_YCP,   // open reactor: sum cp_i y_in,i
+  J_OBASE, // (bits) offset of the state's output block
+  J_CMOFF, // (bits) offset of the flamelet point's cmajor row
+  J_TTC,   // flamelet (T,T) enthalpy-flux correction
+  J_SPARE0,
+  J_SPARE1
+};
+static_assert(J_SPARE1 < JP_NSC, "JP_NSC too small");
+
 #define SMG(arr, idx, g) (arr)[(idx)*G + (g)]
 
 __device__ __forceinline__ double u2d(unsigned long long u) { return __longlong_as_double((long long)u); }
 
+struct JacSmem
+{
+  double *sc, *sy, *sC, *sg, *sdb, *sh, *scp, *sdcp, *su, *snm, *sim, *sR, *sTH;
+  unsigned short *semap;
+};
+
 // ------------------------------------------------------------------------------------------------------------------
-// reaction phase: record of reaction P (packed parameters in global memory, gb_plan.cu) for state g.
-// rates_sensitivities_exact.cpp:128-1009 restated per reaction; the `for s < ns-1` dense loops (:522-525, :807-810,
-// :849-850, :859-862, ...) are carried by the two scalars a, b.
+// fast path: simple reaction A + B (<)=> C + D with unit coefficients, none of them the last species.
+// rates_sensitivities_exact.cpp:128-1009 specialised; record = {q, dq/drho, dq/dT, dq/dY_A, dq/dY_B, dq/dY_C, dq/dY_D}
 // ------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsigned long long *__restrict__ P, int g,
-                                                const double *sc, const double *sy, const double *sg,
-                                                const double *sdb, const double *sh, double *srec)
+__device__ __forceinline__ void react_fast(const DeviceMech &dm, const unsigned long long *__restrict__ P, int g,
+                                           const JacSmem &s)
+{
+  const ulonglong2 *P2 = reinterpret_cast<const ulonglong2 *>(P);
+  const ulonglong2 q0 = __ldg(P2), q1 = __ldg(P2 + 1), q2 = __ldg(P2 + 2), q3 = __ldg(P2 + 3), q4 = __ldg(P2 + 4),
+                   q5 = __ldg(P2 + 5);
+  const int f = (int)(unsigned int)q0.x;
+  double *rec = s.sR + (size_t)(unsigned int)(q0.x >> 32) * G + g;
+  const int ia = (int)(q0.y & 0xffff), ib = (int)((q0.y >> 16) & 0xffff);
+  const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
+  const double rho = SMG(s.sc, J_RHO, g), drhof = SMG(s.sc, J_DRHOF, g);
+  const double kfA = u2d(q2.x), kfb = u2d(q2.y), kfE = u2d(q3.x);
+  const double kf = rate_constant(f_kform(f), kfA, kfb, kfE, T, invT, logT);
+  const double kf_sens = invT * (kfb + kfE * invT); // ARRHENIUS_SENS_OVER_K, :25
+  const double cA = SMG(s.sC, ia, g), cB = SMG(s.sC, ib, g);
+  const double kfr = kf * rho;
+  double Rnet = kf * cA * cB;                  // :287-325
+  double dRdrho = Rnet * drhof * 2.;           // sum of reactant coefficients = 2
+  double dRdT = Rnet * kf_sens;
+  rec[3 * G] = kfr * u2d(q3.y) * cB;           // :332-526
+  rec[4 * G] = kfr * u2d(q4.x) * cA;
+  if (f & F_REVERSIBLE)
+  { // :528-812
+    const int ic = (int)((q0.y >> 32) & 0xffff), id = (int)((q0.y >> 48) & 0xffff);
+    const unsigned long long ni = q1.x, nn = q1.y;
+    double gs, ds;
+    {
+      const int i0 = (int)(ni & 0xffff);
+      const double s0 = (double)(int)(signed char)(nn & 255);
+      gs = s0 * SMG(s.sg, i0, g);
+      ds = s0 * SMG(s.sdb, i0, g);
+    }
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+    {
+      const int ii = (int)((ni >> (16 * i)) & 0xffff);
+      const double si = (double)(int)(signed char)((nn >> (8 * i)) & 255);
+      gs = fma(si, SMG(s.sg, ii, g), gs);
+      ds = fma(si, SMG(s.sdb, ii, g), ds);
+    }
+    const double sum_stoich = (double)(int)(signed char)((nn >> 32) & 255);
+    const double invRu = 1. / dm.Ru;
+    const double invKc = exp(sum_stoich * SMG(s.sc, J_LPRT, g) - invT * invRu * (gs)); // 1/K_c, :535
+    const double kr = kf * invKc;
+    const double cC = SMG(s.sC, ic, g), cD = SMG(s.sC, id, g);
+    const double Rr = kr * cC * cD;
+    Rnet -= Rr;
+    dRdrho -= Rr * drhof * 2.;
+    dRdT -= Rr * (kf_sens + ds);
+    const double krr = kr * rho;
+    rec[5 * G] = -(krr * u2d(q4.y) * cD);
+    rec[6 * G] = -(krr * u2d(q5.x) * cC);
+  }
+  rec[0] = Rnet;
+  rec[G] = dRdrho;
+  rec[2 * G] = dRdT;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic path: any reaction without non-elementary orders. rates_sensitivities_exact.cpp:128-1009 restated per
+// reaction; the `for s < ns-1` dense loops (:522-525, :807-810, :849-850, :859-862, ...) are carried by the two
+// scalars a, b. Record = {q, dq/drho, dq/dT, a, b, dq/dY_slot...}
+// ------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void react_generic(const DeviceMech &dm, const unsigned long long *__restrict__ P, int g,
+                                              const JacSmem &s)
 {
   const unsigned long long w0 = P[0], w1 = P[1];
   const int f = (int)(unsigned int)w0;
-  double *rec = srec + (size_t)(unsigned int)(w0 >> 32) * G + g;
+  double *rec = s.sR + (size_t)(unsigned int)(w0 >> 32) * G + g;
   const int nrc = (int)(w1 & 255), npd = (int)((w1 >> 8) & 255), nn = (int)((w1 >> 16) & 255),
             ntb = (int)((w1 >> 24) & 255), nslots = (int)((w1 >> 32) & 255);
   const int sum_stoich = (int)(signed char)((w1 >> 40) & 255), sum_rc = (int)((w1 >> 48) & 255),
@@ -57,16 +153,15 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
   const unsigned long long *Prc = P + (type == RT_SIMPLE ? 5 : 13);
   const unsigned long long *Ppd = Prc + 2 * nrc;
   const unsigned long long *Pnet = Ppd + 2 * npd;
-  const unsigned long long *Ptb = Pnet + 2 * nn;
+  const unsigned long long *Ptb = Pnet + nn;
 
   const int last = dm.ns - 1;
-  const double T = SMG(sc, Tile::S_T, g), invT = SMG(sc, Tile::S_INVT, g), logT = SMG(sc, Tile::S_LOGT, g);
-  const double rho = SMG(sc, Tile::S_RHO, g);
-  const double invM = 1. / SMG(sc, Tile::S_MMW, g);
-  const double ct = rho * invM;
+  const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
+  const double rho = SMG(s.sc, J_RHO, g), drhof = SMG(s.sc, J_DRHOF, g);
+  const double invM = SMG(s.sc, J_INVM, g), ct = SMG(s.sc, J_CT, g);
   const double invRu = 1. / dm.Ru;
   for (int k = 0; k < nslots; ++k)
-    rec[(JP_REC_HDR + k) * G] = 0.;
+    rec[(JP_HDR_GEN + k) * G] = 0.;
 
   const double kfb = u2d(P[3]), kfE = u2d(P[4]);
   const double kf = rate_constant(f_kform(f), u2d(P[2]), kfb, kfE, T, invT, logT);
@@ -77,7 +172,7 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
 #define SP_ST(Q, i) ((int)((Q[2 * (i)] >> 16) & 255))
 #define SP_SLOT(Q, i) ((int)(signed char)((Q[2 * (i)] >> 24) & 255))
 #define SP_INVMW(Q, i) u2d(Q[2 * (i) + 1])
-#define SP_CONC(Q, i) (SMG(sy, SP_IDX(Q, i), g) * rho * SP_INVMW(Q, i))
+#define SP_CONC(Q, i) SMG(s.sC, SP_IDX(Q, i), g)
 
   // v * prod_{i != skip} C_i^nu_i; seq reproduces the reference's special-cased orders ((v*C)*C), otherwise its
   // generic branch (v*(C*C)); use_pow handles |nu| > 3 where the reference does (:702-704)
@@ -121,7 +216,7 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
 
   const bool fseq = (f & F_FWD_SPECIAL) != 0, rseq = (f & F_REV_SPECIAL) != 0;
   double Rnet = mult(kf, Prc, nrc, -1, fseq, false); // :287-325
-  double dRnetdrho = Rnet / ct * invM * sum_rc;
+  double dRnetdrho = Rnet * drhof * sum_rc;
   double dRnetdT = Rnet * kf_sens;
   for (int i = 0; i < nrc; ++i)
   { // :332-526
@@ -129,28 +224,28 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
     if (SP_IDX(Prc, i) == last)
       cR -= d;
     else
-      rec[(JP_REC_HDR + SP_SLOT(Prc, i)) * G] = d;
+      rec[(JP_HDR_GEN + SP_SLOT(Prc, i)) * G] = d;
   }
   if (f & F_REVERSIBLE)
   { // :528-812
     double gs, ds;
     {
       const int i0 = (int)(Pnet[0] & 0xffff), s0 = (int)(signed char)((Pnet[0] >> 16) & 255);
-      gs = s0 * SMG(sg, i0, g);
-      ds = s0 * SMG(sdb, i0, g);
+      gs = s0 * SMG(s.sg, i0, g);
+      ds = s0 * SMG(s.sdb, i0, g);
     }
     for (int i = 1; i < nn; ++i)
     {
-      const int ii = (int)(Pnet[2 * i] & 0xffff), si = (int)(signed char)((Pnet[2 * i] >> 16) & 255);
-      gs = gs + si * SMG(sg, ii, g);
-      ds = ds + si * SMG(sdb, ii, g);
+      const int ii = (int)(Pnet[i] & 0xffff), si = (int)(signed char)((Pnet[i] >> 16) & 255);
+      gs = gs + si * SMG(s.sg, ii, g);
+      ds = ds + si * SMG(s.sdb, ii, g);
     }
-    const double Kc = exp(-(sum_stoich * SMG(sc, Tile::S_AUX7, g) - invT * invRu * (gs)));
+    const double invKc = exp(sum_stoich * SMG(s.sc, J_LPRT, g) - invT * invRu * (gs));
     const double dKc = -ds;
-    const double kr = kf / Kc;
+    const double kr = kf * invKc;
     const double Rr = mult(kr, Ppd, npd, -1, rseq, false);
     Rnet -= Rr;
-    dRnetdrho -= Rr / ct * invM * sum_pd;
+    dRnetdrho -= Rr * drhof * sum_pd;
     dRnetdT -= Rr * (kf_sens - dKc);
     for (int i = 0; i < npd; ++i)
     {
@@ -158,7 +253,7 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
       if (SP_IDX(Ppd, i) == last)
         cR += d;
       else
-        rec[(JP_REC_HDR + SP_SLOT(Ppd, i)) * G] -= d;
+        rec[(JP_HDR_GEN + SP_SLOT(Ppd, i)) * G] -= d;
     }
   }
 
@@ -171,7 +266,7 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
     double dMdrho = base * invM;
     for (int i = 0; i < ntb; ++i)
     {
-      const double e = u2d(Ptb[2 * i + 1]) * SMG(sy, (int)(Ptb[2 * i] & 0xffff), g);
+      const double e = u2d(Ptb[2 * i + 1]) * SMG(s.sy, (int)(Ptb[2 * i] & 0xffff), g);
       M = M + rho * e;
       dMdrho += e;
     }
@@ -249,13 +344,13 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
   if (type != RT_SIMPLE)
   {
     for (int k = 0; k < nslots; ++k)
-      rec[(JP_REC_HDR + k) * G] *= Ctbaf;
+      rec[(JP_HDR_GEN + k) * G] *= Ctbaf;
     for (int i = 0; i < ntb; ++i)
     {
       const double e = coef * u2d(Ptb[2 * i + 1]);
       const int slot = (int)(signed char)((Ptb[2 * i] >> 24) & 255);
       if (slot >= 0)
-        rec[(JP_REC_HDR + slot) * G] += e * Rnet;
+        rec[(JP_HDR_GEN + slot) * G] += e * Rnet;
       else
         b -= e * Rnet; // the last species is a third body: -eps_last on every column (:855-865)
     }
@@ -264,11 +359,6 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
   else
     rec[3 * G] = 0.;
   rec[4 * G] = b;
-  // reaction enthalpy H = sum_net h_i * (-nu_i M_i): sum_i h_i dw_i/dx = sum_r H_r dq_r/dx (isobaric_reactor_kernels.cpp:74-92)
-  double H = 0.;
-  for (int i = 0; i < nn; ++i)
-    H += SMG(sh, (int)(Pnet[2 * i] & 0xffff), g) * u2d(Pnet[2 * i + 1]);
-  rec[5 * G] = H;
 #undef SP_IDX
 #undef SP_ST
 #undef SP_SLOT
@@ -276,33 +366,38 @@ __device__ __forceinline__ void reaction_record(const DeviceMech &dm, const unsi
 #undef SP_CONC
 }
 
-// reactions with non-elementary orders (rare): global-memory parameter path, rates_sensitivities_exact.cpp:198-281
+// reactions with non-elementary orders (rare), rates_sensitivities_exact.cpp:198-281; parameters from the SoA tables
 template <int G>
-__device__ void reaction_record_orders(const DeviceMech &dm, int r, const unsigned long long *__restrict__ P, int g,
-                                       const double *sc, const double *sy, const double *sh, double *srec)
+__device__ __noinline__ void react_orders(int ns, const int *__restrict__ dm_n_sp, const short *__restrict__ dm_sp_idx,
+                                          const double *__restrict__ dm_sp_order,
+                                          const signed char *__restrict__ dm_sp_slot,
+                                          const double *__restrict__ dm_invmw, int r,
+                                          const unsigned long long *__restrict__ P, int g, double *sc, double *sC,
+                                          double *sy, double *sR)
 {
+  JacSmem s;
+  s.sc = sc, s.sC = sC, s.sy = sy, s.sR = sR;
   const unsigned long long w0 = P[0], w1 = P[1];
   const int f = (int)(unsigned int)w0;
-  double *rec = srec + (size_t)(unsigned int)(w0 >> 32) * G + g;
+  double *rec = s.sR + (size_t)(unsigned int)(w0 >> 32) * G + g;
   const int nrc = (int)(w1 & 255), npd = (int)((w1 >> 8) & 255), nn = (int)((w1 >> 16) & 255),
             nslots = (int)((w1 >> 32) & 255);
   const int type = f_type(f);
   const unsigned long long *Pnet = P + (type == RT_SIMPLE ? 5 : 13) + 2 * nrc + 2 * npd;
-  const int last = dm.ns - 1;
-  const double T = SMG(sc, Tile::S_T, g), invT = SMG(sc, Tile::S_INVT, g), logT = SMG(sc, Tile::S_LOGT, g);
-  const double rho = SMG(sc, Tile::S_RHO, g);
-  const double invM = 1. / SMG(sc, Tile::S_MMW, g);
-  const double ct = rho * invM;
+  const int last = ns - 1;
+  const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
+  const double rho = SMG(s.sc, J_RHO, g);
+  const double invM = SMG(s.sc, J_INVM, g), ct = SMG(s.sc, J_CT, g);
   for (int k = 0; k < nslots; ++k)
-    rec[(JP_REC_HDR + k) * G] = 0.;
+    rec[(JP_HDR_GEN + k) * G] = 0.;
   const double kfb = u2d(P[3]), kfE = u2d(P[4]);
   const double kf = rate_constant(f_kform(f), u2d(P[2]), kfb, kfE, T, invT, logT);
   const double kf_sens = invT * (kfb + kfE * invT);
-  const int n = dm.n_sp[r];
-  const short *sp = dm.sp_idx + NSR * (size_t)r;
-  const double *ord = dm.sp_order + NSR * (size_t)r;
-  const signed char *spslot = dm.sp_slot + NSR * (size_t)r;
-#define CS(i) (SMG(sy, sp[i], g) * rho * dm.invmw[sp[i]])
+  const int n = dm_n_sp[r];
+  const short *sp = dm_sp_idx + NSR * (size_t)r;
+  const double *ord = dm_sp_order + NSR * (size_t)r;
+  const signed char *spslot = dm_sp_slot + NSR * (size_t)r;
+#define CS(i) SMG(s.sC, sp[i], g)
   double sumOrders = 0., Rnet = kf, cR = 0.;
   for (int i = 0; i < n; ++i)
     if (fabs(ord[i]) > 1.e-12)
@@ -328,7 +423,7 @@ __device__ void reaction_record_orders(const DeviceMech &dm, int r, const unsign
       }
       else
       {
-        const double pre = ord[l] * rho * dm.invmw[sp[l]];
+        const double pre = ord[l] * rho * dm_invmw[sp[l]];
         if (ord[l] > 1 || is_last)
           v *= pre * pow(fmax(cl, 1.e-16), ord[l] - 1.);
         else
@@ -338,20 +433,20 @@ __device__ void reaction_record_orders(const DeviceMech &dm, int r, const unsign
     if (is_last)
       cR -= v;
     else
-      rec[(JP_REC_HDR + spslot[j]) * G] = v;
+      rec[(JP_HDR_GEN + spslot[j]) * G] = v;
   }
 #undef CS
   // third-body factors of non-elementary reactions: only the plain third-body form is supported here
   double Ctbaf = 1., dCdrho = 0., coef = 0., b = 0.;
   const double base = (type != RT_SIMPLE) ? u2d(P[5]) : 0.;
   const int ntb = (int)((w1 >> 24) & 255);
-  const unsigned long long *Ptb = Pnet + 2 * nn;
+  const unsigned long long *Ptb = Pnet + nn;
   if (type == RT_THIRD_BODY)
   {
     double M = base * ct, dMdrho = base * invM;
     for (int i = 0; i < ntb; ++i)
     {
-      const double e = u2d(Ptb[2 * i + 1]) * SMG(sy, (int)(Ptb[2 * i] & 0xffff), g);
+      const double e = u2d(Ptb[2 * i + 1]) * SMG(s.sy, (int)(Ptb[2 * i] & 0xffff), g);
       M = M + rho * e;
       dMdrho += e;
     }
@@ -368,13 +463,13 @@ __device__ void reaction_record_orders(const DeviceMech &dm, int r, const unsign
   if (type == RT_THIRD_BODY)
   {
     for (int k = 0; k < nslots; ++k)
-      rec[(JP_REC_HDR + k) * G] *= Ctbaf;
+      rec[(JP_HDR_GEN + k) * G] *= Ctbaf;
     for (int i = 0; i < ntb; ++i)
     {
       const double e = coef * u2d(Ptb[2 * i + 1]);
       const int slot = (int)(signed char)((Ptb[2 * i] >> 24) & 255);
       if (slot >= 0)
-        rec[(JP_REC_HDR + slot) * G] += e * Rnet;
+        rec[(JP_HDR_GEN + slot) * G] += e * Rnet;
       else
         b -= e * Rnet;
     }
@@ -383,10 +478,26 @@ __device__ void reaction_record_orders(const DeviceMech &dm, int r, const unsign
   else
     rec[3 * G] = 0.;
   rec[4 * G] = b;
-  double H = 0.;
-  for (int i = 0; i < nn; ++i)
-    H += SMG(sh, (int)(Pnet[2 * i] & 0xffff), g) * u2d(Pnet[2 * i + 1]);
-  rec[5 * G] = H;
+}
+
+// one gather step: acc[g] += nu * record[row][g]
+template <int G>
+__device__ __forceinline__ void gather_step(unsigned int u, const double *sR, double (&acc)[G])
+{
+  const double nu = (double)(((int)(u << 8)) >> 24);
+  const double *p = sR + (size_t)(u & 0xffff) * G;
+  if (G == 1)
+    acc[0] = fma(nu, p[0], acc[0]);
+  else
+  {
+#pragma unroll
+    for (int g = 0; g < G; g += 2)
+    {
+      const double2 v = *reinterpret_cast<const double2 *>(p + g);
+      acc[g] = fma(nu, v.x, acc[g]);
+      acc[g + 1] = fma(nu, v.y, acc[g + 1]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -394,30 +505,47 @@ template <int G>
 __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 {
   extern __shared__ __align__(16) double smem[];
+  constexpr int LPR = 32 / G, RMAX = 32 / G;
   const DeviceMech &dm = a.dm;
-  const int ns = dm.ns, nr = dm.nr, nsm1 = ns - 1;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  double *sc = smem;                    // [NSC][G] per-state scalars
-  double *sy = sc + Tile::NSC * G;      // [ns][G] mass fractions
-  double *sg = sy + ns * G;             // Gibbs              -> later: row quantity P[1+i, rho]
-  double *sdb = sg + ns * G;            // dB/dT              -> later: row quantity nm_i * RA_i
-  double *sh = sdb + ns * G;            // enthalpies
-  double *scp = sh + ns * G;            // species cp
-  double *sdcp = scp + ns * G;          // species dcp/dT     -> later: row quantity nm_i * RB_i
-  double *su = sdcp + ns * G;           // [ns] u_k = 1/M_k - 1/M_ns
-  double *snm = su + ns;                // [ns] -M_i
-  double *srec = snm + ns;              // [rec_total][G] reaction records
-  double *sJ = srec + (size_t)dm.jp_rec_total * G; // [nslots][G] gathered sums
-  unsigned short *semap = (unsigned short *)(sJ + (size_t)dm.jp_nslots * G); // [ns*(ns-1)]
+  const int ns = dm.ns, nsm1 = ns - 1;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int region = max(dm.jp_rec_rows, dm.jp_rows) + 2;
+  JacSmem s;
+  s.sc = smem;                         // [JP_NSC][G] per-state scalars
+  s.sy = s.sc + JP_NSC * G;            // [ns][G] mass fractions
+  s.sC = s.sy + ns * G;                // concentrations
+  s.sg = s.sC + ns * G;                // Gibbs              -> later: c1 of the output transform
+  s.sdb = s.sg + ns * G;               // dB/dT              -> later: c2
+  s.sh = s.sdb + ns * G;               // enthalpies
+  s.scp = s.sh + ns * G;               // species cp
+  s.sdcp = s.scp + ns * G;             // species dcp/dT     -> later: c3
+  s.su = s.sdcp + ns * G;              // [ns] u_k = 1/M_k - 1/M_ns
+  s.snm = s.su + ns;                   // [ns] -M_i
+  s.sim = s.snm + ns;                  // [ns] 1/M_i
+  s.sR = s.sim + ns + (ns & 1);        // [region][G] reaction records, then gathered sums (16-byte aligned)
+  s.sTH = s.sR + (size_t)region * G;   // [ncs][G] column sums
+  s.semap = (unsigned short *)(s.sTH + (size_t)dm.jp_ncs * G); // [(ns+1)*(ns-1)]
+  const int zrow = dm.jp_zrow;
 
   // per-CTA constants
   for (int i = tid; i < ns; i += nt)
   {
-    su[i] = dm.invmw[i] - dm.invmw[nsm1];
-    snm[i] = -dm.mw[i];
+    s.su[i] = dm.invmw[i] - dm.invmw[nsm1];
+    s.snm[i] = -dm.mw[i];
+    s.sim[i] = dm.invmw[i];
   }
-  for (int e = tid; e < ns * nsm1; e += nt)
-    semap[e] = dm.jp_emap[e];
+  for (int e = tid; e < (ns + 1) * nsm1; e += nt)
+    s.semap[e] = dm.jp_emap[e];
+  if (tid < 2 * G)
+    s.sR[(size_t)zrow * G + tid] = 0.;
+
+  const bool state_mode = a.in_state != nullptr;
+  const bool reactor = a.mode == MODE_REACTOR_JAC;
+  const bool flamelet = a.mode == MODE_FLAMELET_JAC;
+  const bool isothermal = reactor && a.rx.heat_option == 1;
+  const bool open = reactor && a.rx.open != 0;
+  const double invTau = open ? 1. / a.rx.tau : 0.;
+  const FlameletDev &fl = a.fl;
 
   const int ntiles = (a.n + G - 1) / G;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
@@ -426,16 +554,16 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     const int gcount = min(G, a.n - tile0);
     __syncthreads();
     // ---- load (states past the end of the batch replicate the tile's first state; they are never written) ----------
-    if (a.in_state != nullptr)
+    if (state_mode)
     {
       for (int item = tid; item < G * ns; item += nt)
       {
         const int g = item / ns, j = item - g * ns;
         const double v = a.in_state[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
         if (j == 0)
-          SMG(sc, Tile::S_T, g) = v;
+          SMG(s.sc, J_T, g) = v;
         else
-          SMG(sy, j - 1, g) = v;
+          SMG(s.sy, j - 1, g) = v;
       }
     }
     else
@@ -443,222 +571,282 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       for (int item = tid; item < G * ns; item += nt)
       {
         const int g = item / ns, j = item - g * ns;
-        SMG(sy, j, g) = a.in_y[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
+        SMG(s.sy, j, g) = a.in_y[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
       }
       if (tid < G)
       {
-        SMG(sc, Tile::S_T, tid) = a.in_T[tile0 + (tid < gcount ? tid : 0)];
-        SMG(sc, Tile::S_RHO, tid) = a.in_rho[tile0 + (tid < gcount ? tid : 0)];
+        SMG(s.sc, J_T, tid) = a.in_T[tile0 + (tid < gcount ? tid : 0)];
+        SMG(s.sc, J_RHO, tid) = a.in_rho[tile0 + (tid < gcount ? tid : 0)];
       }
     }
     __syncthreads();
-    // ---- thermo (threads 32..) overlapped with the order-sensitive per-state sums (warp 0) ------------------------------
+    // ---- thermo, overlapped with the two order-sensitive chains -------------------------------------------------------------
     if (tid < G)
-    { // extract_y (combustion_kernels.h:505-515), mixture_molecular_weight (:381-387), ideal_gas_density (:526-530)
-      const int g = tid;
-      if (a.in_state != nullptr)
+    { // extract_y (combustion_kernels.h:505-515)
+      if (state_mode)
       {
         double yl = 1.;
         for (int j = 0; j < nsm1; ++j)
-          yl -= SMG(sy, j, g);
-        SMG(sy, nsm1, g) = yl;
+          yl -= SMG(s.sy, j, tid);
+        SMG(s.sy, nsm1, tid) = yl;
       }
+    }
+    else if (tid < 2 * G)
+    { // mixture_molecular_weight (:381-387): sum_i Y_i/M_i in species order, all but the last term
+      const int g = tid - G;
       double d = 0.;
-      for (int i = 0; i < ns; ++i)
-        d += dm.invmw[i] * SMG(sy, i, g);
-      const double mmw = 1. / d, T = SMG(sc, Tile::S_T, g), invT = 1. / T;
-      SMG(sc, Tile::S_MMW, g) = mmw;
-      SMG(sc, Tile::S_LOGT, g) = log(T);
-      SMG(sc, Tile::S_INVT, g) = invT;
-      if (a.in_state != nullptr)
-        SMG(sc, Tile::S_RHO, g) = a.p * mmw / (T * dm.Ru);
-      SMG(sc, Tile::S_AUX7, g) = log(dm.p_ref * invT * (1. / dm.Ru)); // log(p0/(R T)), :535
+      for (int i = 0; i < nsm1; ++i)
+        d += s.sim[i] * SMG(s.sy, i, g);
+      SMG(s.sc, J_DPART, g) = d;
     }
     else if (tid >= 32)
     {
-      for (int i = tid - 32; i < ns; i += nt - 32)
+      for (int item = tid - 32; item < ns * G; item += nt - 32)
       {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-        {
-          const double T = SMG(sc, Tile::S_T, g);
-          const SpeciesThermo t = species_thermo<true>(dm, i, T, log(T), 1. / T);
-          SMG(sg, i, g) = t.g;
-          SMG(sdb, i, g) = t.dB;
-          SMG(sh, i, g) = t.h;
-          SMG(scp, i, g) = t.cp;
-          SMG(sdcp, i, g) = t.dcp;
-        }
+        const int i = item / G, g = item - i * G;
+        const double T = SMG(s.sc, J_T, g);
+        const SpeciesThermo t = species_thermo<true>(dm, i, T, log(T), 1. / T);
+        SMG(s.sg, i, g) = t.g;
+        SMG(s.sdb, i, g) = t.dB;
+        SMG(s.sh, i, g) = t.h;
+        SMG(s.scp, i, g) = t.cp;
+        SMG(s.sdcp, i, g) = t.dcp;
       }
     }
     __syncthreads();
-    // ---- reaction phase (the last G threads first form cp and dcp/dT of the mixture, species order) ----------------------
-    if (tid >= nt - G)
+    // ---- concentrations and per-state scalars (every thread re-derives rho: cheaper than another barrier) -------------
+    for (int item = tid; item < ns * G; item += nt)
+    {
+      const int i = item / G, g = item - i * G;
+      const double d = SMG(s.sc, J_DPART, g) + s.sim[nsm1] * SMG(s.sy, nsm1, g);
+      const double mmw = 1. / d, T = SMG(s.sc, J_T, g);
+      // ideal_gas_density (:526-530)
+      const double rho = state_mode ? a.p * mmw / (T * dm.Ru) : SMG(s.sc, J_RHO, g);
+      SMG(s.sC, i, g) = SMG(s.sy, i, g) * rho * s.sim[i];
+      if (i == 0)
+      {
+        const double invT = 1. / T, invM = 1. / mmw, ct = rho * invM;
+        SMG(s.sc, J_MMW, g) = mmw;
+        SMG(s.sc, J_INVM, g) = invM;
+        SMG(s.sc, J_CT, g) = ct;
+        SMG(s.sc, J_RHO, g) = rho;
+        SMG(s.sc, J_IRHO, g) = 1. / rho;
+        SMG(s.sc, J_DRHOF, g) = 1. / ct * invM;
+        SMG(s.sc, J_LOGT, g) = log(T);
+        SMG(s.sc, J_INVT, g) = invT;
+        SMG(s.sc, J_LPRT, g) = log(dm.p_ref * invT * (1. / dm.Ru)); // log(p0/(R T)), :535
+      }
+    }
+    __syncthreads();
+    // ---- reaction phase (the last warp first forms cp and dcp/dT of the mixture in species order) ----------------------
+    if (tid >= nt - 32 && lane < G)
     { // thermodynamics_kernels.cpp:45-131, 183-260
-      const int g = nt - 1 - tid;
+      const int g = lane;
       double cp = 0., dcp = 0.;
       for (int i = 0; i < ns; ++i)
       {
-        cp += SMG(sy, i, g) * SMG(scp, i, g);
+        cp += SMG(s.sy, i, g) * SMG(s.scp, i, g);
         if (dm.cptype[i] == CP_CONST)
           dcp = 0.; // sic, thermodynamics_kernels.cpp:202
         else
-          dcp += SMG(sy, i, g) * SMG(sdcp, i, g);
+          dcp += SMG(s.sy, i, g) * SMG(s.sdcp, i, g);
       }
-      SMG(sc, Tile::S_CP, g) = cp;
-      SMG(sc, Tile::S_CPSENST, g) = dcp;
+      SMG(s.sc, J_CP, g) = cp;
+      SMG(s.sc, J_DCP, g) = dcp;
     }
-    for (int r = tid; r < nr; r += nt)
     {
-      const unsigned long long *P = dm.jp_prm + dm.jp_prm_off[r];
-      if (((int)(unsigned int)P[0]) & F_HAS_ORDERS)
+      const int g = lane % G, sub = lane / G;
+      const int g0 = dm.jp_wg_off[warp], g1 = dm.jp_wg_off[warp + 1];
+      for (int gi = g0; gi < g1; ++gi)
       {
-        for (int g = 0; g < G; ++g)
-          reaction_record_orders<G>(dm, r, P, g, sc, sy, sh, srec);
-      }
-      else
-      {
-#pragma unroll 1
-        for (int g = 0; g < G; ++g)
-          reaction_record<G>(dm, P, g, sc, sy, sg, sdb, sh, srec);
+        const int *grp = dm.jp_groups + (size_t)gi * (1 + LPR);
+        const int kind = grp[0], off = grp[1 + sub];
+        if (off < 0)
+          continue;
+        const unsigned long long *P = dm.jp_prm + off;
+        if (kind == 0)
+          react_fast<G>(dm, P, g, s);
+        else if (((int)(unsigned int)P[0]) & F_HAS_ORDERS)
+          react_orders<G>(ns, dm.n_sp, dm.sp_idx, dm.sp_order, dm.sp_slot, dm.invmw, (int)(((unsigned int)P[0]) >> 14), P, g,
+                          s.sc, s.sC, s.sy, s.sR);
+        else
+          react_generic<G>(dm, P, g, s);
       }
     }
     __syncthreads();
-    // ---- gather phase: this thread's range of the plan stream -----------------------------------------------------------------
+    // ---- gather: every lane sums its parts in registers --------------------------------------------------------------------------
+    double hold[RMAX][G];
+    const int r0 = dm.jp_wr_off[warp], nround = dm.jp_wr_off[warp + 1] - r0;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j)
     {
-      const unsigned int *__restrict__ st = dm.jp_stream;
-      int w = dm.jp_tstart[tid];
-      const int wend = dm.jp_tstart[tid + 1];
-      while (w < wend)
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        hold[j][g] = 0.;
+      if (j < nround)
       {
-        const unsigned int hd = st[w++];
-        const int slot = (int)(hd & 0xfffff), cnt = (int)((hd >> 20) & 0x7ff);
-        double acc[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          acc[g] = 0.;
-        if (hd >> 31)
-        { // product items: sum_r H_r * value_r
-          for (int k = 0; k < cnt; ++k)
-          {
-            const unsigned int u = st[w + k];
-            const double *pa = srec + (size_t)(u & 0xffff) * G, *pb = srec + (size_t)(u >> 16) * G;
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-              acc[g] += pa[g] * pb[g];
-          }
+        const unsigned int *__restrict__ it = dm.jp_items + dm.jp_rounds[2 * (r0 + j)] + lane;
+        const int L = dm.jp_rounds[2 * (r0 + j) + 1];
+        unsigned int u0 = __ldg(it), u1 = __ldg(it + 32);
+        for (int k = 0; k < L; k += JP_BLK)
+        {
+          it += 32 * JP_BLK;
+          const unsigned int n0 = __ldg(it), n1 = __ldg(it + 32);
+          gather_step<G>(u0, s.sR, hold[j]);
+          gather_step<G>(u1, s.sR, hold[j]);
+          u0 = n0;
+          u1 = n1;
         }
-        else
-        { // plain items: sum_r nu_r * value_r
-          for (int k = 0; k < cnt; ++k)
-          {
-            const unsigned int u = st[w + k];
-            const double nu = (double)(((int)u) >> 24);
-            const double *pv = srec + (size_t)(u & 0xffff) * G;
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-              acc[g] += nu * pv[g];
-          }
-        }
-        w += cnt;
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          SMG(sJ, slot, g) = acc[g];
       }
     }
+    __syncthreads();
+    // ---- the sums overwrite the record region ----------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j)
+      if (j < nround)
+      {
+        double *p = s.sR + (size_t)dm.jp_rdest[(size_t)(r0 + j) * 32 + lane] * G;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          p[g] = hold[j][g];
+      }
     __syncthreads();
     // ---- recombine split destinations in part order -------------------------------------------------------------------------------
-    for (int item = tid; item < dm.jp_nfix * G; item += nt)
+    if (dm.jp_nfix > 0)
     {
-      const int fi = item / G, g = item - fi * G;
-      const int dst = dm.jp_fix[3 * fi], first = dm.jp_fix[3 * fi + 1], np = dm.jp_fix[3 * fi + 2];
-      double v = SMG(sJ, dst, g);
-      for (int p = 0; p < np; ++p)
-        v += SMG(sJ, first + p, g);
-      SMG(sJ, dst, g) = v;
+      for (int item = tid; item < dm.jp_nfix * G; item += nt)
+      {
+        const int fi = item / G, g = item - fi * G;
+        const int dst = dm.jp_fix[3 * fi], first = dm.jp_fix[3 * fi + 1], np = dm.jp_fix[3 * fi + 2];
+        double v = SMG(s.sR, dst, g);
+        for (int p = 0; p < np; ++p)
+          v += SMG(s.sR, first + p, g);
+        SMG(s.sR, dst, g) = v;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    const double *R_w = sJ + (size_t)dm.jp_rbase * G; // [5][ns][G]: sums of nu*value for w, dw/drho, dw/dT, A, B
-    const double *TH = sJ + (size_t)dm.jp_tbase * G;  // [ns+1][G]
-    const double *SS = sJ + (size_t)dm.jp_sbase * G;  // [3][G]: w.h, A.h, B.h
+    const unsigned short *rowsrc = dm.jp_rowsrc;
 
     if (a.mode == MODE_SENS)
     { // raw (ns+1)x(ns+1) column-major sensitivities, rates_sensitivities_exact.cpp:68, 1011-1025
       const int nsp1 = ns + 1;
-      int row = tid % nsp1, col = tid / nsp1;
-      const int drow = nt % nsp1, dcol = nt / nsp1;
       for (int e = tid; e < nsp1 * nsp1; e += nt)
       {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
+        const int col = e / nsp1, row = e - col * nsp1;
+        for (int g = 0; g < gcount; ++g)
         {
           double v = 0.;
           if (row < ns)
           {
-            const double nm = snm[row];
+            const double nm = s.snm[row];
             if (col == 0)
-              v = nm * SMG(R_w, ns + row, g);
+              v = nm * SMG(s.sR, rowsrc[ns + row], g);
             else if (col == 1)
-              v = nm * SMG(R_w, 2 * ns + row, g);
+              v = nm * SMG(s.sR, rowsrc[2 * ns + row], g);
             else if (col - 2 < nsm1)
             {
               const int k = col - 2;
-              const unsigned short s = semap[k * ns + row];
-              const double rv = (s == 0xffff) ? 0. : SMG(sJ, s, g);
-              v = nm * (rv + (SMG(R_w, 3 * ns + row, g) * su[k] + SMG(R_w, 4 * ns + row, g)));
+              const double rv = SMG(s.sR, s.semap[k * (ns + 1) + row + 1], g);
+              v = nm * (rv + (SMG(s.sR, rowsrc[3 * ns + row], g) * s.su[k] + SMG(s.sR, rowsrc[4 * ns + row], g)));
             }
           }
-          if (g < gcount)
-            a.out1[(size_t)(tile0 + g) * nsp1 * nsp1 + e] = v;
-        }
-        row += drow;
-        col += dcol;
-        if (row >= nsp1)
-        {
-          row -= nsp1;
-          ++col;
+          a.out1[(size_t)(tile0 + g) * nsp1 * nsp1 + e] = v;
         }
       }
       continue;
     }
 
-    // ---- per-row quantities (threads 32..) and per-state quantities (threads < G) of chem_jac_isobaric (:58-98) -------
-    if (tid < G)
+    // ---- column sums, row constants, open-reactor terms -----------------------------------------------------------------------------
     {
-      const int g = tid;
-      const double rho = SMG(sc, Tile::S_RHO, g), cp = SMG(sc, Tile::S_CP, g), T = SMG(sc, Tile::S_T, g);
-      const double cpsensT = SMG(sc, Tile::S_CPSENST, g);
-      const double invRhoCp = 1. / (rho * cp), invRho = 1. / rho, invCp = 1. / cp;
-      double wcp = 0.; // inner_product(w, cpi)
-      for (int i = 0; i < ns; ++i)
-        wcp += SMG(scp, i, g) * (snm[i] * SMG(R_w, i, g));
-      const double rhs0c = -SMG(SS, 0, g) / (rho * cp);
-      double rhs0 = rhs0c;
-      double P0rho = -invRhoCp * SMG(TH, 0, g) - invRho * rhs0c;
-      double P0T = -invRhoCp * (SMG(TH, 1, g) + wcp) - rhs0c * cpsensT * invCp;
-      double cextra = 0.; // extra coefficient of (cp_k - cp_ns) in the T-row of the Y_k columns
-      if (a.mode == MODE_REACTOR_JAC)
-      { // mass_jac_isobaric :100-140, heat_jac_isobaric :142-168, :289-309
-        if (a.rx.open)
-        {
+      const int ncs = dm.jp_ncs, njobs = ncs * G + ns * G + (open ? G : 0);
+      for (int job = tid; job < njobs; job += nt)
+      {
+        if (job < ncs * G)
+        { // sum over species (ascending) of weight_i * row value
+          const int d = job / G, g = job - d * G;
+          const double *wsrc = (d == ncs - 1) ? s.scp : s.sh;
+          double acc = 0.;
+          const int p0 = dm.jp_cs_off[d], p1 = dm.jp_cs_off[d + 1];
+          for (int p = p0; p < p1; ++p)
+          {
+            const unsigned int u = __ldg(dm.jp_cs_items + p);
+            const int i = (int)(u >> 16);
+            acc += (SMG(wsrc, i, g) * s.snm[i]) * SMG(s.sR, u & 0xffff, g);
+          }
+          SMG(s.sTH, d, g) = acc;
+        }
+        else if (job < ncs * G + ns * G)
+        { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
+          const int item = job - ncs * G;
+          const int i = item / G, g = item - i * G;
+          const double nm = s.snm[i], invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
+          const double w = nm * SMG(s.sR, rowsrc[i], g), wr = nm * SMG(s.sR, rowsrc[ns + i], g);
+          const double wT = nm * SMG(s.sR, rowsrc[2 * ns + i], g);
+          const double nmA = nm * SMG(s.sR, rowsrc[3 * ns + i], g), nmB = nm * SMG(s.sR, rowsrc[4 * ns + i], g);
+          const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
+          const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
+          SMG(s.sg, i, g) = invRho * nm;
+          SMG(s.sdb, i, g) = invRho * nmA + nRM * prho;
+          SMG(s.sdcp, i, g) = invRho * nmB;
+          if (i < nsm1)
+          {
+            SMG(s.sR, dm.jp_c0base + i, g) = wT * invRho - roT * prho; // J[1+i, 0]
+            if (reactor && g < gcount)
+            { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
+              double v = w * invRho;
+              if (open)
+                v += (a.rx.y_in[i] - SMG(s.sy, i, g)) * invTau;
+              a.out0[(size_t)(tile0 + g) * ns + 1 + i] = v;
+            }
+          }
+        }
+        else
+        { // mass_jac_isobaric :100-140: inflow enthalpy term and sum cp_i y_in,i
+          const int g = job - ncs * G - ns * G;
           const double Tin = a.rx.T_in, logTin = log(Tin), invTin = 1. / Tin;
-          const double invTau = 1. / a.rx.tau;
           double m0;
           {
             const SpeciesThermo tl = species_thermo<false>(dm, nsm1, Tin, logTin, invTin);
-            m0 = (tl.h - SMG(sh, nsm1, g)) * a.rx.y_in[nsm1];
+            m0 = (tl.h - SMG(s.sh, nsm1, g)) * a.rx.y_in[nsm1];
           }
           for (int i = 0; i < nsm1; ++i)
           {
             const SpeciesThermo ti = species_thermo<false>(dm, i, Tin, logTin, invTin);
-            m0 += (ti.h - SMG(sh, i, g)) * a.rx.y_in[i];
+            m0 += (ti.h - SMG(s.sh, i, g)) * a.rx.y_in[i];
           }
-          m0 /= cp;
+          m0 /= SMG(s.sc, J_CP, g);
           m0 *= invTau;
           double ycp = 0.;
           for (int i = 0; i < ns; ++i)
-            ycp += SMG(scp, i, g) * a.rx.y_in[i];
-          P0T += -invCp * (cpsensT * m0 + invTau * ycp);
+            ycp += SMG(s.scp, i, g) * a.rx.y_in[i];
+          SMG(s.sc, J_M0, g) = m0;
+          SMG(s.sc, J_YCP, g) = ycp;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- temperature row (:58-98, 142-168; flamelet_kernels.cpp:1290-1320) ----------------------------------------------------
+    for (int item = tid; item < ns * G; item += nt)
+    {
+      const int c = item / G, g = item - c * G;
+      const int ncs = dm.jp_ncs;
+      const double rho = SMG(s.sc, J_RHO, g), cp = SMG(s.sc, J_CP, g), T = SMG(s.sc, J_T, g);
+      const double cpsensT = SMG(s.sc, J_DCP, g);
+      const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
+      const double SW = SMG(s.sTH, nsm1 + 0, g), SWr = SMG(s.sTH, nsm1 + 1, g), SWT = SMG(s.sTH, nsm1 + 2, g);
+      const double SA = SMG(s.sTH, nsm1 + 3, g), SB = SMG(s.sTH, nsm1 + 4, g), wcp = SMG(s.sTH, ncs - 1, g);
+      const double rhs0c = -SW / (rho * cp);
+      double rhs0 = rhs0c;
+      double P0rho = -invRhoCp * SWr - invRho * rhs0c;
+      double P0T = -invRhoCp * (SWT + wcp) - rhs0c * cpsensT * invCp;
+      double cextra = 0.; // extra coefficient of (cp_k - cp_ns) in the T-row of the Y_k columns
+      const int sidx = tile0 + (g < gcount ? g : 0);
+      if (reactor)
+      { // mass_jac_isobaric :100-140, heat_jac_isobaric :142-168, :289-309
+        if (open)
+        {
+          const double m0 = SMG(s.sc, J_M0, g);
+          P0T += -invCp * (cpsensT * m0 + invTau * SMG(s.sc, J_YCP, g));
           cextra += -m0 * invCp;
           rhs0 += m0;
         }
@@ -673,10 +861,9 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           rhs0 += rate;
         }
       }
-      else if (a.mode == MODE_FLAMELET_JAC && !a.fl.adiabatic)
+      else if (flamelet && !fl.adiabatic)
       { // flamelet_kernels.cpp:1290-1320
-        const FlameletDev &fl = a.fl;
-        const int sidx = tile0 + (g < gcount ? g : 0), F = sidx / fl.nzi, iz = sidx - F * fl.nzi;
+        const int F = sidx / fl.nzi, iz = sidx - F * fl.nzi;
         const size_t ho = (size_t)F * fl.stride_heat + iz;
         const double Tc = fl.T_conv[ho], Tr = fl.T_rad[ho], hc = fl.h_conv[ho], hr = fl.h_rad[ho];
         double q;
@@ -696,167 +883,143 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         P0rho -= q / rho;
         cextra += -invCp * q;
       }
-      SMG(sc, Tile::S_AUX0, g) = rhs0;
-      SMG(sc, Tile::S_AUX1, g) = P0rho;
-      SMG(sc, Tile::S_AUX2, g) = P0T;
-      SMG(sc, Tile::S_AUX3, g) = -rhs0c * invCp + cextra; // coefficient of (cp_k - cp_ns) in P[0, Y_k]
-    }
-    else if (tid >= 32)
-    {
-      for (int i = tid - 32; i < ns; i += nt - 32)
+      const double roT = rho / T, nRM = -rho * SMG(s.sc, J_MMW, g);
+      double v;
+      if (isothermal)
+        v = 0.;
+      else if (c == 0)
+        v = P0T - roT * P0rho;
+      else
       {
-        const double nm = snm[i];
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-        {
-          const double invRho = 1. / SMG(sc, Tile::S_RHO, g);
-          const double w = nm * SMG(R_w, i, g), wr = nm * SMG(R_w, ns + i, g);
-          SMG(sg, i, g) = invRho * (wr - invRho * w);        // P[1+i, rho], :75-78
-          SMG(sdb, i, g) = nm * SMG(R_w, 3 * ns + i, g);     // -M_i * RA_i
-          SMG(sdcp, i, g) = nm * SMG(R_w, 4 * ns + i, g);    // -M_i * RB_i
+        const int k = c - 1;
+        const double uk = s.su[k];
+        const double sum = SMG(s.sTH, k, g) + uk * SA + SB;
+        const double pY = -sum / (rho * cp) + (-rhs0c * invCp + cextra) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
+        v = pY + nRM * uk * P0rho;
+      }
+      SMG(s.sR, dm.jp_t0base + c, g) = v;
+      if (c == 0)
+      {
+        if (reactor && g < gcount)
+          a.out0[(size_t)(tile0 + g) * ns] = isothermal ? 0. : rhs0;
+        // destination of the state's block, and the flamelet extras of its grid point
+        size_t obase;
+        double ttc = 0.;
+        if (!flamelet)
+          obase = (size_t)sidx * ns * ns;
+        else
+        { // block iz of flamelet F in BTDDOD storage
+          const int nzi = fl.nzi, F = sidx / nzi, iz = sidx - F * nzi;
+          obase = (size_t)F * ((size_t)ns * ((size_t)nzi * ns + 2 * (nzi - 1))) + (size_t)iz * ns * ns;
+          SMG(s.sc, J_CMOFF, g) = __longlong_as_double((long long)((size_t)F * fl.stride_coeff + (size_t)iz * ns));
+          if (fl.include_enthalpy_flux)
+          { // (T,T) correction, flamelet_kernels.cpp:1350-1381
+            const double *stt = a.in_state + (size_t)F * nzi * ns;
+            const double *cpg = fl.cp_grid + (size_t)F * nzi;
+            const double mc = fl.mcoeff[(size_t)F * fl.stride_mn + iz], nc = fl.ncoeff[(size_t)F * fl.stride_mn + iz];
+            const double Tm = (iz == 0) ? fl.oxy[0] : stt[(size_t)(iz - 1) * ns];
+            const double Tp = (iz == nzi - 1) ? fl.fuel[0] : stt[(size_t)(iz + 1) * ns];
+            const double cpm = (iz == 0) ? fl.cp_bc[0] : cpg[iz - 1];
+            const double cpp = (iz == nzi - 1) ? fl.cp_bc[1] : cpg[iz + 1];
+            const double dTdZ = mc * Tm + nc * Tp, dcpdZ = mc * cpm + nc * cpp;
+            const double f1 = 0.5 * fl.chi[(size_t)F * fl.stride_chi + iz] / cp * dTdZ * dcpdZ;
+            ttc = f1 / cp * cpsensT;
+          }
         }
+        SMG(s.sc, J_OBASE, g) = __longlong_as_double((long long)obase);
+        SMG(s.sc, J_TTC, g) = ttc;
       }
     }
     __syncthreads();
 
-    // ---- output: transform (:319-343) and stream out ---------------------------------------------------------------------------------
-    const bool reactor = a.mode == MODE_REACTOR_JAC;
-    const bool isothermal = reactor && a.rx.heat_option == 1;
-    const bool open = reactor && a.rx.open != 0;
-    const double invTau = open ? 1. / a.rx.tau : 0.;
-    double invRho_[G], roT_[G], nRM_[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
+    // ---- output: column 0, then the columns 1..ns-1 with one row per thread ----------------------------------------------------
+    for (int item = tid; item < ns * G; item += nt)
     {
-      const double rho = SMG(sc, Tile::S_RHO, g);
-      invRho_[g] = 1. / rho;
-      roT_[g] = rho / SMG(sc, Tile::S_T, g);
-      nRM_[g] = -rho * SMG(sc, Tile::S_MMW, g);
-    }
-    // destination of state g's block, and the flamelet extras of its grid point
-    const FlameletDev &fl = a.fl;
-    size_t obase[G];
-    double ttc[G];
-    const double *cmaj[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-    {
-      const int sidx = tile0 + (g < gcount ? g : 0);
-      ttc[g] = 0.;
-      cmaj[g] = nullptr;
-      if (reactor)
-        obase[g] = (size_t)sidx * ns * ns;
-      else
-      { // block iz of flamelet F in BTDDOD storage
-        const int nzi = fl.nzi, F = sidx / nzi, iz = sidx - F * nzi;
-        obase[g] = (size_t)F * ((size_t)ns * ((size_t)nzi * ns + 2 * (nzi - 1))) + (size_t)iz * ns * ns;
-        cmaj[g] = fl.cmajor + (size_t)F * fl.stride_coeff + (size_t)iz * ns;
-        if (fl.include_enthalpy_flux)
-        { // (T,T) correction, flamelet_kernels.cpp:1350-1381
-          const double *stt = a.in_state + (size_t)F * nzi * ns;
-          const double *cpg = fl.cp_grid + (size_t)F * nzi;
-          const double mc = fl.mcoeff[(size_t)F * fl.stride_mn + iz], nc = fl.ncoeff[(size_t)F * fl.stride_mn + iz];
-          const double Tm = (iz == 0) ? fl.oxy[0] : stt[(size_t)(iz - 1) * ns];
-          const double Tp = (iz == nzi - 1) ? fl.fuel[0] : stt[(size_t)(iz + 1) * ns];
-          const double cpm = (iz == 0) ? fl.cp_bc[0] : cpg[iz - 1];
-          const double cpp = (iz == nzi - 1) ? fl.cp_bc[1] : cpg[iz + 1];
-          const double cp = SMG(sc, Tile::S_CP, g);
-          const double dTdZ = mc * Tm + nc * Tp, dcpdZ = mc * cpm + nc * cpp;
-          const double f1 = 0.5 * fl.chi[(size_t)F * fl.stride_chi + iz] / cp * dTdZ * dcpdZ;
-          ttc[g] = f1 / cp * SMG(sc, Tile::S_CPSENST, g);
+      const int g = item / ns, r = item - g * ns;
+      if (g >= gcount)
+        continue;
+      double v = (r == 0) ? SMG(s.sR, dm.jp_t0base, g) : SMG(s.sR, dm.jp_c0base + r - 1, g);
+      const size_t ob = (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g));
+      if (flamelet)
+      {
+        if (r == 0)
+        {
+          v += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, g))];
+          v -= SMG(s.sc, J_TTC, g);
+        }
+        if (fl.scale_and_offset)
+        {
+          v *= fl.prefactor;
+          if (r == 0)
+            v -= 1.;
         }
       }
+      a.out1[ob + r] = v;
     }
     {
-      int row = tid % ns, col = tid / ns;
-      const int drow = nt % ns, dcol = nt / ns;
-      for (int e = tid; e < ns * ns; e += nt)
+      const int cpi = nt / ns; // columns per iteration
+      if (tid < cpi * ns)
       {
-        const double uk = col > 0 ? su[col - 1] : 0.;
-        unsigned short s = 0xffff;
-        if (row > 0 && col > 0)
-          s = semap[(col - 1) * ns + (row - 1)];
+        const int r = tid % ns;
+        int c = 1 + tid / ns;
+        double c1[G], c2[G], c3[G];
+        double *ob[G];
 #pragma unroll
         for (int g = 0; g < G; ++g)
         {
-          double v;
-          if (row == 0)
-          { // temperature row
-            const double P0rho = SMG(sc, Tile::S_AUX1, g);
-            if (isothermal)
-              v = 0.;
-            else if (col == 0)
-              v = SMG(sc, Tile::S_AUX2, g) - roT_[g] * P0rho;
-            else
-            {
-              const int k = col - 1;
-              const double cp = SMG(sc, Tile::S_CP, g);
-              const double sum = SMG(TH, 2 + k, g) + uk * SMG(SS, 1, g) + SMG(SS, 2, g);
-              const double pY = -sum / (SMG(sc, Tile::S_RHO, g) * cp) +
-                                SMG(sc, Tile::S_AUX3, g) * (SMG(scp, k, g) - SMG(scp, nsm1, g));
-              v = pY + nRM_[g] * uk * P0rho;
-            }
-          }
+          c1[g] = r == 0 ? 1. : SMG(s.sg, r - (r > 0), g);
+          c2[g] = r == 0 ? 0. : SMG(s.sdb, r - (r > 0), g);
+          c3[g] = r == 0 ? 0. : SMG(s.sdcp, r - (r > 0), g);
+          ob[g] = a.out1 + (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g)) + r;
+        }
+        for (; c < ns; c += cpi)
+        {
+          const int e = r + (ns + 1) * (c - 1);
+          const double uk = s.su[c - 1];
+          const double *p = s.sR + (size_t)s.semap[e] * G;
+          double v[G];
+          if (G == 1)
+            v[0] = fma(c1[0], p[0], fma(uk, c2[0], c3[0]));
           else
           {
-            const int i = row - 1;
-            const double prho = SMG(sg, i, g);
-            if (col == 0)
-              v = snm[i] * SMG(R_w, 2 * ns + i, g) * invRho_[g] - roT_[g] * prho;
-            else
-            {
-              const double rv = (s == 0xffff) ? 0. : snm[i] * SMG(sJ, s, g);
-              double pY = invRho_[g] * (rv + (SMG(sdb, i, g) * uk + SMG(sdcp, i, g)));
-              if (open && row == col)
-                pY += -invTau;
-              v = pY + nRM_[g] * uk * prho;
-            }
-          }
-          if (!reactor)
-          {
-            if (row == col)
-            {
-              v += cmaj[g][row];
-              if (row == 0)
-                v -= ttc[g];
-            }
-            if (fl.scale_and_offset)
-            {
-              v *= fl.prefactor;
-              if (row == col)
-                v -= 1.;
-            }
-          }
-          if (g < gcount)
-            a.out1[obase[g] + e] = v;
-        }
-        row += drow;
-        col += dcol;
-        if (row >= ns)
-        {
-          row -= ns;
-          ++col;
-        }
-      }
-    }
-    if (reactor)
-    { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
-      for (int j = tid; j < ns; j += nt)
-      {
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-        {
-          double v;
-          if (j == 0)
-            v = isothermal ? 0. : SMG(sc, Tile::S_AUX0, g);
-          else
+            for (int g = 0; g < G; g += 2)
+            {
+              const double2 x = *reinterpret_cast<const double2 *>(p + g);
+              v[g] = fma(c1[g], x.x, fma(uk, c2[g], c3[g]));
+              v[g + 1] = fma(c1[g + 1], x.y, fma(uk, c2[g + 1], c3[g + 1]));
+            }
+          }
+          if (r == c)
           {
-            v = snm[j - 1] * SMG(R_w, j - 1, g) * invRho_[g];
             if (open)
-              v += (a.rx.y_in[j - 1] - SMG(sy, j - 1, g)) * invTau;
+            {
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                v[g] += -invTau;
+            }
+            if (flamelet)
+            {
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                v[g] += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, g)) + r];
+            }
           }
-          if (g < gcount)
-            a.out0[(size_t)(tile0 + g) * ns + j] = v;
+          if (flamelet && fl.scale_and_offset)
+          {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+            {
+              v[g] *= fl.prefactor;
+              if (r == c)
+                v[g] -= 1.;
+            }
+          }
+          const size_t off = (size_t)ns * c;
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (g < gcount)
+              ob[g][off] = v[g];
         }
       }
     }
@@ -864,13 +1027,6 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-static size_t jac_smem_bytes(const DeviceMech &dm, int G)
-{
-  const size_t ns = dm.ns;
-  size_t doubles = (size_t)G * (Tile::NSC + 6 * ns + dm.jp_rec_total + dm.jp_nslots) + 2 * ns;
-  return doubles * sizeof(double) + sizeof(unsigned short) * ns * (ns - 1) + 16;
-}
-
 static int jac_sm_count()
 {
   static int n = 0;
@@ -896,10 +1052,12 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
   }
   const int threads = a.dm.jp_threads;
   const int ntiles = (a.n + G - 1) / G;
-  // CTAs per SM: limited by shared memory and by 64K registers / (threads * ~128)
+  // CTAs per SM: limited by shared memory and by 64K registers / (threads * 128)
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227 * 1024) / (smem + 1024), (size_t)(512 / threads)));
   per_sm = std::min(per_sm, 8);
-  const int grid = std::min(ntiles, jac_sm_count() * per_sm);
+  if (const char *e = getenv("GB_JAC_CTAS"))
+    per_sm = std::max(1, atoi(e));
+  const int grid = std::max(1, std::min(ntiles, jac_sm_count() * per_sm));
   k_jac<G><<<grid, threads, smem, s>>>(a);
   ++g_jac_launches;
   return cudaGetLastError();
@@ -908,27 +1066,21 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
 cudaError_t launch_jac(const ChemArgs &a_in, cudaStream_t s)
 {
   ChemArgs a = a_in;
-  const size_t maxsm = 227 * 1024;
-  int G = 4;
-  if (const char *e = getenv("GB_JAC_G"))
-    G = std::max(1, std::min(4, atoi(e)));
-  while (G > 1 && jac_smem_bytes(a.dm, G) > maxsm)
-    --G;
-  if (jac_smem_bytes(a.dm, G) > maxsm)
-    return cudaErrorInvalidConfiguration; // mechanism too large for the shared-memory resident plan
-  a.G = G;
-  a.GS = G;
-  const size_t smem = jac_smem_bytes(a.dm, G);
-  switch (G)
+  const size_t smem = (size_t)a.dm.jp_smem;
+  a.G = a.dm.jp_G;
+  a.GS = a.G;
+  switch (a.G)
   {
+  case 8:
+    return launch_jac_g<8>(a, smem, s);
   case 4:
     return launch_jac_g<4>(a, smem, s);
-  case 3:
-    return launch_jac_g<3>(a, smem, s);
   case 2:
     return launch_jac_g<2>(a, smem, s);
-  default:
+  case 1:
     return launch_jac_g<1>(a, smem, s);
+  default:
+    return cudaErrorInvalidConfiguration;
   }
 }
 

@@ -331,181 +331,37 @@ int commit(HostMech &m)
   std::stable_sort(row_order.begin(), row_order.end(),
                    [&](short a, short b) { return row_total[a] > row_total[b]; });
 
-  // ---- per-chunk staged images (parameters, gather items, balanced segments) ---------------------------------
-  std::vector<unsigned long long> cprm, csegs;
-  std::vector<unsigned int> citems;
-  std::vector<int> cprm_off(1, 0), citem_off(1, 0), cseg_off(1, 0);
-  int max_prm_words = 2, max_items = 4, max_segs = 2;
-  int seg_target = 12;
-  if (const char *e = std::getenv("GB_SEGMENT_ITEMS"))
-    seg_target = std::max(1, std::atoi(e));
-  auto dbits = [](double v) {
-    unsigned long long u;
-    std::memcpy(&u, &v, 8);
-    return u;
-  };
-  for (int c = 0; c < n_chunks; ++c)
-  {
-    const int r0 = chunk_rxn[c], r1 = chunk_rxn[c + 1], nrc_ = r1 - r0;
-    const size_t base = cprm.size();
-    const int hdr_words = (nrc_ + 1) / 2;
-    cprm.resize(base + hdr_words, 0ull);
-    std::vector<unsigned int> offs(nrc_, 0u);
-    for (int r = r0; r < r1; ++r)
-    {
-      const HostReaction &x = m.reactions[r];
-      offs[r - r0] = (unsigned int)(cprm.size() - base);
-      const int ntb_ = (int)x.tb_idx.size();
-      const int nsl = slot_off[r + 1] - slot_off[r];
-      cprm.push_back((unsigned long long)(unsigned int)flags[r] | ((unsigned long long)(unsigned int)rec_off[r] << 32));
-      unsigned long long w1 = 0;
-      w1 |= (unsigned long long)(x.n_rc & 255);
-      w1 |= (unsigned long long)(x.n_pd & 255) << 8;
-      w1 |= (unsigned long long)(x.n_net & 255) << 16;
-      w1 |= (unsigned long long)(ntb_ & 255) << 24;
-      w1 |= (unsigned long long)(nsl & 255) << 32;
-      w1 |= (unsigned long long)((unsigned char)(signed char)x.sum_stoich) << 40;
-      w1 |= (unsigned long long)(x.sum_rc & 255) << 48;
-      w1 |= (unsigned long long)(x.sum_pd & 255) << 56;
-      cprm.push_back(w1);
-      cprm.push_back(dbits(x.kf[0]));
-      cprm.push_back(dbits(x.kf[1]));
-      cprm.push_back(dbits(x.kf[2]));
-      if (x.type != RT_SIMPLE)
-      {
-        cprm.push_back(dbits(x.base_eff));
-        for (int k = 0; k < 3; ++k)
-          cprm.push_back(dbits(x.kp[k]));
-        for (int k = 0; k < 4; ++k)
-          cprm.push_back(dbits(x.troe[k]));
-      }
-      for (int i = 0; i < x.n_rc; ++i)
-      {
-        const unsigned long long w = (unsigned long long)(unsigned short)x.rc_idx[i] |
-                                     ((unsigned long long)(unsigned char)x.rc_st[i] << 16) |
-                                     ((unsigned long long)(unsigned char)rc_slot[NSR * (size_t)r + i] << 24);
-        cprm.push_back(w);
-        cprm.push_back(dbits(m.invmw[x.rc_idx[i]]));
-      }
-      for (int i = 0; i < x.n_pd; ++i)
-      {
-        const unsigned long long w = (unsigned long long)(unsigned short)x.pd_idx[i] |
-                                     ((unsigned long long)(unsigned char)x.pd_st[i] << 16) |
-                                     ((unsigned long long)(unsigned char)pd_slot[NSR * (size_t)r + i] << 24);
-        cprm.push_back(w);
-        cprm.push_back(dbits(m.invmw[x.pd_idx[i]]));
-      }
-      for (int i = 0; i < x.n_net; ++i)
-        cprm.push_back((unsigned long long)(unsigned short)x.net_idx[i] |
-                       ((unsigned long long)(unsigned char)(signed char)x.net_st[i] << 16));
-      for (int j = 0; j < ntb_; ++j)
-      {
-        cprm.push_back((unsigned long long)(unsigned short)x.tb_idx[j] |
-                       ((unsigned long long)(unsigned char)tb_slot[tb_off[r] + j] << 24));
-        cprm.push_back(dbits(x.tb_eff[j]));
-      }
-      if (x.n_rc > 255 || ntb_ > 255 || nsl > 120 || std::abs(x.sum_stoich) > 127)
-      {
-        set_error("reaction too large for the packed parameter format");
-        return GB_ERR_UNSUPPORTED;
-      }
-    }
-    std::memcpy(&cprm[base], offs.data(), sizeof(unsigned int) * nrc_);
-    if ((cprm.size() - base) & 1)
-      cprm.push_back(0ull);
-    cprm_off.push_back((int)cprm.size());
-    max_prm_words = std::max(max_prm_words, (int)(cprm.size() - base));
-
-    // gather items of the chunk, by row then column then reaction
-    struct Item
-    {
-      int row, col, r, rec, nu;
-    };
-    std::vector<Item> items;
-    for (int r = r0; r < r1; ++r)
-    {
-      const HostReaction &x = m.reactions[r];
-      const int nsl = slot_off[r + 1] - slot_off[r];
-      bool last_involved = false;
-      for (int i = 0; i < x.n_rc; ++i)
-        last_involved |= (x.rc_idx[i] == last && !x.has_orders);
-      for (int i = 0; i < x.n_pd; ++i)
-        last_involved |= (x.pd_idx[i] == last && x.reversible && !x.has_orders);
-      for (int i = 0; i < x.n_sp; ++i)
-        last_involved |= (x.sp_idx[i] == last);
-      for (size_t j = 0; j < x.tb_idx.size(); ++j)
-        last_involved |= (x.tb_idx[j] == last);
-      for (int k = 0; k < x.n_net; ++k)
-      {
-        const int row = x.net_idx[k], nu = x.net_st[k];
-        if (nu < -8 || nu > 7)
-        {
-          set_error("net stoichiometric coefficient outside [-8, 7]");
-          return GB_ERR_UNSUPPORTED;
-        }
-        for (int q = 0; q < nsl; ++q)
-          items.push_back({row, (int)slot_species[slot_off[r] + q], r, rec_off[r] + 5 + q, nu});
-        for (int q = 0; q < 3; ++q)
-          items.push_back({row, ns - 1 + q, r, rec_off[r] + q, nu});
-        if (x.type != RT_SIMPLE)
-          items.push_back({row, ns - 1 + 3, r, rec_off[r] + 3, nu});
-        if (last_involved)
-          items.push_back({row, ns - 1 + 4, r, rec_off[r] + 4, nu});
-      }
-    }
-    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-      if (a.row != b.row)
-        return a.row < b.row;
-      if (a.col != b.col)
-        return a.col < b.col;
-      return a.r < b.r;
-    });
-    const size_t ibase = citems.size(), sbase = csegs.size();
-    size_t k = 0;
-    while (k < items.size())
-    {
-      // grow the segment entry by entry (an entry = run of equal (row, col)) up to ~seg_target items, within one row
-      const size_t begin = k;
-      const int row = items[k].row;
-      while (k < items.size() && items[k].row == row)
-      {
-        size_t e = k;
-        while (e < items.size() && items[e].row == row && items[e].col == items[k].col)
-          ++e;
-        if (k > begin && (int)(e - begin) > seg_target)
-          break;
-        k = e;
-      }
-      if (k - begin > 65535 || begin > 0xffffffffull)
-      {
-        set_error("gather segment too long");
-        return GB_ERR_UNSUPPORTED;
-      }
-      csegs.push_back((unsigned long long)(unsigned short)row | ((unsigned long long)(k - begin) << 16) |
-                      ((unsigned long long)begin << 32));
-    }
-    for (const Item &it : items)
-    {
-      if (it.rec > 65535 || it.col > 4095)
-      {
-        set_error("record offset / column outside the packed item format");
-        return GB_ERR_UNSUPPORTED;
-      }
-      citems.push_back((unsigned int)it.rec | ((unsigned int)it.col << 16) | ((unsigned int)(it.nu & 15) << 28));
-    }
-    while ((citems.size() - ibase) & 3)
-      citems.push_back(0u);
-    if ((csegs.size() - sbase) & 1)
-      csegs.push_back(0ull); // count 0: no-op segment
-    citem_off.push_back((int)citems.size());
-    cseg_off.push_back((int)csegs.size());
-    max_items = std::max(max_items, (int)(citems.size() - ibase));
-    max_segs = std::max(max_segs, (int)(csegs.size() - sbase));
-  }
-
+  // Jacobian plan: the largest tile (G states) whose working set fits in shared memory and whose gather rounds fit in
+  // the register-resident accumulators; CTA size by the amount of work per tile
   JacPlanHost jp;
   {
-    const int rc = build_jac_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, jp);
+    int rc = GB_ERR_UNSUPPORTED;
+    const char *eg = std::getenv("GB_JAC_G"), *et = std::getenv("GB_JAC_THREADS");
+    for (int G = eg ? std::max(1, std::min(8, std::atoi(eg))) : 8; G >= 1; G /= 2)
+    {
+      if (G & (G - 1))
+        continue;
+      // first pass at full width to learn the amount of work, then pick the CTA size
+      rc = build_jac_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, G, 512, jp);
+      if (rc != GB_OK)
+        continue;
+      int threads = 512;
+      if (et)
+        threads = std::max(64, std::min(512, (std::atoi(et) / 32) * 32));
+      else
+      {
+        const int LPR = 32 / G;
+        const int ngroups = (int)jp.groups.size() / (1 + LPR), nrounds = (int)jp.rounds.size() / 2;
+        const int warps = std::max((ngroups + 3) / 4, (nrounds + 1) / 2);
+        threads = std::max(128, std::min(512, 32 * warps));
+      }
+      if (threads != 512)
+        rc = build_jac_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, G, threads, jp);
+      if (rc == GB_OK && jac_smem_bytes(ns, jp) <= (size_t)227 * 1024)
+        break;
+      rc = GB_ERR_UNSUPPORTED;
+      set_error("mechanism too large for the shared-memory resident Jacobian plan");
+    }
     if (rc != GB_OK)
       return rc;
   }
@@ -527,11 +383,10 @@ int commit(HostMech &m)
   const size_t o_chunk = b.add(chunk_rxn), o_recoff = b.add(rec_off);
   const size_t o_rowoff = b.add(row_off), o_rowrxn = b.add(row_rxn), o_rowfac = b.add(row_fac),
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
-  const size_t o_cprm = b.add(cprm), o_cprmoff = b.add(cprm_off), o_citems = b.add(citems),
-               o_citemoff = b.add(citem_off), o_csegs = b.add(csegs), o_csegoff = b.add(cseg_off);
-
-  const size_t o_jpprm = b.add(jp.prm), o_jpoff = b.add(jp.prm_off), o_jpstream = b.add(jp.stream),
-               o_jptstart = b.add(jp.tstart), o_jpfix = b.add(jp.fix), o_jpemap = b.add(jp.emap);
+  const size_t o_jpprm = b.add(jp.prm), o_jpwg = b.add(jp.wg_off), o_jpgroups = b.add(jp.groups),
+               o_jpwr = b.add(jp.wr_off), o_jprounds = b.add(jp.rounds), o_jpitems = b.add(jp.items),
+               o_jprdest = b.add(jp.rdest), o_jpfix = b.add(jp.fix), o_jprowsrc = b.add(jp.rowsrc),
+               o_jpcsoff = b.add(jp.cs_off), o_jpcsitems = b.add(jp.cs_items), o_jpemap = b.add(jp.emap);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -571,16 +426,16 @@ int commit(HostMech &m)
   d.row_off = at<int>(base, o_rowoff), d.row_rxn = at<int>(base, o_rowrxn);
   d.row_fac = at<double>(base, o_rowfac), d.row_stmw = at<double>(base, o_rowstmw);
   d.row_order = at<short>(base, o_roworder);
-  d.cprm = at<unsigned long long>(base, o_cprm), d.cprm_off = at<int>(base, o_cprmoff);
-  d.citems = at<unsigned int>(base, o_citems), d.citem_off = at<int>(base, o_citemoff);
-  d.csegs = at<unsigned long long>(base, o_csegs), d.cseg_off = at<int>(base, o_csegoff);
-  d.max_prm_words = max_prm_words, d.max_items = max_items, d.max_segs = max_segs;
-  d.jp_prm = at<unsigned long long>(base, o_jpprm), d.jp_prm_off = at<int>(base, o_jpoff);
-  d.jp_stream = at<unsigned int>(base, o_jpstream), d.jp_tstart = at<int>(base, o_jptstart);
-  d.jp_fix = at<int>(base, o_jpfix);
+  d.jp_prm = at<unsigned long long>(base, o_jpprm);
+  d.jp_wg_off = at<int>(base, o_jpwg), d.jp_groups = at<int>(base, o_jpgroups);
+  d.jp_wr_off = at<int>(base, o_jpwr), d.jp_rounds = at<int>(base, o_jprounds);
+  d.jp_items = at<unsigned int>(base, o_jpitems), d.jp_rdest = at<unsigned short>(base, o_jprdest);
+  d.jp_fix = at<int>(base, o_jpfix), d.jp_rowsrc = at<unsigned short>(base, o_jprowsrc);
+  d.jp_cs_off = at<int>(base, o_jpcsoff), d.jp_cs_items = at<unsigned int>(base, o_jpcsitems);
   d.jp_emap = at<unsigned short>(base, o_jpemap);
-  d.jp_threads = jp.threads, d.jp_rec_total = jp.rec_total, d.jp_nslots = jp.nslots, d.jp_rbase = jp.rbase;
-  d.jp_tbase = jp.tbase, d.jp_sbase = jp.sbase, d.jp_nfix = (int)jp.fix.size() / 3;
+  d.jp_G = jp.G, d.jp_threads = jp.threads, d.jp_rec_rows = jp.rec_rows, d.jp_rows = jp.rows;
+  d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_t0base = jp.t0base, d.jp_c0base = jp.c0base;
+  d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);
   m.committed = true;
   return GB_OK;
 }

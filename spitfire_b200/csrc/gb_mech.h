@@ -97,40 +97,39 @@ struct DeviceMech
   const double *row_stmw;                          // nu*MW, for production_rates' `w -= nu*MW*(k-kr)`
   // row processing order (heaviest first) for load balance
   const short *row_order;                          // [ns]
-  // ---- per-chunk images staged into shared memory by k_jac (cp.async), see gb_mech.cu pack_chunks() ----
-  // parameter blob of chunk c: 8-byte words cprm[cprm_off[c] .. cprm_off[c+1]); it starts with one 32-bit word offset
-  // per reaction of the chunk (padded to a whole number of 8-byte words), followed by the reactions' packed records
-  const unsigned long long *cprm;
-  const int *cprm_off;                             // [n_chunks+1], even (16-byte aligned chunks)
-  // gather items of chunk c, sorted by (row, column, reaction): rec(16) | col(12) << 16 | (nu & 15) << 28, where rec
-  // is the record slot (in doubles, relative to the chunk's record base), col the column of the extended row
-  // (0..ns-2: Y_k, ns-1..ns+3: w, dw/drho, dw/dT, A, B) and nu the net stoichiometric coefficient (factor -nu*MW_row)
-  const unsigned int *citems;
-  const int *citem_off;                            // [n_chunks+1], multiples of 4
-  // balanced segments of chunk c: row(16) | count(16) << 16 | begin(32) << 32 (begin relative to the chunk's items);
-  // a segment never splits a (row, column) entry
-  const unsigned long long *csegs;
-  const int *cseg_off;                             // [n_chunks+1], even
-  int max_prm_words, max_items, max_segs;
-  // ---- Jacobian plan (gb_plan.cu), consumed by k_jac (gb_jac.cu) ----
-  const unsigned long long *jp_prm; // packed parameters of all reactions
-  const int *jp_prm_off;            // [nr] word offset of reaction r in jp_prm
-  const unsigned int *jp_stream;    // gather stream: header {slot:20, count:11, product:1} followed by `count` items
-  const int *jp_tstart;             // [jp_threads+1] stream range of every CTA thread
-  const int *jp_fix;                // [3*jp_nfix] (dest slot, first extra slot, number of extra parts)
-  const unsigned short *jp_emap;    // [ns*(ns-1)] logical R entry k*ns+i -> compact slot, 0xffff = structurally zero
-  int jp_threads, jp_rec_total, jp_nslots, jp_rbase, jp_tbase, jp_sbase, jp_nfix;
+  // ---- Jacobian plan (gb_plan.cu), consumed by k_jac (gb_jac.cu); see JacPlanHost ----
+  const unsigned long long *jp_prm; // packed reaction parameters (fast records: 12 words, generic: variable)
+  const int *jp_wg_off;             // [nwarps+1] reaction groups of every warp
+  const int *jp_groups;             // per group: kind (0 fast, 1 generic), then 32/G parameter offsets (-1: idle lane set)
+  const int *jp_wr_off;             // [nwarps+1] gather rounds of every warp
+  const int *jp_rounds;             // per round: first item (index into jp_items), number of steps
+  const unsigned int *jp_items;     // [round][step][lane]: record row (16) | nu (int8) << 16
+  const unsigned short *jp_rdest;   // [round][lane] destination row of the gathered sum
+  const int *jp_fix;                // [3*jp_nfix] (destination row, first extra part row, number of extra parts)
+  const unsigned short *jp_rowsrc;  // [5][ns] rows holding sum_r nu*{q, dq/drho, dq/dT, a, b} of every species
+  const int *jp_cs_off;             // [jp_ncs+1] column sums: items of column destination d
+  const unsigned int *jp_cs_items;  // row (16) | species (16) << 16
+  const unsigned short *jp_emap;    // [(ns+1)*(ns-1)] entry (row r: 0 = T, 1+i = species i <= ns-1; column c >= 1) at
+                                    // r + (ns+1)*(c-1) -> row of the gathered-sum array
+  int jp_G, jp_threads, jp_rec_rows, jp_rows, jp_nfix, jp_ncs, jp_t0base, jp_c0base, jp_zrow, jp_smem;
 };
 
-constexpr int JP_REC_HDR = 6; // record = {q, dq/drho, dq/dT, a, b, H, dq/dY_slot...}
+constexpr int JP_FAST_WORDS = 12; // fast-path parameter record, 8-byte words
+constexpr int JP_HDR_FAST = 3;    // fast record = {q, dq/drho, dq/dT, dq/dY_slot...}
+constexpr int JP_HDR_GEN = 5;     // generic record = {q, dq/drho, dq/dT, a, b, dq/dY_slot...}
+constexpr int JP_NSC = 20;        // per-state scalars of a k_jac tile
+constexpr int JP_BLK = 2;         // gather steps per prefetch block (round lengths are multiples of it)
 
 struct JacPlanHost
 {
+  int G = 8, threads = 512;
   std::vector<unsigned long long> prm;
-  std::vector<int> prm_off, tstart, fix;
-  std::vector<unsigned int> stream;
-  std::vector<unsigned short> emap;
-  int threads = 512, rec_total = 0, nslots = 0, rbase = 0, tbase = 0, sbase = 0;
+  std::vector<int> wg_off, groups, wr_off, rounds, fix, cs_off;
+  std::vector<unsigned int> items, cs_items;
+  std::vector<unsigned short> rdest, rowsrc, emap;
+  int rec_rows = 0, rows = 0, ncs = 0, t0base = 0, c0base = 0, zrow = 0;
+  // statistics (printed with GB_PLAN_VERBOSE=1)
+  int n_fast = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;
 };
 
 struct HostMech
@@ -160,10 +159,12 @@ struct HostMech
   size_t d_scratch_bytes[8] = {0};
 };
 
+// builds the plan for tiles of G states and CTAs of `threads` threads; GB_ERR_UNSUPPORTED if it does not fit
 int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
                    const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
                    const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
-                   const std::vector<int> &tb_off, JacPlanHost &out);
+                   const std::vector<int> &tb_off, int G, int threads, JacPlanHost &out);
+size_t jac_smem_bytes(int ns, const JacPlanHost &p);
 
 // returns 0 or a negative GB_ERR_* code; message in gb::last_error
 int finalize_reaction(const HostMech &m, HostReaction &x);

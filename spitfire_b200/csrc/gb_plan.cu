@@ -1,20 +1,27 @@
 // gb_plan.cu -- host-side construction of the static "Jacobian plan" consumed by k_jac (gb_jac.cu).
 //
 // The plan turns the accumulation loop of the reference (rates_sensitivities_exact.cpp:1014-1026: every reaction
-// scatters factor*dq into the rows of its net species) into a gather that needs no atomics and no read-modify-write:
-//   * every reaction owns a record {q, dq/drho, dq/dT, a, b, H, dq/dY_slot...} in shared memory (per state), where
-//     a, b carry the dense part of dq/dY (dq/dY_s = sparse_s + a*u_s + b, u_s = 1/M_s - 1/M_ns) and
-//     H = sum_i h_i * (-nu_i M_i) is the reaction enthalpy used for the temperature row;
-//   * every destination -- a structurally non-zero entry of R[i][k] = sum_r nu_ri dq_r/dY_k, the five row scalars
-//     (w, dw/drho, dw/dT, A, B) of every species, the enthalpy-weighted temperature-row sums and three per-state
-//     scalars -- is a run of 32-bit items in one static stream; an item names a record value and the integer net
-//     stoichiometric coefficient multiplying it (plain: rec | nu << 16) or two record values to be multiplied
-//     (product: rec_a | rec_b << 16); a run starts with a header word slot:20 | count:11 << 20 | product << 31;
-//   * the stream is cut into one contiguous range per CTA thread with balanced cost; destinations with many items are
-//     split into parts that are added in a fixed order afterwards, so results are bit-reproducible run to run.
+// scatters factor*dq into the rows of its net species) into a schedule without atomics or read-modify-write:
+//   * reaction phase: the reactions are sorted by code path and packed into groups of 32/G reactions; a warp evaluates a
+//     group for the G states of the tile at once (lane = state + G * position in the group). The dominant shape
+//     "simple, A + B (<)=> C + D, unit coefficients" has a straight-line fast path with a fixed 96-byte parameter
+//     record; everything else goes through the generic path (variable-length parameter record). Groups are assigned to
+//     warps by estimated cost (longest processing time first).
+//     Every reaction owns a record in shared memory (per state): fast {q, dq/drho, dq/dT, dq/dY_slot...}, generic
+//     {q, dq/drho, dq/dT, a, b, dq/dY_slot...}; a, b carry the dense part of dq/dY (dq/dY_s = sparse_s + a*u_s + b,
+//     u_s = 1/M_s - 1/M_ns) of third-body reactions and of reactions involving the last species.
+//   * gather phase: every destination -- a structurally non-zero entry of R[i][k] = sum_r nu_ri dq_r/dY_k or one of the
+//     five row scalars (sums of nu * {q, dq/drho, dq/dT, a, b}) of a species -- is a list of items (record row, nu) in
+//     ascending reaction order, the reference's accumulation order. Long lists are cut into parts that are added
+//     afterwards in part order. Parts are sorted by length and dealt out 32 at a time ("rounds": the 32 lanes of a
+//     warp gather 32 parts of equal padded length in lock step); rounds are assigned to warps by length (LPT).
+//   * column sums: the temperature row needs sum_i h_i dw_i/dx (isobaric_reactor_kernels.cpp:74-92), formed from the
+//     gathered rows in species order like the reference's inner products.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 #include "../../include/griffon_b200.h"
@@ -23,45 +30,120 @@
 namespace gb
 {
 
+size_t jac_smem_bytes(int ns, const JacPlanHost &p)
+{
+  const size_t region = (size_t)std::max(p.rec_rows, p.rows) + 2;
+  const size_t doubles = (size_t)p.G * (JP_NSC + 7 * (size_t)ns + region + p.ncs) + 3 * (size_t)ns + (ns & 1);
+  return doubles * sizeof(double) + sizeof(unsigned short) * (size_t)(ns + 1) * (ns - 1) + 16;
+}
+
 int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
                    const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
                    const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
-                   const std::vector<int> &tb_off, JacPlanHost &out)
+                   const std::vector<int> &tb_off, int G, int threads, JacPlanHost &out)
 {
   const int ns = (int)m.species.size(), nr = (int)m.reactions.size(), last = ns - 1;
   out = JacPlanHost();
+  out.G = G;
+  out.threads = threads;
+  const int nwarps = threads / 32, LPR = 32 / G, RMAX = 32 / G;
   auto dbits = [](double v) {
     unsigned long long u;
     std::memcpy(&u, &v, 8);
     return u;
   };
 
-  // ---- records and parameter blob -----------------------------------------------------------------------------
-  std::vector<int> rec_off(nr, 0);
-  int rec_total = 0;
-  for (int r = 0; r < nr; ++r)
-  {
-    rec_off[r] = rec_total;
-    rec_total += JP_REC_HDR + (slot_off[r + 1] - slot_off[r]);
-  }
-  if (rec_total > 32767)
-  {
-    set_error("mechanism too large for the packed Jacobian plan (more than 32767 record values per state)");
-    return GB_ERR_UNSUPPORTED;
-  }
-  out.rec_total = rec_total;
-  out.prm_off.assign(nr, 0);
+  // ---- classification, records, parameter blob -----------------------------------------------------------------------
+  std::vector<char> fast(nr, 0), last_involved(nr, 0);
+  std::vector<int> rec_off(nr, 0), prm_off(nr, 0);
+  int rec_rows = 0;
   for (int r = 0; r < nr; ++r)
   {
     const HostReaction &x = m.reactions[r];
-    out.prm_off[r] = (int)out.prm.size();
+    bool li = false;
+    for (int i = 0; i < x.n_rc; ++i)
+      li |= (x.rc_idx[i] == last && !x.has_orders);
+    for (int i = 0; i < x.n_pd; ++i)
+      li |= (x.pd_idx[i] == last && x.reversible && !x.has_orders);
+    for (int i = 0; i < x.n_sp; ++i)
+      li |= (x.sp_idx[i] == last);
+    for (size_t j = 0; j < x.tb_idx.size(); ++j)
+      li |= (x.tb_idx[j] == last);
+    last_involved[r] = li;
+    bool f = x.type == RT_SIMPLE && !x.has_orders && !li && x.n_rc == 2 && x.rc_st[0] == 1 && x.rc_st[1] == 1 &&
+             x.rc_idx[0] != x.rc_idx[1] && x.n_net <= 4 && (flags[r] & F_KC_VALID);
+    if (f && x.reversible)
+    {
+      f = x.n_pd == 2 && x.pd_st[0] == 1 && x.pd_st[1] == 1 && x.pd_idx[0] != x.pd_idx[1];
+      for (int i = 0; f && i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+          f = f && x.rc_idx[i] != x.pd_idx[j];
+    }
+    const int nsl = slot_off[r + 1] - slot_off[r];
+    if (f && nsl != (x.reversible ? 4 : 2))
+      f = false;
+    if (getenv("GB_JAC_NOFAST"))
+      f = false;
+    fast[r] = f;
+    rec_off[r] = rec_rows;
+    rec_rows += (f ? JP_HDR_FAST : JP_HDR_GEN) + nsl;
+  }
+  if (nr >= (1 << 18))
+  {
+    set_error("too many reactions for the packed parameter format");
+    return GB_ERR_UNSUPPORTED;
+  }
+  if (rec_rows > 65000)
+  {
+    set_error("mechanism too large for the packed Jacobian plan (more than 65000 record values per state)");
+    return GB_ERR_UNSUPPORTED;
+  }
+  out.rec_rows = rec_rows;
+  for (int r = 0; r < nr; ++r)
+  {
+    const HostReaction &x = m.reactions[r];
+    if (out.prm.size() & 1)
+      out.prm.push_back(0ull); // 16-byte alignment of every record
+    prm_off[r] = (int)out.prm.size();
     const int ntb = (int)x.tb_idx.size(), nsl = slot_off[r + 1] - slot_off[r];
     if (x.n_rc > 255 || ntb > 255 || nsl > 120 || std::abs(x.sum_stoich) > 127)
     {
       set_error("reaction too large for the packed parameter format");
       return GB_ERR_UNSUPPORTED;
     }
-    out.prm.push_back((unsigned long long)(unsigned int)flags[r] | ((unsigned long long)(unsigned int)rec_off[r] << 32));
+    if (fast[r])
+    {
+      // w0: flags | record row << 32; w1: species a, b, c, d; w2: net species; w3: net nu (int8 x4), sum_stoich, n_net
+      // w4..6: A, b, Ea/R; w7..10: 1/M of a, b, c, d; w11: pad
+      const int c = x.reversible ? x.pd_idx[0] : 0, d = x.reversible ? x.pd_idx[1] : 0;
+      out.prm.push_back((unsigned long long)((unsigned int)flags[r] | ((unsigned int)r << 14)) |
+                        ((unsigned long long)(unsigned int)rec_off[r] << 32));
+      out.prm.push_back((unsigned long long)(unsigned short)x.rc_idx[0] |
+                        ((unsigned long long)(unsigned short)x.rc_idx[1] << 16) |
+                        ((unsigned long long)(unsigned short)c << 32) | ((unsigned long long)(unsigned short)d << 48));
+      unsigned long long w2 = 0, w3 = 0;
+      for (int i = 0; i < 4; ++i)
+      {
+        const int idx = i < x.n_net ? x.net_idx[i] : x.net_idx[0];
+        const int nu = i < x.n_net ? x.net_st[i] : 0;
+        w2 |= (unsigned long long)(unsigned short)idx << (16 * i);
+        w3 |= (unsigned long long)(unsigned char)(signed char)nu << (8 * i);
+      }
+      w3 |= (unsigned long long)(unsigned char)(signed char)x.sum_stoich << 32;
+      w3 |= (unsigned long long)(x.n_net & 255) << 40;
+      out.prm.push_back(w2);
+      out.prm.push_back(w3);
+      for (int k = 0; k < 3; ++k)
+        out.prm.push_back(dbits(x.kf[k]));
+      out.prm.push_back(dbits(m.invmw[x.rc_idx[0]]));
+      out.prm.push_back(dbits(m.invmw[x.rc_idx[1]]));
+      out.prm.push_back(dbits(m.invmw[c]));
+      out.prm.push_back(dbits(m.invmw[d]));
+      out.prm.push_back(0ull);
+      continue;
+    }
+    out.prm.push_back((unsigned long long)((unsigned int)flags[r] | ((unsigned int)r << 14)) |
+                        ((unsigned long long)(unsigned int)rec_off[r] << 32));
     unsigned long long w1 = 0;
     w1 |= (unsigned long long)(x.n_rc & 255);
     w1 |= (unsigned long long)(x.n_pd & 255) << 8;
@@ -96,12 +178,9 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
                         ((unsigned long long)(unsigned char)pd_slot[NSR * (size_t)r + i] << 24));
       out.prm.push_back(dbits(m.invmw[x.pd_idx[i]]));
     }
-    for (int i = 0; i < x.n_net; ++i)
-    { // net species: index | nu, then the factor -nu*MW (rates_sensitivities_exact.cpp:1018)
+    for (int i = 0; i < x.n_net; ++i) // net species: index | nu
       out.prm.push_back((unsigned long long)(unsigned short)x.net_idx[i] |
                         ((unsigned long long)(unsigned char)(signed char)x.net_st[i] << 16));
-      out.prm.push_back(dbits(-x.net_st[i] * (1. / m.invmw[x.net_idx[i]])));
-    }
     for (int j = 0; j < ntb; ++j)
     {
       out.prm.push_back((unsigned long long)(unsigned short)x.tb_idx[j] |
@@ -109,30 +188,122 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       out.prm.push_back(dbits(x.tb_eff[j]));
     }
   }
+  out.prm.push_back(0ull);
+  out.prm.push_back(0ull);
 
-  // ---- logical destinations -------------------------------------------------------------------------------------------
-  // [0, ns*(ns-1))            R[i][k], logical id k*ns + i (column-major like the output block)
-  // [yend, yend + 5*ns)       row scalars q*ns + i, q = 0..4: w, dw/drho, dw/dT, A, B (as sums of nu * value)
-  // [tbase, tbase + ns + 1)   temperature-row sums: sum_r H_r dq_r/d(rho | T | Y_k)
-  // [sbase, sbase + 3)        per-state scalars: w.h, A.h, B.h
-  const int yend = ns * (ns - 1), rbase = yend, tbase = rbase + 5 * ns, sbase = tbase + ns + 1, nlogical = sbase + 3;
+  // ---- reaction groups --------------------------------------------------------------------------------------------------
+  {
+    auto key = [&](int r) {
+      const HostReaction &x = m.reactions[r];
+      long k = fast[r] ? 0 : 1;
+      k = k * 8 + x.type;
+      k = k * 8 + (x.kform == KF_ARRHENIUS ? 0 : 1 + x.kform);
+      k = k * 2 + (x.reversible ? 0 : 1);
+      k = k * 2 + (x.has_orders ? 1 : 0);
+      if (!fast[r])
+      {
+        k = k * 16 + x.n_rc;
+        k = k * 16 + x.n_pd;
+        k = k * 8 + x.troebits;
+        k = k * 64 + std::min<int>(63, (int)x.tb_idx.size());
+      }
+      return k;
+    };
+    auto cost = [&](int r) {
+      const HostReaction &x = m.reactions[r];
+      double c;
+      if (fast[r])
+        c = 60. + (x.kform == KF_ARRHENIUS ? 45. : 0.) + (x.reversible ? 110. : 0.);
+      else
+      {
+        c = 250. + 40. * (x.n_rc + (x.reversible ? x.n_pd : 0)) + (x.reversible ? 120. : 0.) + 12. * x.tb_idx.size();
+        if (x.type == RT_LINDEMANN)
+          c += 150.;
+        if (x.type == RT_TROE)
+          c += 700.;
+        if (x.has_orders)
+          c += 600.;
+      }
+      return c;
+    };
+    std::vector<int> order(nr);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+    struct Group
+    {
+      int kind;
+      double cost;
+      std::vector<int> rx;
+    };
+    std::vector<Group> groups;
+    for (int p = 0; p < nr;)
+    {
+      Group g;
+      g.kind = fast[order[p]] ? 0 : 1;
+      g.cost = 0.;
+      while (p < nr && (int)g.rx.size() < LPR && (fast[order[p]] ? 0 : 1) == g.kind)
+      {
+        g.cost = std::max(g.cost, cost(order[p]));
+        g.rx.push_back(order[p]);
+        ++p;
+      }
+      // lanes of a generic group diverge: the warp pays for (part of) the union of the code paths
+      if (g.kind == 1)
+      {
+        double extra = 0.;
+        for (size_t i = 1; i < g.rx.size(); ++i)
+          if (key(g.rx[i]) != key(g.rx[i - 1]))
+            extra += 0.5 * cost(g.rx[i]);
+        g.cost += extra;
+      }
+      groups.push_back(g);
+    }
+    std::vector<int> gorder(groups.size());
+    std::iota(gorder.begin(), gorder.end(), 0);
+    std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return groups[a].cost > groups[b].cost; });
+    std::vector<double> load(nwarps, 0.);
+    load[nwarps - 1] = 400.; // the last warp starts with the mixture cp chain (k_jac)
+    std::vector<std::vector<int>> per_warp(nwarps);
+    for (int gi : gorder)
+    {
+      const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      per_warp[w].push_back(gi);
+      load[w] += groups[gi].cost;
+    }
+    out.wg_off.assign(nwarps + 1, 0);
+    for (int w = 0; w < nwarps; ++w)
+    {
+      out.wg_off[w] = (int)out.groups.size() / (1 + LPR);
+      for (int gi : per_warp[w])
+      {
+        out.groups.push_back(groups[gi].kind);
+        for (int i = 0; i < LPR; ++i)
+          out.groups.push_back(i < (int)groups[gi].rx.size() ? prm_off[groups[gi].rx[i]] : -1);
+      }
+    }
+    out.wg_off[nwarps] = (int)out.groups.size() / (1 + LPR);
+    for (int r = 0; r < nr; ++r)
+      (fast[r] ? out.n_fast : out.n_generic)++;
+    if (getenv("GB_PLAN_VERBOSE"))
+    {
+      fprintf(stderr, "[gb plan] G=%d threads=%d reactions: %d fast, %d generic, %d groups; warp loads:", G, threads,
+              out.n_fast, out.n_generic, (int)groups.size());
+      for (int w = 0; w < nwarps; ++w)
+        fprintf(stderr, " %.0f", load[w]);
+      fprintf(stderr, "\n");
+    }
+  }
+
+  // ---- logical destinations and their items ----------------------------------------------------------------------------------
+  // [0, ns*(ns-1))       R[i][k], logical id k*ns + i
+  // [rbase, rbase+5*ns)  row scalars q*ns + i, q = 0..4: sums of nu * {q, dq/drho, dq/dT, a, b}
+  const int yend = ns * (ns - 1), rbase = yend, nlogical = rbase + 5 * ns;
   std::vector<std::vector<unsigned int>> dest(nlogical);
   for (int r = 0; r < nr; ++r)
   {
     const HostReaction &x = m.reactions[r];
-    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r];
-    bool last_involved = false;
-    for (int i = 0; i < x.n_rc; ++i)
-      last_involved |= (x.rc_idx[i] == last && !x.has_orders);
-    for (int i = 0; i < x.n_pd; ++i)
-      last_involved |= (x.pd_idx[i] == last && x.reversible && !x.has_orders);
-    for (int i = 0; i < x.n_sp; ++i)
-      last_involved |= (x.sp_idx[i] == last);
-    for (size_t j = 0; j < x.tb_idx.size(); ++j)
-      last_involved |= (x.tb_idx[j] == last);
+    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r], hdr = fast[r] ? JP_HDR_FAST : JP_HDR_GEN;
     const bool tbtype = x.type != RT_SIMPLE;
-    auto plain = [&](int rec, int nu) { return (unsigned int)rec | ((unsigned int)(nu & 255) << 24); };
-    auto prod = [&](int a, int b) { return (unsigned int)a | ((unsigned int)b << 16); };
     for (int k = 0; k < x.n_net; ++k)
     {
       const int row = x.net_idx[k], nu = x.net_st[k];
@@ -141,126 +312,177 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
         set_error("net stoichiometric coefficient outside [-128, 127]");
         return GB_ERR_UNSUPPORTED;
       }
+      auto item = [&](int rec) { return (unsigned int)rec | ((unsigned int)(nu & 255) << 16); };
       for (int q = 0; q < 3; ++q)
-        dest[rbase + q * ns + row].push_back(plain(base + q, nu));
+        dest[rbase + q * ns + row].push_back(item(base + q));
       if (tbtype)
-        dest[rbase + 3 * ns + row].push_back(plain(base + 3, nu));
-      if (last_involved)
-        dest[rbase + 4 * ns + row].push_back(plain(base + 4, nu));
+        dest[rbase + 3 * ns + row].push_back(item(base + 3));
+      if (last_involved[r])
+        dest[rbase + 4 * ns + row].push_back(item(base + 4));
       for (int q = 0; q < nsl; ++q)
-        dest[(int)slot_species[slot_off[r] + q] * ns + row].push_back(plain(base + JP_REC_HDR + q, nu));
+        dest[(int)slot_species[slot_off[r] + q] * ns + row].push_back(item(base + hdr + q));
     }
-    dest[tbase + 0].push_back(prod(base + 5, base + 1));
-    dest[tbase + 1].push_back(prod(base + 5, base + 2));
-    for (int q = 0; q < nsl; ++q)
-      dest[tbase + 2 + (int)slot_species[slot_off[r] + q]].push_back(prod(base + 5, base + JP_REC_HDR + q));
-    dest[sbase + 0].push_back(prod(base + 5, base + 0));
-    if (tbtype)
-      dest[sbase + 1].push_back(prod(base + 5, base + 3));
-    if (last_involved)
-      dest[sbase + 2].push_back(prod(base + 5, base + 4));
   }
 
-  // ---- compact slots: structurally zero R entries get no storage ---------------------------------------------------------
-  out.emap.assign(yend, (unsigned short)0xffff);
-  int nslots = 0;
-  std::vector<int> slot_of(nlogical, -1);
-  for (int s = 0; s < yend; ++s)
+  // ---- rows of the gathered-sum array -----------------------------------------------------------------------------------------
+  std::vector<int> row_of(nlogical, -1);
+  int rows = 0;
+  for (int s = 0; s < nlogical; ++s)
     if (!dest[s].empty())
-    {
-      out.emap[s] = (unsigned short)nslots;
-      slot_of[s] = nslots++;
-    }
-  if (nslots >= 0xffff)
-  {
-    set_error("too many non-zero Jacobian entries for the compact slot map");
-    return GB_ERR_UNSUPPORTED;
-  }
-  out.rbase = nslots;
-  for (int s = rbase; s < tbase; ++s)
-    slot_of[s] = nslots++;
-  out.tbase = nslots;
-  for (int s = tbase; s < sbase; ++s)
-    slot_of[s] = nslots++;
-  out.sbase = nslots;
-  for (int s = sbase; s < nlogical; ++s)
-    slot_of[s] = nslots++;
+      row_of[s] = rows++;
+  out.n_dest = rows;
 
-  // ---- parts, stream, balanced thread partition ------------------------------------------------------------------------------
-  int split = 24;
+  int split = 12;
   if (const char *e = std::getenv("GB_JAC_SPLIT"))
-    split = std::max(4, std::atoi(e));
+    split = std::max(2, std::atoi(e));
   struct Part
   {
-    int logical, slot, begin, count, prod;
+    int logical, row, begin, count;
   };
   std::vector<Part> parts;
-  size_t nitems = 0;
   for (int s = 0; s < nlogical; ++s)
   {
-    if (slot_of[s] < 0)
+    if (row_of[s] < 0)
       continue;
-    const int n = (int)dest[s].size(), pr = s >= tbase ? 1 : 0;
-    nitems += n;
+    const int n = (int)dest[s].size();
+    out.n_items += n;
     if (n <= split + split / 2)
-      parts.push_back({s, slot_of[s], 0, n, pr});
+      parts.push_back({s, row_of[s], 0, n});
     else
     {
       const int np = (n + split - 1) / split;
-      out.fix.push_back(slot_of[s]);
-      out.fix.push_back(nslots);
+      out.fix.push_back(row_of[s]);
+      out.fix.push_back(rows);
       out.fix.push_back(np - 1);
       for (int p = 0; p < np; ++p)
       {
         const int b = (int)((long long)n * p / np), e = (int)((long long)n * (p + 1) / np);
-        parts.push_back({s, p == 0 ? slot_of[s] : nslots + p - 1, b, e - b, pr});
+        parts.push_back({s, p == 0 ? row_of[s] : rows + p - 1, b, e - b});
       }
-      nslots += np - 1;
+      rows += np - 1;
     }
   }
-  if (nslots >= (1 << 20))
+  out.n_parts = (int)parts.size();
+  out.t0base = rows;
+  rows += ns; // final temperature-row values, column c at t0base + c
+  out.c0base = rows;
+  rows += ns; // final column-0 values of the species rows, row 1+i at c0base + i
+  out.rows = rows;
+  const int region = std::max(rows, rec_rows);
+  out.zrow = region; // always zero; region + 1 is the write-only dummy row of idle lanes
+  if (region + 2 > 65535)
   {
-    set_error("too many Jacobian plan destinations");
+    set_error("too many Jacobian plan rows");
     return GB_ERR_UNSUPPORTED;
   }
-  out.nslots = nslots;
-  // CTA size: enough threads for one reaction each and ~16+ items each, a multiple of 32 in [64, 512]
-  int threads = (int)((nitems + parts.size()) / 48);
-  threads = std::min(256, std::max(64, ((threads + 31) / 32) * 32));
-  if (const char *e = std::getenv("GB_JAC_THREADS"))
-    threads = std::max(32, std::min(1024, (std::atoi(e) / 32) * 32));
-  out.threads = threads;
 
-  std::vector<double> cost(parts.size());
-  double total = 0.;
-  for (size_t p = 0; p < parts.size(); ++p)
+  // ---- rounds: 32 parts of similar length per round, rounds dealt to warps by LPT ------------------------------------------
   {
-    cost[p] = 2.0 + parts[p].count * (parts[p].prod ? 1.5 : 1.0);
-    total += cost[p];
-  }
-  out.tstart.assign(threads + 1, 0);
-  size_t p = 0;
-  double done = 0.;
-  for (int t = 0; t < threads; ++t)
-  {
-    out.tstart[t] = (int)out.stream.size();
-    const double target = total * (t + 1) / threads;
-    while (p < parts.size() && (done + 0.5 * cost[p] <= target || t == threads - 1))
+    const int BLK = JP_BLK; // steps are issued in blocks (item prefetch distance), so lengths are padded to BLK
+    std::vector<int> porder(parts.size());
+    std::iota(porder.begin(), porder.end(), 0);
+    std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return parts[a].count > parts[b].count; });
+    struct Round
     {
-      const Part &pt = parts[p];
-      if (pt.count > 2047)
+      int len;
+      std::vector<int> p;
+    };
+    std::vector<Round> rds;
+    for (size_t i = 0; i < porder.size(); i += 32)
+    {
+      Round rd;
+      rd.len = ((parts[porder[i]].count + BLK - 1) / BLK) * BLK;
+      for (size_t j = i; j < std::min(porder.size(), i + 32); ++j)
+        rd.p.push_back(porder[j]);
+      rds.push_back(rd);
+    }
+    if ((int)rds.size() > nwarps * RMAX)
+    {
+      set_error("Jacobian plan needs more gather rounds than the register-resident accumulators allow for this tile size");
+      return GB_ERR_UNSUPPORTED;
+    }
+    std::vector<double> load(nwarps, 0.);
+    std::vector<std::vector<int>> per_warp(nwarps);
+    for (size_t i = 0; i < rds.size(); ++i) // already in descending length
+    {
+      int w = -1;
+      for (int c = 0; c < nwarps; ++c)
+        if ((int)per_warp[c].size() < RMAX && (w < 0 || load[c] < load[w]))
+          w = c;
+      per_warp[w].push_back((int)i);
+      load[w] += rds[i].len + 3.;
+    }
+    out.wr_off.assign(nwarps + 1, 0);
+    for (int w = 0; w < nwarps; ++w)
+    {
+      out.wr_off[w] = (int)out.rounds.size() / 2;
+      out.max_rounds = std::max(out.max_rounds, (int)per_warp[w].size());
+      for (int ri : per_warp[w])
       {
-        set_error("Jacobian plan part too long");
-        return GB_ERR_UNSUPPORTED;
+        const Round &rd = rds[ri];
+        out.rounds.push_back((int)out.items.size());
+        out.rounds.push_back(rd.len);
+        out.n_steps += rd.len;
+        for (int k = 0; k < rd.len; ++k)
+          for (int l = 0; l < 32; ++l)
+          {
+            unsigned int it = (unsigned int)out.zrow; // nu = 0 on the zero row: a no-op
+            if (l < (int)rd.p.size() && k < parts[rd.p[l]].count)
+              it = dest[parts[rd.p[l]].logical][parts[rd.p[l]].begin + k];
+            out.items.push_back(it);
+          }
+        for (int l = 0; l < 32; ++l)
+          out.rdest.push_back((unsigned short)(l < (int)rd.p.size() ? parts[rd.p[l]].row : out.zrow + 1));
       }
-      out.stream.push_back((unsigned int)pt.slot | ((unsigned int)pt.count << 20) | ((unsigned int)pt.prod << 31));
-      for (int k = 0; k < pt.count; ++k)
-        out.stream.push_back(dest[pt.logical][pt.begin + k]);
-      done += cost[p];
-      ++p;
+    }
+    out.wr_off[nwarps] = (int)out.rounds.size() / 2;
+    for (int k = 0; k < 32 * (BLK + 2); ++k)
+      out.items.push_back((unsigned int)out.zrow); // the prefetch of the last block reads past the end
+    if (getenv("GB_PLAN_VERBOSE"))
+    {
+      fprintf(stderr, "[gb plan] rec_rows=%d rows=%d dests=%d parts=%d items=%d steps*32=%d rounds=%d fix=%d; warp steps:",
+              rec_rows, rows, out.n_dest, out.n_parts, out.n_items, out.n_steps * 32, (int)rds.size(),
+              (int)out.fix.size() / 3);
+      for (int w = 0; w < nwarps; ++w)
+        fprintf(stderr, " %.0f", load[w]);
+      fprintf(stderr, "\n");
     }
   }
-  out.tstart[threads] = (int)out.stream.size();
+
+  // ---- row-scalar sources, column sums, output map ---------------------------------------------------------------------------------
+  out.rowsrc.assign(5 * (size_t)ns, (unsigned short)out.zrow);
+  for (int q = 0; q < 5; ++q)
+    for (int i = 0; i < ns; ++i)
+      if (row_of[rbase + q * ns + i] >= 0)
+        out.rowsrc[(size_t)q * ns + i] = (unsigned short)row_of[rbase + q * ns + i];
+  // column destinations: 0..ns-2: sum_i hm_i R[i][k]; then sums over species of hm_i * {W, Wrho, WT, A, B}_i and of
+  // cpm_i * W_i (hm_i = -M_i h_i, cpm_i = -M_i cp_i); items in species order
+  out.ncs = ns - 1 + 6;
+  out.cs_off.assign(1, 0);
+  for (int k = 0; k < ns - 1; ++k)
+  {
+    for (int i = 0; i < ns; ++i)
+      if (row_of[k * ns + i] >= 0)
+        out.cs_items.push_back((unsigned int)row_of[k * ns + i] | ((unsigned int)i << 16));
+    out.cs_off.push_back((int)out.cs_items.size());
+  }
+  for (int q = 0; q < 6; ++q)
+  {
+    const int src = q < 5 ? q : 0;
+    for (int i = 0; i < ns; ++i)
+      if (row_of[rbase + src * ns + i] >= 0)
+        out.cs_items.push_back((unsigned int)row_of[rbase + src * ns + i] | ((unsigned int)i << 16));
+    out.cs_off.push_back((int)out.cs_items.size());
+  }
+  out.cs_items.push_back(0u);
+  out.emap.assign((size_t)(ns + 1) * (ns - 1), (unsigned short)out.zrow);
+  for (int c = 1; c < ns; ++c)
+  {
+    out.emap[(size_t)(ns + 1) * (c - 1)] = (unsigned short)(out.t0base + c);
+    for (int r = 1; r <= ns; ++r)
+      if (row_of[(c - 1) * ns + (r - 1)] >= 0)
+        out.emap[(size_t)(ns + 1) * (c - 1) + r] = (unsigned short)row_of[(c - 1) * ns + (r - 1)];
+  }
   return GB_OK;
 }
 
