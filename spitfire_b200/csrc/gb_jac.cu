@@ -480,24 +480,56 @@ __device__ __noinline__ void react_orders(int ns, const int *__restrict__ dm_n_s
   rec[4 * G] = b;
 }
 
-// one gather step: acc[g] += nu * record[row][g]
+// ------------------------------------------------------------------------------------------------------------------
+// Rows of G doubles are read and written 16 bytes at a time. Lanes of a warp usually address different rows at the
+// same moment, and a row is G*8 bytes, so without care all lanes hit the same few banks. Every lane therefore visits
+// the G/2 chunks of a row in an order rotated by its lane number; its registers hold the states in that rotated
+// order ("slots"): slot s <-> state 2*(((s>>1) + rot) & (G/2-1)) + (s&1).
+// ------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ void gather_step(unsigned int u, const double *sR, double (&acc)[G])
+struct Rows
 {
-  const double nu = (double)(((int)(u << 8)) >> 24);
-  const double *p = sR + (size_t)(u & 0xffff) * G;
-  if (G == 1)
-    acc[0] = fma(nu, p[0], acc[0]);
-  else
+  static constexpr int NCH = G >= 2 ? G / 2 : 1;
+  __device__ __forceinline__ static int chunk(int j, int rot) { return (j + rot) & (NCH - 1); }
+  __device__ __forceinline__ static int state_of(int slot, int rot) { return G == 1 ? 0 : 2 * chunk(slot >> 1, rot) + (slot & 1); }
+  __device__ __forceinline__ static void load(const double *p, int rot, double (&v)[G])
   {
-#pragma unroll
-    for (int g = 0; g < G; g += 2)
+    if (G == 1)
+      v[0] = p[0];
+    else
     {
-      const double2 v = *reinterpret_cast<const double2 *>(p + g);
-      acc[g] = fma(nu, v.x, acc[g]);
-      acc[g + 1] = fma(nu, v.y, acc[g + 1]);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+      {
+        const double2 x = *reinterpret_cast<const double2 *>(p + 2 * chunk(j, rot));
+        v[2 * j] = x.x;
+        v[2 * j + (G >= 2 ? 1 : 0)] = x.y;
+      }
     }
   }
+  __device__ __forceinline__ static void store(double *p, int rot, const double (&v)[G])
+  {
+    if (G == 1)
+      p[0] = v[0];
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+        *reinterpret_cast<double2 *>(p + 2 * chunk(j, rot)) = make_double2(v[2 * j], v[2 * j + (G >= 2 ? 1 : 0)]);
+    }
+  }
+};
+
+// one gather step: acc[slot] += nu * record[row][state(slot)]
+template <int G>
+__device__ __forceinline__ void gather_step(unsigned int u, const double *sR, int rot, double (&acc)[G])
+{
+  const double nu = (double)(((int)(u << 8)) >> 24);
+  double v[G];
+  Rows<G>::load(sR + (size_t)(u & 0xffff) * G, rot, v);
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+    acc[g] = fma(nu, v[g], acc[g]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -509,6 +541,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const DeviceMech &dm = a.dm;
   const int ns = dm.ns, nsm1 = ns - 1;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int rot = lane & (Rows<G>::NCH - 1);
   const int region = max(dm.jp_rec_rows, dm.jp_rows) + 2;
   JacSmem s;
   s.sc = smem;                         // [JP_NSC][G] per-state scalars
@@ -516,16 +549,21 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   s.sC = s.sy + ns * G;                // concentrations
   s.sg = s.sC + ns * G;                // Gibbs              -> later: c1 of the output transform
   s.sdb = s.sg + ns * G;               // dB/dT              -> later: c2
-  s.sh = s.sdb + ns * G;               // enthalpies
+  s.sh = s.sdb + ns * G;               // enthalpies         -> later: hm_i = -M_i h_i
   s.scp = s.sh + ns * G;               // species cp
   s.sdcp = s.scp + ns * G;             // species dcp/dT     -> later: c3
   s.su = s.sdcp + ns * G;              // [ns] u_k = 1/M_k - 1/M_ns
   s.snm = s.su + ns;                   // [ns] -M_i
   s.sim = s.snm + ns;                  // [ns] 1/M_i
   s.sR = s.sim + ns + (ns & 1);        // [region][G] reaction records, then gathered sums (16-byte aligned)
-  s.sTH = s.sR + (size_t)region * G;   // [ncs][G] column sums
-  s.semap = (unsigned short *)(s.sTH + (size_t)dm.jp_ncs * G); // [(ns+1)*(ns-1)]
+  s.sTH = s.sR + (size_t)region * G;   // [ncsp][G] column-sum parts
+  int *stab = (int *)(s.sTH + (size_t)dm.jp_ncsp * G); // plan tables (gb_mech.h)
+  s.semap = (unsigned short *)(stab + dm.jp_tab_words); // [(ns+1)*(ns-1)]
   const int zrow = dm.jp_zrow;
+  const int *t_groups = stab + dm.jp_t_groups, *t_rounds = stab + dm.jp_t_rounds, *t_fix = stab + dm.jp_t_fix;
+  const int *t_csparts = stab + dm.jp_t_csparts, *t_cspfirst = stab + dm.jp_t_cspfirst;
+  const unsigned short *t_rdest = (const unsigned short *)(stab + dm.jp_t_rdest);
+  const unsigned short *rowsrc = (const unsigned short *)(stab + dm.jp_t_rowsrc);
 
   // per-CTA constants
   for (int i = tid; i < ns; i += nt)
@@ -534,6 +572,8 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     s.snm[i] = -dm.mw[i];
     s.sim[i] = dm.invmw[i];
   }
+  for (int e = tid; e < dm.jp_tab_words; e += nt)
+    stab[e] = dm.jp_tab[e];
   for (int e = tid; e < (ns + 1) * nsm1; e += nt)
     s.semap[e] = dm.jp_emap[e];
   if (tid < 2 * G)
@@ -638,7 +678,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       }
     }
     __syncthreads();
-    // ---- reaction phase (the last warp first forms cp and dcp/dT of the mixture in species order) ----------------------
+    // ---- reaction phase (the last warp first forms cp, dcp/dT and the open-reactor terms in species order) -------------
     if (tid >= nt - 32 && lane < G)
     { // thermodynamics_kernels.cpp:45-131, 183-260
       const int g = lane;
@@ -653,13 +693,34 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       }
       SMG(s.sc, J_CP, g) = cp;
       SMG(s.sc, J_DCP, g) = dcp;
+      if (open)
+      { // mass_jac_isobaric :100-140: inflow enthalpy term and sum cp_i y_in,i
+        const double Tin = a.rx.T_in, logTin = log(Tin), invTin = 1. / Tin;
+        double m0;
+        {
+          const SpeciesThermo tl = species_thermo<false>(dm, nsm1, Tin, logTin, invTin);
+          m0 = (tl.h - SMG(s.sh, nsm1, g)) * a.rx.y_in[nsm1];
+        }
+        for (int i = 0; i < nsm1; ++i)
+        {
+          const SpeciesThermo ti = species_thermo<false>(dm, i, Tin, logTin, invTin);
+          m0 += (ti.h - SMG(s.sh, i, g)) * a.rx.y_in[i];
+        }
+        m0 /= cp;
+        m0 *= invTau;
+        double ycp = 0.;
+        for (int i = 0; i < ns; ++i)
+          ycp += SMG(s.scp, i, g) * a.rx.y_in[i];
+        SMG(s.sc, J_M0, g) = m0;
+        SMG(s.sc, J_YCP, g) = ycp;
+      }
     }
     {
       const int g = lane % G, sub = lane / G;
-      const int g0 = dm.jp_wg_off[warp], g1 = dm.jp_wg_off[warp + 1];
+      const int g0 = stab[dm.jp_t_wg + warp], g1 = stab[dm.jp_t_wg + warp + 1];
       for (int gi = g0; gi < g1; ++gi)
       {
-        const int *grp = dm.jp_groups + (size_t)gi * (1 + LPR);
+        const int *grp = t_groups + gi * (1 + LPR);
         const int kind = grp[0], off = grp[1 + sub];
         if (off < 0)
           continue;
@@ -676,7 +737,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     __syncthreads();
     // ---- gather: every lane sums its parts in registers --------------------------------------------------------------------------
     double hold[RMAX][G];
-    const int r0 = dm.jp_wr_off[warp], nround = dm.jp_wr_off[warp + 1] - r0;
+    const int r0 = stab[dm.jp_t_wr + warp], nround = stab[dm.jp_t_wr + warp + 1] - r0;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
     {
@@ -685,31 +746,28 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         hold[j][g] = 0.;
       if (j < nround)
       {
-        const unsigned int *__restrict__ it = dm.jp_items + dm.jp_rounds[2 * (r0 + j)] + lane;
-        const int L = dm.jp_rounds[2 * (r0 + j) + 1];
+        const unsigned int *__restrict__ it = dm.jp_items + t_rounds[2 * (r0 + j)] + lane;
+        const int L = t_rounds[2 * (r0 + j) + 1];
         unsigned int u0 = __ldg(it), u1 = __ldg(it + 32);
         for (int k = 0; k < L; k += JP_BLK)
         {
           it += 32 * JP_BLK;
           const unsigned int n0 = __ldg(it), n1 = __ldg(it + 32);
-          gather_step<G>(u0, s.sR, hold[j]);
-          gather_step<G>(u1, s.sR, hold[j]);
+          gather_step<G>(u0, s.sR, rot, hold[j]);
+          gather_step<G>(u1, s.sR, rot, hold[j]);
           u0 = n0;
           u1 = n1;
         }
       }
     }
     __syncthreads();
-    // ---- the sums overwrite the record region ----------------------------------------------------------------------------------------
+    // ---- the sums overwrite the record region; enthalpies become the column-sum weights hm_i = -M_i h_i ---------------
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
       if (j < nround)
-      {
-        double *p = s.sR + (size_t)dm.jp_rdest[(size_t)(r0 + j) * 32 + lane] * G;
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          p[g] = hold[j][g];
-      }
+        Rows<G>::store(s.sR + (size_t)t_rdest[(r0 + j) * 32 + lane] * G, rot, hold[j]);
+    for (int item = tid; item < ns * G; item += nt)
+      s.sh[item] *= s.snm[item / G];
     __syncthreads();
     // ---- recombine split destinations in part order -------------------------------------------------------------------------------
     if (dm.jp_nfix > 0)
@@ -717,7 +775,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       for (int item = tid; item < dm.jp_nfix * G; item += nt)
       {
         const int fi = item / G, g = item - fi * G;
-        const int dst = dm.jp_fix[3 * fi], first = dm.jp_fix[3 * fi + 1], np = dm.jp_fix[3 * fi + 2];
+        const int dst = t_fix[3 * fi], first = t_fix[3 * fi + 1], np = t_fix[3 * fi + 2];
         double v = SMG(s.sR, dst, g);
         for (int p = 0; p < np; ++p)
           v += SMG(s.sR, first + p, g);
@@ -725,7 +783,6 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       }
       __syncthreads();
     }
-    const unsigned short *rowsrc = dm.jp_rowsrc;
 
     if (a.mode == MODE_SENS)
     { // raw (ns+1)x(ns+1) column-major sensitivities, rates_sensitivities_exact.cpp:68, 1011-1025
@@ -756,28 +813,55 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       continue;
     }
 
-    // ---- column sums, row constants, open-reactor terms -----------------------------------------------------------------------------
+    // ---- column-sum parts (lane per part, G accumulators) and row constants (thread per (species, state)) --------------
     {
-      const int ncs = dm.jp_ncs, njobs = ncs * G + ns * G + (open ? G : 0);
-      for (int job = tid; job < njobs; job += nt)
+      const int ncsp = dm.jp_ncsp, ncs = dm.jp_ncs;
+      // parts first, on whole warps, so that the row jobs start on a warp boundary
+      const int npw = (ncsp + 31) & ~31;
+      for (int job = tid; job < npw + ns * G; job += nt)
       {
-        if (job < ncs * G)
-        { // sum over species (ascending) of weight_i * row value
-          const int d = job / G, g = job - d * G;
-          const double *wsrc = (d == ncs - 1) ? s.scp : s.sh;
-          double acc = 0.;
-          const int p0 = dm.jp_cs_off[d], p1 = dm.jp_cs_off[d + 1];
-          for (int p = p0; p < p1; ++p)
-          {
-            const unsigned int u = __ldg(dm.jp_cs_items + p);
-            const int i = (int)(u >> 16);
-            acc += (SMG(wsrc, i, g) * s.snm[i]) * SMG(s.sR, u & 0xffff, g);
+        if (job < npw)
+        {
+          if (job >= ncsp)
+            continue;
+          const int d = t_csparts[3 * job], p0 = t_csparts[3 * job + 1], p1 = t_csparts[3 * job + 2];
+          double acc[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            acc[g] = 0.;
+          if (d == ncs - 1)
+          { // sum_i (cp_i * -M_i) * W_i
+            for (int p = p0; p < p1; ++p)
+            {
+              const unsigned int u = __ldg(dm.jp_cs_items + p);
+              const int i = (int)(u >> 16);
+              double w[G], v[G];
+              Rows<G>::load(s.scp + (size_t)i * G, rot, w);
+              Rows<G>::load(s.sR + (size_t)(u & 0xffff) * G, rot, v);
+              const double nm = s.snm[i];
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                acc[g] += (w[g] * nm) * v[g];
+            }
           }
-          SMG(s.sTH, d, g) = acc;
+          else
+          { // sum_i hm_i * row value, species ascending (isobaric_reactor_kernels.cpp:74-92)
+            for (int p = p0; p < p1; ++p)
+            {
+              const unsigned int u = __ldg(dm.jp_cs_items + p);
+              double w[G], v[G];
+              Rows<G>::load(s.sh + (size_t)(u >> 16) * G, rot, w);
+              Rows<G>::load(s.sR + (size_t)(u & 0xffff) * G, rot, v);
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                acc[g] += w[g] * v[g];
+            }
+          }
+          Rows<G>::store(s.sTH + (size_t)job * G, rot, acc);
         }
-        else if (job < ncs * G + ns * G)
+        else
         { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
-          const int item = job - ncs * G;
+          const int item = job - npw;
           const int i = item / G, g = item - i * G;
           const double nm = s.snm[i], invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
           const double w = nm * SMG(s.sR, rowsrc[i], g), wr = nm * SMG(s.sR, rowsrc[ns + i], g);
@@ -800,28 +884,6 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
             }
           }
         }
-        else
-        { // mass_jac_isobaric :100-140: inflow enthalpy term and sum cp_i y_in,i
-          const int g = job - ncs * G - ns * G;
-          const double Tin = a.rx.T_in, logTin = log(Tin), invTin = 1. / Tin;
-          double m0;
-          {
-            const SpeciesThermo tl = species_thermo<false>(dm, nsm1, Tin, logTin, invTin);
-            m0 = (tl.h - SMG(s.sh, nsm1, g)) * a.rx.y_in[nsm1];
-          }
-          for (int i = 0; i < nsm1; ++i)
-          {
-            const SpeciesThermo ti = species_thermo<false>(dm, i, Tin, logTin, invTin);
-            m0 += (ti.h - SMG(s.sh, i, g)) * a.rx.y_in[i];
-          }
-          m0 /= SMG(s.sc, J_CP, g);
-          m0 *= invTau;
-          double ycp = 0.;
-          for (int i = 0; i < ns; ++i)
-            ycp += SMG(s.scp, i, g) * a.rx.y_in[i];
-          SMG(s.sc, J_M0, g) = m0;
-          SMG(s.sc, J_YCP, g) = ycp;
-        }
       }
     }
     __syncthreads();
@@ -830,11 +892,18 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     {
       const int c = item / G, g = item - c * G;
       const int ncs = dm.jp_ncs;
+      auto colsum = [&](int d) {
+        const int p0 = t_cspfirst[d], p1 = t_cspfirst[d + 1];
+        double v = SMG(s.sTH, p0, g);
+        for (int p = p0 + 1; p < p1; ++p)
+          v += SMG(s.sTH, p, g);
+        return v;
+      };
       const double rho = SMG(s.sc, J_RHO, g), cp = SMG(s.sc, J_CP, g), T = SMG(s.sc, J_T, g);
       const double cpsensT = SMG(s.sc, J_DCP, g);
       const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
-      const double SW = SMG(s.sTH, nsm1 + 0, g), SWr = SMG(s.sTH, nsm1 + 1, g), SWT = SMG(s.sTH, nsm1 + 2, g);
-      const double SA = SMG(s.sTH, nsm1 + 3, g), SB = SMG(s.sTH, nsm1 + 4, g), wcp = SMG(s.sTH, ncs - 1, g);
+      const double SW = colsum(nsm1 + 0), SWr = colsum(nsm1 + 1), SWT = colsum(nsm1 + 2);
+      const double SA = colsum(nsm1 + 3), SB = colsum(nsm1 + 4), wcp = colsum(ncs - 1);
       const double rhs0c = -SW / (rho * cp);
       double rhs0 = rhs0c;
       double P0rho = -invRhoCp * SWr - invRho * rhs0c;
@@ -893,7 +962,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const int k = c - 1;
         const double uk = s.su[k];
-        const double sum = SMG(s.sTH, k, g) + uk * SA + SB;
+        const double sum = colsum(k) + uk * SA + SB;
         const double pY = -sum / (rho * cp) + (-rhs0c * invCp + cextra) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
         v = pY + nRM * uk * P0rho;
       }
@@ -962,64 +1031,68 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const int r = tid % ns;
         int c = 1 + tid / ns;
+        // registers hold the states in this lane's slot order
         double c1[G], c2[G], c3[G];
         double *ob[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g)
+        if (r == 0)
         {
-          c1[g] = r == 0 ? 1. : SMG(s.sg, r - (r > 0), g);
-          c2[g] = r == 0 ? 0. : SMG(s.sdb, r - (r > 0), g);
-          c3[g] = r == 0 ? 0. : SMG(s.sdcp, r - (r > 0), g);
-          ob[g] = a.out1 + (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g)) + r;
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            c1[g] = 1., c2[g] = 0., c3[g] = 0.;
+        }
+        else
+        {
+          Rows<G>::load(s.sg + (size_t)(r - 1) * G, rot, c1);
+          Rows<G>::load(s.sdb + (size_t)(r - 1) * G, rot, c2);
+          Rows<G>::load(s.sdcp + (size_t)(r - 1) * G, rot, c3);
+        }
+        unsigned int live = 0;
+#pragma unroll
+        for (int sl = 0; sl < G; ++sl)
+        {
+          const int g = Rows<G>::state_of(sl, rot);
+          ob[sl] = a.out1 + (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g)) + r;
+          live |= (g < gcount ? 1u : 0u) << sl;
         }
         for (; c < ns; c += cpi)
         {
           const int e = r + (ns + 1) * (c - 1);
           const double uk = s.su[c - 1];
-          const double *p = s.sR + (size_t)s.semap[e] * G;
           double v[G];
-          if (G == 1)
-            v[0] = fma(c1[0], p[0], fma(uk, c2[0], c3[0]));
-          else
-          {
+          Rows<G>::load(s.sR + (size_t)s.semap[e] * G, rot, v);
 #pragma unroll
-            for (int g = 0; g < G; g += 2)
-            {
-              const double2 x = *reinterpret_cast<const double2 *>(p + g);
-              v[g] = fma(c1[g], x.x, fma(uk, c2[g], c3[g]));
-              v[g + 1] = fma(c1[g + 1], x.y, fma(uk, c2[g + 1], c3[g + 1]));
-            }
-          }
+          for (int sl = 0; sl < G; ++sl)
+            v[sl] = fma(c1[sl], v[sl], fma(uk, c2[sl], c3[sl]));
           if (r == c)
           {
             if (open)
             {
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                v[g] += -invTau;
+              for (int sl = 0; sl < G; ++sl)
+                v[sl] += -invTau;
             }
             if (flamelet)
             {
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                v[g] += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, g)) + r];
+              for (int sl = 0; sl < G; ++sl)
+                v[sl] += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, Rows<G>::state_of(sl, rot))) + r];
             }
           }
           if (flamelet && fl.scale_and_offset)
           {
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+            for (int sl = 0; sl < G; ++sl)
             {
-              v[g] *= fl.prefactor;
+              v[sl] *= fl.prefactor;
               if (r == c)
-                v[g] -= 1.;
+                v[sl] -= 1.;
             }
           }
-          const size_t off = (size_t)ns * c;
+          const int off = ns * c;
 #pragma unroll
-          for (int g = 0; g < G; ++g)
-            if (g < gcount)
-              ob[g][off] = v[g];
+          for (int sl = 0; sl < G; ++sl)
+            if (live & (1u << sl))
+              ob[sl][off] = v[sl];
         }
       }
     }

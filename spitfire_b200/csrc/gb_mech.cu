@@ -383,10 +383,8 @@ int commit(HostMech &m)
   const size_t o_chunk = b.add(chunk_rxn), o_recoff = b.add(rec_off);
   const size_t o_rowoff = b.add(row_off), o_rowrxn = b.add(row_rxn), o_rowfac = b.add(row_fac),
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
-  const size_t o_jpprm = b.add(jp.prm), o_jpwg = b.add(jp.wg_off), o_jpgroups = b.add(jp.groups),
-               o_jpwr = b.add(jp.wr_off), o_jprounds = b.add(jp.rounds), o_jpitems = b.add(jp.items),
-               o_jprdest = b.add(jp.rdest), o_jpfix = b.add(jp.fix), o_jprowsrc = b.add(jp.rowsrc),
-               o_jpcsoff = b.add(jp.cs_off), o_jpcsitems = b.add(jp.cs_items), o_jpemap = b.add(jp.emap);
+  const size_t o_jpprm = b.add(jp.prm), o_jpitems = b.add(jp.items), o_jpcsitems = b.add(jp.cs_items),
+               o_jpemap = b.add(jp.emap), o_jptab = b.add(jp.tab);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -427,15 +425,15 @@ int commit(HostMech &m)
   d.row_fac = at<double>(base, o_rowfac), d.row_stmw = at<double>(base, o_rowstmw);
   d.row_order = at<short>(base, o_roworder);
   d.jp_prm = at<unsigned long long>(base, o_jpprm);
-  d.jp_wg_off = at<int>(base, o_jpwg), d.jp_groups = at<int>(base, o_jpgroups);
-  d.jp_wr_off = at<int>(base, o_jpwr), d.jp_rounds = at<int>(base, o_jprounds);
-  d.jp_items = at<unsigned int>(base, o_jpitems), d.jp_rdest = at<unsigned short>(base, o_jprdest);
-  d.jp_fix = at<int>(base, o_jpfix), d.jp_rowsrc = at<unsigned short>(base, o_jprowsrc);
-  d.jp_cs_off = at<int>(base, o_jpcsoff), d.jp_cs_items = at<unsigned int>(base, o_jpcsitems);
-  d.jp_emap = at<unsigned short>(base, o_jpemap);
+  d.jp_items = at<unsigned int>(base, o_jpitems), d.jp_cs_items = at<unsigned int>(base, o_jpcsitems);
+  d.jp_emap = at<unsigned short>(base, o_jpemap), d.jp_tab = at<int>(base, o_jptab);
+  d.jp_tab_words = (int)jp.tab.size();
+  d.jp_t_wg = jp.t_wg, d.jp_t_groups = jp.t_groups, d.jp_t_wr = jp.t_wr, d.jp_t_rounds = jp.t_rounds;
+  d.jp_t_rdest = jp.t_rdest, d.jp_t_fix = jp.t_fix, d.jp_t_rowsrc = jp.t_rowsrc, d.jp_t_csparts = jp.t_csparts;
+  d.jp_t_cspfirst = jp.t_cspfirst;
   d.jp_G = jp.G, d.jp_threads = jp.threads, d.jp_rec_rows = jp.rec_rows, d.jp_rows = jp.rows;
-  d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_t0base = jp.t0base, d.jp_c0base = jp.c0base;
-  d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);
+  d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_ncsp = jp.ncsp, d.jp_t0base = jp.t0base;
+  d.jp_c0base = jp.c0base, d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);
   m.committed = true;
   return GB_OK;
 }

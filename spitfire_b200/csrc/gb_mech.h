@@ -99,19 +99,20 @@ struct DeviceMech
   const short *row_order;                          // [ns]
   // ---- Jacobian plan (gb_plan.cu), consumed by k_jac (gb_jac.cu); see JacPlanHost ----
   const unsigned long long *jp_prm; // packed reaction parameters (fast records: 12 words, generic: variable)
-  const int *jp_wg_off;             // [nwarps+1] reaction groups of every warp
-  const int *jp_groups;             // per group: kind (0 fast, 1 generic), then 32/G parameter offsets (-1: idle lane set)
-  const int *jp_wr_off;             // [nwarps+1] gather rounds of every warp
-  const int *jp_rounds;             // per round: first item (index into jp_items), number of steps
   const unsigned int *jp_items;     // [round][step][lane]: record row (16) | nu (int8) << 16
-  const unsigned short *jp_rdest;   // [round][lane] destination row of the gathered sum
-  const int *jp_fix;                // [3*jp_nfix] (destination row, first extra part row, number of extra parts)
-  const unsigned short *jp_rowsrc;  // [5][ns] rows holding sum_r nu*{q, dq/drho, dq/dT, a, b} of every species
-  const int *jp_cs_off;             // [jp_ncs+1] column sums: items of column destination d
-  const unsigned int *jp_cs_items;  // row (16) | species (16) << 16
+  const unsigned int *jp_cs_items;  // column sums: row (16) | species (16) << 16
   const unsigned short *jp_emap;    // [(ns+1)*(ns-1)] entry (row r: 0 = T, 1+i = species i <= ns-1; column c >= 1) at
                                     // r + (ns+1)*(c-1) -> row of the gathered-sum array
-  int jp_G, jp_threads, jp_rec_rows, jp_rows, jp_nfix, jp_ncs, jp_t0base, jp_c0base, jp_zrow, jp_smem;
+  // small tables, copied to shared memory by every CTA (offsets in ints into jp_tab):
+  //  t_wg [nwarps+1] reaction groups of every warp; t_groups: per group kind (0 fast, 1 generic) and 32/G parameter
+  //  offsets (-1: idle); t_wr [nwarps+1] gather rounds of every warp; t_rounds: per round first item and number of
+  //  steps; t_rdest (u16) [round][lane] destination row; t_fix (dst row, first extra part row, extra parts);
+  //  t_rowsrc (u16) [5][ns] rows of sum_r nu*{q, dq/drho, dq/dT, a, b}; t_csparts (dest, begin, end);
+  //  t_cspfirst [ncs+1] first part of every column destination
+  const int *jp_tab;
+  int jp_tab_words, jp_t_wg, jp_t_groups, jp_t_wr, jp_t_rounds, jp_t_rdest, jp_t_fix, jp_t_rowsrc, jp_t_csparts,
+      jp_t_cspfirst;
+  int jp_G, jp_threads, jp_rec_rows, jp_rows, jp_nfix, jp_ncs, jp_ncsp, jp_t0base, jp_c0base, jp_zrow, jp_smem;
 };
 
 constexpr int JP_FAST_WORDS = 12; // fast-path parameter record, 8-byte words
@@ -127,7 +128,9 @@ struct JacPlanHost
   std::vector<int> wg_off, groups, wr_off, rounds, fix, cs_off;
   std::vector<unsigned int> items, cs_items;
   std::vector<unsigned short> rdest, rowsrc, emap;
-  int rec_rows = 0, rows = 0, ncs = 0, t0base = 0, c0base = 0, zrow = 0;
+  std::vector<int> tab;
+  int t_wg = 0, t_groups = 0, t_wr = 0, t_rounds = 0, t_rdest = 0, t_fix = 0, t_rowsrc = 0, t_csparts = 0, t_cspfirst = 0;
+  int rec_rows = 0, rows = 0, ncs = 0, ncsp = 0, t0base = 0, c0base = 0, zrow = 0;
   // statistics (printed with GB_PLAN_VERBOSE=1)
   int n_fast = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;
 };

@@ -33,8 +33,9 @@ namespace gb
 size_t jac_smem_bytes(int ns, const JacPlanHost &p)
 {
   const size_t region = (size_t)std::max(p.rec_rows, p.rows) + 2;
-  const size_t doubles = (size_t)p.G * (JP_NSC + 7 * (size_t)ns + region + p.ncs) + 3 * (size_t)ns + (ns & 1);
-  return doubles * sizeof(double) + sizeof(unsigned short) * (size_t)(ns + 1) * (ns - 1) + 16;
+  const size_t doubles = (size_t)p.G * (JP_NSC + 7 * (size_t)ns + region + p.ncsp) + 3 * (size_t)ns + (ns & 1);
+  return doubles * sizeof(double) + sizeof(int) * p.tab.size() +
+         sizeof(unsigned short) * (size_t)(ns + 1) * (ns - 1) + 16;
 }
 
 int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
@@ -475,6 +476,52 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     out.cs_off.push_back((int)out.cs_items.size());
   }
   out.cs_items.push_back(0u);
+  // column sums are formed by one lane per part (G accumulators in registers); parts of a destination are added
+  // in part order afterwards
+  std::vector<int> csparts, cspfirst(1, 0);
+  {
+    int csplit = 14;
+    if (const char *e = std::getenv("GB_JAC_CSPLIT"))
+      csplit = std::max(2, std::atoi(e));
+    for (int d = 0; d < out.ncs; ++d)
+    {
+      const int b0 = out.cs_off[d], n = out.cs_off[d + 1] - b0;
+      const int np = std::max(1, (n + csplit - 1) / csplit);
+      for (int q = 0; q < np; ++q)
+      {
+        csparts.push_back(d);
+        csparts.push_back(b0 + (int)((long long)n * q / np));
+        csparts.push_back(b0 + (int)((long long)n * (q + 1) / np));
+      }
+      cspfirst.push_back((int)csparts.size() / 3);
+    }
+    out.ncsp = (int)csparts.size() / 3;
+  }
+  // ---- small tables copied to shared memory by every CTA -----------------------------------------------------------------
+  {
+    auto add = [&](const std::vector<int> &v) {
+      const int off = (int)out.tab.size();
+      out.tab.insert(out.tab.end(), v.begin(), v.end());
+      return off;
+    };
+    auto add16 = [&](const std::vector<unsigned short> &v) {
+      const int off = (int)out.tab.size();
+      for (size_t i = 0; i < v.size(); i += 2)
+        out.tab.push_back((int)((unsigned int)v[i] | ((unsigned int)(i + 1 < v.size() ? v[i + 1] : 0) << 16)));
+      return off;
+    };
+    out.t_wg = add(out.wg_off);
+    out.t_groups = add(out.groups);
+    out.t_wr = add(out.wr_off);
+    out.t_rounds = add(out.rounds);
+    out.t_rdest = add16(out.rdest);
+    out.t_fix = add(out.fix);
+    out.t_rowsrc = add16(out.rowsrc);
+    out.t_csparts = add(csparts);
+    out.t_cspfirst = add(cspfirst);
+    if (out.tab.size() & 1)
+      out.tab.push_back(0);
+  }
   out.emap.assign((size_t)(ns + 1) * (ns - 1), (unsigned short)out.zrow);
   for (int c = 1; c < ns; ++c)
   {
