@@ -34,7 +34,7 @@ def stale(target):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, parity=True, out=LIB, verbose=True):
+def build(force=False, parity=True, out=LIB, verbose=True, defines=()):
     if not force and not stale(out):
         return out
     flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -44,7 +44,7 @@ def build(force=False, parity=True, out=LIB, verbose=True):
     if parity:
         flags += ['--fmad=false']
         tag += ' --fmad=false'
-    flags += ['-DGB_FLAGS="%s"' % tag]
+    flags += ['-DGB_FLAGS="%s"' % tag] + ['-D' + d for d in defines]
     cmd = [NVCC] + flags + ['-o', out] + sources()
     if verbose:
         print(' '.join(cmd), flush=True)
@@ -63,7 +63,9 @@ def build(force=False, parity=True, out=LIB, verbose=True):
 
 
 if __name__ == '__main__':
-    if '--fma' in sys.argv:
+    if '--timeline' in sys.argv:  # debug build: per-warp phase timeline of k_jac (tools/timeline.py)
+        build(force=True, out=os.path.join(HERE, 'libgriffon_b200_tl.so'), defines=('GB_JAC_TIMELINE',))
+    elif '--fma' in sys.argv:
         build(force=True, parity=False, out=os.path.join(HERE, 'libgriffon_b200_fma.so'))
     else:
         build(force='--force' in sys.argv)

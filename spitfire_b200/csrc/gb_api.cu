@@ -118,6 +118,9 @@ extern "C"
 {
 
   long gb_kernel_launch_count(void) { return kernel_launch_count(); }
+#ifdef GB_JAC_TIMELINE
+  int gb_debug_jac_timeline(long long *out /* [16*32] */) { return gb::debug_jac_timeline(out); }
+#endif
   const char *gb_build_info(void) { return "griffon_b200 sm_100a fp64, nvcc " GB_STR(__CUDACC_VER_MAJOR__) "." GB_STR(__CUDACC_VER_MINOR__) GB_FLAGS; }
 
   // ---- thermo ----------------------------------------------------------------------------------------------------

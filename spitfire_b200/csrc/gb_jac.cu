@@ -62,6 +62,17 @@ static_assert(J_SPARE1 < JP_NSC, "JP_NSC too small");
 
 #define SMG(arr, idx, g) (arr)[(idx)*G + (g)]
 
+// Debug build only (-DGB_JAC_TIMELINE): every warp of CTA 0 records clock64() when it ARRIVES at each barrier of its
+// second tile; read back through gb_debug_jac_timeline (gb_api.cu), tools/timeline.py prints the table.
+#ifdef GB_JAC_TIMELINE
+__device__ long long g_jac_timeline[16 * 32];
+#define TL_MARK(k)                                                                  \
+  if (blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && lane == 0)               \
+    g_jac_timeline[(k)*32 + warp] = clock64();
+#else
+#define TL_MARK(k)
+#endif
+
 __device__ __forceinline__ double u2d(unsigned long long u) { return __longlong_as_double((long long)u); }
 
 struct JacSmem
@@ -507,6 +518,41 @@ struct Rows
       }
     }
   }
+  // The gathered sums are stored with the chunks of row R rotated by R ("swizzled"): chunk c sits at position
+  // (c + R) & (NCH-1). Lanes that read different rows in canonical register order (slot = state, needed for
+  // coalesced global stores) then spread over all banks as well.
+  __device__ __forceinline__ static int swz(int row, int g)
+  {
+    return G == 1 ? row : row * G + 2 * chunk(g >> 1, row) + (g & 1);
+  }
+  // slot j <-> state chunk (j + rot): rot = 0 gives canonical order
+  __device__ __forceinline__ static void load_swz(const double *base, int row, int rot, double (&v)[G])
+  {
+    if (G == 1)
+      v[0] = base[row];
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+      {
+        const double2 x = *reinterpret_cast<const double2 *>(base + (size_t)row * G + 2 * chunk(j, rot + row));
+        v[2 * j] = x.x;
+        v[2 * j + (G >= 2 ? 1 : 0)] = x.y;
+      }
+    }
+  }
+  __device__ __forceinline__ static void store_swz(double *base, int row, int rot, const double (&v)[G])
+  {
+    if (G == 1)
+      base[row] = v[0];
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+        *reinterpret_cast<double2 *>(base + (size_t)row * G + 2 * chunk(j, rot + row)) =
+            make_double2(v[2 * j], v[2 * j + (G >= 2 ? 1 : 0)]);
+    }
+  }
   __device__ __forceinline__ static void store(double *p, int rot, const double (&v)[G])
   {
     if (G == 1)
@@ -578,6 +624,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     s.semap[e] = dm.jp_emap[e];
   if (tid < 2 * G)
     s.sR[(size_t)zrow * G + tid] = 0.;
+#define SJ(row, g) s.sR[Rows<G>::swz((row), (g))] /* gathered sums: swizzled rows */
 
   const bool state_mode = a.in_state != nullptr;
   const bool reactor = a.mode == MODE_REACTOR_JAC;
@@ -588,10 +635,24 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const FlameletDev &fl = a.fl;
 
   const int ntiles = (a.n + G - 1) / G;
+  // CTAs start together and do identical work, so without help they would all be in the same phase at the same time
+  // (every SM streaming its output to HBM in the same burst, nobody using the FP64 pipes meanwhile). Each CTA
+  // therefore times its first tile and then waits a fraction of that time given by its index, which spreads the
+  // phases of co-resident and neighbouring CTAs evenly over a tile period for the rest of the launch.
+  const long long t_start = clock64();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
     const int tile0 = tile * G;
     const int gcount = min(G, a.n - tile0);
+    if (a.stagger > 1 && tile == blockIdx.x + gridDim.x)
+    {
+      const long long t_tile = clock64() - t_start;
+      const long long wait = t_tile * (long long)(blockIdx.x % a.stagger) / a.stagger;
+      const long long t1 = clock64();
+      while (clock64() - t1 < wait)
+        __nanosleep(200);
+    }
+    TL_MARK(0)
     __syncthreads();
     // ---- load (states past the end of the batch replicate the tile's first state; they are never written) ----------
     if (state_mode)
@@ -619,6 +680,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         SMG(s.sc, J_RHO, tid) = a.in_rho[tile0 + (tid < gcount ? tid : 0)];
       }
     }
+    TL_MARK(1)
     __syncthreads();
     // ---- thermo, overlapped with the two order-sensitive chains -------------------------------------------------------------
     if (tid < G)
@@ -653,6 +715,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         SMG(s.sdcp, i, g) = t.dcp;
       }
     }
+    TL_MARK(2)
     __syncthreads();
     // ---- concentrations and per-state scalars (every thread re-derives rho: cheaper than another barrier) -------------
     for (int item = tid; item < ns * G; item += nt)
@@ -677,6 +740,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         SMG(s.sc, J_LPRT, g) = log(dm.p_ref * invT * (1. / dm.Ru)); // log(p0/(R T)), :535
       }
     }
+    TL_MARK(3)
     __syncthreads();
     // ---- reaction phase (the last warp first forms cp, dcp/dT and the open-reactor terms in species order) -------------
     if (tid >= nt - 32 && lane < G)
@@ -734,6 +798,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           react_generic<G>(dm, P, g, s);
       }
     }
+    TL_MARK(4)
     __syncthreads();
     // ---- gather: every lane sums its parts in registers --------------------------------------------------------------------------
     double hold[RMAX][G];
@@ -760,14 +825,16 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         }
       }
     }
+    TL_MARK(5)
     __syncthreads();
     // ---- the sums overwrite the record region; enthalpies become the column-sum weights hm_i = -M_i h_i ---------------
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
       if (j < nround)
-        Rows<G>::store(s.sR + (size_t)t_rdest[(r0 + j) * 32 + lane] * G, rot, hold[j]);
+        Rows<G>::store_swz(s.sR, t_rdest[(r0 + j) * 32 + lane], rot, hold[j]);
     for (int item = tid; item < ns * G; item += nt)
       s.sh[item] *= s.snm[item / G];
+    TL_MARK(6)
     __syncthreads();
     // ---- recombine split destinations in part order -------------------------------------------------------------------------------
     if (dm.jp_nfix > 0)
@@ -776,11 +843,12 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const int fi = item / G, g = item - fi * G;
         const int dst = t_fix[3 * fi], first = t_fix[3 * fi + 1], np = t_fix[3 * fi + 2];
-        double v = SMG(s.sR, dst, g);
+        double v = SJ(dst, g);
         for (int p = 0; p < np; ++p)
-          v += SMG(s.sR, first + p, g);
-        SMG(s.sR, dst, g) = v;
+          v += SJ(first + p, g);
+        SJ(dst, g) = v;
       }
+      TL_MARK(7)
       __syncthreads();
     }
 
@@ -797,14 +865,14 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           {
             const double nm = s.snm[row];
             if (col == 0)
-              v = nm * SMG(s.sR, rowsrc[ns + row], g);
+              v = nm * SJ(rowsrc[ns + row], g);
             else if (col == 1)
-              v = nm * SMG(s.sR, rowsrc[2 * ns + row], g);
+              v = nm * SJ(rowsrc[2 * ns + row], g);
             else if (col - 2 < nsm1)
             {
               const int k = col - 2;
-              const double rv = SMG(s.sR, s.semap[k * (ns + 1) + row + 1], g);
-              v = nm * (rv + (SMG(s.sR, rowsrc[3 * ns + row], g) * s.su[k] + SMG(s.sR, rowsrc[4 * ns + row], g)));
+              const double rv = SJ(s.semap[k * (ns + 1) + row + 1], g);
+              v = nm * (rv + (SJ(rowsrc[3 * ns + row], g) * s.su[k] + SJ(rowsrc[4 * ns + row], g)));
             }
           }
           a.out1[(size_t)(tile0 + g) * nsp1 * nsp1 + e] = v;
@@ -837,7 +905,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
               const int i = (int)(u >> 16);
               double w[G], v[G];
               Rows<G>::load(s.scp + (size_t)i * G, rot, w);
-              Rows<G>::load(s.sR + (size_t)(u & 0xffff) * G, rot, v);
+              Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
               const double nm = s.snm[i];
 #pragma unroll
               for (int g = 0; g < G; ++g)
@@ -851,7 +919,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
               const unsigned int u = __ldg(dm.jp_cs_items + p);
               double w[G], v[G];
               Rows<G>::load(s.sh + (size_t)(u >> 16) * G, rot, w);
-              Rows<G>::load(s.sR + (size_t)(u & 0xffff) * G, rot, v);
+              Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
 #pragma unroll
               for (int g = 0; g < G; ++g)
                 acc[g] += w[g] * v[g];
@@ -864,9 +932,9 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           const int item = job - npw;
           const int i = item / G, g = item - i * G;
           const double nm = s.snm[i], invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
-          const double w = nm * SMG(s.sR, rowsrc[i], g), wr = nm * SMG(s.sR, rowsrc[ns + i], g);
-          const double wT = nm * SMG(s.sR, rowsrc[2 * ns + i], g);
-          const double nmA = nm * SMG(s.sR, rowsrc[3 * ns + i], g), nmB = nm * SMG(s.sR, rowsrc[4 * ns + i], g);
+          const double w = nm * SJ(rowsrc[i], g), wr = nm * SJ(rowsrc[ns + i], g);
+          const double wT = nm * SJ(rowsrc[2 * ns + i], g);
+          const double nmA = nm * SJ(rowsrc[3 * ns + i], g), nmB = nm * SJ(rowsrc[4 * ns + i], g);
           const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
           const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
           SMG(s.sg, i, g) = invRho * nm;
@@ -874,7 +942,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           SMG(s.sdcp, i, g) = invRho * nmB;
           if (i < nsm1)
           {
-            SMG(s.sR, dm.jp_c0base + i, g) = wT * invRho - roT * prho; // J[1+i, 0]
+            SJ(dm.jp_c0base + i, g) = wT * invRho - roT * prho; // J[1+i, 0]
             if (reactor && g < gcount)
             { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
               double v = w * invRho;
@@ -886,6 +954,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         }
       }
     }
+    TL_MARK(8)
     __syncthreads();
     // ---- temperature row (:58-98, 142-168; flamelet_kernels.cpp:1290-1320) ----------------------------------------------------
     for (int item = tid; item < ns * G; item += nt)
@@ -966,7 +1035,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         const double pY = -sum / (rho * cp) + (-rhs0c * invCp + cextra) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
         v = pY + nRM * uk * P0rho;
       }
-      SMG(s.sR, dm.jp_t0base + c, g) = v;
+      SJ(dm.jp_t0base + c, g) = v;
       if (c == 0)
       {
         if (reactor && g < gcount)
@@ -999,6 +1068,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         SMG(s.sc, J_TTC, g) = ttc;
       }
     }
+    TL_MARK(9)
     __syncthreads();
 
     // ---- output: column 0, then the columns 1..ns-1 with one row per thread ----------------------------------------------------
@@ -1007,7 +1077,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       const int g = item / ns, r = item - g * ns;
       if (g >= gcount)
         continue;
-      double v = (r == 0) ? SMG(s.sR, dm.jp_t0base, g) : SMG(s.sR, dm.jp_c0base + r - 1, g);
+      double v = (r == 0) ? SJ(dm.jp_t0base, g) : SJ(dm.jp_c0base + r - 1, g);
       const size_t ob = (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g));
       if (flamelet)
       {
@@ -1031,7 +1101,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const int r = tid % ns;
         int c = 1 + tid / ns;
-        // registers hold the states in this lane's slot order
+        // registers hold the states in canonical order (slot = state): every store instruction writes one state
         double c1[G], c2[G], c3[G];
         double *ob[G];
         if (r == 0)
@@ -1042,24 +1112,19 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         }
         else
         {
-          Rows<G>::load(s.sg + (size_t)(r - 1) * G, rot, c1);
-          Rows<G>::load(s.sdb + (size_t)(r - 1) * G, rot, c2);
-          Rows<G>::load(s.sdcp + (size_t)(r - 1) * G, rot, c3);
+          Rows<G>::load(s.sg + (size_t)(r - 1) * G, 0, c1);
+          Rows<G>::load(s.sdb + (size_t)(r - 1) * G, 0, c2);
+          Rows<G>::load(s.sdcp + (size_t)(r - 1) * G, 0, c3);
         }
-        unsigned int live = 0;
 #pragma unroll
-        for (int sl = 0; sl < G; ++sl)
-        {
-          const int g = Rows<G>::state_of(sl, rot);
-          ob[sl] = a.out1 + (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g)) + r;
-          live |= (g < gcount ? 1u : 0u) << sl;
-        }
+        for (int g = 0; g < G; ++g)
+          ob[g] = a.out1 + (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g)) + r;
         for (; c < ns; c += cpi)
         {
           const int e = r + (ns + 1) * (c - 1);
           const double uk = s.su[c - 1];
           double v[G];
-          Rows<G>::load(s.sR + (size_t)s.semap[e] * G, rot, v);
+          Rows<G>::load_swz(s.sR, (int)s.semap[e], 0, v);
 #pragma unroll
           for (int sl = 0; sl < G; ++sl)
             v[sl] = fma(c1[sl], v[sl], fma(uk, c2[sl], c3[sl]));
@@ -1075,7 +1140,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
             {
 #pragma unroll
               for (int sl = 0; sl < G; ++sl)
-                v[sl] += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, Rows<G>::state_of(sl, rot))) + r];
+                v[sl] += fl.cmajor[(size_t)__double_as_longlong(SMG(s.sc, J_CMOFF, sl)) + r];
             }
           }
           if (flamelet && fl.scale_and_offset)
@@ -1091,11 +1156,12 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           const int off = ns * c;
 #pragma unroll
           for (int sl = 0; sl < G; ++sl)
-            if (live & (1u << sl))
+            if (sl < gcount)
               ob[sl][off] = v[sl];
         }
       }
     }
+    TL_MARK(10)
   }
 }
 
@@ -1131,10 +1197,24 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
   if (const char *e = getenv("GB_JAC_CTAS"))
     per_sm = std::max(1, atoi(e));
   const int grid = std::max(1, std::min(ntiles, jac_sm_count() * per_sm));
-  k_jac<G><<<grid, threads, smem, s>>>(a);
+  ChemArgs b = a;
+  b.stagger = 4;
+  if (const char *e = getenv("GB_JAC_STAGGER"))
+    b.stagger = std::max(1, atoi(e));
+  if (ntiles < 4 * grid)
+    b.stagger = 1; // too few tiles per CTA to win the waiting time back
+  k_jac<G><<<grid, threads, smem, s>>>(b);
   ++g_jac_launches;
   return cudaGetLastError();
 }
+
+#ifdef GB_JAC_TIMELINE
+int debug_jac_timeline(long long *out)
+{
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_jac_timeline, sizeof(long long) * 16 * 32) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 cudaError_t launch_jac(const ChemArgs &a_in, cudaStream_t s)
 {

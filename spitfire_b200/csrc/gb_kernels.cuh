@@ -57,6 +57,7 @@ struct ChemArgs
   FlameletDev fl;
   int G;           // states per CTA tile
   int GS;          // smem stride per index (G padded to odd)
+  int stagger;     // k_jac: number of phase offsets CTAs are spread over (1 = none)
 };
 
 // launches; return cudaError_t of the launch
@@ -69,5 +70,8 @@ cudaError_t launch_flamelet_prepass(const DeviceMech &dm, int F, const double *s
                                     double *cp_grid, double *maxT, double *cp_bc, cudaStream_t s);
 cudaError_t launch_flamelet_offdiag(const DeviceMech &dm, int F, const FlameletDev &fl, double *out_jac, cudaStream_t s);
 long kernel_launch_count();
+#ifdef GB_JAC_TIMELINE
+int debug_jac_timeline(long long *out);
+#endif
 
 } // namespace gb
