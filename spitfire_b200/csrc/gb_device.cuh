@@ -64,8 +64,7 @@ __device__ __forceinline__ SpeciesThermo species_thermo(const DeviceMech &dm, in
     o.g = b5 + T * (b0 - b6 - b0 * logT - T * (b1 + T * (b2 + T * (b3 + T * b4))));
     if (JAC)
     {
-      const double invRu = 1. / dm.Ru;
-      const double Ru = 1. / invRu;
+      const double invRu = dm.invRu, Ru = dm.RuR;
       o.dB = invRu * ((b0 - Ru) * invT + b1 + T * (2 * b2 + T * (3 * b3 + T * 4 * b4)) + b5 * invT * invT);
     }
     else
@@ -97,7 +96,7 @@ __device__ __forceinline__ SpeciesThermo species_thermo(const DeviceMech &dm, in
     o.g = c[1] + c[3] * (T - c[0]) - T * (c[2] + c[3] * (logT - log(c[0])));
     if (JAC)
     {
-      const double invRu = 1. / dm.Ru;
+      const double invRu = dm.invRu;
       o.dB = invT * (dm.mw[i] * invRu * (c[3] - invT * (c[3] * c[0] - c[1])) - 1);
     }
     else

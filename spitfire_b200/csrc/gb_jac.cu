@@ -127,7 +127,7 @@ __device__ __forceinline__ void react_fast(const DeviceMech &dm, const unsigned 
       ds = fma(si, SMG(s.sdb, ii, g), ds);
     }
     const double sum_stoich = (double)(int)(signed char)((nn >> 32) & 255);
-    const double invRu = 1. / dm.Ru;
+    const double invRu = dm.invRu;
     const double invKc = exp(sum_stoich * SMG(s.sc, J_LPRT, g) - invT * invRu * (gs)); // 1/K_c, :535
     const double kr = kf * invKc;
     const double cC = SMG(s.sC, ic, g), cD = SMG(s.sC, id, g);
@@ -170,7 +170,7 @@ __device__ __forceinline__ void react_generic(const DeviceMech &dm, const unsign
   const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
   const double rho = SMG(s.sc, J_RHO, g), drhof = SMG(s.sc, J_DRHOF, g);
   const double invM = SMG(s.sc, J_INVM, g), ct = SMG(s.sc, J_CT, g);
-  const double invRu = 1. / dm.Ru;
+  const double invRu = dm.invRu;
   for (int k = 0; k < nslots; ++k)
     rec[(JP_HDR_GEN + k) * G] = 0.;
 
@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const int zrow = dm.jp_zrow;
   const int *t_groups = stab + dm.jp_t_groups, *t_rounds = stab + dm.jp_t_rounds, *t_fix = stab + dm.jp_t_fix;
   const int *t_csparts = stab + dm.jp_t_csparts, *t_cspfirst = stab + dm.jp_t_cspfirst;
+  const unsigned int *t_csitems = (const unsigned int *)(stab + dm.jp_t_csitems);
   const unsigned short *t_rdest = (const unsigned short *)(stab + dm.jp_t_rdest);
   const unsigned short *rowsrc = (const unsigned short *)(stab + dm.jp_t_rowsrc);
 
@@ -635,34 +636,36 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const FlameletDev &fl = a.fl;
 
   const int ntiles = (a.n + G - 1) / G;
-  // CTAs start together and do identical work, so without help they would all be in the same phase at the same time
-  // (every SM streaming its output to HBM in the same burst, nobody using the FP64 pipes meanwhile). Each CTA
-  // therefore times its first tile and then waits a fraction of that time given by its index, which spreads the
-  // phases of co-resident and neighbouring CTAs evenly over a tile period for the rest of the launch.
-  const long long t_start = clock64();
+  auto fetch_state = [&](int tile) { // this thread's first element of a tile's state block
+    double v = 0.;
+    if (state_mode && tile < ntiles && tid < G * ns)
+    {
+      const int g = tid / ns, j = tid - g * ns, gc = min(G, a.n - tile * G);
+      v = a.in_state[(size_t)(tile * G + (g < gc ? g : 0)) * ns + j];
+    }
+    return v;
+  };
+  double pre = fetch_state(blockIdx.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
     const int tile0 = tile * G;
     const int gcount = min(G, a.n - tile0);
-    if (a.stagger > 1 && tile == blockIdx.x + gridDim.x)
-    {
-      const long long t_tile = clock64() - t_start;
-      const long long wait = t_tile * (long long)(blockIdx.x % a.stagger) / a.stagger;
-      const long long t1 = clock64();
-      while (clock64() - t1 < wait)
-        __nanosleep(200);
-    }
     TL_MARK(0)
     __syncthreads();
-    // ---- load (states past the end of the batch replicate the tile's first state; they are never written) ----------
+    // ---- load (states past the end of the batch replicate the tile's first state; they are never written). The
+    // first G*ns values of the tile were fetched into registers during the previous tile's output phase ------------
     if (state_mode)
     {
-      for (int item = tid; item < G * ns; item += nt)
+      for (int item = tid, k = 0; item < G * ns; item += nt, ++k)
       {
         const int g = item / ns, j = item - g * ns;
-        const double v = a.in_state[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
+        const double v = (k == 0) ? pre : a.in_state[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
         if (j == 0)
+        {
           SMG(s.sc, J_T, g) = v;
+          SMG(s.sc, J_LOGT, g) = log(v);
+          SMG(s.sc, J_INVT, g) = 1. / v;
+        }
         else
           SMG(s.sy, j - 1, g) = v;
       }
@@ -676,38 +679,61 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       }
       if (tid < G)
       {
-        SMG(s.sc, J_T, tid) = a.in_T[tile0 + (tid < gcount ? tid : 0)];
+        const double T = a.in_T[tile0 + (tid < gcount ? tid : 0)];
+        SMG(s.sc, J_T, tid) = T;
+        SMG(s.sc, J_LOGT, tid) = log(T);
+        SMG(s.sc, J_INVT, tid) = 1. / T;
         SMG(s.sc, J_RHO, tid) = a.in_rho[tile0 + (tid < gcount ? tid : 0)];
       }
     }
     TL_MARK(1)
     __syncthreads();
-    // ---- thermo, overlapped with the two order-sensitive chains -------------------------------------------------------------
-    if (tid < G)
-    { // extract_y (combustion_kernels.h:505-515)
-      if (state_mode)
+    // ---- thermo, overlapped with the two order-sensitive chains and the per-state scalars (warp 0) ---------------------
+    if (warp == 0)
+    {
+      double d = 0.;
+      if (lane < G)
+      { // extract_y (combustion_kernels.h:505-515)
+        if (state_mode)
+        {
+          double yl = 1.;
+          for (int j = 0; j < nsm1; ++j)
+            yl -= SMG(s.sy, j, lane);
+          SMG(s.sy, nsm1, lane) = yl;
+          d = yl;
+        }
+        else
+          d = SMG(s.sy, nsm1, lane);
+      }
+      else if (lane < 2 * G)
+      { // mixture_molecular_weight (:381-387): sum_i Y_i/M_i in species order, all but the last term
+        const int g = lane - G;
+        for (int i = 0; i < nsm1; ++i)
+          d += s.sim[i] * SMG(s.sy, i, g);
+      }
+      const double dpart = __shfl_down_sync(0xffffffffu, d, G);
+      if (lane < G)
       {
-        double yl = 1.;
-        for (int j = 0; j < nsm1; ++j)
-          yl -= SMG(s.sy, j, tid);
-        SMG(s.sy, nsm1, tid) = yl;
+        const int g = lane;
+        const double mmw = 1. / (dpart + s.sim[nsm1] * d), T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g);
+        // ideal_gas_density (:526-530)
+        const double rho = state_mode ? a.p * mmw / (T * dm.Ru) : SMG(s.sc, J_RHO, g);
+        const double invM = 1. / mmw, ct = rho * invM;
+        SMG(s.sc, J_MMW, g) = mmw;
+        SMG(s.sc, J_INVM, g) = invM;
+        SMG(s.sc, J_CT, g) = ct;
+        SMG(s.sc, J_RHO, g) = rho;
+        SMG(s.sc, J_IRHO, g) = 1. / rho;
+        SMG(s.sc, J_DRHOF, g) = 1. / ct * invM;
+        SMG(s.sc, J_LPRT, g) = log(dm.p_ref * invT * dm.invRu); // log(p0/(R T)), :535
       }
     }
-    else if (tid < 2 * G)
-    { // mixture_molecular_weight (:381-387): sum_i Y_i/M_i in species order, all but the last term
-      const int g = tid - G;
-      double d = 0.;
-      for (int i = 0; i < nsm1; ++i)
-        d += s.sim[i] * SMG(s.sy, i, g);
-      SMG(s.sc, J_DPART, g) = d;
-    }
-    else if (tid >= 32)
+    else
     {
       for (int item = tid - 32; item < ns * G; item += nt - 32)
       {
         const int i = item / G, g = item - i * G;
-        const double T = SMG(s.sc, J_T, g);
-        const SpeciesThermo t = species_thermo<true>(dm, i, T, log(T), 1. / T);
+        const SpeciesThermo t = species_thermo<true>(dm, i, SMG(s.sc, J_T, g), SMG(s.sc, J_LOGT, g), SMG(s.sc, J_INVT, g));
         SMG(s.sg, i, g) = t.g;
         SMG(s.sdb, i, g) = t.dB;
         SMG(s.sh, i, g) = t.h;
@@ -717,28 +743,11 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     }
     TL_MARK(2)
     __syncthreads();
-    // ---- concentrations and per-state scalars (every thread re-derives rho: cheaper than another barrier) -------------
+    // ---- concentrations ---------------------------------------------------------------------------------------------------------------
     for (int item = tid; item < ns * G; item += nt)
     {
       const int i = item / G, g = item - i * G;
-      const double d = SMG(s.sc, J_DPART, g) + s.sim[nsm1] * SMG(s.sy, nsm1, g);
-      const double mmw = 1. / d, T = SMG(s.sc, J_T, g);
-      // ideal_gas_density (:526-530)
-      const double rho = state_mode ? a.p * mmw / (T * dm.Ru) : SMG(s.sc, J_RHO, g);
-      SMG(s.sC, i, g) = SMG(s.sy, i, g) * rho * s.sim[i];
-      if (i == 0)
-      {
-        const double invT = 1. / T, invM = 1. / mmw, ct = rho * invM;
-        SMG(s.sc, J_MMW, g) = mmw;
-        SMG(s.sc, J_INVM, g) = invM;
-        SMG(s.sc, J_CT, g) = ct;
-        SMG(s.sc, J_RHO, g) = rho;
-        SMG(s.sc, J_IRHO, g) = 1. / rho;
-        SMG(s.sc, J_DRHOF, g) = 1. / ct * invM;
-        SMG(s.sc, J_LOGT, g) = log(T);
-        SMG(s.sc, J_INVT, g) = invT;
-        SMG(s.sc, J_LPRT, g) = log(dm.p_ref * invT * (1. / dm.Ru)); // log(p0/(R T)), :535
-      }
+      SMG(s.sC, i, g) = SMG(s.sy, i, g) * SMG(s.sc, J_RHO, g) * s.sim[i];
     }
     TL_MARK(3)
     __syncthreads();
@@ -901,7 +910,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           { // sum_i (cp_i * -M_i) * W_i
             for (int p = p0; p < p1; ++p)
             {
-              const unsigned int u = __ldg(dm.jp_cs_items + p);
+              const unsigned int u = t_csitems[p];
               const int i = (int)(u >> 16);
               double w[G], v[G];
               Rows<G>::load(s.scp + (size_t)i * G, rot, w);
@@ -916,7 +925,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           { // sum_i hm_i * row value, species ascending (isobaric_reactor_kernels.cpp:74-92)
             for (int p = p0; p < p1; ++p)
             {
-              const unsigned int u = __ldg(dm.jp_cs_items + p);
+              const unsigned int u = t_csitems[p];
               double w[G], v[G];
               Rows<G>::load(s.sh + (size_t)(u >> 16) * G, rot, w);
               Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
@@ -973,7 +982,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
       const double SW = colsum(nsm1 + 0), SWr = colsum(nsm1 + 1), SWT = colsum(nsm1 + 2);
       const double SA = colsum(nsm1 + 3), SB = colsum(nsm1 + 4), wcp = colsum(ncs - 1);
-      const double rhs0c = -SW / (rho * cp);
+      const double rhs0c = -SW * invRhoCp;
       double rhs0 = rhs0c;
       double P0rho = -invRhoCp * SWr - invRho * rhs0c;
       double P0T = -invRhoCp * (SWT + wcp) - rhs0c * cpsensT * invCp;
@@ -1021,7 +1030,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         P0rho -= q / rho;
         cextra += -invCp * q;
       }
-      const double roT = rho / T, nRM = -rho * SMG(s.sc, J_MMW, g);
+      const double roT = rho * SMG(s.sc, J_INVT, g), nRM = -rho * SMG(s.sc, J_MMW, g);
       double v;
       if (isothermal)
         v = 0.;
@@ -1032,7 +1041,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         const int k = c - 1;
         const double uk = s.su[k];
         const double sum = colsum(k) + uk * SA + SB;
-        const double pY = -sum / (rho * cp) + (-rhs0c * invCp + cextra) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
+        const double pY = -sum * invRhoCp + (-rhs0c * invCp + cextra) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
         v = pY + nRM * uk * P0rho;
       }
       SJ(dm.jp_t0base + c, g) = v;
@@ -1072,6 +1081,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     __syncthreads();
 
     // ---- output: column 0, then the columns 1..ns-1 with one row per thread ----------------------------------------------------
+    pre = fetch_state(tile + gridDim.x);
     for (int item = tid; item < ns * G; item += nt)
     {
       const int g = item / ns, r = item - g * ns;
@@ -1184,7 +1194,7 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
   static bool attr = false;
   if (!attr)
   {
-    cudaError_t e = cudaFuncSetAttribute(k_jac<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_jac<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
     if (e != cudaSuccess)
       return e;
     attr = true;
@@ -1197,13 +1207,7 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
   if (const char *e = getenv("GB_JAC_CTAS"))
     per_sm = std::max(1, atoi(e));
   const int grid = std::max(1, std::min(ntiles, jac_sm_count() * per_sm));
-  ChemArgs b = a;
-  b.stagger = 4;
-  if (const char *e = getenv("GB_JAC_STAGGER"))
-    b.stagger = std::max(1, atoi(e));
-  if (ntiles < 4 * grid)
-    b.stagger = 1; // too few tiles per CTA to win the waiting time back
-  k_jac<G><<<grid, threads, smem, s>>>(b);
+  k_jac<G><<<grid, threads, smem, s>>>(a);
   ++g_jac_launches;
   return cudaGetLastError();
 }

@@ -57,7 +57,6 @@ struct ChemArgs
   FlameletDev fl;
   int G;           // states per CTA tile
   int GS;          // smem stride per index (G padded to odd)
-  int stagger;     // k_jac: number of phase offsets CTAs are spread over (1 = none)
 };
 
 // launches; return cudaError_t of the launch

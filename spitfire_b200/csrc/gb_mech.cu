@@ -357,7 +357,7 @@ int commit(HostMech &m)
       }
       if (threads != 512)
         rc = build_jac_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, G, threads, jp);
-      if (rc == GB_OK && jac_smem_bytes(ns, jp) <= (size_t)227 * 1024)
+      if (rc == GB_OK && jac_smem_bytes(ns, jp) <= (size_t)227 * 1024 - 64)
         break;
       rc = GB_ERR_UNSUPPORTED;
       set_error("mechanism too large for the shared-memory resident Jacobian plan");
@@ -383,8 +383,8 @@ int commit(HostMech &m)
   const size_t o_chunk = b.add(chunk_rxn), o_recoff = b.add(rec_off);
   const size_t o_rowoff = b.add(row_off), o_rowrxn = b.add(row_rxn), o_rowfac = b.add(row_fac),
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
-  const size_t o_jpprm = b.add(jp.prm), o_jpitems = b.add(jp.items), o_jpcsitems = b.add(jp.cs_items),
-               o_jpemap = b.add(jp.emap), o_jptab = b.add(jp.tab);
+  const size_t o_jpprm = b.add(jp.prm), o_jpitems = b.add(jp.items), o_jpemap = b.add(jp.emap),
+               o_jptab = b.add(jp.tab);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -398,6 +398,7 @@ int commit(HostMech &m)
   void *base = m.d_blob;
   DeviceMech &d = m.dm;
   d.ns = ns, d.nr = nr, d.Ru = m.Ru, d.p_ref = m.p_ref;
+  d.invRu = 1. / m.Ru, d.RuR = 1. / d.invRu;
   d.mw = at<double>(base, o_mw), d.invmw = at<double>(base, o_invmw);
   d.tmin = at<double>(base, o_tmin), d.tmax = at<double>(base, o_tmax);
   d.cpc = at<double>(base, o_cpc), d.cptype = at<int>(base, o_cptype);
@@ -425,12 +426,12 @@ int commit(HostMech &m)
   d.row_fac = at<double>(base, o_rowfac), d.row_stmw = at<double>(base, o_rowstmw);
   d.row_order = at<short>(base, o_roworder);
   d.jp_prm = at<unsigned long long>(base, o_jpprm);
-  d.jp_items = at<unsigned int>(base, o_jpitems), d.jp_cs_items = at<unsigned int>(base, o_jpcsitems);
+  d.jp_items = at<unsigned int>(base, o_jpitems);
   d.jp_emap = at<unsigned short>(base, o_jpemap), d.jp_tab = at<int>(base, o_jptab);
   d.jp_tab_words = (int)jp.tab.size();
   d.jp_t_wg = jp.t_wg, d.jp_t_groups = jp.t_groups, d.jp_t_wr = jp.t_wr, d.jp_t_rounds = jp.t_rounds;
   d.jp_t_rdest = jp.t_rdest, d.jp_t_fix = jp.t_fix, d.jp_t_rowsrc = jp.t_rowsrc, d.jp_t_csparts = jp.t_csparts;
-  d.jp_t_cspfirst = jp.t_cspfirst;
+  d.jp_t_cspfirst = jp.t_cspfirst, d.jp_t_csitems = jp.t_csitems;
   d.jp_G = jp.G, d.jp_threads = jp.threads, d.jp_rec_rows = jp.rec_rows, d.jp_rows = jp.rows;
   d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_ncsp = jp.ncsp, d.jp_t0base = jp.t0base;
   d.jp_c0base = jp.c0base, d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);

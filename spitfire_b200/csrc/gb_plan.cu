@@ -480,7 +480,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
   // in part order afterwards
   std::vector<int> csparts, cspfirst(1, 0);
   {
-    int csplit = 14;
+    int csplit = 8;
     if (const char *e = std::getenv("GB_JAC_CSPLIT"))
       csplit = std::max(2, std::atoi(e));
     for (int d = 0; d < out.ncs; ++d)
@@ -519,6 +519,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     out.t_rowsrc = add16(out.rowsrc);
     out.t_csparts = add(csparts);
     out.t_cspfirst = add(cspfirst);
+    out.t_csitems = add(std::vector<int>(out.cs_items.begin(), out.cs_items.end()));
     if (out.tab.size() & 1)
       out.tab.push_back(0);
   }
