@@ -145,6 +145,244 @@ __device__ __forceinline__ void react_fast(const DeviceMech &dm, const unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// structured path: up to three reactant and three product entries with coefficients 1..3, none of them the last
+// species, optionally with a third-body / Lindemann / Troe factor (the last species may be a third body).
+// rates_sensitivities_exact.cpp:128-1009 with every loop unrolled and the parameter record decoded once.
+// Record = {q, dq/drho, dq/dT, dq/dY_slot...} (simple) or {q, dq/drho, dq/dT, a, b, dq/dY_slot...} (other types)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mul_pow(double v, double c, int nu, bool seq)
+{ // v * c^nu with the association of the reference: special-cased orders (v*c)*c, generic branch v*(c*c)
+  if (nu == 1)
+    return v * c;
+  if (seq)
+  {
+    v = v * c * c;
+    return nu == 3 ? v * c : v;
+  }
+  return nu == 2 ? v * (c * c) : v * (c * c * c);
+}
+
+template <int G>
+__device__ __forceinline__ void react_struct(const DeviceMech &dm, const unsigned long long *__restrict__ P, int g,
+                                             const JacSmem &s)
+{
+  const ulonglong2 *P2 = reinterpret_cast<const ulonglong2 *>(P);
+  const ulonglong2 q0 = __ldg(P2), q1 = __ldg(P2 + 1), q2 = __ldg(P2 + 2), q3 = __ldg(P2 + 3), q4 = __ldg(P2 + 4),
+                   q5 = __ldg(P2 + 5);
+  const int f = (int)(unsigned int)q0.x;
+  const unsigned long long w1 = q0.y;
+  const int nrc = (int)(w1 & 255), npd = (int)((w1 >> 8) & 255), ntb = (int)((w1 >> 24) & 255),
+            nslots = (int)((w1 >> 32) & 255);
+  const double sum_stoich = (double)(int)(signed char)((w1 >> 40) & 255);
+  const double sum_rc = (double)(int)((w1 >> 48) & 255), sum_pd = (double)(int)((w1 >> 56) & 255);
+  const int type = f_type(f);
+  const int hdr = type == RT_SIMPLE ? JP_HDR_FAST : JP_HDR_GEN;
+  double *rec = s.sR + (size_t)(unsigned int)(q0.x >> 32) * G + g;
+  const unsigned int ent[6] = {(unsigned int)q2.y, (unsigned int)(q2.y >> 32), (unsigned int)q3.x,
+                               (unsigned int)(q3.x >> 32), (unsigned int)q3.y, (unsigned int)(q3.y >> 32)};
+  const unsigned int net[6] = {(unsigned int)q4.x, (unsigned int)(q4.x >> 32), (unsigned int)q4.y,
+                               (unsigned int)(q4.y >> 32), (unsigned int)q5.x, (unsigned int)(q5.x >> 32)};
+
+  const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
+  const double rho = SMG(s.sc, J_RHO, g), drhof = SMG(s.sc, J_DRHOF, g);
+  const double kfb = u2d(q1.y), kfE = u2d(q2.x);
+  const double kf = rate_constant(f_kform(f), u2d(q1.x), kfb, kfE, T, invT, logT);
+  const double kf_sens = invT * (kfb + kfE * invT); // ARRHENIUS_SENS_OVER_K, :25
+  const bool fseq = (f & F_FWD_SPECIAL) != 0, rseq = (f & F_REV_SPECIAL) != 0;
+
+  for (int k = 0; k < nslots; ++k)
+    rec[(hdr + k) * G] = 0.;
+
+  // concentrations, coefficients, 1/M of the entries (unused entries: species 0, coefficient 0)
+  double c[6], im[6];
+  int nu[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+  {
+    const int idx = (int)(ent[i] & 0xffff);
+    c[i] = SMG(s.sC, idx, g);
+    im[i] = s.sim[idx];
+    nu[i] = (int)((ent[i] >> 16) & 255);
+  }
+  // forward rate and its derivatives, :287-526
+  double Rnet = kf;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < nrc)
+      Rnet = mul_pow(Rnet, c[i], nu[i], fseq);
+  double dRdrho = Rnet * drhof * sum_rc;
+  double dRdT = Rnet * kf_sens;
+  const double kfr = kf * rho;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < nrc)
+    {
+      double d = kfr * im[i];
+      if (nu[i] == 2)
+        d = d * 2. * c[i];
+      else if (nu[i] == 3)
+        d = d * 3. * c[i] * c[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j != i && j < nrc)
+          d = mul_pow(d, c[j], nu[j], fseq);
+      rec[(hdr + (int)(ent[i] >> 24)) * G] = d;
+    }
+  if (f & F_REVERSIBLE)
+  { // :528-812
+    double gs, ds;
+    {
+      const double s0 = (double)(int)(signed char)((net[0] >> 16) & 255);
+      gs = s0 * SMG(s.sg, (int)(net[0] & 0xffff), g);
+      ds = s0 * SMG(s.sdb, (int)(net[0] & 0xffff), g);
+    }
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+    {
+      const double si = (double)(int)(signed char)((net[i] >> 16) & 255);
+      gs = fma(si, SMG(s.sg, (int)(net[i] & 0xffff), g), gs);
+      ds = fma(si, SMG(s.sdb, (int)(net[i] & 0xffff), g), ds);
+    }
+    const double invKc = exp(sum_stoich * SMG(s.sc, J_LPRT, g) - invT * dm.invRu * (gs)); // 1/K_c, :535
+    const double kr = kf * invKc;
+    double Rr = kr;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < npd)
+        Rr = mul_pow(Rr, c[3 + i], nu[3 + i], rseq);
+    Rnet -= Rr;
+    dRdrho -= Rr * drhof * sum_pd;
+    dRdT -= Rr * (kf_sens + ds);
+    const double krr = kr * rho;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < npd)
+      {
+        double d = krr * im[3 + i];
+        if (nu[3 + i] == 2)
+          d = d * 2. * c[3 + i];
+        else if (nu[3 + i] == 3)
+          d = d * 3. * c[3 + i] * c[3 + i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j != i && j < npd)
+            d = mul_pow(d, c[3 + j], nu[3 + j], rseq);
+        rec[(hdr + (int)(ent[3 + i] >> 24)) * G] -= d;
+      }
+  }
+  if (type == RT_SIMPLE)
+  {
+    rec[0] = Rnet;
+    rec[G] = dRdrho;
+    rec[2 * G] = dRdT;
+    return;
+  }
+
+  // third-body / falloff factor C_tbaf and its sensitivities, :826-1000
+  const unsigned long long *Ptb = P + 20;
+  const double base = u2d(P[12]);
+  const double invM = SMG(s.sc, J_INVM, g), ct = SMG(s.sc, J_CT, g);
+  double Ctbaf, dCdrho, dCdT = 0., coef; // dCtbaf/dY_s = coef*(base*u_s + eps_s - eps_last)
+  double M = base * ct;
+  double dMdrho = base * invM;
+  for (int i = 0; i < ntb; ++i)
+  {
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(Ptb) + i);
+    const double e = u2d(t.y) * SMG(s.sy, (int)(t.x & 0xffff), g);
+    M = M + rho * e;
+    dMdrho += e;
+  }
+  if (type == RT_THIRD_BODY)
+  {
+    Ctbaf = M;
+    dCdrho = dMdrho;
+    coef = rho;
+  }
+  else
+  {
+    const ulonglong2 k0 = __ldg(P2 + 6), k1 = __ldg(P2 + 7); // base, kpA | kpb, kpE
+    const double kpb = u2d(k1.x), kpE = u2d(k1.y);
+    const double kp_over_kf = u2d(k0.y) * exp(kpb * logT - kpE * invT) / kf;
+    const double kp_sens = invT * (kpb + kpE * invT);
+    const double pr = kp_over_kf * M;
+    double nsTmp;
+    if (type == RT_LINDEMANN)
+    { // :867-903
+      Ctbaf = pr / (1. + pr);
+      dCdT = Ctbaf / (1. + pr) * (kp_sens - kf_sens);
+      nsTmp = kp_over_kf / ((1. + pr) * (1. + pr));
+    }
+    else
+    { // TROE, :905-995. Absent terms are evaluated as exp(-inf) = 0 so that the three exponentials and the three
+      // logarithms are independent instruction streams
+      const ulonglong2 t0 = __ldg(P2 + 8), t1 = __ldg(P2 + 9);
+      const double tr0 = u2d(t0.x), tr1 = u2d(t0.y), tr2 = u2d(t1.x), tr3 = u2d(t1.y);
+      const int tb = f_troe(f);
+      const double ninf = __longlong_as_double(0xfff0000000000000LL);
+      const double a1 = (tb & TROE_T3) ? -T / tr1 : ninf, a2 = (tb & TROE_T1) ? -T / tr2 : ninf,
+                   a3 = (tb & TROE_T2) ? -invT * tr3 : ninf;
+      const double t1exp = exp(a1), t2exp = exp(a2), t3exp = exp(a3);
+      double fCent = 0., dfCentdT = 0.;
+      if (tb & TROE_T3)
+      {
+        fCent = (1 - tr0) * t1exp;
+        dfCentdT = (tr0 - 1) / tr1 * t1exp;
+      }
+      if (tb & TROE_T1)
+      {
+        fCent = (tb & TROE_T3) ? fCent + tr0 * t2exp : tr0 * t2exp;
+        dfCentdT = (tb & TROE_T3) ? dfCentdT - tr0 / tr2 * t2exp : -tr0 / tr2 * t2exp;
+      }
+      if (tb & TROE_T2)
+      {
+        const bool any = (tb & (TROE_T3 | TROE_T1)) != 0;
+        fCent = any ? fCent + t3exp : t3exp;
+        dfCentdT = any ? dfCentdT + t3exp * tr3 * invT * invT : t3exp * tr3 * invT * invT;
+      }
+      const double fc = fmax(fCent, 1.e-300);
+      const double log10pr = log10(fmax(pr, 1.e-300));
+      const double log10fcent = log10(fc);
+      const double logfcent = log(fc);
+      const double ln10 = 2.302585092994046; // log(10.)
+      const double aTroe = log10pr - 0.67 * log10fcent - 0.4;
+      const double bTroe = -0.14 * log10pr - 1.1762 * log10fcent + 0.806;
+      const double gTroe = 1 / (1 + (aTroe / bTroe) * (aTroe / bTroe));
+      const double fTroe = pow(fCent, gTroe);
+      Ctbaf = fTroe * pr / (1 + pr);
+      const double dfTroedT =
+          fTroe * (gTroe / fCent * dfCentdT +
+                   logfcent * (-2.0 * gTroe * gTroe / ln10 * aTroe / (bTroe * bTroe * bTroe) *
+                               ((bTroe + 0.14 * aTroe) * (kp_sens - kf_sens) -
+                                (0.67 * bTroe - 1.1762 * aTroe) * dfCentdT / fCent)));
+      dCdT = 1. / (1. + 1. / pr) * dfTroedT + fTroe * pr / ((1. + pr) * (1. + pr)) * (kp_sens - kf_sens);
+      nsTmp = kp_over_kf * (-2.0 / (1. + pr) * fTroe * logfcent * gTroe * gTroe / ln10 * aTroe /
+                                (bTroe * bTroe * bTroe) * (bTroe + 0.14 * aTroe) +
+                            fTroe / ((1. + pr) * (1 + pr)));
+    }
+    dCdrho = nsTmp * dMdrho;
+    coef = nsTmp * rho;
+  }
+  rec[0] = Rnet * Ctbaf;                      // q, :1002
+  rec[G] = dRdrho * Ctbaf + dCdrho * Rnet;    // dq/drho
+  rec[2 * G] = dRdT * Ctbaf + dCdT * Rnet;    // dq/dT
+  double b = 0.;
+  for (int k = 0; k < nslots; ++k)
+    rec[(JP_HDR_GEN + k) * G] *= Ctbaf;
+  for (int i = 0; i < ntb; ++i)
+  {
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(Ptb) + i);
+    const double e = coef * u2d(t.y);
+    const int slot = (int)(signed char)((t.x >> 24) & 255);
+    if (slot >= 0)
+      rec[(JP_HDR_GEN + slot) * G] += e * Rnet;
+    else
+      b -= e * Rnet; // the last species is a third body: -eps_last on every column (:855-865)
+  }
+  rec[3 * G] = coef * base * Rnet;
+  rec[4 * G] = b;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // generic path: any reaction without non-elementary orders. rates_sensitivities_exact.cpp:128-1009 restated per
 // reaction; the `for s < ns-1` dense loops (:522-525, :807-810, :849-850, :859-862, ...) are carried by the two
 // scalars a, b. Record = {q, dq/drho, dq/dT, a, b, dq/dY_slot...}
@@ -636,6 +874,21 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const FlameletDev &fl = a.fl;
 
   const int ntiles = (a.n + G - 1) / G;
+  // The parameter records of a reaction group are pulled into L1 one group ahead: the G lanes that share a reaction
+  // touch 512 bytes of its record between them, so the (dependent) parameter reads of the generic path hit L1.
+  auto prefetch_group = [&](int gi, int gend) {
+    if (gi < gend)
+    {
+      const int off = t_groups[gi * (1 + LPR) + 1 + lane / G];
+      if (off >= 0)
+      {
+        const char *p = reinterpret_cast<const char *>(dm.jp_prm + off) + (lane % G) * (512 / G);
+#pragma unroll
+        for (int k = 0; k < 512 / G; k += 32)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k));
+      }
+    }
+  };
   auto fetch_state = [&](int tile) { // this thread's first element of a tile's state block
     double v = 0.;
     if (state_mode && tile < ntiles && tid < G * ns)
@@ -689,6 +942,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     TL_MARK(1)
     __syncthreads();
     // ---- thermo, overlapped with the two order-sensitive chains and the per-state scalars (warp 0) ---------------------
+    prefetch_group(stab[dm.jp_t_wg + warp], stab[dm.jp_t_wg + warp + 1]);
     if (warp == 0)
     {
       double d = 0.;
@@ -697,6 +951,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         if (state_mode)
         {
           double yl = 1.;
+#pragma unroll 8
           for (int j = 0; j < nsm1; ++j)
             yl -= SMG(s.sy, j, lane);
           SMG(s.sy, nsm1, lane) = yl;
@@ -708,6 +963,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       else if (lane < 2 * G)
       { // mixture_molecular_weight (:381-387): sum_i Y_i/M_i in species order, all but the last term
         const int g = lane - G;
+#pragma unroll 8
         for (int i = 0; i < nsm1; ++i)
           d += s.sim[i] * SMG(s.sy, i, g);
       }
@@ -793,18 +1049,31 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       const int g0 = stab[dm.jp_t_wg + warp], g1 = stab[dm.jp_t_wg + warp + 1];
       for (int gi = g0; gi < g1; ++gi)
       {
+        prefetch_group(gi + 1, g1);
         const int *grp = t_groups + gi * (1 + LPR);
         const int kind = grp[0], off = grp[1 + sub];
         if (off < 0)
           continue;
         const unsigned long long *P = dm.jp_prm + off;
+#ifdef GB_JAC_TIMELINE
+        const long long tl0 = clock64();
+#endif
         if (kind == 0)
           react_fast<G>(dm, P, g, s);
+        else if (kind == 1)
+          react_struct<G>(dm, P, g, s);
         else if (((int)(unsigned int)P[0]) & F_HAS_ORDERS)
           react_orders<G>(ns, dm.n_sp, dm.sp_idx, dm.sp_order, dm.sp_slot, dm.invmw, (int)(((unsigned int)P[0]) >> 14), P, g,
                           s.sc, s.sC, s.sy, s.sR);
         else
           react_generic<G>(dm, P, g, s);
+#ifdef GB_JAC_TIMELINE
+        if (blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && lane == 0)
+        {
+          g_jac_timeline[(11 + min(kind, 1)) * 32 + warp] += clock64() - tl0;
+          g_jac_timeline[(13 + min(kind, 1)) * 32 + warp] += 1;
+        }
+#endif
       }
     }
     TL_MARK(4)

@@ -104,7 +104,7 @@ struct DeviceMech
   const unsigned short *jp_emap;    // [(ns+1)*(ns-1)] entry (row r: 0 = T, 1+i = species i <= ns-1; column c >= 1) at
                                     // r + (ns+1)*(c-1) -> row of the gathered-sum array
   // small tables, copied to shared memory by every CTA (offsets in ints into jp_tab):
-  //  t_wg [nwarps+1] reaction groups of every warp; t_groups: per group kind (0 fast, 1 generic) and 32/G parameter
+  //  t_wg [nwarps+1] reaction groups of every warp; t_groups: per group kind (0 fast, 1 structured, 2 generic) and 32/G parameter
   //  offsets (-1: idle); t_wr [nwarps+1] gather rounds of every warp; t_rounds: per round first item and number of
   //  steps; t_rdest (u16) [round][lane] destination row; t_fix (dst row, first extra part row, extra parts);
   //  t_rowsrc (u16) [5][ns] rows of sum_r nu*{q, dq/drho, dq/dT, a, b}; t_csparts (dest, begin, end);
@@ -133,7 +133,7 @@ struct JacPlanHost
       t_csitems = 0;
   int rec_rows = 0, rows = 0, ncs = 0, ncsp = 0, t0base = 0, c0base = 0, zrow = 0;
   // statistics (printed with GB_PLAN_VERBOSE=1)
-  int n_fast = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;
+  int n_fast = 0, n_struct = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;
 };
 
 struct HostMech

@@ -55,7 +55,8 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
   };
 
   // ---- classification, records, parameter blob -----------------------------------------------------------------------
-  std::vector<char> fast(nr, 0), last_involved(nr, 0);
+  std::vector<char> fast(nr, 0), last_involved(nr, 0), kind(nr, 2);
+  std::vector<int> hdr_of(nr, JP_HDR_GEN);
   std::vector<int> rec_off(nr, 0), prm_off(nr, 0);
   int rec_rows = 0;
   for (int r = 0; r < nr; ++r)
@@ -86,8 +87,25 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     if (getenv("GB_JAC_NOFAST"))
       f = false;
     fast[r] = f;
+    // structured path: straight-line code for up to three reactant and three product entries with coefficients
+    // <= 3, optionally with a third-body / falloff factor; the last species may only appear as a third body
+    bool st = !f && !x.has_orders && x.n_rc <= 3 && x.n_net <= 6 && nsl <= 100 && (flags[r] & F_KC_VALID);
+    for (int i = 0; st && i < x.n_rc; ++i)
+      st = x.rc_st[i] >= 1 && x.rc_st[i] <= 3 && x.rc_idx[i] != last;
+    if (st && x.reversible)
+    {
+      st = x.n_pd <= 3;
+      for (int i = 0; st && i < x.n_pd; ++i)
+        st = x.pd_st[i] >= 1 && x.pd_st[i] <= 3 && x.pd_idx[i] != last;
+    }
+    if (st && x.type == RT_SIMPLE && li)
+      st = false;
+    if (getenv("GB_JAC_NOSTRUCT"))
+      st = false;
+    kind[r] = f ? 0 : (st ? 1 : 2);
+    hdr_of[r] = (f || (st && x.type == RT_SIMPLE)) ? JP_HDR_FAST : JP_HDR_GEN;
     rec_off[r] = rec_rows;
-    rec_rows += (f ? JP_HDR_FAST : JP_HDR_GEN) + nsl;
+    rec_rows += hdr_of[r] + nsl;
   }
   if (nr >= (1 << 18))
   {
@@ -143,6 +161,62 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       out.prm.push_back(0ull);
       continue;
     }
+    if (kind[r] == 1)
+    {
+      // w0: flags | reaction << 14 | record row << 32; w1: counts; w2..4: A, b, Ea/R; w5..7: reactant and product
+      // entries (idx 16 | coefficient 8 | slot 8), 32 bits each; w8..10: net entries (idx 16 | nu 8); w11: pad;
+      // third-body / falloff types continue with w12: default efficiency, w13..15: low-pressure A, b, Ea/R,
+      // w16..19: Troe parameters, then (idx 16 | slot 8 << 24, efficiency) per third body
+      out.prm.push_back((unsigned long long)((unsigned int)flags[r] | ((unsigned int)r << 14)) |
+                        ((unsigned long long)(unsigned int)rec_off[r] << 32));
+      unsigned long long w1 = 0;
+      w1 |= (unsigned long long)(x.n_rc & 255);
+      w1 |= (unsigned long long)((x.reversible ? x.n_pd : 0) & 255) << 8;
+      w1 |= (unsigned long long)(x.n_net & 255) << 16;
+      w1 |= (unsigned long long)(ntb & 255) << 24;
+      w1 |= (unsigned long long)(nsl & 255) << 32;
+      w1 |= (unsigned long long)((unsigned char)(signed char)x.sum_stoich) << 40;
+      w1 |= (unsigned long long)(x.sum_rc & 255) << 48;
+      w1 |= (unsigned long long)(x.sum_pd & 255) << 56;
+      out.prm.push_back(w1);
+      for (int k = 0; k < 3; ++k)
+        out.prm.push_back(dbits(x.kf[k]));
+      unsigned int e[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < x.n_rc; ++i)
+        e[i] = (unsigned int)(unsigned short)x.rc_idx[i] | ((unsigned int)(unsigned char)x.rc_st[i] << 16) |
+               ((unsigned int)(unsigned char)rc_slot[NSR * (size_t)r + i] << 24);
+      if (x.reversible)
+        for (int i = 0; i < x.n_pd; ++i)
+          e[3 + i] = (unsigned int)(unsigned short)x.pd_idx[i] | ((unsigned int)(unsigned char)x.pd_st[i] << 16) |
+                     ((unsigned int)(unsigned char)pd_slot[NSR * (size_t)r + i] << 24);
+      for (int i = 0; i < 6; i += 2)
+        out.prm.push_back((unsigned long long)e[i] | ((unsigned long long)e[i + 1] << 32));
+      unsigned int ne[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < 6; ++i)
+      { // unused entries repeat species 0 with nu = 0 (adds an exact zero)
+        const int idx = i < x.n_net ? x.net_idx[i] : x.net_idx[0];
+        const int nu = i < x.n_net ? x.net_st[i] : 0;
+        ne[i] = (unsigned int)(unsigned short)idx | ((unsigned int)(unsigned char)(signed char)nu << 16);
+      }
+      for (int i = 0; i < 6; i += 2)
+        out.prm.push_back((unsigned long long)ne[i] | ((unsigned long long)ne[i + 1] << 32));
+      out.prm.push_back(0ull);
+      if (x.type != RT_SIMPLE)
+      {
+        out.prm.push_back(dbits(x.base_eff));
+        for (int k = 0; k < 3; ++k)
+          out.prm.push_back(dbits(x.kp[k]));
+        for (int k = 0; k < 4; ++k)
+          out.prm.push_back(dbits(x.troe[k]));
+        for (int j = 0; j < ntb; ++j)
+        {
+          out.prm.push_back((unsigned long long)(unsigned short)x.tb_idx[j] |
+                            ((unsigned long long)(unsigned char)tb_slot[tb_off[r] + j] << 24));
+          out.prm.push_back(dbits(x.tb_eff[j]));
+        }
+      }
+      continue;
+    }
     out.prm.push_back((unsigned long long)((unsigned int)flags[r] | ((unsigned int)r << 14)) |
                         ((unsigned long long)(unsigned int)rec_off[r] << 32));
     unsigned long long w1 = 0;
@@ -189,14 +263,14 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       out.prm.push_back(dbits(x.tb_eff[j]));
     }
   }
-  out.prm.push_back(0ull);
-  out.prm.push_back(0ull);
+  for (int k = 0; k < 66; ++k)
+    out.prm.push_back(0ull); // the group prefetch touches up to 512 bytes past the start of the last record
 
   // ---- reaction groups --------------------------------------------------------------------------------------------------
   {
     auto key = [&](int r) {
       const HostReaction &x = m.reactions[r];
-      long k = fast[r] ? 0 : 1;
+      long k = kind[r];
       k = k * 8 + x.type;
       k = k * 8 + (x.kform == KF_ARRHENIUS ? 0 : 1 + x.kform);
       k = k * 2 + (x.reversible ? 0 : 1);
@@ -210,20 +284,22 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       }
       return k;
     };
-    auto cost = [&](int r) {
+    auto cost = [&](int r) { // measured group times (tools/timeline.py), cycles
       const HostReaction &x = m.reactions[r];
       double c;
-      if (fast[r])
-        c = 60. + (x.kform == KF_ARRHENIUS ? 45. : 0.) + (x.reversible ? 110. : 0.);
+      if (kind[r] == 0)
+        c = 500. + (x.kform == KF_ARRHENIUS ? 250. : 0.) + (x.reversible ? 500. : 0.);
       else
       {
-        c = 250. + 40. * (x.n_rc + (x.reversible ? x.n_pd : 0)) + (x.reversible ? 120. : 0.) + 12. * x.tb_idx.size();
+        c = 700. + 150. * (x.n_rc + (x.reversible ? x.n_pd : 0)) + (x.reversible ? 500. : 0.) + 60. * x.tb_idx.size();
+        if (x.type == RT_THIRD_BODY)
+          c += 300.;
         if (x.type == RT_LINDEMANN)
-          c += 150.;
+          c += 1200.;
         if (x.type == RT_TROE)
-          c += 700.;
-        if (x.has_orders)
-          c += 600.;
+          c += 3500.;
+        if (kind[r] == 2)
+          c = 2.5 * c + (x.has_orders ? 6000. : 0.);
       }
       return c;
     };
@@ -240,16 +316,16 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     for (int p = 0; p < nr;)
     {
       Group g;
-      g.kind = fast[order[p]] ? 0 : 1;
+      g.kind = kind[order[p]];
       g.cost = 0.;
-      while (p < nr && (int)g.rx.size() < LPR && (fast[order[p]] ? 0 : 1) == g.kind)
+      while (p < nr && (int)g.rx.size() < LPR && kind[order[p]] == g.kind)
       {
         g.cost = std::max(g.cost, cost(order[p]));
         g.rx.push_back(order[p]);
         ++p;
       }
       // lanes of a generic group diverge: the warp pays for (part of) the union of the code paths
-      if (g.kind == 1)
+      if (g.kind != 0)
       {
         double extra = 0.;
         for (size_t i = 1; i < g.rx.size(); ++i)
@@ -263,7 +339,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     std::iota(gorder.begin(), gorder.end(), 0);
     std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return groups[a].cost > groups[b].cost; });
     std::vector<double> load(nwarps, 0.);
-    load[nwarps - 1] = 400.; // the last warp starts with the mixture cp chain (k_jac)
+    load[nwarps - 1] = 900.; // the last warp starts with the mixture cp chain (k_jac)
     std::vector<std::vector<int>> per_warp(nwarps);
     for (int gi : gorder)
     {
@@ -284,11 +360,11 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     }
     out.wg_off[nwarps] = (int)out.groups.size() / (1 + LPR);
     for (int r = 0; r < nr; ++r)
-      (fast[r] ? out.n_fast : out.n_generic)++;
+      (kind[r] == 0 ? out.n_fast : (kind[r] == 1 ? out.n_struct : out.n_generic))++;
     if (getenv("GB_PLAN_VERBOSE"))
     {
-      fprintf(stderr, "[gb plan] G=%d threads=%d reactions: %d fast, %d generic, %d groups; warp loads:", G, threads,
-              out.n_fast, out.n_generic, (int)groups.size());
+      fprintf(stderr, "[gb plan] G=%d threads=%d reactions: %d fast, %d structured, %d generic, %d groups; warp loads:", G,
+              threads, out.n_fast, out.n_struct, out.n_generic, (int)groups.size());
       for (int w = 0; w < nwarps; ++w)
         fprintf(stderr, " %.0f", load[w]);
       fprintf(stderr, "\n");
@@ -303,7 +379,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
   for (int r = 0; r < nr; ++r)
   {
     const HostReaction &x = m.reactions[r];
-    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r], hdr = fast[r] ? JP_HDR_FAST : JP_HDR_GEN;
+    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r], hdr = hdr_of[r];
     const bool tbtype = x.type != RT_SIMPLE;
     for (int k = 0; k < x.n_net; ++k)
     {
@@ -316,9 +392,9 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       auto item = [&](int rec) { return (unsigned int)rec | ((unsigned int)(nu & 255) << 16); };
       for (int q = 0; q < 3; ++q)
         dest[rbase + q * ns + row].push_back(item(base + q));
-      if (tbtype)
+      if (tbtype && hdr == JP_HDR_GEN)
         dest[rbase + 3 * ns + row].push_back(item(base + 3));
-      if (last_involved[r])
+      if (last_involved[r] && hdr == JP_HDR_GEN)
         dest[rbase + 4 * ns + row].push_back(item(base + 4));
       for (int q = 0; q < nsl; ++q)
         dest[(int)slot_species[slot_off[r] + q] * ns + row].push_back(item(base + hdr + q));

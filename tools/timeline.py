@@ -27,6 +27,7 @@ lib.gb_debug_jac_timeline.argtypes = [C.c_void_p]
 assert lib.gb_debug_jac_timeline(buf) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(16, 32)
 nw = int((t[0] != 0).sum())
+tk = t[11:15, :nw]
 t = t[:11, :nw]
 t0 = t[0].min()
 names = ['top', 'load', 'thermo', 'conc', 'react', 'gather', 'write', 'fix', 'rows/cols', 'T-row', 'output']
@@ -35,3 +36,9 @@ rel = (t - t0).max(axis=1)
 for k in range(11):
     print(f'  {names[k]:10s} release {rel[k]:8d}  phase {rel[k] - (rel[k-1] if k else 0):8d}   warp arrivals (rel. to previous release): '
           + ' '.join(f'{int(x - t0 - (rel[k-1] if k else 0)):6d}' for x in t[k]))
+
+print('reaction phase per warp: fast groups (count, total cycles), generic groups (count, total cycles)')
+for w in range(nw):
+    print(f'  warp {w:2d}: fast {int(tk[2,w]):2d} groups {int(tk[0,w]):7d} cyc   generic {int(tk[3,w]):2d} groups {int(tk[1,w]):7d} cyc')
+nf, ng = tk[2].sum(), tk[3].sum()
+print(f'  mean cycles per fast group {tk[0].sum()/max(nf,1):.0f}, per generic group {tk[1].sum()/max(ng,1):.0f}')
