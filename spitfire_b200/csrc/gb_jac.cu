@@ -65,7 +65,7 @@ static_assert(J_SPARE1 < JP_NSC, "JP_NSC too small");
 // Debug build only (-DGB_JAC_TIMELINE): every warp of CTA 0 records clock64() when it ARRIVES at each barrier of its
 // second tile; read back through gb_debug_jac_timeline (gb_api.cu), tools/timeline.py prints the table.
 #ifdef GB_JAC_TIMELINE
-__device__ long long g_jac_timeline[16 * 32];
+__device__ long long g_jac_timeline[20 * 32];
 #define TL_MARK(k)                                                                  \
   if (blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && lane == 0)               \
     g_jac_timeline[(k)*32 + warp] = clock64();
@@ -95,53 +95,69 @@ __device__ __forceinline__ void react_fast(const DeviceMech &dm, const unsigned 
   const int f = (int)(unsigned int)q0.x;
   double *rec = s.sR + (size_t)(unsigned int)(q0.x >> 32) * G + g;
   const int ia = (int)(q0.y & 0xffff), ib = (int)((q0.y >> 16) & 0xffff);
+  const int ic = (int)((q0.y >> 32) & 0xffff), id = (int)((q0.y >> 48) & 0xffff);
+  const bool rev = (f & F_REVERSIBLE) != 0;
   const double T = SMG(s.sc, J_T, g), invT = SMG(s.sc, J_INVT, g), logT = SMG(s.sc, J_LOGT, g);
   const double rho = SMG(s.sc, J_RHO, g), drhof = SMG(s.sc, J_DRHOF, g);
   const double kfA = u2d(q2.x), kfb = u2d(q2.y), kfE = u2d(q3.x);
-  const double kf = rate_constant(f_kform(f), kfA, kfb, kfE, T, invT, logT);
+  const double cA = SMG(s.sC, ia, g), cB = SMG(s.sC, ib, g), cC = SMG(s.sC, ic, g), cD = SMG(s.sC, id, g);
+  // sum_net nu_i g_i and sum_net nu_i dB_i/dT in ascending species order (:528-560)
+  const unsigned long long ni = q1.x, nn = q1.y;
+  double gs, ds;
+  {
+    const int i0 = (int)(ni & 0xffff);
+    const double s0 = (double)(int)(signed char)(nn & 255);
+    gs = s0 * SMG(s.sg, i0, g);
+    ds = s0 * SMG(s.sdb, i0, g);
+  }
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+  {
+    const int ii = (int)((ni >> (16 * i)) & 0xffff);
+    const double si = (double)(int)(signed char)((nn >> (8 * i)) & 255);
+    gs = fma(si, SMG(s.sg, ii, g), gs);
+    ds = fma(si, SMG(s.sdb, ii, g), ds);
+  }
+  const double sum_stoich = (double)(int)(signed char)((nn >> 32) & 255);
+  // the two exponentials are independent instruction streams: Arrhenius factor and 1/K_c (0 if irreversible)
+  const int kform = f_kform(f);
+  const double ninf = __longlong_as_double(0xfff0000000000000LL);
+  const double ef = exp(kform == KF_ARRHENIUS ? kfb * logT - kfE * invT : 0.);
+  const double invKc = exp(rev ? sum_stoich * SMG(s.sc, J_LPRT, g) - invT * dm.invRu * (gs) : ninf); // :535
+  double kf; // chemistry_kernels.cpp:140-157
+  switch (kform)
+  {
+  case KF_CONSTANT:
+    kf = kfA;
+    break;
+  case KF_LINEAR:
+    kf = kfA * T;
+    break;
+  case KF_QUADRATIC:
+    kf = kfA * T * T;
+    break;
+  case KF_RECIPROCAL:
+    kf = kfA * invT;
+    break;
+  default:
+    kf = kfA * ef;
+  }
   const double kf_sens = invT * (kfb + kfE * invT); // ARRHENIUS_SENS_OVER_K, :25
-  const double cA = SMG(s.sC, ia, g), cB = SMG(s.sC, ib, g);
   const double kfr = kf * rho;
-  double Rnet = kf * cA * cB;                  // :287-325
-  double dRdrho = Rnet * drhof * 2.;           // sum of reactant coefficients = 2
-  double dRdT = Rnet * kf_sens;
+  const double Rf = kf * cA * cB;              // :287-325
+  const double kr = kf * invKc;
+  const double Rr = kr * cC * cD;
+  const double krr = kr * rho;
+  rec[0] = Rf - Rr;
+  rec[G] = Rf * drhof * 2. - Rr * drhof * 2.; // sums of the coefficients = 2
+  rec[2 * G] = Rf * kf_sens - Rr * (kf_sens + ds);
   rec[3 * G] = kfr * u2d(q3.y) * cB;           // :332-526
   rec[4 * G] = kfr * u2d(q4.x) * cA;
-  if (f & F_REVERSIBLE)
+  if (rev)
   { // :528-812
-    const int ic = (int)((q0.y >> 32) & 0xffff), id = (int)((q0.y >> 48) & 0xffff);
-    const unsigned long long ni = q1.x, nn = q1.y;
-    double gs, ds;
-    {
-      const int i0 = (int)(ni & 0xffff);
-      const double s0 = (double)(int)(signed char)(nn & 255);
-      gs = s0 * SMG(s.sg, i0, g);
-      ds = s0 * SMG(s.sdb, i0, g);
-    }
-#pragma unroll
-    for (int i = 1; i < 4; ++i)
-    {
-      const int ii = (int)((ni >> (16 * i)) & 0xffff);
-      const double si = (double)(int)(signed char)((nn >> (8 * i)) & 255);
-      gs = fma(si, SMG(s.sg, ii, g), gs);
-      ds = fma(si, SMG(s.sdb, ii, g), ds);
-    }
-    const double sum_stoich = (double)(int)(signed char)((nn >> 32) & 255);
-    const double invRu = dm.invRu;
-    const double invKc = exp(sum_stoich * SMG(s.sc, J_LPRT, g) - invT * invRu * (gs)); // 1/K_c, :535
-    const double kr = kf * invKc;
-    const double cC = SMG(s.sC, ic, g), cD = SMG(s.sC, id, g);
-    const double Rr = kr * cC * cD;
-    Rnet -= Rr;
-    dRdrho -= Rr * drhof * 2.;
-    dRdT -= Rr * (kf_sens + ds);
-    const double krr = kr * rho;
     rec[5 * G] = -(krr * u2d(q4.y) * cD);
     rec[6 * G] = -(krr * u2d(q5.x) * cC);
   }
-  rec[0] = Rnet;
-  rec[G] = dRdrho;
-  rec[2 * G] = dRdT;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -300,20 +316,23 @@ __device__ __forceinline__ void react_struct(const DeviceMech &dm, const unsigne
   }
   else
   {
+    // Reciprocals are formed once and reused (1/(1+pr), 1/bTroe, 1/fCent): the reference divides each time, which
+    // differs by an ulp or so per factor; the divisions sit on the critical path of the longest reaction groups
     const ulonglong2 k0 = __ldg(P2 + 6), k1 = __ldg(P2 + 7); // base, kpA | kpb, kpE
     const double kpb = u2d(k1.x), kpE = u2d(k1.y);
     const double kp_over_kf = u2d(k0.y) * exp(kpb * logT - kpE * invT) / kf;
-    const double kp_sens = invT * (kpb + kpE * invT);
+    const double dsens = invT * (kpb + kpE * invT) - kf_sens; // kp_sens - kf_sens
     const double pr = kp_over_kf * M;
+    const double inv1p = 1. / (1. + pr);
     double nsTmp;
     if (type == RT_LINDEMANN)
     { // :867-903
-      Ctbaf = pr / (1. + pr);
-      dCdT = Ctbaf / (1. + pr) * (kp_sens - kf_sens);
-      nsTmp = kp_over_kf / ((1. + pr) * (1. + pr));
+      Ctbaf = pr * inv1p;
+      dCdT = Ctbaf * inv1p * dsens;
+      nsTmp = kp_over_kf * (inv1p * inv1p);
     }
     else
-    { // TROE, :905-995. Absent terms are evaluated as exp(-inf) = 0 so that the three exponentials and the three
+    { // TROE, :905-995. Absent terms are evaluated as exp(-inf) = 0 so that the three exponentials and the
       // logarithms are independent instruction streams
       const ulonglong2 t0 = __ldg(P2 + 8), t1 = __ldg(P2 + 9);
       const double tr0 = u2d(t0.x), tr1 = u2d(t0.y), tr2 = u2d(t1.x), tr3 = u2d(t1.y);
@@ -322,6 +341,7 @@ __device__ __forceinline__ void react_struct(const DeviceMech &dm, const unsigne
       const double a1 = (tb & TROE_T3) ? -T / tr1 : ninf, a2 = (tb & TROE_T1) ? -T / tr2 : ninf,
                    a3 = (tb & TROE_T2) ? -invT * tr3 : ninf;
       const double t1exp = exp(a1), t2exp = exp(a2), t3exp = exp(a3);
+      const double log10pr = log10(fmax(pr, 1.e-300));
       double fCent = 0., dfCentdT = 0.;
       if (tb & TROE_T3)
       {
@@ -340,24 +360,24 @@ __device__ __forceinline__ void react_struct(const DeviceMech &dm, const unsigne
         dfCentdT = any ? dfCentdT + t3exp * tr3 * invT * invT : t3exp * tr3 * invT * invT;
       }
       const double fc = fmax(fCent, 1.e-300);
-      const double log10pr = log10(fmax(pr, 1.e-300));
       const double log10fcent = log10(fc);
       const double logfcent = log(fc);
-      const double ln10 = 2.302585092994046; // log(10.)
+      const double invfc = 1. / fCent;
+      const double invln10 = 1. / 2.302585092994046; // 1/log(10.)
       const double aTroe = log10pr - 0.67 * log10fcent - 0.4;
       const double bTroe = -0.14 * log10pr - 1.1762 * log10fcent + 0.806;
-      const double gTroe = 1 / (1 + (aTroe / bTroe) * (aTroe / bTroe));
+      const double invb = 1. / bTroe;
+      const double ab = aTroe * invb;
+      const double gTroe = 1 / (1 + ab * ab);
       const double fTroe = pow(fCent, gTroe);
-      Ctbaf = fTroe * pr / (1 + pr);
+      const double prinv = pr * inv1p; // pr/(1+pr) = 1/(1+1/pr)
+      Ctbaf = fTroe * prinv;
+      const double common = -2.0 * gTroe * gTroe * invln10 * aTroe * (invb * invb * invb); // -2 g^2/ln10 a/b^3
+      const double dfc = dfCentdT * invfc;
       const double dfTroedT =
-          fTroe * (gTroe / fCent * dfCentdT +
-                   logfcent * (-2.0 * gTroe * gTroe / ln10 * aTroe / (bTroe * bTroe * bTroe) *
-                               ((bTroe + 0.14 * aTroe) * (kp_sens - kf_sens) -
-                                (0.67 * bTroe - 1.1762 * aTroe) * dfCentdT / fCent)));
-      dCdT = 1. / (1. + 1. / pr) * dfTroedT + fTroe * pr / ((1. + pr) * (1. + pr)) * (kp_sens - kf_sens);
-      nsTmp = kp_over_kf * (-2.0 / (1. + pr) * fTroe * logfcent * gTroe * gTroe / ln10 * aTroe /
-                                (bTroe * bTroe * bTroe) * (bTroe + 0.14 * aTroe) +
-                            fTroe / ((1. + pr) * (1 + pr)));
+          fTroe * (gTroe * dfc + logfcent * (common * ((bTroe + 0.14 * aTroe) * dsens - (0.67 * bTroe - 1.1762 * aTroe) * dfc)));
+      dCdT = prinv * dfTroedT + fTroe * prinv * inv1p * dsens;
+      nsTmp = kp_over_kf * (inv1p * fTroe * logfcent * common * (bTroe + 0.14 * aTroe) + fTroe * (inv1p * inv1p));
     }
     dCdrho = nsTmp * dMdrho;
     coef = nsTmp * rho;
@@ -804,16 +824,17 @@ struct Rows
   }
 };
 
-// one gather step: acc[slot] += nu * record[row][state(slot)]
+// one gather step: acc[slot] += (nu * -M_row) * record[row][state(slot)], the factor and the two roundings of the
+// reference's `wsens += factor * dq` (rates_sensitivities_exact.cpp:1014-1026)
 template <int G>
-__device__ __forceinline__ void gather_step(unsigned int u, const double *sR, int rot, double (&acc)[G])
+__device__ __forceinline__ void gather_step(unsigned int u, const double *sR, int rot, double nm, double (&acc)[G])
 {
-  const double nu = (double)(((int)(u << 8)) >> 24);
+  const double coef = (double)(((int)(u << 8)) >> 24) * nm;
   double v[G];
   Rows<G>::load(sR + (size_t)(u & 0xffff) * G, rot, v);
 #pragma unroll
   for (int g = 0; g < G; ++g)
-    acc[g] = fma(nu, v[g], acc[g]);
+    acc[g] = acc[g] + coef * v[g];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -833,7 +854,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   s.sC = s.sy + ns * G;                // concentrations
   s.sg = s.sC + ns * G;                // Gibbs              -> later: c1 of the output transform
   s.sdb = s.sg + ns * G;               // dB/dT              -> later: c2
-  s.sh = s.sdb + ns * G;               // enthalpies         -> later: hm_i = -M_i h_i
+  s.sh = s.sdb + ns * G;               // enthalpies
   s.scp = s.sh + ns * G;               // species cp
   s.sdcp = s.scp + ns * G;             // species dcp/dT     -> later: c3
   s.su = s.sdcp + ns * G;              // [ns] u_k = 1/M_k - 1/M_ns
@@ -848,13 +869,14 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   const int *t_csparts = stab + dm.jp_t_csparts, *t_cspfirst = stab + dm.jp_t_cspfirst;
   const unsigned int *t_csitems = (const unsigned int *)(stab + dm.jp_t_csitems);
   const unsigned short *t_rdest = (const unsigned short *)(stab + dm.jp_t_rdest);
+  const unsigned short *t_rspec = (const unsigned short *)(stab + dm.jp_t_rspec);
   const unsigned short *rowsrc = (const unsigned short *)(stab + dm.jp_t_rowsrc);
 
   // per-CTA constants
   for (int i = tid; i < ns; i += nt)
   {
     s.su[i] = dm.invmw[i] - dm.invmw[nsm1];
-    s.snm[i] = -dm.mw[i];
+    s.snm[i] = -dm.netmw[i];
     s.sim[i] = dm.invmw[i];
   }
   for (int e = tid; e < dm.jp_tab_words; e += nt)
@@ -1070,8 +1092,10 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 #ifdef GB_JAC_TIMELINE
         if (blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && lane == 0)
         {
-          g_jac_timeline[(11 + min(kind, 1)) * 32 + warp] += clock64() - tl0;
-          g_jac_timeline[(13 + min(kind, 1)) * 32 + warp] += 1;
+          // bucket: 0 fast, 1 structured simple, 2 third body, 3 Lindemann, 4 Troe, 5 generic (rows 11.., counts 17..)
+          const int bucket = kind == 0 ? 0 : (kind == 2 ? 5 : f_type((int)(unsigned int)P[0]));
+          atomicAdd((unsigned long long *)&g_jac_timeline[(11 + bucket) * 32], (unsigned long long)(clock64() - tl0));
+          atomicAdd((unsigned long long *)&g_jac_timeline[(11 + bucket) * 32 + 1], 1ull);
         }
 #endif
       }
@@ -1091,13 +1115,14 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const unsigned int *__restrict__ it = dm.jp_items + t_rounds[2 * (r0 + j)] + lane;
         const int L = t_rounds[2 * (r0 + j) + 1];
+        const double nm = s.snm[t_rspec[(r0 + j) * 32 + lane]];
         unsigned int u0 = __ldg(it), u1 = __ldg(it + 32);
         for (int k = 0; k < L; k += JP_BLK)
         {
           it += 32 * JP_BLK;
           const unsigned int n0 = __ldg(it), n1 = __ldg(it + 32);
-          gather_step<G>(u0, s.sR, rot, hold[j]);
-          gather_step<G>(u1, s.sR, rot, hold[j]);
+          gather_step<G>(u0, s.sR, rot, nm, hold[j]);
+          gather_step<G>(u1, s.sR, rot, nm, hold[j]);
           u0 = n0;
           u1 = n1;
         }
@@ -1105,13 +1130,11 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     }
     TL_MARK(5)
     __syncthreads();
-    // ---- the sums overwrite the record region; enthalpies become the column-sum weights hm_i = -M_i h_i ---------------
+    // ---- the sums overwrite the record region -----------------------------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < RMAX; ++j)
       if (j < nround)
         Rows<G>::store_swz(s.sR, t_rdest[(r0 + j) * 32 + lane], rot, hold[j]);
-    for (int item = tid; item < ns * G; item += nt)
-      s.sh[item] *= s.snm[item / G];
     TL_MARK(6)
     __syncthreads();
     // ---- recombine split destinations in part order -------------------------------------------------------------------------------
@@ -1141,16 +1164,15 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           double v = 0.;
           if (row < ns)
           {
-            const double nm = s.snm[row];
             if (col == 0)
-              v = nm * SJ(rowsrc[ns + row], g);
+              v = SJ(rowsrc[ns + row], g);
             else if (col == 1)
-              v = nm * SJ(rowsrc[2 * ns + row], g);
+              v = SJ(rowsrc[2 * ns + row], g);
             else if (col - 2 < nsm1)
             {
               const int k = col - 2;
               const double rv = SJ(s.semap[k * (ns + 1) + row + 1], g);
-              v = nm * (rv + (SJ(rowsrc[3 * ns + row], g) * s.su[k] + SJ(rowsrc[4 * ns + row], g)));
+              v = rv + (SJ(rowsrc[3 * ns + row], g) * s.su[k] + SJ(rowsrc[4 * ns + row], g));
             }
           }
           a.out1[(size_t)(tile0 + g) * nsp1 * nsp1 + e] = v;
@@ -1175,33 +1197,18 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 #pragma unroll
           for (int g = 0; g < G; ++g)
             acc[g] = 0.;
-          if (d == ncs - 1)
-          { // sum_i (cp_i * -M_i) * W_i
-            for (int p = p0; p < p1; ++p)
-            {
-              const unsigned int u = t_csitems[p];
-              const int i = (int)(u >> 16);
-              double w[G], v[G];
-              Rows<G>::load(s.scp + (size_t)i * G, rot, w);
-              Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
-              const double nm = s.snm[i];
+          // sum over species (ascending) of h_i (cp_i for the last destination) times the row value: the inner
+          // products of isobaric_reactor_kernels.cpp:74-92
+          const double *wsrc = (d == ncs - 1) ? s.scp : s.sh;
+          for (int p = p0; p < p1; ++p)
+          {
+            const unsigned int u = t_csitems[p];
+            double w[G], v[G];
+            Rows<G>::load(wsrc + (size_t)(u >> 16) * G, rot, w);
+            Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                acc[g] += (w[g] * nm) * v[g];
-            }
-          }
-          else
-          { // sum_i hm_i * row value, species ascending (isobaric_reactor_kernels.cpp:74-92)
-            for (int p = p0; p < p1; ++p)
-            {
-              const unsigned int u = t_csitems[p];
-              double w[G], v[G];
-              Rows<G>::load(s.sh + (size_t)(u >> 16) * G, rot, w);
-              Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
-#pragma unroll
-              for (int g = 0; g < G; ++g)
-                acc[g] += w[g] * v[g];
-            }
+            for (int g = 0; g < G; ++g)
+              acc[g] += w[g] * v[g];
           }
           Rows<G>::store(s.sTH + (size_t)job * G, rot, acc);
         }
@@ -1209,13 +1216,13 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
           const int item = job - npw;
           const int i = item / G, g = item - i * G;
-          const double nm = s.snm[i], invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
-          const double w = nm * SJ(rowsrc[i], g), wr = nm * SJ(rowsrc[ns + i], g);
-          const double wT = nm * SJ(rowsrc[2 * ns + i], g);
-          const double nmA = nm * SJ(rowsrc[3 * ns + i], g), nmB = nm * SJ(rowsrc[4 * ns + i], g);
+          const double invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
+          const double w = SJ(rowsrc[i], g), wr = SJ(rowsrc[ns + i], g);
+          const double wT = SJ(rowsrc[2 * ns + i], g);
+          const double nmA = SJ(rowsrc[3 * ns + i], g), nmB = SJ(rowsrc[4 * ns + i], g);
           const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
           const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
-          SMG(s.sg, i, g) = invRho * nm;
+          SMG(s.sg, i, g) = invRho;
           SMG(s.sdb, i, g) = invRho * nmA + nRM * prho;
           SMG(s.sdcp, i, g) = invRho * nmB;
           if (i < nsm1)
@@ -1485,7 +1492,7 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
 int debug_jac_timeline(long long *out)
 {
   cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, g_jac_timeline, sizeof(long long) * 16 * 32) == cudaSuccess ? 0 : -3;
+  return cudaMemcpyFromSymbol(out, g_jac_timeline, sizeof(long long) * 20 * 32) == cudaSuccess ? 0 : -3;
 }
 #endif
 

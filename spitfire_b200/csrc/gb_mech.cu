@@ -368,6 +368,10 @@ int commit(HostMech &m)
 
   std::vector<double> cpc = m.cpc;
   Blob b;
+  std::vector<double> netmw(ns);
+  for (int i = 0; i < ns; ++i)
+    netmw[i] = 1. / m.invmw[i];
+  const size_t o_netmw = b.add(netmw);
   const size_t o_mw = b.add(m.mw), o_invmw = b.add(m.invmw), o_tmin = b.add(m.tmin), o_tmax = b.add(m.tmax);
   const size_t o_cpc = b.add(cpc), o_cptype = b.add(m.cptype);
   const size_t o_flags = b.add(flags), o_kfA = b.add(kfA), o_kfb = b.add(kfb), o_kfE = b.add(kfE), o_kpA = b.add(kpA),
@@ -399,7 +403,7 @@ int commit(HostMech &m)
   DeviceMech &d = m.dm;
   d.ns = ns, d.nr = nr, d.Ru = m.Ru, d.p_ref = m.p_ref;
   d.invRu = 1. / m.Ru, d.RuR = 1. / d.invRu;
-  d.mw = at<double>(base, o_mw), d.invmw = at<double>(base, o_invmw);
+  d.mw = at<double>(base, o_mw), d.invmw = at<double>(base, o_invmw), d.netmw = at<double>(base, o_netmw);
   d.tmin = at<double>(base, o_tmin), d.tmax = at<double>(base, o_tmax);
   d.cpc = at<double>(base, o_cpc), d.cptype = at<int>(base, o_cptype);
   d.flags = at<int>(base, o_flags);
@@ -431,7 +435,7 @@ int commit(HostMech &m)
   d.jp_tab_words = (int)jp.tab.size();
   d.jp_t_wg = jp.t_wg, d.jp_t_groups = jp.t_groups, d.jp_t_wr = jp.t_wr, d.jp_t_rounds = jp.t_rounds;
   d.jp_t_rdest = jp.t_rdest, d.jp_t_fix = jp.t_fix, d.jp_t_rowsrc = jp.t_rowsrc, d.jp_t_csparts = jp.t_csparts;
-  d.jp_t_cspfirst = jp.t_cspfirst, d.jp_t_csitems = jp.t_csitems;
+  d.jp_t_cspfirst = jp.t_cspfirst, d.jp_t_csitems = jp.t_csitems, d.jp_t_rspec = jp.t_rspec;
   d.jp_G = jp.G, d.jp_threads = jp.threads, d.jp_rec_rows = jp.rec_rows, d.jp_rows = jp.rows;
   d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_ncsp = jp.ncsp, d.jp_t0base = jp.t0base;
   d.jp_c0base = jp.c0base, d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);

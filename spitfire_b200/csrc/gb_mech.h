@@ -62,6 +62,7 @@ struct DeviceMech
   double invRu, RuR; // 1/Ru and 1/(1/Ru), rounded as the reference's expressions round them
   // species
   const double *mw, *invmw, *tmin, *tmax; // [ns]
+  const double *netmw;                    // [ns] 1/invmw: the molecular weight the net factors -nu*M use (chemistry_setup.cpp:538)
   const double *cpc;                      // [ns][NCP]
   const int *cptype;                      // [ns]
   // reactions, SoA [nr]
@@ -106,12 +107,12 @@ struct DeviceMech
   // small tables, copied to shared memory by every CTA (offsets in ints into jp_tab):
   //  t_wg [nwarps+1] reaction groups of every warp; t_groups: per group kind (0 fast, 1 structured, 2 generic) and 32/G parameter
   //  offsets (-1: idle); t_wr [nwarps+1] gather rounds of every warp; t_rounds: per round first item and number of
-  //  steps; t_rdest (u16) [round][lane] destination row; t_fix (dst row, first extra part row, extra parts);
+  //  steps; t_rdest (u16) [round][lane] destination row, t_rspec (u16) its species; t_fix (dst row, first extra part row, extra parts);
   //  t_rowsrc (u16) [5][ns] rows of sum_r nu*{q, dq/drho, dq/dT, a, b}; t_csparts (dest, begin, end);
   //  t_cspfirst [ncs+1] first part of every column destination; t_csitems: row (16) | species (16) << 16
   const int *jp_tab;
   int jp_tab_words, jp_t_wg, jp_t_groups, jp_t_wr, jp_t_rounds, jp_t_rdest, jp_t_fix, jp_t_rowsrc, jp_t_csparts,
-      jp_t_cspfirst, jp_t_csitems;
+      jp_t_cspfirst, jp_t_csitems, jp_t_rspec;
   int jp_G, jp_threads, jp_rec_rows, jp_rows, jp_nfix, jp_ncs, jp_ncsp, jp_t0base, jp_c0base, jp_zrow, jp_smem;
 };
 
@@ -127,10 +128,10 @@ struct JacPlanHost
   std::vector<unsigned long long> prm;
   std::vector<int> wg_off, groups, wr_off, rounds, fix, cs_off;
   std::vector<unsigned int> items, cs_items;
-  std::vector<unsigned short> rdest, rowsrc, emap;
+  std::vector<unsigned short> rdest, rspec, rowsrc, emap;
   std::vector<int> tab;
   int t_wg = 0, t_groups = 0, t_wr = 0, t_rounds = 0, t_rdest = 0, t_fix = 0, t_rowsrc = 0, t_csparts = 0, t_cspfirst = 0,
-      t_csitems = 0;
+      t_csitems = 0, t_rspec = 0;
   int rec_rows = 0, rows = 0, ncs = 0, ncsp = 0, t0base = 0, c0base = 0, zrow = 0;
   // statistics (printed with GB_PLAN_VERBOSE=1)
   int n_fast = 0, n_struct = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;

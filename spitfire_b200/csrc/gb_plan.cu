@@ -284,22 +284,16 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       }
       return k;
     };
-    auto cost = [&](int r) { // measured group times (tools/timeline.py), cycles
+    auto cost = [&](int r) { // measured group times on B200 (tools/timeline.py, GRI-3.0), cycles
       const HostReaction &x = m.reactions[r];
       double c;
       if (kind[r] == 0)
-        c = 500. + (x.kform == KF_ARRHENIUS ? 250. : 0.) + (x.reversible ? 500. : 0.);
+        c = 600. + (x.kform == KF_ARRHENIUS ? 300. : 0.) + (x.reversible ? 460. : 0.);
       else
       {
-        c = 700. + 150. * (x.n_rc + (x.reversible ? x.n_pd : 0)) + (x.reversible ? 500. : 0.) + 60. * x.tb_idx.size();
-        if (x.type == RT_THIRD_BODY)
-          c += 300.;
-        if (x.type == RT_LINDEMANN)
-          c += 1200.;
-        if (x.type == RT_TROE)
-          c += 3500.;
+        c = x.type == RT_SIMPLE ? 4600. : (x.type == RT_THIRD_BODY ? 9300. : (x.type == RT_LINDEMANN ? 10000. : 14000.));
         if (kind[r] == 2)
-          c = 2.5 * c + (x.has_orders ? 6000. : 0.);
+          c = 1.5 * c + (x.has_orders ? 6000. : 0.);
       }
       return c;
     };
@@ -330,7 +324,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
         double extra = 0.;
         for (size_t i = 1; i < g.rx.size(); ++i)
           if (key(g.rx[i]) != key(g.rx[i - 1]))
-            extra += 0.5 * cost(g.rx[i]);
+            extra += 0.25 * cost(g.rx[i]);
         g.cost += extra;
       }
       groups.push_back(g);
@@ -339,7 +333,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     std::iota(gorder.begin(), gorder.end(), 0);
     std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return groups[a].cost > groups[b].cost; });
     std::vector<double> load(nwarps, 0.);
-    load[nwarps - 1] = 900.; // the last warp starts with the mixture cp chain (k_jac)
+    load[nwarps - 1] = 1500.; // the last warp starts with the mixture cp chain (k_jac)
     std::vector<std::vector<int>> per_warp(nwarps);
     for (int gi : gorder)
     {
@@ -509,7 +503,12 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
             out.items.push_back(it);
           }
         for (int l = 0; l < 32; ++l)
+        {
           out.rdest.push_back((unsigned short)(l < (int)rd.p.size() ? parts[rd.p[l]].row : out.zrow + 1));
+          // species whose row the destination belongs to (its factor -nu*M_i multiplies every item)
+          const int lg = l < (int)rd.p.size() ? parts[rd.p[l]].logical : 0;
+          out.rspec.push_back((unsigned short)(lg < yend ? lg % ns : (lg - rbase) % ns));
+        }
       }
     }
     out.wr_off[nwarps] = (int)out.rounds.size() / 2;
@@ -532,8 +531,8 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     for (int i = 0; i < ns; ++i)
       if (row_of[rbase + q * ns + i] >= 0)
         out.rowsrc[(size_t)q * ns + i] = (unsigned short)row_of[rbase + q * ns + i];
-  // column destinations: 0..ns-2: sum_i hm_i R[i][k]; then sums over species of hm_i * {W, Wrho, WT, A, B}_i and of
-  // cpm_i * W_i (hm_i = -M_i h_i, cpm_i = -M_i cp_i); items in species order
+  // column destinations: 0..ns-2: sum_i h_i R[i][k]; then sums over species of h_i * {W, Wrho, WT, A, B}_i and of
+  // cp_i * W_i (the gathered rows already carry the factor -nu*M_i); items in species order
   out.ncs = ns - 1 + 6;
   out.cs_off.assign(1, 0);
   for (int k = 0; k < ns - 1; ++k)
@@ -591,6 +590,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     out.t_wr = add(out.wr_off);
     out.t_rounds = add(out.rounds);
     out.t_rdest = add16(out.rdest);
+    out.t_rspec = add16(out.rspec);
     out.t_fix = add(out.fix);
     out.t_rowsrc = add16(out.rowsrc);
     out.t_csparts = add(csparts);

@@ -29,7 +29,13 @@ ORACLE = 'reference' if oracle_available('reference') else 'port'
 MEDIAN_TOL, BIG_TOL, SCALED_TOL = 1e-15, 1e-12, 1e-12
 
 
-def assert_parity(a, ref, what, big_tol=None, scaled_tol=None):
+GROSS_TOL = 3e-14
+
+
+def assert_parity(a, ref, what, big_tol=None, scaled_tol=None, gross=None):
+    """gross (optional, same shape): sum of the absolute values of the terms the reference adds up to form the entry.
+    An entry whose difference is below GROSS_TOL * gross (about a hundred ulp of the summands) is rounding noise of a
+    cancelling sum -- the reference moves by as much when its own summation order changes -- and is taken as equal."""
     big_tol = BIG_TOL if big_tol is None else big_tol
     scaled_tol = SCALED_TOL if scaled_tol is None else scaled_tol
     a, ref = np.asarray(a), np.asarray(ref)
@@ -38,6 +44,10 @@ def assert_parity(a, ref, what, big_tol=None, scaled_tol=None):
     fin = np.isfinite(ref)
     if not fin.all():
         a, ref = np.where(fin, a, 0.), np.where(fin, ref, 0.)
+    if gross is not None:
+        with np.errstate(all='ignore'):
+            noise = np.abs(a - ref) <= GROSS_TOL * np.where(np.isfinite(gross), gross, 0.)
+        a = np.where(noise, ref, a)
     s = error_stats(a, ref)
     assert s['strict_median'] <= MEDIAN_TOL, f'{what}: {s}'
     assert s['big_max'] <= big_tol, f'{what}: {s}'
@@ -56,6 +66,29 @@ def oracle_batch(o, ns, state, y, p, rho):
                                out['jac'][i])
         o.production_rates(state[i, 0], rho[i], y[i], out['w'][i])
         o.prod_rates_primitive_sensitivities(rho[i], state[i, 0], y[i], 0, out['sens'][i])
+    return out
+
+
+def temperature_row_gross(o, ns, state, y, rho, sens):
+    """sum_i |h_i dw_i/dx| / (rho cp) behind every entry of the Jacobian's temperature row (the inner products of
+    isobaric_reactor_kernels.cpp:74-92 and the chain rule :319-343), from the oracle's own sensitivities; zero for the
+    other rows. Shape [n, ns*ns] like the column-major Jacobian."""
+    n = state.shape[0]
+    out = np.zeros((n, ns * ns))
+    h = np.zeros(ns)
+    mw = np.array([o.mixture_molecular_weight(np.eye(ns)[i]) for i in range(ns)])
+    for s in range(n):
+        T = state[s, 0]
+        o.species_enthalpies(T, h)
+        cp = o.cp_mix(T, y[s])
+        mmw = o.mixture_molecular_weight(y[s])
+        ws = np.abs(sens[s].reshape(ns + 1, ns + 1).T[:ns, :])  # [i, col]: col 0 rho, 1 T, 2+k Y_k
+        g = (np.abs(h)[:, None] * ws).sum(axis=0) / (rho[s] * cp)
+        row = np.zeros(ns)
+        row[0] = g[1] + rho[s] / T * g[0]
+        for k in range(ns - 1):
+            row[1 + k] = g[2 + k] + rho[s] * mmw * abs(1. / mw[k] - 1. / mw[ns - 1]) * g[0]
+        out[s, 0::ns] = row
     return out
 
 
@@ -93,8 +126,10 @@ def test_reactor_and_rates_parity_all_fixture_mechanisms(name):
         rho = np.array([mo.griffon.ideal_gas_density(p, state[i, 0], y[i]) for i in range(n)])
         ref = oracle_batch(mo.griffon, ns, state, y, p, rho)
         got = gpu_batch(mg.griffon, ns, state, y, p, rho)
+        gross = temperature_row_gross(mo.griffon, ns, state, y, rho, ref['sens'])
         for k in ref:
-            assert_parity(got[k], ref[k], f'{name} p={p} {k}', big_tol=1e-11, scaled_tol=1e-11)
+            assert_parity(got[k], ref[k], f'{name} p={p} {k}', big_tol=1e-11, scaled_tol=1e-11,
+                          gross=gross if k == 'jac' else None)
 
 
 @pytest.mark.parametrize('name,fuel', [('h2-burke', 'H2'), ('methane-gri30', 'CH4')])
@@ -109,8 +144,9 @@ def test_synthetic_batch_parity_subset(name, fuel):
     ref = oracle_batch(mo.griffon, ns, state, y, p, rho)
     got = gpu_batch(mg.griffon, ns, state, y, p, rho)
     report = {}
+    gross = temperature_row_gross(mo.griffon, ns, state, y, rho, ref['sens'])
     for k in ref:
-        s = assert_parity(got[k], ref[k], f'{name} synthetic {k}')
+        s = assert_parity(got[k], ref[k], f'{name} synthetic {k}', gross=gross if k == 'jac' else None)
         report[k] = s
         print(name, k, s)
     import json

@@ -22,12 +22,12 @@ for _ in range(2):
     g.reactor_jac_isobaric_batch(d_state, 101325., d_rhs, d_jac)
 torch.cuda.synchronize()
 lib = griffon.load_library()
-buf = (C.c_longlong * (16 * 32))()
+buf = (C.c_longlong * (20 * 32))()
 lib.gb_debug_jac_timeline.argtypes = [C.c_void_p]
 assert lib.gb_debug_jac_timeline(buf) == 0
-t = np.array(buf[:], dtype=np.int64).reshape(16, 32)
+t = np.array(buf[:], dtype=np.int64).reshape(20, 32)
 nw = int((t[0] != 0).sum())
-tk = t[11:15, :nw]
+tk = t[11:17]
 t = t[:11, :nw]
 t0 = t[0].min()
 names = ['top', 'load', 'thermo', 'conc', 'react', 'gather', 'write', 'fix', 'rows/cols', 'T-row', 'output']
@@ -37,8 +37,8 @@ for k in range(11):
     print(f'  {names[k]:10s} release {rel[k]:8d}  phase {rel[k] - (rel[k-1] if k else 0):8d}   warp arrivals (rel. to previous release): '
           + ' '.join(f'{int(x - t0 - (rel[k-1] if k else 0)):6d}' for x in t[k]))
 
-print('reaction phase per warp: fast groups (count, total cycles), generic groups (count, total cycles)')
-for w in range(nw):
-    print(f'  warp {w:2d}: fast {int(tk[2,w]):2d} groups {int(tk[0,w]):7d} cyc   generic {int(tk[3,w]):2d} groups {int(tk[1,w]):7d} cyc')
-nf, ng = tk[2].sum(), tk[3].sum()
-print(f'  mean cycles per fast group {tk[0].sum()/max(nf,1):.0f}, per generic group {tk[1].sum()/max(ng,1):.0f}')
+
+print('reaction phase, mean cycles per group by kind:')
+for k, name in enumerate(['fast A+B<=>C+D', 'structured simple', 'third body', 'Lindemann', 'Troe', 'generic']):
+    if tk[k, 1]:
+        print(f'  {name:18s} {int(tk[k,1])//2:4d} groups  {tk[k,0]/tk[k,1]:8.0f} cycles')
