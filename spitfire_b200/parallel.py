@@ -1,0 +1,72 @@
+"""
+Multi-GPU partition of the library sweeps: one process per GPU (torchrun), whole flamelets owned by one rank.
+
+The reference's only parallel construct is `multiprocessing.Pool.starmap` over the stoichiometric dissipation rates of
+the non-adiabatic builder with the results collected through a `Manager().dict()` (tabulation.py:542-568). Here the same
+units of work (one heat-loss expansion per chi_st, one member of a wave of adiabatic flamelets) are dealt block-cyclically
+to the ranks of `torch.distributed` -- high-chi members near extinction take more iterations, cyclic assignment
+balances them -- and the per-rank result dictionaries are exchanged once at the end with an all-gather over NCCL
+(NVLink) on GPU boxes or gloo in the CPU tests. There is no collective inside the data path.
+"""
+import os
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except ImportError:  # pragma: no cover
+        return None
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def rank():
+    d = _dist()
+    return d.get_rank() if d else 0
+
+
+def world_size():
+    d = _dist()
+    return d.get_world_size() if d else 1
+
+
+def init_from_env(backend=None):
+    """initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / MASTER_*) if it is present and
+    not initialised yet; binds the rank to its GPU. Returns (rank, world_size)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    if 'RANK' not in os.environ or int(os.environ.get('WORLD_SIZE', '1')) < 2:
+        return 0, 1
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def my_share(items):
+    """the items (a sequence) this rank owns: block-cyclic by position"""
+    r, w = rank(), world_size()
+    return [x for k, x in enumerate(items) if k % w == r]
+
+
+def gather_dicts(local):
+    """merge the per-rank dictionaries on every rank (the `Manager().dict()` of the reference). Keys must be unique
+    across ranks."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return dict(local)
+    parts = [None] * d.get_world_size()
+    d.all_gather_object(parts, dict(local))
+    merged = dict()
+    for p in parts:
+        merged.update(p)
+    return merged
+
+
+def barrier():
+    d = _dist()
+    if d is not None:
+        d.barrier()

@@ -1,0 +1,424 @@
+"""
+Tabulated-chemistry library builders on the B200 Griffon path (mirror of the sweep drivers of tabulation.py:55-842;
+the presumed-PDF part of that file is out of scope).
+
+Same public functions, arguments, defaults, library layout (dimension and property names) and extinction /
+sub-sampling rules as the reference. What is different is how the flamelets are advanced:
+  * every flamelet solve runs through spitfire_b200.flamelet on the GPU (batched kernels behind the C-ABI);
+  * `build_adiabatic_slfm_library(..., wave=W)` may solve W consecutive dissipation rates at once, all started from
+    the last converged member (the reference's chain is W = 1, the default, and is followed step for step then);
+  * the per-chi_st heat-loss expansions of the non-adiabatic builders -- the reference's `Pool.starmap` units -- are
+    dealt to the ranks of torch.distributed (one process per GPU) and gathered once at the end
+    (spitfire_b200.parallel); `num_procs` is accepted and ignored;
+  * specific enthalpies come from Griffon's `enthalpy_mix` instead of a Cantera SolutionArray (analysis.py:77-98);
+  * the structured-defect interpolation (a Python triple loop over chi, property and grid point in the reference,
+    tabulation.py:629-654) is done with array operations.
+"""
+import copy
+from time import perf_counter
+
+import numpy as np
+
+from spitfire_b200 import parallel
+from spitfire_b200.flamelet import Flamelet, FlameletBatch, FlameletSpec
+from spitfire_b200.library import Dimension, Library
+
+_mixture_fraction_name = 'mixture_fraction'
+_dissipation_rate_name = 'dissipation_rate'
+_enthalpy_defect_name = 'enthalpy_defect'
+_stoich_suffix = '_stoich'
+
+
+def _write_library_header(lib_type, mech, fuel, oxy, verbose):
+    if verbose and parallel.rank() == 0:
+        print('-' * 82)
+        print(f'building {lib_type} library')
+        print('-' * 82)
+        print(f'- mechanism: {mech.mech_file_path}')
+        print(f'- {mech.n_species} species, {mech.n_reactions} reactions')
+        print(f'- stoichiometric mixture fraction: {mech.stoich_mixture_fraction(fuel, oxy):.3f}')
+        print('-' * 82)
+    return perf_counter()
+
+
+def _write_library_footer(cput0, verbose):
+    if verbose and parallel.rank() == 0:
+        print('-' * 82)
+        print(f'library built in {perf_counter() - cput0:6.2f} s')
+        print('-' * 82, flush=True)
+
+
+def compute_specific_enthalpy(mechanism, output_library):
+    """add the mixture's specific enthalpy, 'enthalpy', to a library holding temperature and mass fractions
+    (the role of analysis.compute_specific_enthalpy, analysis.py:77-98, with Griffon's enthalpy_mix)"""
+    names = mechanism.species_names
+    T = np.ascontiguousarray(output_library['temperature'], dtype=np.float64)
+    Y = np.stack([np.asarray(output_library['mass fraction ' + s], dtype=np.float64) for s in names], axis=-1)
+    Tf, Yf = T.reshape(-1), np.ascontiguousarray(Y.reshape(-1, len(names)))
+    g = mechanism.griffon
+    h = np.zeros(Tf.size)
+    if hasattr(g, 'thermo_batch'):
+        from spitfire_b200.griffon import load_library  # noqa: F401  (product path: one batched launch)
+        g.thermo_batch(5, Tf, Yf, h)  # GB_THERMO_H_MIX
+    else:
+        for i in range(Tf.size):
+            h[i] = g.enthalpy_mix(Tf[i], Yf[i])
+    output_library['enthalpy'] = h.reshape(T.shape)
+    return output_library
+
+
+def _copy_specs(flamelet_specs):
+    return FlameletSpec(**flamelet_specs) if isinstance(flamelet_specs, dict) else copy.copy(flamelet_specs)
+
+
+def _initial_state_library(flamelet_specs, name):
+    fs = _copy_specs(flamelet_specs)
+    fs.initial_condition = name
+    flamelet = Flamelet(fs)
+    return flamelet.make_library_from_interior_state(flamelet.initial_interior_state)
+
+
+def build_unreacted_library(flamelet_specs, verbose=True):
+    """pure mixing of the streams, no reaction (tabulation.py:55-73)"""
+    return _initial_state_library(flamelet_specs, 'unreacted')
+
+
+def build_adiabatic_eq_library(flamelet_specs, verbose=True):
+    """chemical equilibrium (infinitely fast chemistry) at every mixture fraction (tabulation.py:76-95)"""
+    return _initial_state_library(flamelet_specs, 'equilibrium')
+
+
+def build_adiabatic_bs_library(flamelet_specs, verbose=True):
+    """Burke-Schumann (idealised complete combustion) chemistry (tabulation.py:98-116)"""
+    return _initial_state_library(flamelet_specs, 'Burke-Schumann')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_adiabatic_slfm_library(flamelet_specs, diss_rate_values=np.logspace(-3, 2, 16),
+                                 diss_rate_ref='stoichiometric', verbose=True, solver_verbose=False,
+                                 _return_intermediates=False, include_extinguished=False, diss_rate_log_scaled=True,
+                                 wave=1, tolerance=1.e-6):
+    """Adiabatic strained-laminar-flamelet library over (mixture fraction, stoichiometric dissipation rate)
+    (tabulation.py:229-336): equilibrium start, steady solve per dissipation rate in the given order, each started from
+    the previous solution, stopping at the first extinguished member (max(T - T_linear) < 10 K) unless
+    include_extinguished.
+
+    wave : int
+        (extension) how many consecutive dissipation rates are solved together on the device, all started from the
+        last converged solution. 1 reproduces the reference's chain exactly."""
+    if isinstance(flamelet_specs, dict):
+        flamelet_specs = FlameletSpec(**flamelet_specs)
+    m, fuel, oxy = flamelet_specs.mech_spec, flamelet_specs.fuel_stream, flamelet_specs.oxy_stream
+    flamelet_specs.initial_condition = 'equilibrium'
+    use_max = diss_rate_ref == 'maximum'
+
+    def set_chi(value):
+        if use_max:
+            flamelet_specs.max_dissipation_rate = value
+        else:
+            flamelet_specs.stoich_dissipation_rate = value
+
+    set_chi(0.)
+    cput00 = _write_library_header('adiabatic SLFM', m, fuel, oxy, verbose)
+    f = Flamelet(flamelet_specs)  # evaluates the equilibrium initial condition once
+    flamelet_specs.initial_condition = np.copy(f.initial_interior_state)
+    say = verbose and parallel.rank() == 0
+    table_dict, x_values = dict(), list()
+    nchi = diss_rate_values.size
+    suffix = _stoich_suffix if not use_max else '_max'
+    z_st = m.stoich_mixture_fraction(fuel, oxy)
+    idx, stop = 0, False
+    wave = max(1, int(wave))
+    while idx < nchi and not stop:
+        members = []
+        for chival in diss_rate_values[idx:idx + wave]:
+            set_chi(chival)
+            members.append(Flamelet(flamelet_specs))
+        cput0 = perf_counter()
+        if len(members) == 1:
+            libs = [members[0].compute_steady_state(tolerance=tolerance, verbose=solver_verbose, use_psitc=True)]
+        else:
+            states, _ = FlameletBatch(members).compute_steady_state(tolerance=tolerance, verbose=solver_verbose)
+            libs = [fl.make_library_from_interior_state(s) for fl, s in zip(members, states)]
+        dcput = perf_counter() - cput0
+        for k, (flamelet, x_library) in enumerate(zip(members, libs)):
+            if say:
+                print(f'{idx + k + 1:4}/{nchi:4} (chi{suffix} = {diss_rate_values[idx + k]:8.1e} 1/s) ', end='')
+            if np.max(flamelet.current_temperature - flamelet.linear_temperature) < 10. and not include_extinguished:
+                if say:
+                    print(' extinction detected, stopping. The extinguished state will not be included in the table.')
+                stop = True
+                break
+            if say:
+                print(f' converged in {dcput / len(members):6.2f} s, T_max = {np.max(flamelet.current_temperature):6.1f}',
+                      flush=True)
+            chi_st = flamelet._compute_dissipation_rate(np.array([z_st]), flamelet._max_dissipation_rate,
+                                                        flamelet._dissipation_rate_form)[0]
+            x_values.append(chi_st)
+            table_dict[chi_st] = {k2: x_library[k2].ravel() for k2 in x_library.props}
+            flamelet_specs.initial_condition = np.copy(flamelet.current_interior_state)
+            if _return_intermediates:
+                table_dict[chi_st]['adiabatic_state'] = np.copy(flamelet.current_interior_state)
+        idx += len(members)
+    if _return_intermediates:
+        _write_library_footer(cput00, verbose)
+        return table_dict, f.mixfrac_grid, np.array(x_values)
+    z_dim = Dimension(_mixture_fraction_name, f.mixfrac_grid)
+    x_dim = Dimension(_dissipation_rate_name + _stoich_suffix, np.array(x_values), diss_rate_log_scaled)
+    output_library = Library(z_dim, x_dim)
+    output_library.extra_attributes['mech_spec'] = m
+    for quantity in table_dict[x_values[-1]]:
+        values = output_library.get_empty_dataset()
+        for ix, x in enumerate(x_values):
+            values[:, ix] = table_dict[x][quantity]
+        output_library[quantity] = values
+    _write_library_footer(cput00, verbose)
+    return output_library
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _subsample_by_stoich_enthalpy(z, z_st, h_profiles, h_stoich_spacing, include_last):
+    """indices of the profiles (rows of h_profiles) kept: the first one and every one whose stoichiometric enthalpy has
+    dropped by more than h_stoich_spacing since the last kept one (tabulation.py:381-390, 498-505)"""
+    indices = [0]
+    n = h_profiles.shape[0]
+    last_hst = np.interp(z_st, z, h_profiles[0])
+    for i in range(n if include_last else n - 1):
+        this_hst = np.interp(z_st, z, h_profiles[i])
+        if last_hst - this_hst > h_stoich_spacing:
+            indices.append(i)
+            last_hst = this_hst
+    if include_last and n - 1 not in indices:
+        indices.append(n - 1)
+    return indices
+
+
+def _store_defect_profiles(managed_dict, chi_st, z, z_st, lib_get, props, h_profiles, indices):
+    h_ad = h_profiles[0]
+    for i in indices:
+        defect = h_profiles[i] - h_ad
+        gst = float(np.interp(z_st, z, defect))
+        data = dict()
+        data['enthalpy_defect'] = np.copy(defect)
+        data['enthalpy_cons'] = np.copy(h_ad)
+        data['enthalpy'] = np.copy(h_profiles[i])
+        data[_mixture_fraction_name] = z
+        for q in props:
+            data[q] = lib_get(q, i)
+        managed_dict[(chi_st, gst)] = data
+
+
+def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
+                                                verbose, input_integration_args, solver_verbose):
+    """one rapid-extinction trajectory at chi_st: ESDIRK64 with strong scaled convective heat loss until the
+    temperature profile is nearly linear, sub-sampled in stoichiometric enthalpy (tabulation.py:339-405)"""
+    fs = copy.copy(flamelet_specs)
+    fs.initial_condition = table_dict[chi_st]['adiabatic_state']
+    fs.stoich_dissipation_rate = chi_st
+    fs.heat_transfer = 'nonadiabatic'
+    fs.scale_heat_loss_by_temp_range = True
+    fs.scale_convection_by_dissipation = True
+    fs.use_linear_ref_temp_profile = True
+    fs.convection_coefficient = fs.convection_coefficient if fs.convection_coefficient is not None else 1.e7
+    fs.radiative_emissivity = 0.
+    integration_args = {'first_time_step': 1.e-9, 'max_time_step': 1.e-1, 'write_log': solver_verbose, 'log_rate': 100,
+                        'print_exception_on_failure': False}
+    if input_integration_args is not None:
+        integration_args.update(input_integration_args)
+    integration_args.setdefault('transient_tolerance', 1.e-8)
+    cput0 = perf_counter()
+    transient_lib, fnonad = None, None
+    while transient_lib is None and integration_args['transient_tolerance'] > 1.e-15:
+        try:
+            fnonad = Flamelet(fs)
+            transient_lib = fnonad.integrate_for_heat_loss(**integration_args)
+        except Exception:
+            if solver_verbose:
+                print(f'Transient heat loss calculation failed with tolerance of '
+                      f'{integration_args["transient_tolerance"]:.1e}, retrying with 100x lower...')
+            integration_args['transient_tolerance'] *= 1.e-2
+    if transient_lib is None:
+        raise RuntimeError(f'heat-loss expansion at chi_st = {chi_st} failed at every tolerance')
+    z = fnonad.mixfrac_grid
+    z_st = fnonad.mechanism.stoich_mixture_fraction(fnonad.fuel_stream, fnonad.oxy_stream)
+    h_tz = compute_specific_enthalpy(fs.mech_spec, transient_lib)['enthalpy']
+    indices = _subsample_by_stoich_enthalpy(z, z_st, h_tz, h_stoich_spacing, include_last=True)
+    props = [q for q in transient_lib.props]
+    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_tz, indices)
+    if verbose:
+        print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
+
+
+def _expand_enthalpy_defect_dimension_steady(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
+                                             verbose, input_integration_args, solver_verbose):
+    """quasi-steady heat loss at chi_st: continuation in the convection coefficient with an adaptive increment until
+    the flamelet extinguishes (tabulation.py:408-519)"""
+    fs = copy.copy(flamelet_specs)
+    fs.initial_condition = table_dict[chi_st]['adiabatic_state']
+    fs.stoich_dissipation_rate = chi_st
+    fs.heat_transfer = 'nonadiabatic'
+    fs.scale_heat_loss_by_temp_range = False
+    fs.scale_convection_by_dissipation = False
+    fs.use_linear_ref_temp_profile = True
+    fs.radiative_emissivity = 0.
+    fs.convection_coefficient = 0.
+    flamelet = Flamelet(fs)
+    state_old = np.copy(flamelet.current_interior_state)
+    hval, dh, diff_target, hval_max = 0., 1.e-1, 1.e-1, 1.e10
+    solutions = [{p: table_dict[chi_st][p] for p in table_dict[chi_st] if p != 'adiabatic_state'}]
+    hvalues = [hval]
+    current_state = table_dict[chi_st]['adiabatic_state']
+    cput0 = perf_counter()
+    first, extinguished = True, False
+    while first or (not extinguished and hval < hval_max):
+        hval += dh
+        first = False
+        fs.convection_coefficient = hval
+        fs.initial_condition = current_state
+        flamelet = Flamelet(fs)
+        g_library = flamelet.compute_steady_state(verbose=solver_verbose)
+        current_state = flamelet.current_interior_state
+        maxT = np.max(current_state)
+        diff_norm = np.max(np.abs(current_state - state_old) / (np.abs(current_state) + 1.e-4))
+        extinguished = maxT < (np.max([flamelet.oxy_stream.T, flamelet.fuel_stream.T]) + 10.)
+        state_old = np.copy(current_state)
+        dh *= np.min([np.max([np.sqrt(diff_target / diff_norm), 0.1]), 2.])
+        hvalues.append(hval)
+        solutions.append({p: g_library[p].ravel() for p in g_library.props})
+    z = flamelet.mixfrac_grid
+    steady_lib = Library(Dimension(_mixture_fraction_name, z),
+                         Dimension(_enthalpy_defect_name + _stoich_suffix, np.array(hvalues)))
+    steady_lib.extra_attributes['mech_spec'] = fs.mech_spec
+    props = [p for p in table_dict[chi_st] if p != 'adiabatic_state']
+    for p in props:
+        values = steady_lib.get_empty_dataset()
+        for ig, sol in enumerate(solutions):
+            values[:, ig] = sol[p].ravel()
+        steady_lib[p] = values
+    z_st = flamelet.mechanism.stoich_mixture_fraction(flamelet.fuel_stream, flamelet.oxy_stream)
+    h_zt = compute_specific_enthalpy(fs.mech_spec, steady_lib)['enthalpy']
+    indices = _subsample_by_stoich_enthalpy(z, z_st, h_zt.T, h_stoich_spacing, include_last=False)
+    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: steady_lib[q][:, i], steady_lib.props, h_zt.T,
+                           indices)
+    if verbose:
+        print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
+
+
+def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion='transient',
+                                                         diss_rate_values=np.logspace(-3, 2, 16),
+                                                         diss_rate_ref='stoichiometric', verbose=True,
+                                                         solver_verbose=False, h_stoich_spacing=10.e3, num_procs=1,
+                                                         integration_args=None, wave=1):
+    """adiabatic chain on every rank (it is short and every rank needs all of it), then this rank's share of the
+    independent heat-loss expansions, then one gather (tabulation.py:522-591)"""
+    table_dict, z_values, x_values = build_adiabatic_slfm_library(flamelet_specs, diss_rate_values, diss_rate_ref,
+                                                                  verbose, solver_verbose, _return_intermediates=True,
+                                                                  wave=wave)
+    expand = _expand_enthalpy_defect_dimension_transient if heat_loss_expansion == 'transient' else \
+        _expand_enthalpy_defect_dimension_steady
+    if verbose and parallel.rank() == 0:
+        print(f'expanding ({heat_loss_expansion}) enthalpy defect dimension on {parallel.world_size()} rank(s) ...',
+              flush=True)
+    cput0 = perf_counter()
+    local = dict()
+    for chi_st in parallel.my_share(list(table_dict.keys())):
+        expand(chi_st, local, flamelet_specs, table_dict, h_stoich_spacing, verbose, integration_args, solver_verbose)
+    merged = parallel.gather_dicts(local)
+    if verbose and parallel.rank() == 0:
+        print('-' * 82)
+        print('enthalpy defect dimension expanded in {:6.2f} s'.format(perf_counter() - cput0))
+        print('-' * 82, flush=True)
+    return merged
+
+
+def _interpolate_to_structured_defect_dimension(unstructured_table, n_defect_stoich, verbose=False, extend=False):
+    """piecewise-linear interpolation of every property at every (chi_st, z) onto n_defect_stoich equispaced
+    stoichiometric enthalpy defects, held constant outside each chi_st's range (tabulation.py:594-665)"""
+    cput0 = perf_counter()
+    by_chi = dict()
+    for (chi_st, g_st) in unstructured_table.keys():
+        by_chi.setdefault(chi_st, []).append(g_st)
+    all_g = [g for gs in by_chi.values() for g in gs]
+    min_g, max_g = np.min(all_g), np.max(all_g)
+    defect_space = np.linspace(min_g, max_g, n_defect_stoich)
+    if extend:
+        spacing = np.abs(defect_space[1] - defect_space[0])
+        defect_space = np.linspace(min_g - 2 * spacing, max_g, n_defect_stoich + 2)
+    structured = dict()
+    for chi_st, gs in by_chi.items():
+        g_sorted = np.sort(np.array(gs))
+        first = unstructured_table[(chi_st, g_sorted[0])]
+        for q in first.keys():
+            data = np.array([np.asarray(unstructured_table[(chi_st, g)][q], dtype=np.float64) for g in g_sorted])
+            nz = data.shape[1]
+            out = np.empty((defect_space.size, nz))
+            for iz in range(nz):
+                out[:, iz] = np.interp(defect_space, g_sorted, data[:, iz])
+            if extend and q in ('enthalpy', 'enthalpy_defect') and g_sorted.size > 1:
+                lo = defect_space < g_sorted[0]
+                slope = (data[1] - data[0]) / (g_sorted[1] - g_sorted[0])
+                out[lo] = data[0] + (defect_space[lo, None] - g_sorted[0]) * slope
+                hi = defect_space > g_sorted[-1]
+                slope = (data[-1] - data[-2]) / (g_sorted[-1] - g_sorted[-2])
+                out[hi] = data[-1] + (defect_space[hi, None] - g_sorted[-1]) * slope
+            if q in ('density', 'temperature') and np.any(out < 1.e-14):
+                raise ValueError(f'{q} < 1.e-14 detected!')
+            for ig, g in enumerate(defect_space):
+                structured.setdefault((chi_st, g), dict())[q] = out[ig]
+    if verbose and parallel.rank() == 0:
+        print('Structured enthalpy defect dimension built in {:6.2f} s'.format(perf_counter() - cput0), flush=True)
+    return structured, np.array(sorted(by_chi.keys())), defect_space[::-1]
+
+
+def _build_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion='transient',
+                                            diss_rate_values=np.logspace(-3, 2, 16), diss_rate_ref='stoichiometric',
+                                            verbose=True, solver_verbose=False, h_stoich_spacing=10.e3, num_procs=1,
+                                            integration_args=None, n_defect_st=32, extend_defect_dim=False,
+                                            diss_rate_log_scaled=True, wave=1):
+    if isinstance(flamelet_specs, dict):
+        flamelet_specs = FlameletSpec(**flamelet_specs)
+    m, fuel, oxy = flamelet_specs.mech_spec, flamelet_specs.fuel_stream, flamelet_specs.oxy_stream
+    cput00 = _write_library_header('nonadiabatic (defect) SLFM', m, fuel, oxy, verbose)
+    ugt = _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion, diss_rate_values,
+                                                               diss_rate_ref, verbose, solver_verbose, h_stoich_spacing,
+                                                               num_procs, integration_args, wave=wave)
+    table, x_values, g_values = _interpolate_to_structured_defect_dimension(ugt, n_defect_st, verbose=verbose,
+                                                                            extend=extend_defect_dim)
+    key0 = list(table.keys())[0]
+    z_values = table[key0][_mixture_fraction_name]
+    output_library = Library(Dimension(_mixture_fraction_name, z_values),
+                             Dimension(_dissipation_rate_name + _stoich_suffix, x_values, diss_rate_log_scaled),
+                             Dimension(_enthalpy_defect_name + _stoich_suffix, g_values))
+    output_library.extra_attributes['mech_spec'] = m
+    for quantity in table[key0]:
+        values = output_library.get_empty_dataset()
+        for ix, x in enumerate(x_values):
+            for ig, g in enumerate(g_values):
+                values[:, ix, ig] = table[(x, g)][quantity]
+        output_library[quantity] = values
+    _write_library_footer(cput00, verbose)
+    return output_library
+
+
+def build_nonadiabatic_defect_transient_slfm_library(flamelet_specs, diss_rate_values=np.logspace(-3, 2, 16),
+                                                     diss_rate_ref='stoichiometric', verbose=True, solver_verbose=False,
+                                                     h_stoich_spacing=10.e3, num_procs=1, integration_args=None,
+                                                     n_defect_st=32, extend_defect_dim=False, diss_rate_log_scaled=True,
+                                                     wave=1):
+    """SLFM library with heat loss through the enthalpy defect, the heat-loss profiles generated by rapid transient
+    extinction (tabulation.py:727-783)"""
+    return _build_nonadiabatic_defect_slfm_library(flamelet_specs, 'transient', diss_rate_values, diss_rate_ref, verbose,
+                                                   solver_verbose, h_stoich_spacing, num_procs, integration_args,
+                                                   n_defect_st, extend_defect_dim, diss_rate_log_scaled, wave=wave)
+
+
+def build_nonadiabatic_defect_steady_slfm_library(flamelet_specs, diss_rate_values=np.logspace(-3, 2, 16),
+                                                  diss_rate_ref='stoichiometric', verbose=True, solver_verbose=False,
+                                                  h_stoich_spacing=10.e3, num_procs=1, integration_args=None,
+                                                  n_defect_st=32, extend_defect_dim=False, diss_rate_log_scaled=True,
+                                                  wave=1):
+    """SLFM library with heat loss through the enthalpy defect, the heat-loss profiles generated by quasi-steady
+    extinction (tabulation.py:786-842)"""
+    return _build_nonadiabatic_defect_slfm_library(flamelet_specs, 'steady', diss_rate_values, diss_rate_ref, verbose,
+                                                   solver_verbose, h_stoich_spacing, num_procs, integration_args,
+                                                   n_defect_st, extend_defect_dim, diss_rate_log_scaled, wave=wave)
