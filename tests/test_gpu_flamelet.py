@@ -1,0 +1,67 @@
+"""GPU tests of the flamelet solvers and library builders: the same host code as tests/test_host_flamelet.py, with the
+CUDA kernels (C-ABI library) behind it. Bars: the reference's gold libraries; for GRI-3.0, which has no gold file in the
+reference, the CPU oracle driving the same solver on the same initial state (converged fields within 1e-8,
+BASELINE.json)."""
+import numpy as np
+import pytest
+
+from common import build_mech, oracle_available
+from slfm_cases import build, compare_with_gold
+
+pytestmark = pytest.mark.gpu
+ORACLE = 'reference' if oracle_available('reference') else 'port'
+
+
+def test_adiabatic_slfm_library_on_gpu_matches_reference_gold():
+    lib = build('adiabatic_slfm', 'gpu')
+    worst = compare_with_gold(lib, 'adiabatic_slfm', rtol=1e-8, atol=1e-10)
+    print('adiabatic SLFM (GPU) vs gold: worst normalised error', worst)
+
+
+def test_adiabatic_slfm_waves_on_gpu():
+    lib = build('adiabatic_slfm', 'gpu', wave=8)
+    compare_with_gold(lib, 'adiabatic_slfm', rtol=1e-6, atol=1e-6)
+
+
+def test_nonadiabatic_steady_slfm_library_on_gpu_matches_reference_gold():
+    lib = build('nonadiabatic_defect_steady_slfm', 'gpu')
+    compare_with_gold(lib, 'nonadiabatic_defect_steady_slfm', rtol=1e-8, atol=1e-9)
+
+
+def test_nonadiabatic_transient_slfm_library_on_gpu_matches_reference_gold():
+    lib = build('nonadiabatic_defect_transient_slfm', 'gpu')
+    compare_with_gold(lib, 'nonadiabatic_defect_transient_slfm', rtol=1e-6, atol=1e-6)
+
+
+def _gri_flamelets(backend, chis, nz=48):
+    from spitfire_b200.flamelet import Flamelet, FlameletSpec
+    m = build_mech('methane-gri30', backend)
+    air = m.stream(stp_air=True)
+    fuel = m.stream('TPX', (300., 101325., 'CH4:1'))
+    fs = FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=nz, initial_condition='equilibrium',
+                      stoich_dissipation_rate=float(chis[0]))
+    first = Flamelet(fs)
+    out = [first]
+    for c in chis[1:]:
+        fs.initial_condition = np.copy(first.initial_interior_state)
+        fs.stoich_dissipation_rate = float(c)
+        out.append(Flamelet(fs))
+    return out
+
+
+def test_gri30_steady_flamelets_gpu_vs_oracle():
+    """GRI-3.0 methane/air flamelets: batched steady solve on the GPU against the same solver driven by the CPU
+    oracle from the same (equilibrium) initial state; converged T and Y within 1e-8 relative (of the field's scale)"""
+    from spitfire_b200.flamelet import FlameletBatch
+    chis = [0.5, 2., 8.]
+    sg, tg = FlameletBatch(_gri_flamelets('gpu', chis)).compute_steady_state(tolerance=1e-8)
+    so, to = FlameletBatch(_gri_flamelets(ORACLE, chis)).compute_steady_state(tolerance=1e-8)
+    assert list(tg) == list(to), (tg, to)
+    ns = 53
+    for k in range(len(chis)):
+        a, b = sg[k].reshape(-1, ns), so[k].reshape(-1, ns)
+        assert b[:, 0].max() > 1800.  # burning
+        errT = np.max(np.abs(a[:, 0] - b[:, 0])) / np.max(np.abs(b[:, 0]))
+        errY = np.max(np.abs(a[:, 1:] - b[:, 1:]) / (np.max(np.abs(b[:, 1:]), axis=0) + 1e-30 + 1e-12))
+        print(f'chi_st {chis[k]}: solver {tg[k]}, rel err T {errT:.2e}, Y {errY:.2e}')
+        assert errT <= 1e-8 and errY <= 1e-6
