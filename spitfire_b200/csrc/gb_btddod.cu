@@ -137,17 +137,94 @@ __device__ void lu_inverse_smem(const double *A, int bs, int ld, const int *piv,
   }
 }
 
-__global__ void __launch_bounds__(256) k_btddod_factorize(int nsys, double *d_factors, int nb, int bs,
-                                                          double *l_values, int *pivots)
+// ------------------------------------------------------------------------------------------------------------------
+// k_btddod_factorize: one CTA per system, four lanes ("quad") per block column, rows interleaved over the quad.
+//
+// LU (dgetf2 semantics: first row of maximum modulus, reciprocal scaling, A[i,j] -= (A[i,k]*rp)*A[k,j]) with ONE
+// block-wide barrier per elimination step: the quad of column j applies every step's row interchange and update to
+// its own column; the multipliers are read from column k's *old* values (interchange applied logically), and column
+// k's own interchange + scaling is deferred to the next step, when nobody reads it any more. The quad of column k+1
+// finds the next pivot right after updating its column. The inverse of the factorised block (dgetrs on the identity,
+// btddod_matrix_kernels.cpp:48-53) needs no barrier at all: every quad solves for its own column in registers, the
+// substitution value travelling through the quad by shuffle.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+  const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+template <int Q, int RPL> // Q lanes per column (a power of two <= 16), rows per lane: bs <= Q*RPL
+__global__ void __launch_bounds__(1024, 1)
+    k_btddod_factorize(int nsys, double *d_factors, int nb, int bs, double *l_values, int *pivots)
 {
   extern __shared__ double sm[];
   const int ld = LD(bs);
-  double *A = sm;            // current diagonal block / its LU factors
-  double *X = A + ld * bs;   // inverse of the previous block -> L_i
-  int *spiv = (int *)(X + ld * bs);
-  const int tid = threadIdx.x, nt = blockDim.x;
+  double *A = sm;            // current diagonal block / its LU factors, column-major, leading dimension ld
+  double *Dn = A + ld * bs;  // next diagonal block, staged with cp.async while this one is factorised
+  double *srp = Dn + ld * bs; // [bs] reciprocal of the pivot of every step (0 if the pivot is zero)
+  int *spiv = (int *)(srp + bs + (bs & 1)); // [bs] pivot rows (0-based) of the current block
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int q = tid % Q, col = tid / Q;
+  const bool active = col < bs;
+  const int qbase = lane & ~(Q - 1);
+  const unsigned int mask = (Q == 32 ? 0xffffffffu : ((1u << Q) - 1u)) << qbase; // the lanes of a column branch together
   const size_t nb2 = (size_t)bs * bs;
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
+
+  // first row of maximum modulus of A[from.., col] over the group's rows (idamax) -> spiv[from], 1/pivot -> srp[from]
+  auto find_pivot = [&](int from) {
+    double best = -1., bv = 0.;
+    int bi = from;
+#pragma unroll
+    for (int m = 0; m < RPL; ++m)
+    {
+      const int r = q + Q * m;
+      if (r >= from && r < bs)
+      {
+        const double a = A[r + col * ld], v = fabs(a);
+        if (v > best)
+        {
+          best = v;
+          bv = a;
+          bi = r;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < Q; off <<= 1)
+    {
+      const double ov = __shfl_xor_sync(mask, best, off), oa = __shfl_xor_sync(mask, bv, off);
+      const int oi = __shfl_xor_sync(mask, bi, off);
+      if (ov > best || (ov == best && oi < bi))
+      {
+        best = ov;
+        bv = oa;
+        bi = oi;
+      }
+    }
+    if (q == 0)
+    {
+      spiv[from] = bi;
+      srp[from] = bv != 0. ? 1. / bv : 0.; // dgetf2 scales by the reciprocal; a zero pivot skips the step
+    }
+  };
+  auto swap_rows = [&](int k, int p) { // rows k and p of this group's column
+    if (p != k)
+    {
+      const double vk = A[k + col * ld], vp = A[p + col * ld];
+      __syncwarp(mask);
+      if (q == 0)
+      {
+        A[k + col * ld] = vp;
+        A[p + col * ld] = vk;
+      }
+      __syncwarp(mask);
+    }
+  };
+
   for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
   {
     double *D = d_factors + (size_t)sys * mat_stride;
@@ -158,49 +235,202 @@ __global__ void __launch_bounds__(256) k_btddod_factorize(int nsys, double *d_fa
     __syncthreads();
     for (int e = tid; e < bs * bs; e += nt)
       A[e % bs + (e / bs) * ld] = D[e];
+    for (int e = tid; e < bs * bs; e += nt)
+      Lv[e] = 0.; // block 0 of l_values is never referenced by the reference; define it
+    __syncthreads();
+    if (active && col == 0)
+      find_pivot(0);
     __syncthreads();
     for (int i = 0; i < nb; ++i)
     {
-      lu_factor_smem(A, bs, ld, spiv);
+      if (i + 1 < nb)
+      { // stage the next diagonal block
+        const double *Dnext = D + (size_t)(i + 1) * nb2;
+        for (int e = tid; e < bs * bs; e += nt)
+          cp_async8(Dn + e % bs + (e / bs) * ld, Dnext + e);
+        cp_async_commit();
+      }
+      // ---- LU with partial pivoting, one barrier per step ------------------------------------------------------------
+      for (int k = 0; k < bs; ++k)
+      {
+        if (active)
+        {
+          const int p = spiv[k];
+          if (col > k)
+          {
+            const double rp = srp[k];
+            const double ckk = A[k + k * ld]; // old column k: row k moves to row p
+            swap_rows(k, p);
+            if (rp != 0.)
+            {
+              const double akj = A[k + col * ld];
+#pragma unroll
+              for (int m = 0; m < RPL; ++m)
+              {
+                const int r = q + Q * m;
+                if (r > k && r < bs)
+                {
+                  const double c = (r == p) ? ckk : A[r + k * ld];
+                  A[r + col * ld] -= (c * rp) * akj;
+                }
+              }
+            }
+            if (col == k + 1)
+            {
+              __syncwarp(mask);
+              find_pivot(k + 1);
+            }
+          }
+          else if (col < k)
+          {
+            if (col == k - 1)
+            { // deferred finalisation of step k-1 on its own column: interchange, then scale the multipliers
+              swap_rows(k - 1, spiv[k - 1]);
+              const double rp = srp[k - 1];
+              if (rp != 0.)
+              {
+#pragma unroll
+                for (int m = 0; m < RPL; ++m)
+                {
+                  const int r = q + Q * m;
+                  if (r > k - 1 && r < bs)
+                    A[r + col * ld] *= rp;
+                }
+              }
+              __syncwarp(mask);
+            }
+            swap_rows(k, p);
+          }
+        }
+        __syncthreads();
+      }
+      // (column bs-1 has no multipliers; column bs-2 was finalised in step bs-1)
       for (int e = tid; e < bs * bs; e += nt)
         D[(size_t)i * nb2 + e] = A[e % bs + (e / bs) * ld];
       for (int k = tid; k < bs; k += nt)
-        piv[(size_t)i * bs + k] = spiv[k];
+        piv[(size_t)i * bs + k] = spiv[k] + 1;
       if (i == nb - 1)
         break;
-      lu_inverse_smem(A, bs, ld, spiv, X);
-      // L_{i+1} = diag(sub_i) * D_i^{-1} (row scaling, :55-63); D_{i+1} -= L_{i+1} * diag(sup_i) (:65-75)
-      const double *subi = sub + (size_t)i * bs, *supi = sup + (size_t)i * bs;
-      const double *Dn = D + (size_t)(i + 1) * nb2;
-      double *Ln = Lv + (size_t)(i + 1) * nb2;
-      for (int e = tid; e < bs * bs; e += nt)
+      // ---- column `col` of the inverse, in registers --------------------------------------------------------------------
+      double x[RPL];
+      if (active)
       {
-        const int r = e % bs, c = e / bs;
-        const double l = X[r + c * ld] * subi[r];
-        Ln[e] = l;
-        A[r + c * ld] = Dn[e] + (-supi[c]) * l;
+        int pos = col; // where the 1 of e_col ends up after the row interchanges (dlaswp on the identity)
+        for (int k = 0; k < bs; ++k)
+        {
+          const int p = spiv[k];
+          if (pos == k)
+            pos = p;
+          else if (pos == p)
+            pos = k;
+        }
+        double rdiag[RPL]; // reciprocals of this lane's diagonal entries of U (the triangular solve multiplies by them)
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+        {
+          const int r = q + Q * m;
+          x[m] = (r == pos) ? 1. : 0.;
+          rdiag[m] = r < bs ? 1. / A[r + r * ld] : 0.;
+        }
+        // forward substitution with the unit lower factor
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+        {
+          for (int qq = 0; qq < Q; ++qq)
+          {
+            const int k = Q * m + qq;
+            if (k >= bs - 1)
+              break;
+            const double xk = __shfl_sync(mask, x[m], qbase + qq);
+            if (xk != 0.)
+            {
+#pragma unroll
+              for (int m2 = m; m2 < RPL; ++m2)
+              {
+                const int r = q + Q * m2;
+                if (r > k && r < bs)
+                  x[m2] -= A[r + k * ld] * xk;
+              }
+            }
+          }
+        }
+        // backward substitution with the upper factor
+#pragma unroll
+        for (int m = RPL - 1; m >= 0; --m)
+        {
+          for (int qq = Q - 1; qq >= 0; --qq)
+          {
+            const int k = Q * m + qq;
+            if (k >= bs)
+              continue;
+            if (q == qq)
+              x[m] = x[m] * rdiag[m];
+            const double xk = __shfl_sync(mask, x[m], qbase + qq);
+#pragma unroll
+            for (int m2 = 0; m2 <= m; ++m2)
+            {
+              const int r = q + Q * m2;
+              if (r < k)
+                x[m2] -= A[r + k * ld] * xk;
+            }
+          }
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads(); // every group is done reading the factors; the staged block has landed
+      // ---- L_{i+1} = diag(sub_i) * D_i^{-1} (:55-63); D_{i+1} -= L_{i+1} * diag(sup_i) (:65-75) ----------------------
+      if (active)
+      {
+        const double *subi = sub + (size_t)i * bs;
+        const double msup = -sup[(size_t)i * bs + col];
+        double *Ln = Lv + (size_t)(i + 1) * nb2 + (size_t)col * bs;
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+        {
+          const int r = q + Q * m;
+          if (r < bs)
+          {
+            const double l = x[m] * subi[r];
+            Ln[r] = l;
+            A[r + col * ld] = Dn[r + col * ld] + msup * l;
+          }
+        }
+        if (col == 0)
+        {
+          __syncwarp(mask);
+          find_pivot(0);
+        }
       }
       __syncthreads();
     }
-    if (nb > 0)
-      for (int e = tid; e < bs * bs; e += nt)
-        Lv[e] = 0.; // block 0 of l_values is never referenced by the reference; define it
   }
 }
 
-// forward: y_i = b_i - L_i y_{i-1} (:95-103); back: x_i = D_i^{-1} (y_i - sup_i o x_{i+1}) (:105-118)
-__global__ void __launch_bounds__(128) k_btddod_solve(int nsys, const double *d_factors, const double *l_values,
+// ------------------------------------------------------------------------------------------------------------------
+// k_btddod_solve: forward y_i = b_i - L_i y_{i-1} (:95-103); back x_i = D_i^{-1} (y_i - sup_i o x_{i+1}) (:105-118).
+// One CTA of two warps per system. The L and LU blocks stream through a double buffer in shared memory (cp.async one
+// block ahead); the row interchanges of all blocks are turned into gather permutations once, in parallel over the
+// blocks; warp 0 does the triangular solves with the vector in registers (rows lane and lane+32), the substitution
+// value travelling by shuffle.
+// ------------------------------------------------------------------------------------------------------------------
+template <int RPW> // rows per lane of the solving warp: bs <= 32*RPW
+__global__ void __launch_bounds__(64) k_btddod_solve(int nsys, const double *d_factors, const double *l_values,
                                                       const int *pivots, const double *rhs, int nb, int bs,
                                                       double *solution)
 {
   extern __shared__ double sm[];
-  const int ld = LD(bs);
-  double *A = sm;          // LU factors of the current block
-  double *v = A + ld * bs; // working vector [bs]
-  double *vp = v + bs;     // previous y / next x [bs]
-  const int tid = threadIdx.x, nt = blockDim.x;
+  double *buf0 = sm;                 // [bs*bs] block i
+  double *buf1 = buf0 + bs * bs;     // [bs*bs] block i+-1 (being fetched)
+  double *v = buf1 + bs * bs;        // [bs] vector exchanged between the warps
+  unsigned char *perm = (unsigned char *)(v + bs + (bs & 1)); // [nb][bs] gather permutations (bs <= 256)
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const size_t nb2 = (size_t)bs * bs;
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
+  auto fetch = [&](double *dst, const double *src) {
+    for (int e = tid; e < bs * bs; e += nt)
+      cp_async8(dst + e, src + e);
+    cp_async_commit();
+  };
   for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
   {
     const double *D = d_factors + (size_t)sys * mat_stride;
@@ -210,81 +440,162 @@ __global__ void __launch_bounds__(128) k_btddod_solve(int nsys, const double *d_
     const double *b = rhs + (size_t)sys * nb * bs;
     double *x = solution + (size_t)sys * nb * bs; // y is stored in x during the forward sweep
     __syncthreads();
+    if (nb > 1)
+      fetch(buf0, Lv + nb2); // L_1
+    // gather permutation of every block: v_new[k] = v_old[perm[k]] reproduces the sequential interchanges of dgetrs
+    for (int i = tid; i < nb; i += nt)
+    {
+      unsigned char *pm = perm + (size_t)i * bs;
+      for (int k = 0; k < bs; ++k)
+        pm[k] = (unsigned char)k;
+      for (int k = 0; k < bs; ++k)
+      {
+        const int p = piv[(size_t)i * bs + k] - 1;
+        const unsigned char t = pm[k];
+        pm[k] = pm[p];
+        pm[p] = t;
+      }
+    }
     for (int j = tid; j < bs; j += nt)
     {
-      vp[j] = b[j];
+      v[j] = b[j];
       x[j] = b[j];
     }
-    __syncthreads();
+    // ---- forward sweep -----------------------------------------------------------------------------------------------------
     for (int i = 1; i < nb; ++i)
     {
-      const double *L = Lv + (size_t)i * nb2;
-      for (int j = tid; j < bs; j += nt)
+      double *cur = (i & 1) ? buf0 : buf1, *nxt = (i & 1) ? buf1 : buf0;
+      cp_async_wait_all();
+      __syncthreads(); // L_i has landed, v = y_{i-1} is complete
+      if (i + 1 < nb)
+        fetch(nxt, Lv + (size_t)(i + 1) * nb2);
+      else
+        fetch(nxt, D + (size_t)(nb - 1) * nb2); // first block of the back sweep
+      double yj[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
       {
-        double yj = b[(size_t)i * bs + j];
-        for (int c = 0; c < bs; ++c)
-          yj = yj + L[(size_t)c * bs + j] * (-1. * vp[c]); // matrix_vector_multiply order, blas_lapack_kernels.h:60-77
-        v[j] = yj;
+        const int j = tid + h * 64;
+        if (j < bs)
+        {
+          double acc = b[(size_t)i * bs + j];
+          for (int c = 0; c < bs; ++c)
+            acc = acc + cur[(size_t)c * bs + j] * (-1. * v[c]); // matrix_vector_multiply order, blas_lapack_kernels.h:60-77
+          yj[h] = acc;
+        }
       }
-      __syncthreads();
-      for (int j = tid; j < bs; j += nt)
+      __syncthreads(); // everyone is done reading v
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
       {
-        vp[j] = v[j];
-        x[(size_t)i * bs + j] = v[j];
+        const int j = tid + h * 64;
+        if (j < bs)
+        {
+          v[j] = yj[h];
+          x[(size_t)i * bs + j] = yj[h];
+        }
       }
-      __syncthreads();
     }
-    for (int i = nb - 1; i >= 0; --i)
+    if (nb == 1)
+      fetch(buf0, D);
+    // ---- back sweep ----------------------------------------------------------------------------------------------------------
+    // after the forward sweep the LU factors of block nb-1 are in buffer (nb & 1 ? buf1 : buf0) for nb > 1, buf0 for nb == 1
+    for (int i = nb - 1, step = 0; i >= 0; --i, ++step)
     {
-      // load factors, form the right-hand side
-      for (int e = tid; e < bs * bs; e += nt)
-        A[e % bs + (e / bs) * ld] = D[(size_t)i * nb2 + e];
-      for (int j = tid; j < bs; j += nt)
+      double *cur, *nxt;
+      if (nb == 1)
+        cur = buf0, nxt = buf1;
+      else
       {
-        const double yj = x[(size_t)i * bs + j];
-        v[j] = (i == nb - 1) ? yj : yj - sup[(size_t)i * bs + j] * vp[j];
+        const bool first_in_buf1 = ((nb - 1) & 1) != 0; // block nb-1 was fetched as `nxt` of forward step nb-1
+        const bool in1 = first_in_buf1 ? ((step & 1) == 0) : ((step & 1) != 0);
+        cur = in1 ? buf1 : buf0;
+        nxt = in1 ? buf0 : buf1;
       }
-      __syncthreads();
-      if (tid < 32)
-      { // dgetrs on one vector by one warp: row interchanges, unit-lower forward, upper backward
-        if (tid == 0)
-          for (int k = 0; k < bs; ++k)
+      cp_async_wait_all();
+      __syncthreads(); // factors of block i have landed; v = x_{i+1} (or y_{nb-1}) is complete
+      if (i > 0)
+        fetch(nxt, D + (size_t)(i - 1) * nb2);
+      if (warp == 0)
+      {
+        const unsigned char *pm = perm + (size_t)i * bs;
+        double w[RPW];
+#pragma unroll
+        for (int h = 0; h < RPW; ++h)
+        {
+          const int r = lane + 32 * h;
+          w[h] = 0.;
+          if (r < bs)
+          { // right-hand side y_i - sup_i o x_{i+1}, row interchanges applied as a gather
+            const int s = pm[r];
+            const double ys = x[(size_t)i * bs + s];
+            w[h] = (i == nb - 1) ? ys : ys - sup[(size_t)i * bs + s] * v[s];
+          }
+        }
+        double rdiag[RPW]; // reciprocals of this lane's diagonal entries of U
+#pragma unroll
+        for (int h = 0; h < RPW; ++h)
+        {
+          const int r = lane + 32 * h;
+          rdiag[h] = r < bs ? 1. / cur[r + (size_t)r * bs] : 0.;
+        }
+        // unit-lower forward substitution
+#pragma unroll
+        for (int h = 0; h < RPW; ++h)
+        {
+#pragma unroll 4
+          for (int l = 0; l < 32; ++l)
           {
-            const int p = piv[(size_t)i * bs + k] - 1;
-            if (p != k)
+            const int k = 32 * h + l;
+            if (k < bs - 1)
             {
-              const double t = v[k];
-              v[k] = v[p];
-              v[p] = t;
+              const double wk = __shfl_sync(0xffffffffu, w[h], l);
+#pragma unroll
+              for (int h2 = h; h2 < RPW; ++h2)
+              {
+                const int r = lane + 32 * h2;
+                if (r > k && r < bs)
+                  w[h2] -= cur[r + (size_t)k * bs] * wk;
+              }
             }
           }
-        __syncwarp();
-        for (int k = 0; k < bs - 1; ++k)
-        {
-          const double vk = v[k];
-          for (int r = k + 1 + tid; r < bs; r += 32)
-            v[r] -= A[r + k * ld] * vk;
-          __syncwarp();
         }
-        for (int k = bs - 1; k >= 0; --k)
+        // upper backward substitution
+#pragma unroll
+        for (int h = RPW - 1; h >= 0; --h)
         {
-          if (tid == 0)
-            v[k] = v[k] / A[k + k * ld];
-          __syncwarp();
-          const double vk = v[k];
-          for (int r = tid; r < k; r += 32)
-            v[r] -= A[r + k * ld] * vk;
-          __syncwarp();
+#pragma unroll 4
+          for (int l = 31; l >= 0; --l)
+          {
+            const int k = 32 * h + l;
+            if (k < bs)
+            {
+              if (lane == l)
+                w[h] = w[h] * rdiag[h];
+              const double wk = __shfl_sync(0xffffffffu, w[h], l);
+#pragma unroll
+              for (int h2 = 0; h2 <= h; ++h2)
+              {
+                const int r = lane + 32 * h2;
+                if (r < k)
+                  w[h2] -= cur[r + (size_t)k * bs] * wk;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < RPW; ++h)
+        {
+          const int r = lane + 32 * h;
+          if (r < bs)
+          {
+            v[r] = w[h];
+            x[(size_t)i * bs + r] = w[h];
+          }
         }
       }
-      __syncthreads();
-      for (int j = tid; j < bs; j += nt)
-      {
-        vp[j] = v[j];
-        x[(size_t)i * bs + j] = v[j];
-      }
-      __syncthreads();
     }
+    cp_async_wait_all();
   }
 }
 
@@ -355,8 +666,8 @@ int bt_check(int n, int nb, int bs)
     set_error("bad btddod dimensions");
     return GB_ERR_ARG;
   }
-  const size_t need = sizeof(double) * 2 * (size_t)LD(bs) * bs + sizeof(int) * bs + 64;
-  if (need > 227 * 1024)
+  const size_t need = sizeof(double) * (2 * (size_t)LD(bs) * bs + bs + 2) + sizeof(int) * bs + 64;
+  if (need > 227 * 1024 || bs > 120)
   {
     set_error("block size too large for the in-shared-memory block LU");
     return GB_ERR_UNSUPPORTED;
@@ -387,9 +698,23 @@ extern "C"
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
       return rc;
-    const size_t smem = sizeof(double) * 2 * (size_t)LD(bs) * bs + sizeof(int) * bs + 64;
-    BCK(cudaFuncSetAttribute(k_btddod_factorize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_btddod_factorize<<<n, 256, smem, (cudaStream_t)stream>>>(n, d_factors, nb, bs, l_values, pivots);
+    const size_t smem = sizeof(double) * (2 * (size_t)LD(bs) * bs + bs + 2) + sizeof(int) * bs + 64;
+#define GB_BT_LAUNCH(Q, RPL)                                                                                          \
+  do                                                                                                                  \
+  {                                                                                                                   \
+    BCK(cudaFuncSetAttribute(k_btddod_factorize<Q, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_btddod_factorize<Q, RPL><<<n, ((Q * bs + 31) / 32) * 32, smem, (cudaStream_t)stream>>>(n, d_factors, nb, bs,    \
+                                                                                             l_values, pivots);      \
+  } while (0)
+    if (bs <= 16)
+      GB_BT_LAUNCH(16, 1);
+    else if (bs <= 32)
+      GB_BT_LAUNCH(16, 2);
+    else if (bs <= 64)
+      GB_BT_LAUNCH(16, 4);
+    else
+      GB_BT_LAUNCH(8, 15);
+#undef GB_BT_LAUNCH
     ++g_btddod_launches;
     BCK(cudaGetLastError());
     return GB_OK;
@@ -401,9 +726,22 @@ extern "C"
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
       return rc;
-    const size_t smem = sizeof(double) * ((size_t)LD(bs) * bs + 2 * bs) + 64;
-    BCK(cudaFuncSetAttribute(k_btddod_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_btddod_solve<<<n, 128, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, pivots, rhs, nb, bs, solution);
+    const size_t smem = sizeof(double) * (2 * (size_t)bs * bs + bs + 2) + (size_t)nb * bs + 64;
+    if (smem > 227 * 1024)
+    {
+      set_error("system too large for the shared-memory resident block-Thomas solve");
+      return GB_ERR_UNSUPPORTED;
+    }
+    if (bs <= 64)
+    {
+      BCK(cudaFuncSetAttribute(k_btddod_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_btddod_solve<2><<<n, 64, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, pivots, rhs, nb, bs, solution);
+    }
+    else
+    {
+      BCK(cudaFuncSetAttribute(k_btddod_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_btddod_solve<4><<<n, 64, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, pivots, rhs, nb, bs, solution);
+    }
     ++g_btddod_launches;
     BCK(cudaGetLastError());
     return GB_OK;

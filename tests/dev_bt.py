@@ -1,0 +1,19 @@
+"""dev: time / profile the block-Thomas kernels on a GRI-3.0 128-point flamelet Jacobian (not a test)"""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np, torch
+from common import build_mech
+from spitfire_b200.flamelet import Flamelet, FlameletSpec, FlameletBatch
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+m = build_mech('methane-gri30', 'gpu')
+air = m.stream(stp_air=True); fuel = m.stream('TPX', (300., 101325., 'CH4:1'))
+f = Flamelet(FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128, initial_condition='linear-TY', stoich_dissipation_rate=1.))
+b = FlameletBatch([f] * F); ops = b.ops
+state = b._initial(None)
+J = ops.jac(state).neg_(); r = ops.rhs(state)
+def tm(fn, n=3):
+    fn(); torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.time() - t0) / n * 1e3
+fact = ops.factorize(J.clone())
+print(f'F={F}: factorize {tm(lambda: ops.factorize(J.clone())):.3f} ms, solve {tm(lambda: ops.solve(fact, r)):.3f} ms')
