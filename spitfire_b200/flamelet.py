@@ -14,8 +14,8 @@ Deviations from the reference, all on cold or fallback paths:
   * initial conditions 'equilibrium' / 'unreacted' / 'Burke-Schumann' use spitfire_b200.streams / equilibrium instead of
     Cantera (flamelet.py:525-586);
   * the explosive eigenvalues of the pseudo-transient solver (LAPACK dgeev per grid point inside Griffon in the
-    reference, flamelet_kernels.cpp:1329-1341) are taken with torch.linalg.eigvals from the Jacobian blocks where they
-    live; they only set the pseudo-time step, not the converged answer;
+    reference, flamelet_kernels.cpp:1329-1341) are taken with LAPACK on the host from the Jacobian blocks the device
+    produced (a device eigen-solver is the first "next" item of SURVEY 8(f)); they only set the pseudo-time step;
   * the SuperLU linear solver option is not provided (block Thomas only).
 """
 import numpy as np
@@ -240,15 +240,16 @@ class _BatchOps(object):
 
     def explosive_bound(self, J, diffterm):
         """max(Re(lambda)) of every grid point's ns x ns block minus `diffterm`, clipped at zero and repeated for the
-        point's dofs (flamelet_kernels.cpp:1329-1341). The eigenvalues come from torch.linalg.eigvals on the device
-        the blocks live on; if that routine is unavailable the Gershgorin bound of the block (rows or columns,
-        whichever is tighter) is used, which is safe but gives smaller pseudo-time steps.
+        point's dofs (flamelet_kernels.cpp:1329-1341). If the eigenvalue routine is unavailable the Gershgorin bound of
+        the block (rows or columns, whichever is tighter) is used, which is safe but gives smaller pseudo-time steps.
         J: [n, nelem] positive Jacobian; diffterm: [n]"""
         torch = self.torch
         n = J.shape[0]
         B = J[:, :self.nzi * self.ns * self.ns].reshape(n, self.nzi, self.ns, self.ns)  # [.., col, row]
         try:
-            bound = torch.linalg.eigvals(B).real.amax(dim=2)  # eigenvalues of B^T = eigenvalues of B
+            # LAPACK dgeev on the host, as the reference does inside Griffon; 2.8 MB per GRI-128 flamelet cross PCIe.
+            # (torch's CUDA eigvals goes through MAGMA and is ~9x slower for these 53 x 53 blocks: 355 vs 41 ms.)
+            bound = torch.linalg.eigvals(B.cpu()).real.amax(dim=2).to(B.device)  # eig(B^T) = eig(B)
         except RuntimeError:
             diag = torch.diagonal(B, dim1=2, dim2=3)
             absB = B.abs()

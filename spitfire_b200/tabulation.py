@@ -104,8 +104,10 @@ def build_adiabatic_slfm_library(flamelet_specs, diss_rate_values=np.logspace(-3
     include_extinguished.
 
     wave : int
-        (extension) how many consecutive dissipation rates are solved together on the device, all started from the
-        last converged solution. 1 reproduces the reference's chain exactly."""
+        (extension) how many consecutive dissipation rates are attempted together on the device with Newton's method,
+        all started from the last converged solution; the converged prefix is kept and the chain continues from its
+        last member (a member Newton cannot reach is solved on its own with the full solver chain, as in the
+        reference). 1 reproduces the reference's chain exactly."""
     if isinstance(flamelet_specs, dict):
         flamelet_specs = FlameletSpec(**flamelet_specs)
     m, fuel, oxy = flamelet_specs.mech_spec, flamelet_specs.fuel_stream, flamelet_specs.oxy_stream
@@ -130,16 +132,23 @@ def build_adiabatic_slfm_library(flamelet_specs, diss_rate_values=np.logspace(-3
     idx, stop = 0, False
     wave = max(1, int(wave))
     while idx < nchi and not stop:
-        members = []
+        members, libs = [], []
         for chival in diss_rate_values[idx:idx + wave]:
             set_chi(chival)
             members.append(Flamelet(flamelet_specs))
         cput0 = perf_counter()
-        if len(members) == 1:
+        if len(members) > 1:
+            # speculative wave: Newton only, all members from the last converged state; keep the converged prefix
+            states, _, conv = FlameletBatch(members).steady_solve_newton(tolerance=tolerance, max_iterations=38,
+                                                                         verbose=solver_verbose)
+            n_ok = 0
+            while n_ok < len(members) and conv[n_ok]:
+                members[n_ok]._current_state = np.copy(states[n_ok])
+                n_ok += 1
+            members = members[:max(n_ok, 1)]
+            libs = [fl.make_library_from_interior_state(fl._current_state) for fl in members[:n_ok]]
+        if len(members) == 1 and (wave == 1 or not libs):
             libs = [members[0].compute_steady_state(tolerance=tolerance, verbose=solver_verbose, use_psitc=True)]
-        else:
-            states, _ = FlameletBatch(members).compute_steady_state(tolerance=tolerance, verbose=solver_verbose)
-            libs = [fl.make_library_from_interior_state(s) for fl, s in zip(members, states)]
         dcput = perf_counter() - cput0
         for k, (flamelet, x_library) in enumerate(zip(members, libs)):
             if say:

@@ -65,3 +65,10 @@ def test_gri30_steady_flamelets_gpu_vs_oracle():
         errY = np.max(np.abs(a[:, 1:] - b[:, 1:]) / (np.max(np.abs(b[:, 1:]), axis=0) + 1e-30 + 1e-12))
         print(f'chi_st {chis[k]}: solver {tg[k]}, rel err T {errT:.2e}, Y {errY:.2e}')
         assert errT <= 1e-8 and errY <= 1e-6
+
+
+def test_homogeneous_reactor_on_gpu_matches_reference_gold():
+    """BASELINE config 1: H2/air isobaric adiabatic ignition, single-state calls through the C-ABI host entry points"""
+    from reactor_cases import compare_with_gold, run
+    m, lib = run('gpu', 'adiabatic')
+    print('steps', lib.time_values.size, 'max rel err T', compare_with_gold(m, lib, 'adiabatic'))

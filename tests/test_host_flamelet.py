@@ -79,3 +79,11 @@ def test_library_slice_round_trip():
     f2 = Flamelet(FlameletSpec(library_slice=lib, stoich_dissipation_rate=1.))
     assert np.allclose(f2.initial_interior_state, f.initial_interior_state, rtol=0, atol=1e-14)
     assert np.array_equal(f2.mixfrac_grid, f.mixfrac_grid)
+
+
+@pytest.mark.parametrize('heat_transfer', ['adiabatic', 'isothermal'])
+def test_homogeneous_reactor_matches_reference_gold(heat_transfer):
+    """BASELINE config 1 (H2/air isobaric ignition) through HomogeneousReactor + ESDIRK64 with the oracle kernels"""
+    from reactor_cases import compare_with_gold, run
+    m, lib = run(ORACLE, heat_transfer)
+    print(heat_transfer, 'steps', lib.time_values.size, 'max rel err T', compare_with_gold(m, lib, heat_transfer))
