@@ -238,14 +238,18 @@ class _BatchOps(object):
                                          prefactor, self.rsopt, self.stopt, *self.flags, null, on[k])
         return out
 
-    def explosive_bound(self, J, diffterm):
+    def explosive_bound(self, J, diffterm, idx=None):
         """max(Re(lambda)) of every grid point's ns x ns block minus `diffterm`, clipped at zero and repeated for the
         point's dofs (flamelet_kernels.cpp:1329-1341). If the eigenvalue routine is unavailable the Gershgorin bound of
         the block (rows or columns, whichever is tighter) is used, which is safe but gives smaller pseudo-time steps.
         J: [n, nelem] positive Jacobian; diffterm: [n]"""
         torch = self.torch
         n = J.shape[0]
-        B = J[:, :self.nzi * self.ns * self.ns].reshape(n, self.nzi, self.ns, self.ns)  # [.., col, row]
+        B = J[:, :self.nzi * self.ns * self.ns].reshape(n, self.nzi, self.ns, self.ns).clone()  # [.., col, row]
+        # the reference takes the eigenvalues of the chemical block before the diffusion diagonal (cmajor) is added
+        idx = self._all() if idx is None else idx
+        cm = self.cmaj.index_select(0, idx).reshape(n, self.nzi, self.ns)
+        torch.diagonal(B, dim1=2, dim2=3).sub_(cm)
         try:
             # LAPACK dgeev on the host, as the reference does inside Griffon; 2.8 MB per GRI-128 flamelet cross PCIe.
             # (torch's CUDA eigvals goes through MAGMA and is ~9x slower for these 53 x 53 blocks: 355 vs 41 ms.)
@@ -469,7 +473,7 @@ class FlameletBatch(object):
             ij = torch.nonzero(active & need_jac).flatten()
             if ij.numel():
                 Jp = ops.jac(state.index_select(0, ij), ij)
-                expeig = ops.explosive_bound(Jp, diffterm.index_select(0, ij))
+                expeig = ops.explosive_bound(Jp, diffterm.index_select(0, ij), ij)
                 dsj = torch.minimum(torch.minimum(ds_safety / (expeig + 1.e-16), ds_ramp * ds.index_select(0, ij)),
                                     torch.full_like(expeig, ds_max))
                 first = (iters.index_select(0, ij) == 1) | bool(global_ds)
