@@ -555,6 +555,37 @@ class FlameletBatch(object):
         return out, tags
 
 
+    # ------------------------------------------------------------------------------------------------------------------
+    def integrate_for_heat_loss(self, temperature_tolerance=0.05, steady_tolerance=1.e-4, first_time_step=1.e-6,
+                                max_time_step=1.e-3, minimum_time_step_count=40, transient_tolerance=1.e-10,
+                                maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12, **unused):
+        """`Flamelet.integrate_for_heat_loss` (flamelet.py:1263-1286) for every member at once: ESDIRK64 with each
+        member's own adaptive step until its temperature profile is nearly linear or it is steady
+        (spitfire_b200.time.batched). Returns (libraries over (time, mixture fraction), failed flags)."""
+        from spitfire_b200.time.batched import integrate_batch
+        ops = self.ops
+        T_bc_max = max(self.flamelets[0]._oxy_stream.T, self.flamelets[0]._fuel_stream.T)
+
+        def stop(t, q, residual, nsteps):
+            return (q.amax(dim=1) < (1. + temperature_tolerance) * T_bc_max) | (residual < steady_tolerance)
+
+        q0 = ops.torch.as_tensor(np.array([fl._current_state for fl in self.flamelets])).to(ops.device)
+        times, states, failed = integrate_batch(ops, q0, stop, first_time_step=first_time_step,
+                                                max_time_step=max_time_step,
+                                                minimum_time_step_count=minimum_time_step_count,
+                                                transient_tolerance=transient_tolerance,
+                                                maximum_steps_per_jacobian=maximum_steps_per_jacobian,
+                                                nonlinear_solve_tolerance=nonlinear_solve_tolerance)
+        libs = []
+        for fl, t, st in zip(self.flamelets, times, states):
+            fl._current_state, fl._current_time = np.copy(st[-1]), float(t[-1])
+            lib = Library(Dimension('time', t), Dimension('mixture_fraction', fl._z))
+            lib.extra_attributes['mech_spec'] = fl._mechanism
+            fl._fill_library(lib, st, lead=True)
+            libs.append(lib)
+        return libs, failed
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 class Flamelet(object):
     """Solve the nonpremixed flamelet equations (mirror of flamelet.py:269-1778 on the B200 Griffon path)"""

@@ -217,10 +217,7 @@ def _store_defect_profiles(managed_dict, chi_st, z, z_st, lib_get, props, h_prof
         managed_dict[(chi_st, gst)] = data
 
 
-def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
-                                                verbose, input_integration_args, solver_verbose):
-    """one rapid-extinction trajectory at chi_st: ESDIRK64 with strong scaled convective heat loss until the
-    temperature profile is nearly linear, sub-sampled in stoichiometric enthalpy (tabulation.py:339-405)"""
+def _transient_heat_loss_specs(flamelet_specs, table_dict, chi_st):
     fs = copy.copy(flamelet_specs)
     fs.initial_condition = table_dict[chi_st]['adiabatic_state']
     fs.stoich_dissipation_rate = chi_st
@@ -230,11 +227,34 @@ def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_s
     fs.use_linear_ref_temp_profile = True
     fs.convection_coefficient = fs.convection_coefficient if fs.convection_coefficient is not None else 1.e7
     fs.radiative_emissivity = 0.
+    return fs
+
+
+def _transient_integration_args(input_integration_args, solver_verbose):
     integration_args = {'first_time_step': 1.e-9, 'max_time_step': 1.e-1, 'write_log': solver_verbose, 'log_rate': 100,
                         'print_exception_on_failure': False}
     if input_integration_args is not None:
         integration_args.update(input_integration_args)
     integration_args.setdefault('transient_tolerance', 1.e-8)
+    return integration_args
+
+
+def _store_transient_library(managed_dict, chi_st, fnonad, transient_lib, h_stoich_spacing):
+    """sub-sample the trajectory in stoichiometric enthalpy and store the kept profiles (tabulation.py:375-400)"""
+    z = fnonad.mixfrac_grid
+    z_st = fnonad.mechanism.stoich_mixture_fraction(fnonad.fuel_stream, fnonad.oxy_stream)
+    h_tz = compute_specific_enthalpy(fnonad.mechanism, transient_lib)['enthalpy']
+    indices = _subsample_by_stoich_enthalpy(z, z_st, h_tz, h_stoich_spacing, include_last=True)
+    props = [q for q in transient_lib.props]
+    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_tz, indices)
+
+
+def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
+                                                verbose, input_integration_args, solver_verbose):
+    """one rapid-extinction trajectory at chi_st: ESDIRK64 with strong scaled convective heat loss until the
+    temperature profile is nearly linear, sub-sampled in stoichiometric enthalpy (tabulation.py:339-405)"""
+    fs = _transient_heat_loss_specs(flamelet_specs, table_dict, chi_st)
+    integration_args = _transient_integration_args(input_integration_args, solver_verbose)
     cput0 = perf_counter()
     transient_lib, fnonad = None, None
     while transient_lib is None and integration_args['transient_tolerance'] > 1.e-15:
@@ -248,14 +268,33 @@ def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_s
             integration_args['transient_tolerance'] *= 1.e-2
     if transient_lib is None:
         raise RuntimeError(f'heat-loss expansion at chi_st = {chi_st} failed at every tolerance')
-    z = fnonad.mixfrac_grid
-    z_st = fnonad.mechanism.stoich_mixture_fraction(fnonad.fuel_stream, fnonad.oxy_stream)
-    h_tz = compute_specific_enthalpy(fs.mech_spec, transient_lib)['enthalpy']
-    indices = _subsample_by_stoich_enthalpy(z, z_st, h_tz, h_stoich_spacing, include_last=True)
-    props = [q for q in transient_lib.props]
-    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_tz, indices)
+    _store_transient_library(managed_dict, chi_st, fnonad, transient_lib, h_stoich_spacing)
     if verbose:
         print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
+
+
+def _expand_enthalpy_defect_dimension_transient_batch(chi_list, managed_dict, flamelet_specs, table_dict,
+                                                      h_stoich_spacing, verbose, input_integration_args,
+                                                      solver_verbose):
+    """all of this rank's rapid-extinction trajectories advanced together on the device (FlameletBatch); every member
+    keeps its own adaptive step sequence, so its trajectory is the one the one-at-a-time path computes. A member whose
+    batched run fails is redone on its own with the reference's retry ladder."""
+    if not chi_list:
+        return
+    cput0 = perf_counter()
+    flamelets = [Flamelet(_transient_heat_loss_specs(flamelet_specs, table_dict, chi_st)) for chi_st in chi_list]
+    integration_args = _transient_integration_args(input_integration_args, solver_verbose)
+    libs, failed = FlameletBatch(flamelets).integrate_for_heat_loss(**integration_args)
+    for chi_st, fl, lib, bad in zip(chi_list, flamelets, libs, failed):
+        if bad:
+            _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict,
+                                                        h_stoich_spacing, verbose, input_integration_args,
+                                                        solver_verbose)
+        else:
+            _store_transient_library(managed_dict, chi_st, fl, lib, h_stoich_spacing)
+    if verbose:
+        print('{:} heat-loss trajectories (chi_st {:8.1e} .. {:8.1e} 1/s) advanced together in {:6.2f} s'.format(
+            len(chi_list), min(chi_list), max(chi_list), perf_counter() - cput0), flush=True)
 
 
 def _expand_enthalpy_defect_dimension_steady(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
@@ -317,7 +356,7 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
                                                          diss_rate_values=np.logspace(-3, 2, 16),
                                                          diss_rate_ref='stoichiometric', verbose=True,
                                                          solver_verbose=False, h_stoich_spacing=10.e3, num_procs=1,
-                                                         integration_args=None, wave=1):
+                                                         integration_args=None, wave=1, batch_expansions=True):
     """adiabatic chain on every rank (it is short and every rank needs all of it), then this rank's share of the
     independent heat-loss expansions, then one gather (tabulation.py:522-591)"""
     table_dict, z_values, x_values = build_adiabatic_slfm_library(flamelet_specs, diss_rate_values, diss_rate_ref,
@@ -330,8 +369,14 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
               flush=True)
     cput0 = perf_counter()
     local = dict()
-    for chi_st in parallel.my_share(list(table_dict.keys())):
-        expand(chi_st, local, flamelet_specs, table_dict, h_stoich_spacing, verbose, integration_args, solver_verbose)
+    mine = parallel.my_share(list(table_dict.keys()))
+    if heat_loss_expansion == 'transient' and batch_expansions and len(mine) > 1:
+        _expand_enthalpy_defect_dimension_transient_batch(mine, local, flamelet_specs, table_dict, h_stoich_spacing,
+                                                          verbose, integration_args, solver_verbose)
+    else:
+        for chi_st in mine:
+            expand(chi_st, local, flamelet_specs, table_dict, h_stoich_spacing, verbose, integration_args,
+                   solver_verbose)
     merged = parallel.gather_dicts(local)
     if verbose and parallel.rank() == 0:
         print('-' * 82)
