@@ -158,7 +158,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int Q, int RPL> // Q lanes per column (a power of two <= 16), rows per lane: bs <= Q*RPL
 __global__ void __launch_bounds__(1024, 1)
-    k_btddod_factorize(int nsys, double *d_factors, int nb, int bs, double *l_values, int *pivots)
+    k_btddod_factorize(int nsys, double *d_factors, int nb, int bs, double *l_values, int *pivots, double *dinv)
 {
   extern __shared__ double sm[];
   const int ld = LD(bs);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(1024, 1)
         D[(size_t)i * nb2 + e] = A[e % bs + (e / bs) * ld];
       for (int k = tid; k < bs; k += nt)
         piv[(size_t)i * bs + k] = spiv[k] + 1;
-      if (i == nb - 1)
+      if (i == nb - 1 && dinv == nullptr)
         break;
       // ---- column `col` of the inverse, in registers --------------------------------------------------------------------
       double x[RPL];
@@ -376,6 +376,19 @@ __global__ void __launch_bounds__(1024, 1)
           }
         }
       }
+      if (dinv != nullptr && active)
+      { // extension: keep the explicit inverse for the matvec-only back sweep of k_btddod_solve_inv
+        double *Xo = dinv + ((size_t)sys * nb + i) * nb2 + (size_t)col * bs;
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+        {
+          const int r = q + Q * m;
+          if (r < bs)
+            Xo[r] = x[m];
+        }
+      }
+      if (i == nb - 1)
+        break;
       cp_async_wait_all();
       __syncthreads(); // every group is done reading the factors; the staged block has landed
       // ---- L_{i+1} = diag(sub_i) * D_i^{-1} (:55-63); D_{i+1} -= L_{i+1} * diag(sup_i) (:65-75) ----------------------
@@ -599,6 +612,94 @@ __global__ void __launch_bounds__(64) k_btddod_solve(int nsys, const double *d_f
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_btddod_solve_inv (extension, not in the reference API): the same block-Thomas solve with the explicit inverses
+// D_i^{-1} that the factorisation forms anyway for L_{i+1}: the back sweep x_i = D_i^{-1} (y_i - sup_i o x_{i+1})
+// becomes a matrix-vector product, fully parallel over the rows, instead of two dependent triangular solves. Used
+// inside the Newton loops of the batched ESDIRK integrator, where the linear solve only preconditions an iteration that
+// converges on the true residual.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_btddod_solve_inv(int nsys, const double *d_factors, const double *l_values,
+                                                          const double *dinv, const double *rhs, int nb, int bs,
+                                                          double *solution)
+{
+  extern __shared__ double sm[];
+  double *buf0 = sm;
+  double *buf1 = buf0 + bs * bs;
+  double *v = buf1 + bs * bs; // [bs] y_{i-1} / right-hand side of the back sweep
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t nb2 = (size_t)bs * bs;
+  const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
+  auto fetch = [&](double *dst, const double *src) {
+    for (int e = tid; e < bs * bs; e += nt)
+      cp_async8(dst + e, src + e);
+    cp_async_commit();
+  };
+  for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
+  {
+    const double *D = d_factors + (size_t)sys * mat_stride;
+    const double *Lv = l_values + (size_t)sys * nb * nb2;
+    const double *Di = dinv + (size_t)sys * nb * nb2;
+    const double *sup = D + (size_t)nb * nb2 + (size_t)(nb - 1) * bs;
+    const double *b = rhs + (size_t)sys * nb * bs;
+    double *x = solution + (size_t)sys * nb * bs;
+    __syncthreads();
+    // blocks stream through the two buffers in the order L_1 .. L_{nb-1}, Dinv_{nb-1} .. Dinv_0
+    const int nstream = 2 * nb - 1;
+    auto src_of = [&](int s) { return s < nb - 1 ? Lv + (size_t)(s + 1) * nb2 : Di + (size_t)(nstream - 1 - s) * nb2; };
+    fetch(buf0, src_of(0));
+    for (int j = tid; j < bs; j += nt)
+    {
+      v[j] = b[j];
+      x[j] = b[j];
+    }
+    for (int s = 0; s < nstream; ++s)
+    {
+      double *cur = (s & 1) ? buf1 : buf0, *nxt = (s & 1) ? buf0 : buf1;
+      cp_async_wait_all();
+      __syncthreads(); // block s has landed, v is complete
+      if (s + 1 < nstream)
+        fetch(nxt, src_of(s + 1));
+      double out = 0.;
+      int i;
+      if (s < nb - 1)
+      { // forward: y_i = b_i - L_i y_{i-1}
+        i = s + 1;
+        if (tid < bs)
+        {
+          double acc = b[(size_t)i * bs + tid];
+          for (int c = 0; c < bs; ++c)
+            acc = acc + cur[(size_t)c * bs + tid] * (-1. * v[c]);
+          out = acc;
+        }
+      }
+      else
+      { // back: x_i = Dinv_i * v, v = y_i - sup_i o x_{i+1} (v prepared at the end of the previous step)
+        i = nstream - 1 - s;
+        if (tid < bs)
+        {
+          double acc = 0.;
+          for (int c = 0; c < bs; ++c)
+            acc += cur[(size_t)c * bs + tid] * v[c];
+          out = acc;
+        }
+      }
+      __syncthreads(); // everyone is done reading v
+      if (tid < bs)
+      {
+        x[(size_t)i * bs + tid] = out;
+        if (s < nb - 2)
+          v[tid] = out; // y_i feeds the next forward step
+        else if (s == nb - 2)
+          v[tid] = out; // y_{nb-1}: right-hand side of the first back step
+        else if (i > 0)
+          v[tid] = x[(size_t)(i - 1) * bs + tid] - sup[(size_t)(i - 1) * bs + tid] * out; // y_{i-1} - sup_{i-1} o x_i
+      }
+    }
+    cp_async_wait_all();
+  }
+}
+
 __global__ void k_btddod_matvec(int nsys, const double *matrix, const double *vec, int nb, int bs, double *out)
 {
   // one thread per output row: block-diagonal matvec in the reference's column order, then the off-diagonals
@@ -692,8 +793,47 @@ int sm_count_bt()
 
 extern "C"
 {
+  static int factorize_impl(int n, double *d_factors, int nb, int bs, double *l_values, int *pivots, double *dinv,
+                            void *stream);
+
   int gb_btddod_full_factorize_batch(int n, double *d_factors, int nb, int bs, double *l_values, int *pivots,
                                      void *stream)
+  {
+    return factorize_impl(n, d_factors, nb, bs, l_values, pivots, nullptr, stream);
+  }
+
+  int gb_btddod_full_factorize_inv_batch(int n, double *d_factors, int nb, int bs, double *l_values, int *pivots,
+                                         double *out_dinv, void *stream)
+  {
+    if (out_dinv == nullptr)
+    {
+      set_error("gb_btddod_full_factorize_inv_batch needs the out_dinv array");
+      return GB_ERR_ARG;
+    }
+    return factorize_impl(n, d_factors, nb, bs, l_values, pivots, out_dinv, stream);
+  }
+
+  int gb_btddod_full_solve_inv_batch(int n, const double *d_factors, const double *l_values, const double *dinv,
+                                     const double *rhs, int nb, int bs, double *solution, void *stream)
+  {
+    int rc = bt_check(n, nb, bs);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (bs > 128)
+    {
+      set_error("block size too large for k_btddod_solve_inv");
+      return GB_ERR_UNSUPPORTED;
+    }
+    const size_t smem = sizeof(double) * (2 * (size_t)bs * bs + bs + 2) + 64;
+    BCK(cudaFuncSetAttribute(k_btddod_solve_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_btddod_solve_inv<<<n, 128, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution);
+    ++g_btddod_launches;
+    BCK(cudaGetLastError());
+    return GB_OK;
+  }
+
+  static int factorize_impl(int n, double *d_factors, int nb, int bs, double *l_values, int *pivots, double *dinv,
+                            void *stream)
   {
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
@@ -704,7 +844,7 @@ extern "C"
   {                                                                                                                   \
     BCK(cudaFuncSetAttribute(k_btddod_factorize<Q, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     k_btddod_factorize<Q, RPL><<<n, ((Q * bs + 31) / 32) * 32, smem, (cudaStream_t)stream>>>(n, d_factors, nb, bs,    \
-                                                                                             l_values, pivots);      \
+                                                                                             l_values, pivots, dinv); \
   } while (0)
     if (bs <= 16)
       GB_BT_LAUNCH(16, 1);

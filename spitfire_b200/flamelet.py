@@ -263,12 +263,18 @@ class _BatchOps(object):
         e = torch.clamp(bound - diffterm[:, None], min=0.)
         return e.repeat_interleave(self.ns, dim=1)
 
-    def factorize(self, J):
-        """block-Thomas factorisation in place of the systems J [n, nelem]; returns (J, L, pivots)"""
+    def factorize(self, J, with_inverse=False):
+        """block-Thomas factorisation in place of the systems J [n, nelem]; returns (J, L, pivots[, Dinv]).
+        with_inverse (device path only) also keeps the explicit inverses of the factorised diagonal blocks so that
+        `solve` can run its back sweep as matrix-vector products (griffon_b200.h, gb_btddod_full_*_inv_batch)."""
         torch = self.torch
         n = J.shape[0]
         L = torch.zeros((n, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device)
         piv = torch.zeros((n, self.ndof), dtype=torch.int32, device=self.device)
+        if self.on_device and with_inverse:
+            Dinv = torch.empty((n, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device)
+            self.gmod.btddod_full_factorize_inv(J, self.nzi, self.ns, L, piv, Dinv, n_systems=n)
+            return J, L, piv, Dinv
         if self.on_device:
             self.gmod.py_btddod_full_factorize(J, self.nzi, self.ns, L, piv, n_systems=n)
         else:
@@ -280,12 +286,15 @@ class _BatchOps(object):
     def solve(self, fact, rhs, rows=None):
         """solve with the factors of the members `rows` (positions in the factor arrays; default all)"""
         torch = self.torch
-        J, L, piv = fact
         if rows is not None:
-            J, L, piv = J.index_select(0, rows), L.index_select(0, rows), piv.index_select(0, rows)
+            fact = tuple(a.index_select(0, rows) for a in fact)
+        J, L, piv = fact[:3]
         n = rhs.shape[0]
         x = torch.zeros_like(rhs)
-        if self.on_device:
+        if self.on_device and len(fact) == 4:
+            self.gmod.btddod_full_solve_inv(J.contiguous(), L.contiguous(), fact[3].contiguous(), rhs.contiguous(),
+                                            self.nzi, self.ns, x, n_systems=n)
+        elif self.on_device:
             self.gmod.py_btddod_full_solve(J.contiguous(), L.contiguous(), piv.contiguous(), rhs.contiguous(), self.nzi,
                                            self.ns, x, n_systems=n)
         else:

@@ -88,6 +88,8 @@ def load_library():
     sig('gb_flamelet_jacobian_host', I, [P, I, V, FP, I, D, I, D, I, I, V, V])
     sig('gb_btddod_full_factorize_batch', I, [I, V, I, I, V, V, V])
     sig('gb_btddod_full_solve_batch', I, [I, V, V, V, V, I, I, V, V])
+    sig('gb_btddod_full_factorize_inv_batch', I, [I, V, I, I, V, V, V, V])
+    sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V])
     sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
     sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
@@ -406,6 +408,22 @@ def py_btddod_full_solve(d_factors, l_values, d_pivots, rhs, num_blocks, block_s
         _on_device(d_factors, l_values, d_pivots, rhs, out_solution),
         int(n_systems), _addr(d_factors), _addr(l_values), _addr(d_pivots, np.int32), _addr(rhs), int(num_blocks),
         int(block_size), _addr(out_solution))
+
+
+def btddod_full_factorize_inv(out_d_factors, num_blocks, block_size, out_l_values, out_d_pivots, out_dinv, n_systems=1):
+    """extension (device arrays only): factorisation that also returns the explicit inverses of the diagonal blocks"""
+    check(load_library().gb_btddod_full_factorize_inv_batch(int(n_systems), _addr(out_d_factors), int(num_blocks),
+                                                            int(block_size), _addr(out_l_values),
+                                                            _addr(out_d_pivots, np.int32), _addr(out_dinv), _stream()),
+          'gb_btddod_full_factorize_inv_batch')
+
+
+def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1):
+    """extension (device arrays only): block-Thomas solve whose back sweep multiplies by the stored inverses"""
+    check(load_library().gb_btddod_full_solve_inv_batch(int(n_systems), _addr(d_factors), _addr(l_values), _addr(dinv),
+                                                        _addr(rhs), int(num_blocks), int(block_size),
+                                                        _addr(out_solution), _stream()),
+          'gb_btddod_full_solve_inv_batch')
 
 
 def py_btddod_full_matvec(matrix_values, vec, num_blocks, block_size, out_matvec, n_systems=1):

@@ -70,3 +70,11 @@ def barrier():
     d = _dist()
     if d is not None:
         d.barrier()
+
+
+def finalize():
+    """tear the process group down (torchrun scripts call this last)"""
+    d = _dist()
+    if d is not None:
+        d.barrier()
+        d.destroy_process_group()

@@ -30,7 +30,8 @@ _BH = [4586570599. / 29645900160., 0., 178811875. / 945068544., 814220225. / 115
 def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, minimum_time_step_count=40,
                     transient_tolerance=1.e-10, maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12,
                     max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
-                    fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True):
+                    fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
+                    explicit_inverse_solves=True):
     """advance every member of `ops` (flamelet._BatchOps) from q0 [F, ndof] until `stop(t, q, residual, nsteps)` (all
     [F]-shaped tensors; returns a bool tensor) holds for it and it has taken at least minimum_time_step_count steps.
     Returns per member the lists of saved times and states (numpy), initial state included, and a `failed` flag
@@ -50,6 +51,10 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
     J = torch.zeros((F, ops.nelem), dtype=torch.float64, device=dev)
     L = torch.zeros((F, ops.nzi * ops.ns * ops.ns), dtype=torch.float64, device=dev)
     piv = torch.zeros((F, ops.ndof), dtype=torch.int32, device=dev)
+    # on the device the Newton iterations use the explicit block inverses the factorisation forms anyway: the linear
+    # solve only preconditions an iteration that converges on the true residual (to nonlinear_solve_tolerance)
+    use_inv = bool(ops.on_device) and explicit_inverse_solves
+    Dinv = torch.zeros_like(L) if use_inv else None
     ones = torch.ones((F, ops.ndof), dtype=torch.float64, device=dev)
     t_hist = [[0.] for _ in range(F)]
     q_hist = [[q0[f].cpu().numpy().copy()] for f in range(F)]
@@ -70,8 +75,10 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             Jn = ops.jac(qa.index_select(0, ij_local), ij)
             Jn.mul_((dta.index_select(0, ij_local) * _G)[:, None])
             ops.add_to_block_diagonal(Jn, 1., ones[:ij.numel()], -1.)
-            Jf, Lf, pf = ops.factorize(Jn)
-            J[ij], L[ij], piv[ij] = Jf, Lf, pf
+            fact = ops.factorize(Jn, with_inverse=use_inv)
+            J[ij], L[ij], piv[ij] = fact[:3]
+            if use_inv:
+                Dinv[ij] = fact[3]
         setup_count[idx] += 1
         # ---- one ESDIRK64 step for every active member --------------------------------------------------------------------
         k = [ops.rhs(qa, idx)]
@@ -91,7 +98,7 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
                 if loc.numel() == 0:
                     break
                 gl = idx.index_select(0, loc)
-                dx = ops.solve((J, L, piv), res.index_select(0, loc), rows=gl)
+                dx = ops.solve((J, L, piv, Dinv) if use_inv else (J, L, piv), res.index_select(0, loc), rows=gl)
                 xn = x.index_select(0, loc) - dx
                 fn = ops.rhs(xn, gl)
                 rn = dta.index_select(0, loc)[:, None] * (_G * fn + explicit.index_select(0, loc)) - \

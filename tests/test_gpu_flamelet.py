@@ -72,3 +72,32 @@ def test_homogeneous_reactor_on_gpu_matches_reference_gold():
     from reactor_cases import compare_with_gold, run
     m, lib = run('gpu', 'adiabatic')
     print('steps', lib.time_values.size, 'max rel err T', compare_with_gold(m, lib, 'adiabatic'))
+
+
+def test_inverse_based_block_thomas_solve_matches_lu_solve():
+    """extension entry points gb_btddod_full_{factorize,solve}_inv_batch against the LU-based solve"""
+    import torch
+    from spitfire_b200 import griffon
+    from cases import flamelet_all, flamelet_case
+    mg, mo = build_mech('methane-gri30', 'gpu'), build_mech('methane-gri30', ORACLE)
+    c = flamelet_case(mg, 24)
+    ns, nzi = c['ns'], c['nzi']
+    A0 = flamelet_all(mo.griffon, c, eig=False)['jac0True']
+    F = 3
+    rng = np.random.default_rng(5)
+    rhs = rng.normal(size=(F, nzi * ns))
+    dA = torch.from_numpy(np.array([A0] * F)).cuda()
+    dA2 = dA.clone()
+    dL, dL2 = torch.zeros((F, nzi * ns * ns), dtype=torch.float64, device='cuda'), torch.zeros((F, nzi * ns * ns), dtype=torch.float64, device='cuda')
+    dP, dP2 = torch.zeros((F, nzi * ns), dtype=torch.int32, device='cuda'), torch.zeros((F, nzi * ns), dtype=torch.int32, device='cuda')
+    dI = torch.zeros((F, nzi * ns * ns), dtype=torch.float64, device='cuda')
+    dR = torch.from_numpy(rhs).cuda()
+    x1, x2 = torch.zeros_like(dR), torch.zeros_like(dR)
+    griffon.py_btddod_full_factorize(dA, nzi, ns, dL, dP, n_systems=F)
+    griffon.py_btddod_full_solve(dA, dL, dP, dR, nzi, ns, x1, n_systems=F)
+    griffon.btddod_full_factorize_inv(dA2, nzi, ns, dL2, dP2, dI, n_systems=F)
+    griffon.btddod_full_solve_inv(dA2, dL2, dI, dR, nzi, ns, x2, n_systems=F)
+    torch.cuda.synchronize()
+    assert torch.equal(dA, dA2) and torch.equal(dL, dL2) and torch.equal(dP, dP2)
+    a, b = x2.cpu().numpy(), x1.cpu().numpy()
+    assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))

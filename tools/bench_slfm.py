@@ -62,7 +62,7 @@ def main():
         say(dict(metric='nonadiabatic (transient defect) SLFM library build wall time', unit='s',
                  value=time.perf_counter() - t0, higher_is_better=False, n_chi=args.nonadiabatic, n_defect_st=16,
                  shape=list(lib.shape), wave=args.wave))
-    parallel.barrier()
+    parallel.finalize()
 
 
 if __name__ == '__main__':
