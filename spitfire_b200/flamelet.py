@@ -174,11 +174,17 @@ class _BatchOps(object):
                          ('_T_conv', '_T_rad', '_h_conv', '_h_rad')]
         self.scales = t(np.array([fl._variable_scales for fl in flamelets]))
         self.max_chi = t(np.array([fl._max_dissipation_rate for fl in flamelets]))
+        self._prm_cache = dict()
 
     # -- helpers -----------------------------------------------------------------------------------------------------
-    def _params(self, idx):
-        """C-ABI parameter block for the members `idx` (a LongTensor) -- compacts the per-member arrays"""
-        sel = lambda a: a.index_select(0, idx).contiguous()
+    def _params(self, idx, key=None):
+        """C-ABI parameter block for the members `idx` (a LongTensor) -- compacts the per-member arrays. `key` (a
+        hashable naming the member set, e.g. the tuple of indices) lets repeated selections reuse the compacted
+        arrays and the parameter struct."""
+        if key is not None and key in self._prm_cache:
+            return self._prm_cache[key]
+        full = idx.numel() == self.F and (key is None or key == tuple(range(self.F)))
+        sel = (lambda a: a) if full else (lambda a: a.index_select(0, idx).contiguous())
         d = dict(cmaj=sel(self.cmaj), csub=sel(self.csub), csup=sel(self.csup), mc=sel(self.mc), nc=sel(self.nc),
                  chi=sel(self.chi))
         heat = [None] * 4 if self.adiabatic else [sel(h) for h in self.heat]
@@ -186,19 +192,24 @@ class _BatchOps(object):
         prm = self.g._flamelet_params(self.pressure, self.oxy, self.fuel, self.adiabatic, heat[0], heat[1], heat[2],
                                       heat[3], self.nzi, d['cmaj'], d['csub'], d['csup'], d['mc'], d['nc'], d['chi'],
                                       *self.flags, strides=(0 if self.adiabatic else self.nzi, self.ndof, self.nzi, nz))
-        return prm, (d, heat)  # keep the tensors alive while the kernels run
+        out = (prm, (d, heat))  # keep the tensors alive while the kernels run
+        if key is not None:
+            if len(self._prm_cache) > 256:
+                self._prm_cache.clear()
+            self._prm_cache[key] = out
+        return out
 
     def _all(self):
         return self.torch.arange(self.F, device=self.device)
 
     # -- kernels -----------------------------------------------------------------------------------------------------
-    def rhs(self, state, idx=None):
+    def rhs(self, state, idx=None, key=None):
         """flamelet_rhs for the members idx (default all); state [len(idx), ndof]"""
         torch = self.torch
         idx = self._all() if idx is None else idx
         out = torch.empty_like(state)
         if self.on_device:
-            prm, keep = self._params(idx)
+            prm, keep = self._params(idx, key)
             self.g.flamelet_rhs_batch(state.shape[0], state.contiguous(), prm, out)
             del keep
         else:
@@ -217,14 +228,14 @@ class _BatchOps(object):
     def _host_rhs(self, f, state, out):
         self.g.flamelet_rhs(np.ascontiguousarray(state), *self._host_args(f), *self.flags, out)
 
-    def jac(self, state, idx=None, scale_and_offset=False, prefactor=1.):
+    def jac(self, state, idx=None, scale_and_offset=False, prefactor=1., key=None):
         """BTDDOD Jacobian (or prefactor*J - I) of the members idx; [len(idx), nelem]"""
         torch = self.torch
         idx = self._all() if idx is None else idx
         n = state.shape[0]
         if self.on_device:
             out = torch.empty((n, self.nelem), dtype=torch.float64, device=self.device)
-            prm, keep = self._params(idx)
+            prm, keep = self._params(idx, key)
             self.g.flamelet_jacobian_batch(n, state.contiguous(), prm, out, scale_and_offset=scale_and_offset,
                                            prefactor=prefactor, rates_sens_option=self.rsopt,
                                            sens_transform_option=self.stopt)

@@ -41,13 +41,15 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
     F = q0.shape[0]
     w = 1. / ops.scales  # norm weighting
     q = q0.clone()
-    t = torch.zeros(F, dtype=torch.float64, device=dev)
-    dt = torch.full((F,), float(first_time_step), dtype=torch.float64, device=dev)
-    nsteps = torch.zeros(F, dtype=torch.int64, device=dev)
-    setup_count = torch.zeros(F, dtype=torch.int64, device=dev)
-    refresh = torch.ones(F, dtype=torch.bool, device=dev)
-    going = torch.ones(F, dtype=torch.bool, device=dev)
-    attempts = torch.zeros(F, dtype=torch.int64, device=dev)
+    # control state lives on the host (F is small; the step-size and refresh arithmetic is then literally the
+    # reference's numpy arithmetic); q, the stage derivatives and the Newton iterates live on the device
+    t = np.zeros(F)
+    dt = np.full(F, float(first_time_step))
+    nsteps = np.zeros(F, dtype=np.int64)
+    setup_count = np.zeros(F, dtype=np.int64)
+    refresh = np.ones(F, dtype=bool)
+    going = np.ones(F, dtype=bool)
+    attempts = np.zeros(F, dtype=np.int64)
     J = torch.zeros((F, ops.nelem), dtype=torch.float64, device=dev)
     L = torch.zeros((F, ops.nzi * ops.ns * ops.ns), dtype=torch.float64, device=dev)
     piv = torch.zeros((F, ops.ndof), dtype=torch.int32, device=dev)
@@ -58,32 +60,46 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
     ones = torch.ones((F, ops.ndof), dtype=torch.float64, device=dev)
     t_hist = [[0.] for _ in range(F)]
     q_hist = [[q0[f].cpu().numpy().copy()] for f in range(F)]
+    residual_full = np.full(F, np.inf)
 
-    def wnorm(x, idx):
-        return (x * w.index_select(0, idx)).abs().amax(dim=1)
+    def dev_idx(a):
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=dev)
+
+    def dev_vec(a):
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+
+    def wnorm(x, widx):
+        return (x * w.index_select(0, widx)).abs().amax(dim=1)
 
     while True:
-        idx = torch.nonzero(going).flatten()
-        if idx.numel() == 0:
+        idx_h = np.nonzero(going)[0]
+        if idx_h.size == 0:
             break
-        n = idx.numel()
-        qa, dta = q.index_select(0, idx), dt.index_select(0, idx)
+        n = idx_h.size
+        idx = dev_idx(idx_h)
+        all_active = n == F
+        qa = q if all_active else q.index_select(0, idx)
+        dta_h = dt[idx_h]
+        dta = dev_vec(dta_h)
         # ---- projector: prefactor*J - I with prefactor = gamma*dt, for the members flagged for a refresh ----------------
-        ij_local = torch.nonzero(refresh.index_select(0, idx)).flatten()
-        if ij_local.numel():
-            ij = idx.index_select(0, ij_local)
-            Jn = ops.jac(qa.index_select(0, ij_local), ij)
-            Jn.mul_((dta.index_select(0, ij_local) * _G)[:, None])
-            ops.add_to_block_diagonal(Jn, 1., ones[:ij.numel()], -1.)
+        loc_h = np.nonzero(refresh[idx_h])[0]
+        if loc_h.size:
+            ij_h = idx_h[loc_h]
+            ij = dev_idx(ij_h)
+            Jn = ops.jac(qa if loc_h.size == n else qa.index_select(0, dev_idx(loc_h)), ij, key=tuple(ij_h.tolist()))
+            Jn.mul_(dev_vec(dta_h[loc_h] * _G)[:, None])
+            ops.add_to_block_diagonal(Jn, 1., ones[:ij_h.size], -1.)
             fact = ops.factorize(Jn, with_inverse=use_inv)
             J[ij], L[ij], piv[ij] = fact[:3]
             if use_inv:
                 Dinv[ij] = fact[3]
-        setup_count[idx] += 1
+        setup_count[idx_h] += 1
+        factors = (J, L, piv, Dinv) if use_inv else (J, L, piv)
+        key_all = tuple(idx_h.tolist())
         # ---- one ESDIRK64 step for every active member --------------------------------------------------------------------
-        k = [ops.rhs(qa, idx)]
+        k = [ops.rhs(qa, idx, key=key_all)]
         qs = qa
-        nl_ok = torch.ones(n, dtype=torch.bool, device=dev)
+        nl_ok = np.ones(n, dtype=bool)
         for s in range(1, 6):
             explicit = _A[s][s - 1] * k[s - 1]
             for j in range(s - 2, -1, -1):
@@ -92,70 +108,84 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             x = qs.clone()
             f = k[-1].clone()
             res = dta[:, None] * (_G * f + explicit) - (x - qa)
-            conv = torch.zeros(n, dtype=torch.bool, device=dev)
+            conv = np.zeros(n, dtype=bool)
             for it in range(max_nonlinear_iter):
-                loc = torch.nonzero(~conv).flatten()
-                if loc.numel() == 0:
+                l_h = np.nonzero(~conv)[0]
+                if l_h.size == 0:
                     break
-                gl = idx.index_select(0, loc)
-                dx = ops.solve((J, L, piv, Dinv) if use_inv else (J, L, piv), res.index_select(0, loc), rows=gl)
-                xn = x.index_select(0, loc) - dx
-                fn = ops.rhs(xn, gl)
-                rn = dta.index_select(0, loc)[:, None] * (_G * fn + explicit.index_select(0, loc)) - \
-                    (xn - qa.index_select(0, loc))
-                x[loc], f[loc], res[loc] = xn, fn, rn
-                conv[loc] = wnorm(rn, gl) < nonlinear_solve_tolerance
+                g_h = idx_h[l_h]
+                if l_h.size == n:
+                    dx = ops.solve(factors, res, rows=None if all_active else idx)
+                    xn = x - dx
+                    fn = ops.rhs(xn, idx, key=key_all)
+                    rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
+                    x, f, res = xn, fn, rn
+                    conv = (wnorm(rn, idx) < nonlinear_solve_tolerance).cpu().numpy()
+                else:
+                    loc, gl = dev_idx(l_h), dev_idx(g_h)
+                    dx = ops.solve(factors, res.index_select(0, loc), rows=gl)
+                    xn = x.index_select(0, loc) - dx
+                    fn = ops.rhs(xn, gl, key=tuple(g_h.tolist()))
+                    rn = dta.index_select(0, loc)[:, None] * (_G * fn + explicit.index_select(0, loc)) - \
+                        (xn - qa.index_select(0, loc))
+                    x[loc], f[loc], res[loc] = xn, fn, rn
+                    conv[l_h] = (wnorm(rn, gl) < nonlinear_solve_tolerance).cpu().numpy()
             nl_ok &= conv
             qs = x
             k.append(f)
         dq = dta[:, None] * (_B[0] * k[0] + _B[1] * k[1] + _B[2] * k[2] + _B[3] * k[3] + _B[4] * k[4] + _B[5] * k[5])
         dqh = dta[:, None] * (_BH[0] * k[0] + _BH[1] * k[1] + _BH[2] * k[2] + _BH[3] * k[3] + _BH[4] * k[4] +
                               _BH[5] * k[5])
-        err = wnorm(dq - dqh, idx)
-        residual = wnorm(dq, idx) / dta
-        ok = torch.isfinite(dq).all(dim=1)
+        stats = torch.stack([wnorm(dq - dqh, idx), wnorm(dq, idx), torch.isfinite(dq).all(dim=1).to(torch.float64)])
+        stats = stats.cpu().numpy()
+        err, ok = stats[0], stats[2] > 0.5
+        with np.errstate(all='ignore'):
+            residual = stats[1] / dta_h
         # ---- accepted members --------------------------------------------------------------------------------------------------
-        acc = torch.nonzero(ok).flatten()
-        ga = idx.index_select(0, acc)
-        if acc.numel():
-            qnew = qa.index_select(0, acc) + dq.index_select(0, acc)
+        a_h = np.nonzero(ok)[0]
+        if a_h.size:
+            ga_h = idx_h[a_h]
+            sel = a_h.size != n
+            qnew = (qa.index_select(0, dev_idx(a_h)) + dq.index_select(0, dev_idx(a_h))) if sel else qa + dq
             if clip_negative:
                 qnew = torch.where(qnew < 0., torch.zeros_like(qnew), qnew)
-            q[ga] = qnew
-            t[ga] = t.index_select(0, ga) + dta.index_select(0, acc)
-            nsteps[ga] += 1
-            # PI controller (the proportional factor of the reference evaluates to one: it divides the error by itself)
-            e = err.index_select(0, acc)
-            d = dta.index_select(0, acc)
-            ratio = (transient_tolerance / e) ** ki
-            dnew = torch.minimum(d * torch.clamp(ratio, max=max_ramp), torch.full_like(d, max_time_step))
-            dnew = torch.where(e < 1.e-16, torch.minimum(d * max_ramp, torch.full_like(d, max_time_step)), dnew)
-            # Jacobian-refresh policy
-            cnt = setup_count.index_select(0, ga)
-            okn = nl_ok.index_select(0, acc)
+            if sel or not all_active:
+                q[dev_idx(ga_h)] = qnew
+            else:
+                q = qnew
+            d = dta_h[a_h]
+            t[ga_h] = t[ga_h] + d
+            nsteps[ga_h] += 1
+            # PI controller, stepcontrol.py:84-101 (its proportional factor divides the newest error by itself: one)
+            e = err[a_h]
+            with np.errstate(all='ignore'):
+                ratio = (transient_tolerance / e) ** ki
+            dnew = np.minimum(d * np.minimum(max_ramp, ratio), max_time_step)
+            dnew = np.where(e < 1.e-16, np.minimum(d * max_ramp, max_time_step), dnew)
+            # Jacobian-refresh policy, integrator.py:100-130
+            cnt = setup_count[ga_h]
+            okn = nl_ok[a_h]
             by_count = cnt == maximum_steps_per_jacobian
             by_fail = ~by_count & ~okn
             by_size = ~by_count & okn & ((dnew > d * grow_limit) | (dnew < d * shrink_limit))
-            dnew = torch.where(by_fail, dnew * fail_factor, dnew)
-            refresh[ga] = by_count | by_fail | by_size
-            setup_count[ga] = torch.where(by_count, torch.zeros_like(cnt), cnt)
-            dt[ga] = dnew
-            th, qh = t.index_select(0, ga).cpu().numpy(), qnew.cpu().numpy()
-            for m, f_ in enumerate(ga.tolist()):
-                t_hist[f_].append(float(th[m]))
+            dnew = np.where(by_fail, dnew * fail_factor, dnew)
+            refresh[ga_h] = by_count | by_fail | by_size
+            setup_count[ga_h] = np.where(by_count, 0, cnt)
+            dt[ga_h] = dnew
+            qh = qnew.cpu().numpy()
+            for m, f_ in enumerate(ga_h.tolist()):
+                t_hist[f_].append(float(t[f_]))
                 q_hist[f_].append(qh[m].copy())
-        rej = torch.nonzero(~ok).flatten()
-        if rej.numel():
-            gr = idx.index_select(0, rej)
-            dt[gr] = dt.index_select(0, gr) * fail_factor
-            refresh[gr] = True
-        attempts[idx] += 1
+        r_h = idx_h[np.nonzero(~ok)[0]]
+        if r_h.size:
+            dt[r_h] = dt[r_h] * fail_factor
+            refresh[r_h] = True
+        attempts[idx_h] += 1
         # ---- stopping --------------------------------------------------------------------------------------------------------------
-        res_full = torch.zeros(F, dtype=torch.float64, device=dev)
-        res_full[idx] = torch.where(torch.isfinite(residual), residual, torch.full_like(residual, float('inf')))
-        done = stop(t, q, res_full, nsteps) & (nsteps >= minimum_time_step_count)
+        residual_full[idx_h] = np.where(np.isfinite(residual), residual, np.inf)
+        done = stop(dev_vec(t), q, dev_vec(residual_full), dev_idx(nsteps)).cpu().numpy() & \
+            (nsteps >= minimum_time_step_count)
         done = done | (attempts > maximum_steps)
         going = going & ~done
-        going[idx] = going.index_select(0, idx)
-    failed = (attempts > maximum_steps).cpu().numpy()
+    failed = attempts > maximum_steps
     return [np.array(th) for th in t_hist], [np.array(qh) for qh in q_hist], failed
