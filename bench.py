@@ -208,6 +208,36 @@ def ncu_traffic_per_launch(mech, n_states):
     return float(e['dram_bytes']) / float(e['states']) * n_states
 
 
+def time_library_builds(args, world):
+    """secondary metric of BASELINE.json, "SLFM library build wall time": BASELINE configs 4 and 5 (GRI-3.0, CH4 300 K /
+    air 300 K, 1 atm, 128-point clustered grid, chi_st in logspace(-3, 2, 64), 16 enthalpy defects) through the
+    repo's public builders, heat-loss trajectories dealt to the ranks. Every rank must call this (one gather)."""
+    from spitfire_b200 import tabulation as tab
+    from spitfire_b200.flamelet import FlameletSpec
+    from spitfire_b200.mechanism import ChemicalMechanismSpec
+    m = ChemicalMechanismSpec(mech_data=load_mech_data('methane-gri30'))
+    air = m.stream(stp_air=True)
+    fuel = m.stream('TPX', (300., PRESSURE, 'CH4:1'))
+    chis = np.logspace(-3, 2, args.library_chi)
+    out = {'config': f'GRI-3.0 CH4/air 300 K 1 atm, {args.library_chi} chi_st in logspace(-3,2), 128-point grid',
+           'n_gpus': world}
+    t0 = time.perf_counter()
+    lib = tab.build_adiabatic_slfm_library(FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128),
+                                           diss_rate_values=chis, verbose=False, wave=8)
+    out['adiabatic_slfm_s'] = time.perf_counter() - t0
+    out['adiabatic_shape'] = list(lib.shape)
+    t0 = time.perf_counter()
+    lib = tab.build_nonadiabatic_defect_transient_slfm_library(
+        FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128), diss_rate_values=chis,
+        verbose=False, n_defect_st=16, wave=8)
+    out['nonadiabatic_defect_slfm_s'] = time.perf_counter() - t0
+    out['nonadiabatic_shape'] = list(lib.shape)
+    out['T_max'] = float(lib['temperature'].max())
+    out['cpu_reference_note'] = ('reference CPU path, 1 core (SURVEY.md section 6 probe): ~0.07 s per adiabatic '
+                                 'continuation step, 7 s first/last member, 13.8 s per heat-loss trajectory')
+    return out
+
+
 def run_gpu_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -291,6 +321,15 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step, e2e_ms = float(t_ms[0]), float(t_ms[1])
+    library = None
+    if args.library_chi > 0:
+        try:
+            if world > 1:
+                from spitfire_b200 import parallel  # the builders find the process group bench.py initialised
+                assert parallel.world_size() == world
+            library = time_library_builds(args, world)
+        except Exception as e:  # the headline line must survive a failure of the secondary metric
+            library = {'error': repr(e)[:300]}
     if rank == 0:
         value = world * n / (ms_per_step * 1e-3)
         peak, peak_src = measured_hbm_peak()
@@ -314,6 +353,7 @@ def run_gpu_arm(args):
                     'api': 'PyCombustionKernels.reactor_jac_isobaric_batch(numpy) -> gb_reactor_jac_isobaric_host',
                     'result_check': check},
             'gpu_launches': int(launches),
+            'library_build': library,
             'clocks': clocks,
             'build': load_build_info(),
         }
@@ -340,6 +380,8 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-states-per-core', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--library-chi', type=int, default=64,
+                    help='dissipation rates of the SLFM library builds timed as the secondary metric (0 = skip)')
     args = ap.parse_args()
     if args.fuel is None:
         args.fuel = 'H2' if args.mech.startswith('h2') else 'CH4'

@@ -17,3 +17,10 @@ def tm(fn, n=3):
     torch.cuda.synchronize(); return (time.time() - t0) / n * 1e3
 fact = ops.factorize(J.clone())
 print(f'F={F}: factorize {tm(lambda: ops.factorize(J.clone())):.3f} ms, solve {tm(lambda: ops.solve(fact, r)):.3f} ms')
+fact_inv = ops.factorize(J.clone(), with_inverse=True)
+print(f'F={F}: factorize_inv {tm(lambda: ops.factorize(J.clone(), with_inverse=True)):.3f} ms, solve_inv {tm(lambda: ops.solve(fact_inv, r)):.3f} ms, rhs {tm(lambda: ops.rhs(state)):.3f} ms, jac {tm(lambda: ops.jac(state)):.3f} ms')
+x = state.clone(); e = r.clone(); dta = torch.ones(F, device='cuda', dtype=torch.float64)
+def elem():
+    rn = dta[:, None] * (0.25 * r + e) - (x - state)
+    c = ((rn * ops.scales).abs().amax(dim=1) < 1e-12).cpu().numpy()
+print(f'elementwise+sync {tm(elem, 20):.3f} ms')
