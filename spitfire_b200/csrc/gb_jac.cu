@@ -122,8 +122,15 @@ __device__ __forceinline__ void react_fast(const DeviceMech &dm, const unsigned 
   // the two exponentials are independent instruction streams: Arrhenius factor and 1/K_c (0 if irreversible)
   const int kform = f_kform(f);
   const double ninf = __longlong_as_double(0xfff0000000000000LL);
-  const double ef = exp(kform == KF_ARRHENIUS ? kfb * logT - kfE * invT : 0.);
-  const double invKc = exp(rev ? sum_stoich * SMG(s.sc, J_LPRT, g) - invT * dm.invRu * (gs) : ninf); // :535
+  const double arg_r = rev ? sum_stoich * SMG(s.sc, J_LPRT, g) - invT * dm.invRu * (gs) : ninf; // :535
+  double ef = 1., invKc;
+  if (kform == KF_ARRHENIUS)
+  { // two independent exponentials back to back
+    ef = exp(kfb * logT - kfE * invT);
+    invKc = exp(arg_r);
+  }
+  else
+    invKc = exp(arg_r);
   double kf; // chemistry_kernels.cpp:140-157
   switch (kform)
   {
@@ -967,27 +974,25 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     prefetch_group(stab[dm.jp_t_wg + warp], stab[dm.jp_t_wg + warp + 1]);
     if (warp == 0)
     {
+      // lanes [0, G): Y_ns = 1 - sum_j Y_j (extract_y, combustion_kernels.h:505-515); lanes [G, 2G): sum_i Y_i/M_i over
+      // all but the last species (mixture_molecular_weight, :381-387). One uniform loop d <- d + c_j * Y_j serves
+      // both chains (c_j = -1 makes the update the exact subtraction of the reference).
       double d = 0.;
-      if (lane < G)
-      { // extract_y (combustion_kernels.h:505-515)
-        if (state_mode)
-        {
-          double yl = 1.;
-#pragma unroll 8
-          for (int j = 0; j < nsm1; ++j)
-            yl -= SMG(s.sy, j, lane);
-          SMG(s.sy, nsm1, lane) = yl;
-          d = yl;
-        }
+      if (lane < 2 * G)
+      {
+        const bool first = lane < G;
+        const int g = first ? lane : lane - G;
+        if (first && !state_mode)
+          d = SMG(s.sy, nsm1, g);
         else
-          d = SMG(s.sy, nsm1, lane);
-      }
-      else if (lane < 2 * G)
-      { // mixture_molecular_weight (:381-387): sum_i Y_i/M_i in species order, all but the last term
-        const int g = lane - G;
-#pragma unroll 8
-        for (int i = 0; i < nsm1; ++i)
-          d += s.sim[i] * SMG(s.sy, i, g);
+        {
+          d = first ? 1. : 0.;
+#pragma unroll 4
+          for (int j = 0; j < nsm1; ++j)
+            d = d + (first ? -1. : s.sim[j]) * SMG(s.sy, j, g);
+          if (first)
+            SMG(s.sy, nsm1, g) = d;
+        }
       }
       const double dpart = __shfl_down_sync(0xffffffffu, d, G);
       if (lane < G)

@@ -291,7 +291,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
         c = 600. + (x.kform == KF_ARRHENIUS ? 300. : 0.) + (x.reversible ? 460. : 0.);
       else
       {
-        c = x.type == RT_SIMPLE ? 4600. : (x.type == RT_THIRD_BODY ? 9300. : (x.type == RT_LINDEMANN ? 10000. : 14000.));
+        c = x.type == RT_SIMPLE ? 4600. : (x.type == RT_THIRD_BODY ? 8800. : (x.type == RT_LINDEMANN ? 10000. : 16500.));
         if (kind[r] == 2)
           c = 1.5 * c + (x.has_orders ? 6000. : 0.);
       }
@@ -323,7 +323,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       {
         double extra = 0.;
         for (size_t i = 1; i < g.rx.size(); ++i)
-          if (key(g.rx[i]) != key(g.rx[i - 1]))
+          if (key(g.rx[i]) / 64 != key(g.rx[i - 1]) / 64) // same code path up to the number of third bodies
             extra += 0.25 * cost(g.rx[i]);
         g.cost += extra;
       }
