@@ -179,7 +179,9 @@ int gb_flamelet_rhs_host(gb_mech *m, int n_flamelets, const double *state, const
                          double *out_rhs);
 /* out_jac: [F][ns*(nzi*ns + 2*(nzi-1))] BTDDOD; written completely (no need to pre-zero, unlike the reference
  * which accumulates into the off-diagonals, flamelet_kernels.cpp:1386-1394). out_expeig [F][nzi*ns] is written
- * only if compute_eigenvalues (max(Re(lambda)) - diffterm clipped at 0, per point). */
+ * only if compute_eigenvalues: max(max_i Re(lambda_i) - diffterm, 0) of the point's transformed chemical block,
+ * repeated for the point's ns unknowns (flamelet_kernels.cpp:1329-1341, where LAPACK dgeev does it on the host;
+ * here balancing + Householder-Hessenberg + double-shift QR run on the device, one warp per block). */
 int gb_flamelet_jacobian_batch(gb_mech *m, int n_flamelets, const double *state, const gb_flamelet_params *prm,
                                int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
                                int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
@@ -188,6 +190,12 @@ int gb_flamelet_jacobian_host(gb_mech *m, int n_flamelets, const double *state, 
                               int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
                               int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
                               double *out_jac);
+
+/* Extension (the reference keeps this inside flamelet_jacobian): largest real part of the eigenvalues of nblocks
+ * dense n x n matrices stored back to back (either major order: the spectrum of the transpose is the same);
+ * replaces griffon::lapack::eigenvalues (blas_lapack_kernels.h:157-180) + the max over Re (flamelet_kernels.cpp:1332-
+ * 1336). blocks, out: device. n <= 169 (the matrix lives in shared memory). */
+int gb_max_real_eigenvalue_batch(int nblocks, int n, const double *blocks, double *out, void *stream);
 
 /* ---- BTDDOD block-Thomas (griffon.pyx:1006-1113; btddod_matrix_kernels.cpp:19-165, 429-465) --------------- */
 /* Batched over n_systems independent matrices stored back to back (stride = block_size*(num_blocks*block_size

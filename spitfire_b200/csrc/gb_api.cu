@@ -410,6 +410,7 @@ int flamelet_dev(gb_mech *m, int F, const double *d_state, const gb_flamelet_par
   fl->include_variable_cp = p->include_variable_cp ? 1 : 0;
   fl->use_scaled_heat_loss = p->use_scaled_heat_loss ? 1 : 0;
   fl->scale_and_offset = 0;
+  fl->chem_only = 0;
   fl->prefactor = 1.;
   void *cpg, *mt, *bc;
   RC(scratch(m, 4, sizeof(double) * (size_t)F * p->nzi, &cpg));
@@ -555,13 +556,12 @@ extern "C"
                                  int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,
                                  double *out_jac, void *stream)
   {
-    (void)diffterm, (void)out_expeig;
     RC(ready(m));
     RC(check_flamelet(F, state, prm, out_jac));
-    if (compute_eigenvalues)
+    if (compute_eigenvalues && !out_expeig)
     {
-      set_error("compute_eigenvalues (PsiTC eigenvalue bound) is not implemented on the device yet");
-      return GB_ERR_UNSUPPORTED;
+      set_error("compute_eigenvalues needs out_expeig");
+      return GB_ERR_ARG;
     }
     if (rates_sensitivity_option < 0 || rates_sensitivity_option > 2 || sensitivity_transform_option != 0)
     {
@@ -580,8 +580,42 @@ extern "C"
     RC(flamelet_dev(m, F, state, prm, &a.fl, (cudaStream_t)stream));
     a.fl.scale_and_offset = scale_and_offset ? 1 : 0;
     a.fl.prefactor = prefactor;
+    if (compute_eigenvalues)
+    { // flamelet_kernels.cpp:1329-1341: the eigenvalues are those of the transformed chemical block as it stands before
+      // the diffusion diagonal, the enthalpy-flux correction and the scaling are applied; a first pass writes exactly
+      // those blocks (densely) into scratch memory, one warp per block reduces each to its largest real part
+      const int ns = m->h.dm.ns, nblocks = F * prm->nzi;
+      void *d_blocks, *d_maxre;
+      RC(scratch(m, 7, sizeof(double) * ((size_t)nblocks * ns * ns + nblocks), &d_blocks));
+      d_maxre = (double *)d_blocks + (size_t)nblocks * ns * ns;
+      ChemArgs e = a;
+      e.out1 = (double *)d_blocks;
+      e.fl.chem_only = 1;
+      e.fl.scale_and_offset = 0;
+      CK(launch_jac(e, (cudaStream_t)stream));
+      CK(launch_block_max_real_eig(nblocks, (const double *)d_blocks, (long)prm->nzi * ns * ns, prm->nzi, ns,
+                                   (double *)d_maxre, (cudaStream_t)stream));
+      CK(launch_expand_expeig(nblocks, ns, (const double *)d_maxre, diffterm, out_expeig, (cudaStream_t)stream));
+    }
     CK(launch_jac(a, (cudaStream_t)stream));
     CK(launch_flamelet_offdiag(m->h.dm, F, a.fl, out_jac, (cudaStream_t)stream));
+    return GB_OK;
+  }
+
+  int gb_max_real_eigenvalue_batch(int nblocks, int n, const double *blocks, double *out, void *stream)
+  {
+    if (nblocks < 0 || n < 1 || (nblocks > 0 && (!blocks || !out)))
+    {
+      set_error("gb_max_real_eigenvalue_batch: bad arguments");
+      return GB_ERR_ARG;
+    }
+    if (sizeof(double) * ((size_t)n * (n | 1) + n + 2) > (size_t)227 * 1024)
+    {
+      set_error("gb_max_real_eigenvalue_batch: matrix does not fit in shared memory (n <= 169)");
+      return GB_ERR_UNSUPPORTED;
+    }
+    CK(launch_block_max_real_eig(nblocks, blocks, (long)nblocks * n * n, nblocks > 0 ? nblocks : 1, n, out,
+                                 (cudaStream_t)stream));
     return GB_OK;
   }
 

@@ -1101,6 +1101,8 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           const int bucket = kind == 0 ? 0 : (kind == 2 ? 5 : f_type((int)(unsigned int)P[0]));
           atomicAdd((unsigned long long *)&g_jac_timeline[(11 + bucket) * 32], (unsigned long long)(clock64() - tl0));
           atomicAdd((unsigned long long *)&g_jac_timeline[(11 + bucket) * 32 + 1], 1ull);
+          atomicAdd((unsigned long long *)&g_jac_timeline[17 * 32 + warp], (unsigned long long)(clock64() - tl0));
+          atomicAdd((unsigned long long *)&g_jac_timeline[18 * 32 + warp], 1ull);
         }
 #endif
       }
@@ -1110,26 +1112,31 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     // ---- gather: every lane sums its parts in registers --------------------------------------------------------------------------
     double hold[RMAX][G];
     const int r0 = stab[dm.jp_t_wr + warp], nround = stab[dm.jp_t_wr + warp + 1] - r0;
-#pragma unroll
-    for (int j = 0; j < RMAX; ++j)
     {
+      // The warp's rounds are contiguous in the item stream, so the item words are prefetched two blocks (four steps)
+      // ahead across round boundaries: they come from L2 (the plan is larger than what is left of L1).
+      const unsigned int *__restrict__ it = dm.jp_items + (nround > 0 ? t_rounds[2 * r0] : 0) + lane;
+      unsigned int u0 = __ldg(it), u1 = __ldg(it + 32), n0 = __ldg(it + 64), n1 = __ldg(it + 96);
+      it += 128;
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        hold[j][g] = 0.;
-      if (j < nround)
+      for (int j = 0; j < RMAX; ++j)
       {
-        const unsigned int *__restrict__ it = dm.jp_items + t_rounds[2 * (r0 + j)] + lane;
-        const int L = t_rounds[2 * (r0 + j) + 1];
-        const double nm = s.snm[t_rspec[(r0 + j) * 32 + lane]];
-        unsigned int u0 = __ldg(it), u1 = __ldg(it + 32);
-        for (int k = 0; k < L; k += JP_BLK)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          hold[j][g] = 0.;
+        if (j < nround)
         {
-          it += 32 * JP_BLK;
-          const unsigned int n0 = __ldg(it), n1 = __ldg(it + 32);
-          gather_step<G>(u0, s.sR, rot, nm, hold[j]);
-          gather_step<G>(u1, s.sR, rot, nm, hold[j]);
-          u0 = n0;
-          u1 = n1;
+          const int L = t_rounds[2 * (r0 + j) + 1];
+          const double nm = s.snm[t_rspec[(r0 + j) * 32 + lane]];
+          for (int k = 0; k < L; k += JP_BLK)
+          {
+            const unsigned int m0 = __ldg(it), m1 = __ldg(it + 32);
+            it += 32 * JP_BLK;
+            gather_step<G>(u0, s.sR, rot, nm, hold[j]);
+            gather_step<G>(u1, s.sR, rot, nm, hold[j]);
+            u0 = n0, u1 = n1;
+            n0 = m0, n1 = m1;
+          }
         }
       }
     }
@@ -1333,8 +1340,8 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         // destination of the state's block, and the flamelet extras of its grid point
         size_t obase;
         double ttc = 0.;
-        if (!flamelet)
-          obase = (size_t)sidx * ns * ns;
+        if (!flamelet || fl.chem_only)
+          obase = (size_t)sidx * ns * ns; // dense blocks (the eigenvalue pass reads them in place)
         else
         { // block iz of flamelet F in BTDDOD storage
           const int nzi = fl.nzi, F = sidx / nzi, iz = sidx - F * nzi;
@@ -1370,7 +1377,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
         continue;
       double v = (r == 0) ? SJ(dm.jp_t0base, g) : SJ(dm.jp_c0base + r - 1, g);
       const size_t ob = (size_t)__double_as_longlong(SMG(s.sc, J_OBASE, g));
-      if (flamelet)
+      if (flamelet && !fl.chem_only)
       {
         if (r == 0)
         {
@@ -1427,7 +1434,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
               for (int sl = 0; sl < G; ++sl)
                 v[sl] += -invTau;
             }
-            if (flamelet)
+            if (flamelet && !fl.chem_only)
             {
 #pragma unroll
               for (int sl = 0; sl < G; ++sl)

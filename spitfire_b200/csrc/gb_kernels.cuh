@@ -43,6 +43,7 @@ struct FlameletDev
   // jacobian extras
   int scale_and_offset;
   double prefactor;
+  int chem_only; // diagonal blocks as they stand at flamelet_kernels.cpp:1327 (before cmajor etc.): the eigenvalue pass
 };
 
 struct ChemArgs
@@ -68,6 +69,11 @@ cudaError_t launch_thermo(const DeviceMech &dm, int what, int n, const double *a
 cudaError_t launch_flamelet_prepass(const DeviceMech &dm, int F, const double *state, const FlameletDev &fl,
                                     double *cp_grid, double *maxT, double *cp_bc, cudaStream_t s);
 cudaError_t launch_flamelet_offdiag(const DeviceMech &dm, int F, const FlameletDev &fl, double *out_jac, cudaStream_t s);
+// gb_eig.cu: out[b] = max Re(lambda) of the n x n matrix at base + (b / per_f) * stride_f + (b % per_f) * n * n
+cudaError_t launch_block_max_real_eig(int nblocks, const double *base, long stride_f, int per_f, int n, double *out,
+                                      cudaStream_t s);
+// out[b * n + q] = max(maxre[b] - diffterm, 0)
+cudaError_t launch_expand_expeig(int nblocks, int n, const double *maxre, double diffterm, double *out, cudaStream_t s);
 long kernel_launch_count();
 #ifdef GB_JAC_TIMELINE
 int debug_jac_timeline(long long *out);

@@ -291,7 +291,7 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
         c = 600. + (x.kform == KF_ARRHENIUS ? 300. : 0.) + (x.reversible ? 460. : 0.);
       else
       {
-        c = x.type == RT_SIMPLE ? 4600. : (x.type == RT_THIRD_BODY ? 8800. : (x.type == RT_LINDEMANN ? 10000. : 16500.));
+        c = x.type == RT_SIMPLE ? 4200. : (x.type == RT_THIRD_BODY ? 7900. : (x.type == RT_LINDEMANN ? 10000. : 13600.));
         if (kind[r] == 2)
           c = 1.5 * c + (x.has_orders ? 6000. : 0.);
       }
@@ -512,8 +512,8 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       }
     }
     out.wr_off[nwarps] = (int)out.rounds.size() / 2;
-    for (int k = 0; k < 32 * (BLK + 2); ++k)
-      out.items.push_back((unsigned int)out.zrow); // the prefetch of the last block reads past the end
+    for (int k = 0; k < 32 * (3 * BLK + 2); ++k)
+      out.items.push_back((unsigned int)out.zrow); // the prefetch runs up to three blocks past the end
     if (getenv("GB_PLAN_VERBOSE"))
     {
       fprintf(stderr, "[gb plan] rec_rows=%d rows=%d dests=%d parts=%d items=%d steps*32=%d rounds=%d fix=%d; warp steps:",

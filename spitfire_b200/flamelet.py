@@ -249,30 +249,29 @@ class _BatchOps(object):
                                          prefactor, self.rsopt, self.stopt, *self.flags, null, on[k])
         return out
 
-    def explosive_bound(self, J, diffterm, idx=None):
-        """max(Re(lambda)) of every grid point's ns x ns block minus `diffterm`, clipped at zero and repeated for the
-        point's dofs (flamelet_kernels.cpp:1329-1341). If the eigenvalue routine is unavailable the Gershgorin bound of
-        the block (rows or columns, whichever is tighter) is used, which is safe but gives smaller pseudo-time steps.
-        J: [n, nelem] positive Jacobian; diffterm: [n]"""
+    def jac_and_eig(self, state, diffterm, idx=None, key=None):
+        """(Jacobian, explosive-mode bound) of the members idx, the pair `Flamelet._*_jac_and_eig` returns
+        (flamelet.py:715-741). diffterm: [n] (one value per member; the reference passes a scalar per call). On the
+        device both come out of one C-ABI call: the eigenvalue bound is computed with diffterm = 0 and shifted per member
+        here, max(max(Re) - d, 0) = max(max(max(Re), 0) - d, 0) for d >= 0."""
         torch = self.torch
-        n = J.shape[0]
-        B = J[:, :self.nzi * self.ns * self.ns].reshape(n, self.nzi, self.ns, self.ns).clone()  # [.., col, row]
-        # the reference takes the eigenvalues of the chemical block before the diffusion diagonal (cmajor) is added
         idx = self._all() if idx is None else idx
-        cm = self.cmaj.index_select(0, idx).reshape(n, self.nzi, self.ns)
-        torch.diagonal(B, dim1=2, dim2=3).sub_(cm)
-        try:
-            # LAPACK dgeev on the host, as the reference does inside Griffon; 2.8 MB per GRI-128 flamelet cross PCIe.
-            # (torch's CUDA eigvals goes through MAGMA and is ~9x slower for these 53 x 53 blocks: 355 vs 41 ms.)
-            bound = torch.linalg.eigvals(B.cpu()).real.amax(dim=2).to(B.device)  # eig(B^T) = eig(B)
-        except RuntimeError:
-            diag = torch.diagonal(B, dim1=2, dim2=3)
-            absB = B.abs()
-            off_rows = absB.sum(dim=2) - diag.abs()
-            off_cols = absB.sum(dim=3) - diag.abs()
-            bound = torch.minimum((diag + off_rows).amax(dim=2), (diag + off_cols).amax(dim=2))
-        e = torch.clamp(bound - diffterm[:, None], min=0.)
-        return e.repeat_interleave(self.ns, dim=1)
+        n = state.shape[0]
+        if not self.on_device:
+            out = torch.zeros((n, self.nelem), dtype=torch.float64)
+            e = torch.zeros((n, self.ndof), dtype=torch.float64)
+            sn, on, en, dn = state.numpy(), out.numpy(), e.numpy(), diffterm.numpy()
+            for k, f in enumerate(idx.tolist()):
+                self.g.flamelet_jacobian(np.ascontiguousarray(sn[k]), *self._host_args(f), True, float(dn[k]), False, 1.,
+                                         self.rsopt, self.stopt, *self.flags, en[k], on[k])
+            return out, e
+        out = torch.empty((n, self.nelem), dtype=torch.float64, device=self.device)
+        e0 = torch.empty((n, self.ndof), dtype=torch.float64, device=self.device)
+        prm, keep = self._params(idx, key)
+        self.g.flamelet_jacobian_batch(n, state.contiguous(), prm, out, compute_eigenvalues=True, diffterm=0.,
+                                       rates_sens_option=self.rsopt, sens_transform_option=self.stopt, out_expeig=e0)
+        del keep
+        return out, torch.clamp(e0 - torch.clamp(diffterm, min=0.)[:, None], min=0.)
 
     def factorize(self, J, with_inverse=False):
         """block-Thomas factorisation in place of the systems J [n, nelem]; returns (J, L, pivots[, Dinv]).
@@ -492,8 +491,7 @@ class FlameletBatch(object):
             iters[idx] += 1
             ij = torch.nonzero(active & need_jac).flatten()
             if ij.numel():
-                Jp = ops.jac(state.index_select(0, ij), ij)
-                expeig = ops.explosive_bound(Jp, diffterm.index_select(0, ij), ij)
+                Jp, expeig = ops.jac_and_eig(state.index_select(0, ij), diffterm.index_select(0, ij), ij)
                 dsj = torch.minimum(torch.minimum(ds_safety / (expeig + 1.e-16), ds_ramp * ds.index_select(0, ij)),
                                     torch.full_like(expeig, ds_max))
                 first = (iters.index_select(0, ij) == 1) | bool(global_ds)

@@ -90,6 +90,7 @@ def load_library():
     sig('gb_btddod_full_solve_batch', I, [I, V, V, V, V, I, I, V, V])
     sig('gb_btddod_full_factorize_inv_batch', I, [I, V, I, I, V, V, V, V])
     sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V])
+    sig('gb_max_real_eigenvalue_batch', I, [I, I, V, V, V])
     sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
     sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
@@ -416,6 +417,12 @@ def btddod_full_factorize_inv(out_d_factors, num_blocks, block_size, out_l_value
                                                             int(block_size), _addr(out_l_values),
                                                             _addr(out_d_pivots, np.int32), _addr(out_dinv), _stream()),
           'gb_btddod_full_factorize_inv_batch')
+
+
+def max_real_eigenvalue(blocks, n, out, n_blocks):
+    """out[b] = max Re(lambda) of the b-th n x n block (device tensors) -- gb_max_real_eigenvalue_batch"""
+    check(load_library().gb_max_real_eigenvalue_batch(int(n_blocks), int(n), _addr(blocks), _addr(out), _stream()),
+          'gb_max_real_eigenvalue_batch')
 
 
 def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1):

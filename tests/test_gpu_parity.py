@@ -355,13 +355,6 @@ def test_flamelet_batch_with_per_flamelet_dissipation_rates():
     assert_parity(d_jac.cpu().numpy(), np.array(ref_j), 'batched flamelet jac')
 
 
-def test_eigenvalue_bound_is_refused_not_faked():
-    mg = build_mech('h2-burke', 'gpu')
-    c = flamelet_case(mg, 12)
-    with pytest.raises(griffon.GriffonB200Error):
-        flamelet_all(mg.griffon, c, eig=True)
-
-
 # ---- block Thomas -----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('name,nz', [('h2-burke', 34), ('methane-gri30', 24)])
 def test_block_thomas_parity(name, nz):

@@ -33,8 +33,32 @@ def main():
     ap.add_argument('--wave', type=int, default=8)
     ap.add_argument('--nonadiabatic', type=int, default=0)
     ap.add_argument('--mech', default='methane-gri30')
+    ap.add_argument('--profile-ops', action='store_true', help='synchronise around every batched operation and '
+                    'print where the time goes (slows the build down)')
     args = ap.parse_args()
     rank, world = parallel.init_from_env()
+    acc = dict()
+    if args.profile_ops:
+        import torch
+        from spitfire_b200 import flamelet as fl
+
+        def wrap(name):
+            f = getattr(fl._BatchOps, name)
+
+            def g(self, *a, **k):
+                if self.on_device:
+                    torch.cuda.synchronize()
+                t = time.perf_counter()
+                r = f(self, *a, **k)
+                if self.on_device:
+                    torch.cuda.synchronize()
+                e = acc.setdefault(name, [0, 0.])
+                e[0] += 1
+                e[1] += time.perf_counter() - t
+                return r
+            setattr(fl._BatchOps, name, g)
+        for nm in ('rhs', 'jac', 'factorize', 'solve', 'jac_and_eig', 'add_to_block_diagonal'):
+            wrap(nm)
     m = build_mech(args.mech, args.backend)
     air = m.stream(stp_air=True)
     fuel = m.stream('TPX', (300., 101325., 'CH4:1' if 'methane' in args.mech or 'gri' in args.mech else 'H2:1'))
@@ -62,6 +86,8 @@ def main():
         say(dict(metric='nonadiabatic (transient defect) SLFM library build wall time', unit='s',
                  value=time.perf_counter() - t0, higher_is_better=False, n_chi=args.nonadiabatic, n_defect_st=16,
                  shape=list(lib.shape), wave=args.wave))
+    if args.profile_ops and rank == 0:
+        print(json.dumps({k: dict(calls=v[0], seconds=round(v[1], 3)) for k, v in acc.items()}), flush=True)
     parallel.finalize()
 
 

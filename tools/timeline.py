@@ -28,6 +28,7 @@ assert lib.gb_debug_jac_timeline(buf) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(20, 32)
 nw = int((t[0] != 0).sum())
 tk = t[11:17]
+tw = t[17:19]
 t = t[:11, :nw]
 t0 = t[0].min()
 names = ['top', 'load', 'thermo', 'conc', 'react', 'gather', 'write', 'fix', 'rows/cols', 'T-row', 'output']
@@ -42,3 +43,5 @@ print('reaction phase, mean cycles per group by kind:')
 for k, name in enumerate(['fast A+B<=>C+D', 'structured simple', 'third body', 'Lindemann', 'Troe', 'generic']):
     if tk[k, 1]:
         print(f'  {name:18s} {int(tk[k,1])//2:4d} groups  {tk[k,0]/tk[k,1]:8.0f} cycles')
+print('reaction phase, cycles inside groups per warp:', ' '.join(str(int(x)//2) for x in tw[0, :nw]))
+print('groups per warp:', ' '.join(str(int(x)//2) for x in tw[1, :nw]))
