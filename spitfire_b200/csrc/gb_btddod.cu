@@ -156,6 +156,20 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+#ifdef GB_JAC_TIMELINE
+__device__ long long g_bt_timeline[8];
+__device__ long long g_bt_timeline2[8];
+#define BT_MARK(k)                                   \
+  if (blockIdx.x == 0 && tid == 0)                   \
+  {                                                  \
+    const long long c__ = clock64();                 \
+    g_bt_timeline[k] += c__ - bt_prev;               \
+    bt_prev = c__;                                   \
+  }
+#else
+#define BT_MARK(k)
+#endif
+
 template <int Q, int RPL> // Q lanes per column (a power of two <= 16), rows per lane: bs <= Q*RPL
 __global__ void __launch_bounds__(1024, 1)
     k_btddod_factorize(int nsys, double *d_factors, int nb, int bs, double *l_values, int *pivots, double *dinv)
@@ -241,8 +255,12 @@ __global__ void __launch_bounds__(1024, 1)
     if (active && col == 0)
       find_pivot(0);
     __syncthreads();
+#ifdef GB_JAC_TIMELINE
+    long long bt_prev = clock64();
+#endif
     for (int i = 0; i < nb; ++i)
     {
+      BT_MARK(0)
       if (i + 1 < nb)
       { // stage the next diagonal block
         const double *Dnext = D + (size_t)(i + 1) * nb2;
@@ -253,6 +271,9 @@ __global__ void __launch_bounds__(1024, 1)
       // ---- LU with partial pivoting, one barrier per step ------------------------------------------------------------
       for (int k = 0; k < bs; ++k)
       {
+#ifdef GB_JAC_TIMELINE
+        long long c0 = clock64(), c1 = 0, c2 = 0, c3 = 0;
+#endif
         if (active)
         {
           const int p = spiv[k];
@@ -261,6 +282,9 @@ __global__ void __launch_bounds__(1024, 1)
             const double rp = srp[k];
             const double ckk = A[k + k * ld]; // old column k: row k moves to row p
             swap_rows(k, p);
+#ifdef GB_JAC_TIMELINE
+            c1 = clock64();
+#endif
             if (rp != 0.)
             {
               const double akj = A[k + col * ld];
@@ -275,10 +299,16 @@ __global__ void __launch_bounds__(1024, 1)
                 }
               }
             }
+#ifdef GB_JAC_TIMELINE
+            c2 = clock64();
+#endif
             if (col == k + 1)
             {
               __syncwarp(mask);
               find_pivot(k + 1);
+#ifdef GB_JAC_TIMELINE
+              c3 = clock64();
+#endif
             }
           }
           else if (col < k)
@@ -303,7 +333,17 @@ __global__ void __launch_bounds__(1024, 1)
           }
         }
         __syncthreads();
+#ifdef GB_JAC_TIMELINE
+        if (blockIdx.x == 0 && active && col == k + 1 && q == 0)
+        {
+          g_bt_timeline2[0] += c1 - c0;
+          g_bt_timeline2[1] += c2 - c1;
+          g_bt_timeline2[2] += c3 - c2;
+          g_bt_timeline2[3] += clock64() - c3;
+        }
+#endif
       }
+      BT_MARK(1)
       // (column bs-1 has no multipliers; column bs-2 was finalised in step bs-1)
       for (int e = tid; e < bs * bs; e += nt)
         D[(size_t)i * nb2 + e] = A[e % bs + (e / bs) * ld];
@@ -311,6 +351,7 @@ __global__ void __launch_bounds__(1024, 1)
         piv[(size_t)i * bs + k] = spiv[k] + 1;
       if (i == nb - 1 && dinv == nullptr)
         break;
+      BT_MARK(2)
       // ---- column `col` of the inverse, in registers --------------------------------------------------------------------
       double x[RPL];
       if (active)
@@ -376,6 +417,7 @@ __global__ void __launch_bounds__(1024, 1)
           }
         }
       }
+      BT_MARK(3)
       if (dinv != nullptr && active)
       { // extension: keep the explicit inverse for the matvec-only back sweep of k_btddod_solve_inv
         double *Xo = dinv + ((size_t)sys * nb + i) * nb2 + (size_t)col * bs;
@@ -391,6 +433,7 @@ __global__ void __launch_bounds__(1024, 1)
         break;
       cp_async_wait_all();
       __syncthreads(); // every group is done reading the factors; the staged block has landed
+      BT_MARK(4)
       // ---- L_{i+1} = diag(sub_i) * D_i^{-1} (:55-63); D_{i+1} -= L_{i+1} * diag(sup_i) (:65-75) ----------------------
       if (active)
       {
@@ -415,9 +458,19 @@ __global__ void __launch_bounds__(1024, 1)
         }
       }
       __syncthreads();
+      BT_MARK(5)
     }
   }
 }
+#ifdef GB_JAC_TIMELINE
+int debug_bt_timeline(long long *out)
+{
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out + 8, g_bt_timeline2, sizeof(long long) * 8) != cudaSuccess)
+    return -3;
+  return cudaMemcpyFromSymbol(out, g_bt_timeline, sizeof(long long) * 8) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_btddod_solve: forward y_i = b_i - L_i y_{i-1} (:95-103); back x_i = D_i^{-1} (y_i - sup_i o x_{i+1}) (:105-118).
@@ -616,25 +669,91 @@ __global__ void __launch_bounds__(64) k_btddod_solve(int nsys, const double *d_f
 // k_btddod_solve_inv (extension, not in the reference API): the same block-Thomas solve with the explicit inverses
 // D_i^{-1} that the factorisation forms anyway for L_{i+1}: the back sweep x_i = D_i^{-1} (y_i - sup_i o x_{i+1})
 // becomes a matrix-vector product, fully parallel over the rows, instead of two dependent triangular solves. Used
-// inside the Newton loops of the batched ESDIRK integrator, where the linear solve only preconditions an iteration that
-// converges on the true residual.
+// inside the Newton loops of the steady solvers and of the batched ESDIRK integrator, where the linear solve only
+// proposes the update of an iteration that converges on the true residual.
+//
+// One CTA of eight warps per system. The 2*nb-1 blocks (L_1..L_{nb-1}, then Dinv_{nb-1}..Dinv_0) stream through a
+// four-deep ring of shared-memory buffers filled with 16-byte cp.async (the blocks are only 8-byte aligned when the
+// block size is odd: the first / last element then travel separately). Every row's dot product is split over four
+// lanes (fma, partial sums combined by shuffle), so the dependent chain per block step is bs/4 long; the vector
+// ping-pongs between two shared arrays, which leaves one barrier per step. The right-hand side is staged in shared
+// memory once and overwritten with y_i, so the back sweep never waits for a global read of its own earlier writes.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_btddod_solve_inv(int nsys, const double *d_factors, const double *l_values,
-                                                          const double *dinv, const double *rhs, int nb, int bs,
-                                                          double *solution)
+constexpr int SI_STAGES = 4;
+constexpr int SI_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gmem_src)
 {
-  extern __shared__ double sm[];
-  double *buf0 = sm;
-  double *buf1 = buf0 + bs * bs;
-  double *v = buf1 + bs * bs; // [bs] y_{i-1} / right-hand side of the back sweep
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const size_t nb2 = (size_t)bs * bs;
+  const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "MBAR_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra MBAR_DONE;\n"
+               "bra MBAR_WAIT;\n"
+               "MBAR_DONE:\n"
+               "}\n" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned addresses and size)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared-memory load that keeps its place in the instruction stream (ptxas otherwise sinks each pair of loads to just
+// before the fma that consumes it, which serialises the shared-memory latency of the whole dot product)
+__device__ __forceinline__ double lds_f64(const double *p)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(smem_u32(p)));
+  return v;
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group()
+{
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const double *d_factors, const double *l_values,
+                                                                 const double *dinv, const double *rhs, int nb, int bs,
+                                                                 double *solution, int staged)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb2 = bs * bs;
+  const int bufsz = (nb2 + 3) & ~1; // room for the one-element shift of an odd-aligned block, multiple of 16 bytes
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm); // [SI_STAGES] "block landed" barriers
+  double *ring = sm + 8;
+  double *v0 = ring + (size_t)SI_STAGES * bufsz; // [2][bsp] ping-pong vector
+  const int bsp = (bs + 1) & ~1;
+  double *yv = v0 + 2 * bsp;                     // [nb*bs] right-hand side, overwritten with y_i (if `staged`: it fits)
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
-  auto fetch = [&](double *dst, const double *src) {
-    for (int e = tid; e < bs * bs; e += nt)
-      cp_async8(dst + e, src + e);
-    cp_async_commit();
-  };
+  const int sub = lane & 7, part = lane >> 3;
+  if (tid == 0)
+  {
+    for (int k = 0; k < SI_STAGES; ++k)
+      mbar_init(bars + k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  int gs0 = 0; // blocks streamed by this CTA before the current system (ring slot and barrier phase follow from it)
+
   for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
   {
     const double *D = d_factors + (size_t)sys * mat_stride;
@@ -643,60 +762,160 @@ __global__ void __launch_bounds__(128) k_btddod_solve_inv(int nsys, const double
     const double *sup = D + (size_t)nb * nb2 + (size_t)(nb - 1) * bs;
     const double *b = rhs + (size_t)sys * nb * bs;
     double *x = solution + (size_t)sys * nb * bs;
-    __syncthreads();
-    // blocks stream through the two buffers in the order L_1 .. L_{nb-1}, Dinv_{nb-1} .. Dinv_0
     const int nstream = 2 * nb - 1;
     auto src_of = [&](int s) { return s < nb - 1 ? Lv + (size_t)(s + 1) * nb2 : Di + (size_t)(nstream - 1 - s) * nb2; };
-    fetch(buf0, src_of(0));
-    for (int j = tid; j < bs; j += nt)
+    // Block s lands at ring[(gs0+s) % STAGES] + (1 if its source address is an odd multiple of 8 bytes): one TMA bulk
+    // copy of the 16-byte aligned span that lies inside the block's neighbourhood (a single SM cannot keep enough
+    // LDGSTS requests in flight to stream 22 KB per step), plus the odd last element, if any, by an 8-byte cp.async.
+    auto fetch = [&](int s) {
+      if (s < nstream)
+      {
+        const double *src = src_of(s);
+        const int g = gs0 + s;
+        double *dst = ring + (size_t)(g % SI_STAGES) * bufsz;
+        const int off = (int)((reinterpret_cast<size_t>(src) >> 3) & 1);
+        const int span = nb2 + off, n16 = span >> 1; // elements from src - off
+        if (tid == 0)
+        {
+          mbar_expect_tx(bars + g % SI_STAGES, (unsigned int)n16 * 16u);
+          bulk_g2s(dst, src - off, (unsigned int)n16 * 16u, bars + g % SI_STAGES);
+        }
+        if ((span & 1) && tid == 32)
+          cp_async8(dst + 2 * n16, src - off + 2 * n16);
+      }
+      cp_async_commit(); // (an empty group keeps the group count in step)
+    };
+    auto buf_of = [&](int s) {
+      return ring + (size_t)((gs0 + s) % SI_STAGES) * bufsz + (int)((reinterpret_cast<size_t>(src_of(s)) >> 3) & 1);
+    };
+    __syncthreads(); // the previous system is done with the shared arrays
+    if (staged)
+      for (int e = tid; e < nb * bs; e += SI_THREADS)
+        yv[e] = b[e];
+    for (int s = 0; s < SI_STAGES - 1; ++s)
+      fetch(s);
+    for (int j = tid; j < bs; j += SI_THREADS)
     {
-      v[j] = b[j];
+      v0[j] = b[j];
       x[j] = b[j];
     }
     for (int s = 0; s < nstream; ++s)
     {
-      double *cur = (s & 1) ? buf1 : buf0, *nxt = (s & 1) ? buf0 : buf1;
-      cp_async_wait_all();
-      __syncthreads(); // block s has landed, v is complete
-      if (s + 1 < nstream)
-        fetch(nxt, src_of(s + 1));
-      double out = 0.;
-      int i;
-      if (s < nb - 1)
-      { // forward: y_i = b_i - L_i y_{i-1}
-        i = s + 1;
-        if (tid < bs)
-        {
-          double acc = b[(size_t)i * bs + tid];
-          for (int c = 0; c < bs; ++c)
-            acc = acc + cur[(size_t)c * bs + tid] * (-1. * v[c]);
-          out = acc;
-        }
-      }
-      else
-      { // back: x_i = Dinv_i * v, v = y_i - sup_i o x_{i+1} (v prepared at the end of the previous step)
-        i = nstream - 1 - s;
-        if (tid < bs)
-        {
-          double acc = 0.;
-          for (int c = 0; c < bs; ++c)
-            acc += cur[(size_t)c * bs + tid] * v[c];
-          out = acc;
-        }
-      }
-      __syncthreads(); // everyone is done reading v
-      if (tid < bs)
+      const bool fwd = s < nb - 1;
+      const int i = fwd ? s + 1 : nstream - 1 - s;
+      // operand of the epilogue that does not depend on this sweep: issued before the wait (first 64 rows)
+      double sup0 = 0.;
+      if (!fwd && i > 0 && part == 0 && warp * 8 + sub < bs)
+        sup0 = __ldg(sup + (size_t)(i - 1) * bs + warp * 8 + sub);
+#ifdef GB_JAC_TIMELINE
+      long long c0 = clock64();
+#endif
+      cp_async_wait_group<SI_STAGES - 2>();
+      mbar_wait(bars + (gs0 + s) % SI_STAGES, (unsigned int)(((gs0 + s) / SI_STAGES) & 1));
+#ifdef GB_JAC_TIMELINE
+      long long c1 = clock64();
+#endif
+      __syncthreads(); // block s has landed for everyone; the vector of this step is complete; ring slot s-1 is free
+#ifdef GB_JAC_TIMELINE
+      if (*((volatile double *)v0) == 1.2345e300) // (a read that needs the barrier's release: the clock below is taken after it)
+        printf("x");
+      long long c2 = clock64();
+#endif
+      fetch(s + SI_STAGES - 1);
+#ifdef GB_JAC_TIMELINE
+      long long c3 = clock64();
+#endif
+      const double *cur = buf_of(s);
+      const double *vin = v0 + (s & 1) * bsp;
+      double *vout = v0 + ((s + 1) & 1) * bsp;
+      for (int row0 = 0; row0 < bs; row0 += 64)
       {
-        x[(size_t)i * bs + tid] = out;
-        if (s < nb - 2)
-          v[tid] = out; // y_i feeds the next forward step
-        else if (s == nb - 2)
-          v[tid] = out; // y_{nb-1}: right-hand side of the first back step
-        else if (i > 0)
-          v[tid] = x[(size_t)(i - 1) * bs + tid] - sup[(size_t)(i - 1) * bs + tid] * out; // y_{i-1} - sup_{i-1} o x_i
+        const int row = row0 + warp * 8 + sub;
+        const bool live = row < bs;
+        const int rr = live ? row : 0;
+        // operands of the epilogue, fetched ahead of the dot product
+        double e0 = 0., e1 = sup0;
+        if (part == 0 && live)
+        {
+          if (fwd)
+            e0 = staged ? yv[(size_t)i * bs + row] : b[(size_t)i * bs + row];
+          else if (i > 0)
+          {
+            e0 = staged ? yv[(size_t)(i - 1) * bs + row] : x[(size_t)(i - 1) * bs + row];
+            if (row0 > 0)
+              e1 = __ldg(sup + (size_t)(i - 1) * bs + row);
+          }
+        }
+        // part p takes the columns 16 j + 8 (p & 1) + 4 (p >> 1) + t, t < 4: the two parts of a half-warp are eight
+        // columns apart, which for an odd block size puts their eight rows in disjoint banks. All loads of a pair of
+        // j are issued before the first fma (two accumulators).
+        const int cpart = 8 * (part & 1) + 4 * (part >> 1);
+        const double *cb = cur + (size_t)cpart * bs + rr, *vb = vin + cpart;
+        double a0 = 0., a1 = 0.;
+        for (int j = 0; j < bs; j += 32)
+        {
+          double mm[8], ww[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+          {
+            const int cj = j + 16 * (u >> 2) + (u & 3);
+            const int cc = cj + cpart < bs ? cj : 0; // (a column past the end re-reads a valid one with weight zero)
+            mm[u] = lds_f64(cb + (size_t)cc * bs);
+            ww[u] = lds_f64(vb + cc);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (j + 16 * (u >> 2) + (u & 3) + cpart >= bs)
+              ww[u] = 0.;
+          // (the accumulators are made to depend on the LAST load, so that the in-order issue cannot stall on the
+          // first fma before every load of the batch is in flight)
+          a0 = fma(mm[7], 0., a0);
+          a1 = fma(ww[7], 0., a1);
+#pragma unroll
+          for (int u = 0; u < 8; u += 2)
+          {
+            a0 = fma(mm[u], ww[u], a0);
+            a1 = fma(mm[u + 1], ww[u + 1], a1);
+          }
+        }
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+#ifdef GB_JAC_TIMELINE
+        if (blockIdx.x == 0 && tid == 0 && acc != 1.2345e300)
+          g_bt_timeline2[3] += clock64() - c3; // (overwrites the LU 'barrier wait' slot while the solve runs)
+#endif
+        if (part == 0 && live)
+        {
+          if (fwd)
+          { // y_i = b_i - L_i y_{i-1}
+            const double y = e0 - acc;
+            if (staged)
+              yv[(size_t)i * bs + row] = y;
+            else
+              x[(size_t)i * bs + row] = y;
+            vout[row] = y; // feeds the next forward step, or is the right-hand side of the first back step
+          }
+          else
+          { // x_i = Dinv_i v; the next right-hand side is y_{i-1} - sup_{i-1} o x_i
+            x[(size_t)i * bs + row] = acc;
+            if (i > 0)
+              vout[row] = e0 - e1 * acc;
+          }
+        }
       }
+#ifdef GB_JAC_TIMELINE
+      if (blockIdx.x == 0 && tid == 0)
+      {
+        g_bt_timeline2[4] += c1 - c0;
+        g_bt_timeline2[5] += c2 - c1;
+        g_bt_timeline2[6] += c3 - c2;
+        g_bt_timeline2[7] += clock64() - c3;
+      }
+#endif
     }
-    cp_async_wait_all();
+    cp_async_wait_group<0>();
+    gs0 += nstream;
   }
 }
 
@@ -819,14 +1038,23 @@ extern "C"
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
       return rc;
-    if (bs > 128)
+    const size_t base = sizeof(double) * ((size_t)SI_STAGES * (((size_t)bs * bs + 3) & ~(size_t)1) + 2 * (((size_t)bs + 1) & ~(size_t)1)) + 64 + 16;
+    const size_t with_rhs = base + sizeof(double) * (size_t)nb * bs;
+    if (base > (size_t)227 * 1024)
     {
-      set_error("block size too large for k_btddod_solve_inv");
+      set_error("block size too large for k_btddod_solve_inv (a ring of four blocks lives in shared memory)");
       return GB_ERR_UNSUPPORTED;
     }
-    const size_t smem = sizeof(double) * (2 * (size_t)bs * bs + bs + 2) + 64;
+    if ((reinterpret_cast<size_t>(l_values) | reinterpret_cast<size_t>(dinv)) & 15)
+    { // the bulk copies start at the 16-byte boundary at or just below a block
+      set_error("gb_btddod_full_solve_inv_batch: l_values and dinv must be 16-byte aligned");
+      return GB_ERR_ARG;
+    }
+    const int staged = with_rhs <= (size_t)227 * 1024 ? 1 : 0; // the right-hand side too, when it fits
+    const size_t smem = staged ? with_rhs : base;
     BCK(cudaFuncSetAttribute(k_btddod_solve_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_btddod_solve_inv<<<n, 128, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution);
+    k_btddod_solve_inv<<<n, SI_THREADS, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution,
+                                                                      staged);
     ++g_btddod_launches;
     BCK(cudaGetLastError());
     return GB_OK;

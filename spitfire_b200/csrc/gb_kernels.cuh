@@ -77,6 +77,7 @@ cudaError_t launch_expand_expeig(int nblocks, int n, const double *maxre, double
 long kernel_launch_count();
 #ifdef GB_JAC_TIMELINE
 int debug_jac_timeline(long long *out);
+int debug_bt_timeline(long long *out);
 #endif
 
 } // namespace gb

@@ -273,6 +273,27 @@ class _BatchOps(object):
         del keep
         return out, torch.clamp(e0 - torch.clamp(diffterm, min=0.)[:, None], min=0.)
 
+    # On the device the steady solvers use the explicit block inverses the factorisation forms anyway: the linear solve
+    # only proposes the update of an iteration that converges on the true residual, and the inverse-based back sweep is
+    # 3-4x shorter than the pivoted triangular solves (griffon_b200.h, gb_btddod_full_*_inv_batch).
+    explicit_inverse_solves = True
+
+    def factor_store(self, F):
+        """zeroed arrays for the factors of F systems: (J, L, pivots[, Dinv])"""
+        torch = self.torch
+        out = [torch.zeros((F, self.nelem), dtype=torch.float64, device=self.device),
+               torch.zeros((F, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device),
+               torch.zeros((F, self.ndof), dtype=torch.int32, device=self.device)]
+        if self.on_device and self.explicit_inverse_solves:
+            out.append(torch.zeros((F, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device))
+        return tuple(out)
+
+    def factorize_into(self, store, rows, J):
+        """factorise the systems J and keep the factors at positions `rows` of `store`"""
+        fact = self.factorize(J, with_inverse=len(store) == 4)
+        for dst, src in zip(store, fact):
+            dst[rows] = src
+
     def factorize(self, J, with_inverse=False):
         """block-Thomas factorisation in place of the systems J [n, nelem]; returns (J, L, pivots[, Dinv]).
         with_inverse (device path only) also keeps the explicit inverses of the factorised diagonal blocks so that
@@ -370,9 +391,7 @@ class FlameletBatch(object):
         active = torch.ones(F, dtype=torch.bool, device=dev)
         failed = torch.zeros(F, dtype=torch.bool, device=dev)
         need_jac = torch.ones(F, dtype=torch.bool, device=dev)
-        J = torch.zeros((F, ops.nelem), dtype=torch.float64, device=dev)
-        L = torch.zeros((F, ops.nzi * ops.ns * ops.ns), dtype=torch.float64, device=dev)
-        piv = torch.zeros((F, ops.ndof), dtype=torch.int32, device=dev)
+        factors = ops.factor_store(F)
         while True:
             active = active & (res > tolerance) & (iters < max_iterations) & ~failed
             idx = torch.nonzero(active).flatten()
@@ -382,10 +401,9 @@ class FlameletBatch(object):
             ij = torch.nonzero(active & need_jac).flatten()
             if ij.numel():
                 Jn = ops.jac(state.index_select(0, ij), ij).neg_()
-                Jf, Lf, pf = ops.factorize(Jn)
-                J[ij], L[ij], piv[ij] = Jf, Lf, pf
+                ops.factorize_into(factors, ij, Jn)
                 need_jac[ij] = False
-            dstate = ops.solve((J, L, piv), rhs.index_select(0, idx), rows=idx)
+            dstate = ops.solve(factors, rhs.index_select(0, idx), rows=idx)
             bad = ~torch.isfinite(dstate).all(dim=1)
             norm_old = self._norm(rhs.index_select(0, idx) * inv_scales.index_select(0, idx), norm_order)
             s_act = state.index_select(0, idx)
@@ -458,9 +476,7 @@ class FlameletBatch(object):
         active = torch.ones(F, dtype=torch.bool, device=dev)
         failed = torch.zeros(F, dtype=torch.bool, device=dev)
         need_jac = torch.ones(F, dtype=torch.bool, device=dev)
-        J = torch.zeros((F, ops.nelem), dtype=torch.float64, device=dev)
-        L = torch.zeros((F, ops.nzi * ops.ns * ops.ns), dtype=torch.float64, device=dev)
-        piv = torch.zeros((F, ops.ndof), dtype=torch.int32, device=dev)
+        factors = ops.factor_store(F)
         jac_refresh_age = 8
 
         def restart(members):
@@ -498,13 +514,12 @@ class FlameletBatch(object):
                 dsj = torch.where(first[:, None], dsj.amin(dim=1, keepdim=True).expand_as(dsj), dsj)
                 ds[ij] = dsj
                 ops.add_to_block_diagonal(Jp, -1., 1. / dsj, 1.)
-                Jf, Lf, pf = ops.factorize(Jp)
-                J[ij], L[ij], piv[ij] = Jf, Lf, pf
+                ops.factorize_into(factors, ij, Jp)
                 jac_age[ij] = 0
             aged = torch.nonzero(active & ~need_jac).flatten()
             jac_age[aged] += 1
             need_jac[idx] = (jac_age.index_select(0, idx) == jac_refresh_age) | (res.index_select(0, idx) > 1.e-2)
-            dstate = ops.solve((J, L, piv), rhs.index_select(0, idx), rows=idx)
+            dstate = ops.solve(factors, rhs.index_select(0, idx), rows=idx)
             bad = ~torch.isfinite(dstate).all(dim=1)
             norm_old = self._norm(rhs.index_select(0, idx) * inv_scales.index_select(0, idx), norm_order)
             s_act = state.index_select(0, idx)

@@ -24,3 +24,26 @@ def elem():
     rn = dta[:, None] * (0.25 * r + e) - (x - state)
     c = ((rn * ops.scales).abs().amax(dim=1) < 1e-12).cpu().numpy()
 print(f'elementwise+sync {tm(elem, 20):.3f} ms')
+if os.environ.get('GRIFFON_B200_LIB', '').endswith('_tl.so'):
+    import ctypes as C
+    from spitfire_b200 import griffon
+    lib = griffon.load_library()
+    buf = (C.c_longlong * 16)()
+    lib.gb_debug_bt_timeline(buf)
+    before = np.array(buf[:], dtype=np.int64)
+    ops.factorize(J.clone(), with_inverse=True); torch.cuda.synchronize()
+    lib.gb_debug_bt_timeline(buf)
+    d = np.array(buf[:], dtype=np.int64) - before
+    names = ['loop top (prev tail)', 'LU', 'store D/piv', 'inverse', 'store inv + wait + barrier', 'L/D update + pivot']
+    for k in range(6):
+        print(f'  {names[k]:28s} {d[k] / 126:10.0f} cycles per block')
+    for k, nm in enumerate(['LU step: read piv + swap', 'update', 'pivot search', 'barrier wait']):
+        print(f'  {nm:28s} {d[8 + k] / 126 / 52:10.0f} cycles per step (pivot column group)')
+    lib.gb_debug_bt_timeline(buf)
+    before = np.array(buf[:], dtype=np.int64)
+    ops.solve(fact_inv, r); torch.cuda.synchronize()
+    lib.gb_debug_bt_timeline(buf)
+    d = np.array(buf[:], dtype=np.int64) - before
+    for k, nm in enumerate(['solve_inv: wait_group+mbar', 'barrier', 'fetch issue', 'dot + epilogue']):
+        print(f'  {nm:28s} {d[12 + k] / 251:10.0f} cycles per step (thread 0)')
+    print(f'  of which dot + shuffles       {d[11] / 251:10.0f}')

@@ -101,3 +101,36 @@ def test_inverse_based_block_thomas_solve_matches_lu_solve():
     assert torch.equal(dA, dA2) and torch.equal(dL, dL2) and torch.equal(dP, dP2)
     a, b = x2.cpu().numpy(), x1.cpu().numpy()
     assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize('bs,nb', [(11, 1), (11, 2), (11, 33), (53, 40), (64, 5), (70, 4), (5, 3), (11, 2600)])
+def test_inverse_based_solve_shapes(bs, nb):
+    """odd / even block sizes (8-byte vs 16-byte aligned blocks), one and two blocks, more than 64 rows per block, and a
+    system whose right-hand side does not fit in shared memory: inverse-based solve against the LU-based one and
+    against the residual of the original matrix"""
+    import torch
+    from spitfire_b200 import griffon
+    rng = np.random.default_rng(bs * 1000 + nb)
+    F = 3
+    nelem = bs * (nb * bs + 2 * (nb - 1))
+    A = rng.normal(size=(F, nelem))
+    diag = A[:, :nb * bs * bs].reshape(F, nb, bs, bs)
+    diag += 2. * bs * np.eye(bs)  # diagonally dominant blocks
+    rhs = rng.normal(size=(F, nb * bs))
+    dA0 = torch.from_numpy(A).cuda()
+    dA, dA2 = dA0.clone(), dA0.clone()
+    z = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt, device='cuda')
+    dL, dL2, dI = z(F, nb * bs * bs), z(F, nb * bs * bs), z(F, nb * bs * bs)
+    dP, dP2 = z(F, nb * bs, dt=torch.int32), z(F, nb * bs, dt=torch.int32)
+    dR = torch.from_numpy(rhs).cuda()
+    x1, x2, mv = torch.zeros_like(dR), torch.zeros_like(dR), torch.zeros_like(dR)
+    griffon.py_btddod_full_factorize(dA, nb, bs, dL, dP, n_systems=F)
+    griffon.py_btddod_full_solve(dA, dL, dP, dR, nb, bs, x1, n_systems=F)
+    griffon.btddod_full_factorize_inv(dA2, nb, bs, dL2, dP2, dI, n_systems=F)
+    griffon.btddod_full_solve_inv(dA2, dL2, dI, dR, nb, bs, x2, n_systems=F)
+    griffon.py_btddod_full_matvec(dA0, x2, nb, bs, mv, n_systems=F)
+    torch.cuda.synchronize()
+    a, b = x2.cpu().numpy(), x1.cpu().numpy()
+    assert np.all(np.isfinite(a))
+    assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b))
+    assert np.max(np.abs(mv.cpu().numpy() - rhs)) <= 1e-11 * np.max(np.abs(rhs))
