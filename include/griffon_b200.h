@@ -215,12 +215,14 @@ int gb_btddod_scale_and_add_diagonal_batch(int n_systems, double *matrix, double
 /* Extension (no counterpart in the reference API): the factorisation also returns the explicit inverses of the
  * factorised diagonal blocks, out_dinv [n_systems][num_blocks*block_size^2] (it forms them anyway for L_{i+1},
  * btddod_matrix_kernels.cpp:48-63), and gb_btddod_full_solve_inv_batch runs the back sweep as matrix-vector
- * products with them (no pivots, no triangular solves). Same result up to rounding; used inside Newton loops. */
+ * products with them (no pivots, no triangular solves). Same result up to rounding; used inside Newton loops.
+ * system_rows (device, may be NULL): the factors of the k-th right-hand side are those of system system_rows[k] of the
+ * factor arrays, so a solver can address a subset of a batch without gathering 8 MB of factors per member. */
 int gb_btddod_full_factorize_inv_batch(int n_systems, double *d_factors, int num_blocks, int block_size,
                                        double *out_l_values, int *out_d_pivots, double *out_dinv, void *stream);
 int gb_btddod_full_solve_inv_batch(int n_systems, const double *d_factors, const double *l_values, const double *dinv,
                                    const double *rhs, int num_blocks, int block_size, double *out_solution,
-                                   void *stream);
+                                   const int *system_rows, void *stream);
 int gb_btddod_full_factorize_host(int n_systems, double *d_factors, int num_blocks, int block_size,
                                   double *out_l_values, int *out_d_pivots);
 int gb_btddod_full_solve_host(int n_systems, const double *d_factors, const double *l_values, const int *d_pivots,

@@ -732,7 +732,7 @@ __device__ __forceinline__ void cp_async_wait_group()
 
 __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const double *d_factors, const double *l_values,
                                                                  const double *dinv, const double *rhs, int nb, int bs,
-                                                                 double *solution, int staged)
+                                                                 double *solution, int staged, const int *rows)
 {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -756,9 +756,10 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
 
   for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
   {
-    const double *D = d_factors + (size_t)sys * mat_stride;
-    const double *Lv = l_values + (size_t)sys * nb * nb2;
-    const double *Di = dinv + (size_t)sys * nb * nb2;
+    const int fsys = rows ? rows[sys] : sys; // where this system's factors live (right-hand sides are compact)
+    const double *D = d_factors + (size_t)fsys * mat_stride;
+    const double *Lv = l_values + (size_t)fsys * nb * nb2;
+    const double *Di = dinv + (size_t)fsys * nb * nb2;
     const double *sup = D + (size_t)nb * nb2 + (size_t)(nb - 1) * bs;
     const double *b = rhs + (size_t)sys * nb * bs;
     double *x = solution + (size_t)sys * nb * bs;
@@ -1033,7 +1034,8 @@ extern "C"
   }
 
   int gb_btddod_full_solve_inv_batch(int n, const double *d_factors, const double *l_values, const double *dinv,
-                                     const double *rhs, int nb, int bs, double *solution, void *stream)
+                                     const double *rhs, int nb, int bs, double *solution, const int *system_rows,
+                                     void *stream)
   {
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
@@ -1054,7 +1056,7 @@ extern "C"
     const size_t smem = staged ? with_rhs : base;
     BCK(cudaFuncSetAttribute(k_btddod_solve_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_btddod_solve_inv<<<n, SI_THREADS, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution,
-                                                                      staged);
+                                                                      staged, system_rows);
     ++g_btddod_launches;
     BCK(cudaGetLastError());
     return GB_OK;

@@ -89,7 +89,7 @@ def load_library():
     sig('gb_btddod_full_factorize_batch', I, [I, V, I, I, V, V, V])
     sig('gb_btddod_full_solve_batch', I, [I, V, V, V, V, I, I, V, V])
     sig('gb_btddod_full_factorize_inv_batch', I, [I, V, I, I, V, V, V, V])
-    sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V])
+    sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V, V])
     sig('gb_max_real_eigenvalue_batch', I, [I, I, V, V, V])
     sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
     sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
@@ -425,11 +425,14 @@ def max_real_eigenvalue(blocks, n, out, n_blocks):
           'gb_max_real_eigenvalue_batch')
 
 
-def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1):
-    """extension (device arrays only): block-Thomas solve whose back sweep multiplies by the stored inverses"""
+def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1,
+                          system_rows=None):
+    """extension (device arrays only): block-Thomas solve whose back sweep multiplies by the stored inverses.
+    system_rows (int32 device tensor, optional): position in the factor arrays of each right-hand side's system"""
     check(load_library().gb_btddod_full_solve_inv_batch(int(n_systems), _addr(d_factors), _addr(l_values), _addr(dinv),
                                                         _addr(rhs), int(num_blocks), int(block_size),
-                                                        _addr(out_solution), _stream()),
+                                                        _addr(out_solution),
+                                                        None if system_rows is None else _addr(system_rows, np.int32), _stream()),
           'gb_btddod_full_solve_inv_batch')
 
 
