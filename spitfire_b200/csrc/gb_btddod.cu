@@ -138,15 +138,21 @@ __device__ void lu_inverse_smem(const double *A, int bs, int ld, const int *piv,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_btddod_factorize: one CTA per system, four lanes ("quad") per block column, rows interleaved over the quad.
+// k_btddod_factorize: one CTA per system, Q lanes per block column, rows interleaved over the lanes, the lanes' rows of
+// their column RESIDENT IN REGISTERS for the whole factorisation of a block.
 //
-// LU (dgetf2 semantics: first row of maximum modulus, reciprocal scaling, A[i,j] -= (A[i,k]*rp)*A[k,j]) with ONE
-// block-wide barrier per elimination step: the quad of column j applies every step's row interchange and update to
-// its own column; the multipliers are read from column k's *old* values (interchange applied logically), and column
-// k's own interchange + scaling is deferred to the next step, when nobody reads it any more. The quad of column k+1
-// finds the next pivot right after updating its column. The inverse of the factorised block (dgetrs on the identity,
-// btddod_matrix_kernels.cpp:48-53) needs no barrier at all: every quad solves for its own column in registers, the
-// substitution value travelling through the quad by shuffle.
+// LU (dgetf2 semantics: first row of maximum modulus, reciprocal scaling, A[i,j] -= l[i]*A[k,j]) with ONE block-wide
+// barrier per elimination step: the group of column j applies every step's row interchange (two shuffles) and update
+// to its own registers, reading only the step's multiplier column from shared memory; the group of column k+1 finds
+// the next pivot right after its update (three warp reductions on the bit pattern of |v|), interchanges, scales and
+// publishes its finished column. Interchanges of already published columns are applied in shared memory by their own
+// group. The inverse of the factorised block (dgetrs on the identity, btddod_matrix_kernels.cpp:48-53) needs no barrier
+// at all: every group solves for its own column in (the same) registers, the substitution value travelling through
+// the group by shuffle.
+// Measured per GRI block (tools: -DGB_JAC_TIMELINE, tests/dev_bt.py): LU 99 k cycles (1.9 k per step: update 0.5-0.7 k,
+// pivot search + publication 0.7-0.9 k, barrier 0.4 k), inverse 51 k, rest 5 k. A barrier-free dataflow variant (column
+// groups spin on a "column k published" flag) was tried and is 7 % SLOWER: the step's own dependent chain, not the
+// barrier, is the limit, and spinning groups take issue slots from it.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
 {
@@ -188,54 +194,97 @@ __global__ void __launch_bounds__(1024, 1)
   const size_t nb2 = (size_t)bs * bs;
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
 
-  // first row of maximum modulus of A[from.., col] over the group's rows (idamax) -> spiv[from], 1/pivot -> srp[from]
-  auto find_pivot = [&](int from) {
-    double best = -1., bv = 0.;
-    int bi = from;
+  // This lane's rows (q, q+Q, ...) of its column live in registers for the whole factorisation of a block: the only
+  // shared-memory traffic of an elimination step is the multiplier column of the step (read) and, once per column, its
+  // publication. Register index m = row / Q is warp-uniform, so the dynamic accesses are short select chains.
+  double a[RPL] = {};
+  auto pick = [&](int m) {
+    double v = a[0];
+#pragma unroll
+    for (int j = 1; j < RPL; ++j)
+      if (m == j)
+        v = a[j];
+    return v;
+  };
+  auto put = [&](int m, double v) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      if (m == j)
+        a[j] = v;
+  };
+  auto row_value = [&](int row) { // value of row `row` of this group's column, on every lane of the group
+    return __shfl_sync(mask, pick(row / Q), qbase + (row & (Q - 1)));
+  };
+  auto swap_reg_rows = [&](int k, int p, double vk, double vp) { // rows k and p of the column (values already known)
+    if (q == (k & (Q - 1)))
+      put(k / Q, vp);
+    if (q == (p & (Q - 1)))
+      put(p / Q, vk);
+  };
+  // Executed by the group of column `from` once its column has received the updates of steps < from: idamax over
+  // rows >= from (first row of maximum modulus), the row interchange and the reciprocal scaling of the multipliers
+  // (dgetf2), then the finished column (U above and on the diagonal, multipliers below) and the pivot are published.
+  auto pivot_and_publish = [&](int from) {
+    double best = 0., bv;
+    int bi = 0x7fffffff;
+    bool has = false;
 #pragma unroll
     for (int m = 0; m < RPL; ++m)
     {
       const int r = q + Q * m;
       if (r >= from && r < bs)
       {
-        const double a = A[r + col * ld], v = fabs(a);
-        if (v > best)
+        const double v = fabs(a[m]);
+        if (!has || v > best)
         {
           best = v;
-          bv = a;
           bi = r;
+          has = true;
         }
       }
     }
-#pragma unroll
-    for (int off = 1; off < Q; off <<= 1)
+    // |v| >= 0 orders like its bit pattern: maximum of the high words, then of the low words among those, then the
+    // lowest row among the ties -- three warp reductions instead of log2(Q) rounds of three shuffles
+    const unsigned long long key = has ? (unsigned long long)__double_as_longlong(best) : 0ull;
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int mh = __reduce_max_sync(mask, hi);
+    const bool c1 = has && hi == mh;
+    const unsigned int ml = __reduce_max_sync(mask, c1 ? lo : 0u);
+    const bool c2 = c1 && lo == ml;
+    bi = (int)__reduce_min_sync(mask, c2 ? (unsigned int)bi : 0x7fffffffu);
+    bv = row_value(bi);
+    const double rp = bv != 0. ? 1. / bv : 0.; // dgetf2 scales by the reciprocal; a zero pivot skips the step
+    if (bi != from)
     {
-      const double ov = __shfl_xor_sync(mask, best, off), oa = __shfl_xor_sync(mask, bv, off);
-      const int oi = __shfl_xor_sync(mask, bi, off);
-      if (ov > best || (ov == best && oi < bi))
+      const double vk = row_value(from);
+      swap_reg_rows(from, bi, vk, bv);
+    }
+    if (rp != 0.)
+    {
+#pragma unroll
+      for (int m = 0; m < RPL; ++m)
       {
-        best = ov;
-        bv = oa;
-        bi = oi;
+        const int r = q + Q * m;
+        if (r > from && r < bs)
+          a[m] *= rp;
       }
+    }
+#pragma unroll
+    for (int m = 0; m < RPL; ++m)
+    {
+      const int r = q + Q * m;
+      if (r < bs)
+        A[r + col * ld] = a[m];
     }
     if (q == 0)
-    {
       spiv[from] = bi;
-      srp[from] = bv != 0. ? 1. / bv : 0.; // dgetf2 scales by the reciprocal; a zero pivot skips the step
-    }
   };
-  auto swap_rows = [&](int k, int p) { // rows k and p of this group's column
-    if (p != k)
+  auto swap_rows = [&](int k, int p) { // rows k and p of this group's published column (shared memory)
+    if (p != k && q == 0)
     {
       const double vk = A[k + col * ld], vp = A[p + col * ld];
-      __syncwarp(mask);
-      if (q == 0)
-      {
-        A[k + col * ld] = vp;
-        A[p + col * ld] = vk;
-      }
-      __syncwarp(mask);
+      A[k + col * ld] = vp;
+      A[p + col * ld] = vk;
     }
   };
 
@@ -252,8 +301,14 @@ __global__ void __launch_bounds__(1024, 1)
     for (int e = tid; e < bs * bs; e += nt)
       Lv[e] = 0.; // block 0 of l_values is never referenced by the reference; define it
     __syncthreads();
+#pragma unroll
+    for (int m = 0; m < RPL; ++m)
+    {
+      const int r = q + Q * m;
+      a[m] = (active && r < bs) ? A[r + col * ld] : 0.;
+    }
     if (active && col == 0)
-      find_pivot(0);
+      pivot_and_publish(0);
     __syncthreads();
 #ifdef GB_JAC_TIMELINE
     long long bt_prev = clock64();
@@ -277,65 +332,47 @@ __global__ void __launch_bounds__(1024, 1)
         if (active)
         {
           const int p = spiv[k];
-          if (col > k)
-          {
-            const double rp = srp[k];
-            const double ckk = A[k + k * ld]; // old column k: row k moves to row p
-            swap_rows(k, p);
 #ifdef GB_JAC_TIMELINE
+          if (p >= 0)
             c1 = clock64();
 #endif
-            if (rp != 0.)
+          if (col > k)
+          { // step k on this column: interchange, then A[r, col] -= l[r] * A[k, col] with the published multipliers
+            const double vk = row_value(k);
+            double akj = vk;
+            if (p != k)
             {
-              const double akj = A[k + col * ld];
+              akj = row_value(p);
+              swap_reg_rows(k, p, vk, akj);
+            }
 #pragma unroll
-              for (int m = 0; m < RPL; ++m)
-              {
-                const int r = q + Q * m;
-                if (r > k && r < bs)
-                {
-                  const double c = (r == p) ? ckk : A[r + k * ld];
-                  A[r + col * ld] -= (c * rp) * akj;
-                }
-              }
+            for (int m = 0; m < RPL; ++m)
+            {
+              const int r = q + Q * m;
+              if (r > k && r < bs)
+                a[m] -= A[r + k * ld] * akj;
             }
 #ifdef GB_JAC_TIMELINE
-            c2 = clock64();
+            if (a[0] != 1.2345e300)
+              c2 = clock64();
 #endif
             if (col == k + 1)
             {
-              __syncwarp(mask);
-              find_pivot(k + 1);
+              pivot_and_publish(k + 1);
 #ifdef GB_JAC_TIMELINE
               c3 = clock64();
 #endif
             }
           }
           else if (col < k)
-          {
-            if (col == k - 1)
-            { // deferred finalisation of step k-1 on its own column: interchange, then scale the multipliers
-              swap_rows(k - 1, spiv[k - 1]);
-              const double rp = srp[k - 1];
-              if (rp != 0.)
-              {
-#pragma unroll
-                for (int m = 0; m < RPL; ++m)
-                {
-                  const int r = q + Q * m;
-                  if (r > k - 1 && r < bs)
-                    A[r + col * ld] *= rp;
-                }
-              }
-              __syncwarp(mask);
-            }
-            swap_rows(k, p);
-          }
+            swap_rows(k, p); // dlaswp on the multipliers to the left
         }
         __syncthreads();
 #ifdef GB_JAC_TIMELINE
         if (blockIdx.x == 0 && active && col == k + 1 && q == 0)
         {
+          if (*((volatile int *)spiv) == -12345)
+            printf("x");
           g_bt_timeline2[0] += c1 - c0;
           g_bt_timeline2[1] += c2 - c1;
           g_bt_timeline2[2] += c3 - c2;
@@ -353,7 +390,7 @@ __global__ void __launch_bounds__(1024, 1)
         break;
       BT_MARK(2)
       // ---- column `col` of the inverse, in registers --------------------------------------------------------------------
-      double x[RPL];
+      double(&x)[RPL] = a; // the column registers are free between the publication of the LU column and the update below
       if (active)
       {
         int pos = col; // where the 1 of e_col ends up after the row interchanges (dlaswp on the identity)
@@ -448,14 +485,11 @@ __global__ void __launch_bounds__(1024, 1)
           {
             const double l = x[m] * subi[r];
             Ln[r] = l;
-            A[r + col * ld] = Dn[r + col * ld] + msup * l;
+            a[m] = Dn[r + col * ld] + msup * l;
           }
         }
         if (col == 0)
-        {
-          __syncwarp(mask);
-          find_pivot(0);
-        }
+          pivot_and_publish(0);
       }
       __syncthreads();
       BT_MARK(5)
