@@ -295,3 +295,141 @@ class HomogeneousReactor(object):
         lib = self.integrate(stop_criteria=stop, save_first_and_last_only=not return_solution, **kwargs)
         tau = lib.time_values[-1]
         return (tau, lib) if return_solution else tau
+
+
+# ---- many reactors at once ---------------------------------------------------------------------------------------------
+class _ReactorBatchOps(object):
+    """What time.batched.integrate_batch needs, for N independent isobaric reactors that share the pressure and the
+    reactor parameters and differ in their states: right-hand side and Jacobian through the batched C-ABI entry points
+    (`gb_reactor_{rhs,jac}_isobaric_batch` -- the headline kernels), the dense ns x ns Newton matrices handled as
+    block-tridiagonal systems of ONE block (`gb_btddod_full_*_batch` with num_blocks = 1: dgetrf / dgetrs per reactor,
+    which is what the reference does through SciPy, reactors.py:20-21, 571-587). With the CPU oracle injected
+    (`griffon_factory`) the same interface loops over the members on the host."""
+
+    def __init__(self, reactor, n):
+        import torch
+        from . import griffon as gmod
+        self.torch, self.gmod = torch, gmod
+        self.r = reactor
+        self.g = reactor._griffon
+        self.ns, self.nzi = reactor._n_equations, 1
+        self.ndof = self.ns
+        self.nelem = self.ns * self.ns
+        self.F = n
+        self.on_device = isinstance(self.g, gmod.PyCombustionKernels)
+        if self.on_device and not torch.cuda.is_available():
+            raise gmod.GriffonB200Error('the batched reactor integrator runs on the GPU: no CUDA device')
+        self.device = torch.device('cuda') if self.on_device else torch.device('cpu')
+        self.scales = torch.as_tensor(np.tile(reactor._variable_scales, (n, 1))).to(self.device)
+        r = reactor
+        self._args = (r._initial_pressure,)
+        self._kw = dict(T_in=r._tf_value, y_in=np.ascontiguousarray(r._yf_value, dtype=np.float64), tau=r._tau_value,
+                        T_inf=r._tc_value, T_surf=r._tr_value, h_conv=r._cc_value, eps_rad=r._re_value,
+                        SoV=r._surface_area_to_volume, heat_option=r._heat_transfer_option, open_=r._is_open)
+        if self.on_device and r._is_open:
+            self._kw['y_in'] = torch.as_tensor(self._kw['y_in']).to(self.device)
+        self._host = (r._initial_pressure, r._tf_value, np.ascontiguousarray(r._yf_value, dtype=np.float64), r._tau_value,
+                      r._tc_value, r._tr_value, r._cc_value, r._re_value, r._surface_area_to_volume,
+                      r._heat_transfer_option, r._is_open)
+
+    def rhs(self, q, idx=None, key=None):
+        torch = self.torch
+        out = torch.empty_like(q)
+        if self.on_device:
+            self.g.reactor_rhs_isobaric_batch(q.contiguous(), self._args[0], out, **self._kw)
+        else:
+            qn, on = q.numpy(), out.numpy()
+            for k in range(q.shape[0]):
+                self.g.reactor_rhs_isobaric(np.ascontiguousarray(qn[k]), *self._host, on[k])
+        return out
+
+    def jac(self, q, idx=None, key=None):
+        torch = self.torch
+        n = q.shape[0]
+        rhs = torch.empty_like(q)
+        if self.on_device:
+            J = torch.empty((n, self.nelem), dtype=torch.float64, device=self.device)
+            self.g.reactor_jac_isobaric_batch(q.contiguous(), self._args[0], rhs, J,
+                                              rates_sens_option=self.r._rates_sensitivity_option,
+                                              sens_transform_option=self.r._sensitivity_transform_option, **self._kw)
+        else:
+            J = torch.zeros((n, self.nelem), dtype=torch.float64)
+            qn, rn, Jn = q.numpy(), rhs.numpy(), J.numpy()
+            for k in range(n):
+                self.g.reactor_jac_isobaric(np.ascontiguousarray(qn[k]), *self._host, self.r._rates_sensitivity_option,
+                                            self.r._sensitivity_transform_option, rn[k], Jn[k])
+        return J  # column-major ns x ns per reactor = one BTDDOD block
+
+
+def _borrow_linear_algebra():
+    from .flamelet import _BatchOps
+    for name in ('factorize', 'solve', 'add_to_block_diagonal', 'factor_store', 'factorize_into'):
+        setattr(_ReactorBatchOps, name, getattr(_BatchOps, name))
+    _ReactorBatchOps.explicit_inverse_solves = _BatchOps.explicit_inverse_solves
+
+
+class HomogeneousReactorBatch(object):
+    """N isobaric reactors integrated together on the GPU ("many ignition reactors at once").
+
+    Same model and integrator as `HomogeneousReactor` (ESDIRK64, PI step control, Newton with the Jacobian refreshed
+    every `maximum_steps_per_jacobian` steps, negative mass fractions clipped after each step); every member keeps its
+    own time, step size and error history (time/batched.py), so a member's trajectory is the one the serial class
+    produces for it. All members share the mechanism, the pressure and the (constant) reactor parameters of `template`
+    and start from `temperatures[i]`, `mass_fractions[i]`.
+
+        batch = HomogeneousReactorBatch(HomogeneousReactor(mech, mix, 'isobaric', 'adiabatic', 'closed'), T0s, Y0s)
+        tau = batch.compute_ignition_delay()
+    """
+
+    def __init__(self, template, temperatures, mass_fractions):
+        if any(template._timevar.values()):
+            raise ValueError('HomogeneousReactorBatch needs constant reactor parameters')
+        self._r = template
+        T = np.atleast_1d(np.asarray(temperatures, dtype=np.float64))
+        Y = np.atleast_2d(np.asarray(mass_fractions, dtype=np.float64))
+        if Y.shape != (T.size, template._n_species):
+            raise ValueError('mass_fractions must be [n_reactors, n_species]')
+        self._initial_states = np.ascontiguousarray(np.hstack((T[:, None], Y[:, :-1])))
+        if not hasattr(_ReactorBatchOps, 'factorize'):
+            _borrow_linear_algebra()
+        self.ops = _ReactorBatchOps(template, T.size)
+
+    n_reactors = property(lambda self: self._initial_states.shape[0])
+    initial_states = property(lambda self: self._initial_states)
+
+    def integrate(self, stop, first_time_step=1.e-6, max_time_step=1.e6, minimum_time_step_count=40,
+                  transient_tolerance=1.e-10, maximum_steps_per_jacobian=1, nonlinear_solve_tolerance=1.e-12,
+                  save_each_step=False, maximum_steps=100000, stop_ignores_minimum=False):
+        """stop(t, states, residual, nsteps) -> bool tensor, all arguments tensors over the members.
+        Returns (times, states, failed): per member arrays of the saved times / states (first and last only unless
+        save_each_step)."""
+        from .time.batched import integrate_batch
+        ops = self.ops
+        q0 = ops.torch.as_tensor(self._initial_states).to(ops.device)
+        return integrate_batch(ops, q0, stop, first_time_step=first_time_step, max_time_step=max_time_step,
+                               minimum_time_step_count=minimum_time_step_count,
+                               transient_tolerance=transient_tolerance,
+                               maximum_steps_per_jacobian=maximum_steps_per_jacobian,
+                               nonlinear_solve_tolerance=nonlinear_solve_tolerance, save_each_step=save_each_step,
+                               maximum_steps=maximum_steps, stop_ignores_minimum=stop_ignores_minimum)
+
+    def integrate_to_steady(self, steady_tolerance=1.e-6, **kwargs):
+        return self.integrate(lambda t, q, residual, nsteps: residual < steady_tolerance, stop_ignores_minimum=True,
+                              **kwargs)
+
+    def integrate_to_time(self, final_time, **kwargs):
+        """(the step that crosses final_time is not shortened, unlike odesolve's stop_at_time)"""
+        return self.integrate(lambda t, q, residual, nsteps: t >= final_time, **kwargs)
+
+    def compute_ignition_delay(self, delta_temperature_ignition=400., minimum_allowable_residual=1.e-12, **kwargs):
+        """time at which each member's temperature has risen by delta_temperature_ignition (reactors.py:724-779); NaN for
+        a member whose residual falls below minimum_allowable_residual first (the serial class raises for it)."""
+        T0 = self.ops.torch.as_tensor(self._initial_states[:, 0]).to(self.ops.device)
+
+        def stop(t, q, residual, nsteps):
+            return ((q[:, 0] - T0) > delta_temperature_ignition) | (residual <= minimum_allowable_residual)
+
+        times, states, failed = self.integrate(stop, **kwargs)
+        tau = np.array([th[-1] for th in times])
+        ignited = np.array([qs[-1][0] for qs in states]) - self._initial_states[:, 0] > delta_temperature_ignition
+        return np.where(ignited & ~np.asarray(failed), tau, np.nan)

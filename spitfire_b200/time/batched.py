@@ -31,11 +31,12 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
                     transient_tolerance=1.e-10, maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12,
                     max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
                     fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
-                    explicit_inverse_solves=True):
+                    explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False):
     """advance every member of `ops` (flamelet._BatchOps) from q0 [F, ndof] until `stop(t, q, residual, nsteps)` (all
     [F]-shaped tensors; returns a bool tensor) holds for it and it has taken at least minimum_time_step_count steps.
     Returns per member the lists of saved times and states (numpy), initial state included, and a `failed` flag
-    (non-finite update that the step-size reduction could not cure within maximum_steps)."""
+    (non-finite update that the step-size reduction could not cure within maximum_steps). With save_each_step=False
+    only the initial and the final time / state of every member are returned (large batches of 0-D reactors)."""
     torch = ops.torch
     dev = ops.device
     F = q0.shape[0]
@@ -172,10 +173,11 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             refresh[ga_h] = by_count | by_fail | by_size
             setup_count[ga_h] = np.where(by_count, 0, cnt)
             dt[ga_h] = dnew
-            qh = qnew.cpu().numpy()
-            for m, f_ in enumerate(ga_h.tolist()):
-                t_hist[f_].append(float(t[f_]))
-                q_hist[f_].append(qh[m].copy())
+            if save_each_step:
+                qh = qnew.cpu().numpy()
+                for m, f_ in enumerate(ga_h.tolist()):
+                    t_hist[f_].append(float(t[f_]))
+                    q_hist[f_].append(qh[m].copy())
         r_h = idx_h[np.nonzero(~ok)[0]]
         if r_h.size:
             dt[r_h] = dt[r_h] * fail_factor
@@ -183,9 +185,15 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
         attempts[idx_h] += 1
         # ---- stopping --------------------------------------------------------------------------------------------------------------
         residual_full[idx_h] = np.where(np.isfinite(residual), residual, np.inf)
-        done = stop(dev_vec(t), q, dev_vec(residual_full), dev_idx(nsteps)).cpu().numpy() & \
-            (nsteps >= minimum_time_step_count)
+        done = stop(dev_vec(t), q, dev_vec(residual_full), dev_idx(nsteps)).cpu().numpy()
+        if not stop_ignores_minimum:  # (odesolve's stop_at_steady test is not subject to the minimum, integrator.py:633-640)
+            done = done & (nsteps >= minimum_time_step_count)
         done = done | (attempts > maximum_steps)
         going = going & ~done
     failed = attempts > maximum_steps
+    if not save_each_step:
+        qf = q.cpu().numpy()
+        for f_ in range(F):
+            t_hist[f_].append(float(t[f_]))
+            q_hist[f_].append(qf[f_].copy())
     return [np.array(th) for th in t_hist], [np.array(qh) for qh in q_hist], failed
