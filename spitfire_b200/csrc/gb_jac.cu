@@ -55,10 +55,10 @@ enum JScalar : int
   J_OBASE, // (bits) offset of the state's output block
   J_CMOFF, // (bits) offset of the flamelet point's cmajor row
   J_TTC,   // flamelet (T,T) enthalpy-flux correction
-  J_SPARE0,
-  J_SPARE1
+  J_NLOGT, // log T and 1/T of the NEXT tile (formed while the last warp idles, see k_jac)
+  J_NINVT
 };
-static_assert(J_SPARE1 < JP_NSC, "JP_NSC too small");
+static_assert(J_NINVT < JP_NSC, "JP_NSC too small");
 
 #define SMG(arr, idx, g) (arr)[(idx)*G + (g)]
 
@@ -928,6 +928,27 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     return v;
   };
   double pre = fetch_state(blockIdx.x);
+  // The last warp is idle during the temperature-row phase: its first G lanes use that time to fetch the NEXT tile's
+  // temperatures and to form log T and 1/T, which otherwise sit (a ~1.5 k cycle dependent chain on G threads) between
+  // two block barriers of the load phase.
+  const bool tkeeper = state_mode && warp == (nt >> 5) - 1 && lane < G;
+  double nxtT = 0.;
+  auto fetch_T = [&](int tile) {
+    if (tkeeper && tile < ntiles)
+    {
+      const int gc = min(G, a.n - tile * G);
+      nxtT = a.in_state[(size_t)(tile * G + (lane < gc ? lane : 0)) * ns];
+    }
+  };
+  auto finish_T = [&]() { // (parked in two spare scalar rows so that nothing but T itself stays in registers)
+    if (tkeeper)
+    {
+      SMG(s.sc, J_NLOGT, lane) = log(nxtT);
+      SMG(s.sc, J_NINVT, lane) = 1. / nxtT;
+    }
+  };
+  fetch_T(blockIdx.x);
+  finish_T();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
     const int tile0 = tile * G;
@@ -942,14 +963,14 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
       {
         const int g = item / ns, j = item - g * ns;
         const double v = (k == 0) ? pre : a.in_state[(size_t)(tile0 + (g < gcount ? g : 0)) * ns + j];
-        if (j == 0)
-        {
-          SMG(s.sc, J_T, g) = v;
-          SMG(s.sc, J_LOGT, g) = log(v);
-          SMG(s.sc, J_INVT, g) = 1. / v;
-        }
-        else
+        if (j != 0)
           SMG(s.sy, j - 1, g) = v;
+      }
+      if (tkeeper)
+      {
+        SMG(s.sc, J_T, lane) = nxtT;
+        SMG(s.sc, J_LOGT, lane) = SMG(s.sc, J_NLOGT, lane);
+        SMG(s.sc, J_INVT, lane) = SMG(s.sc, J_NINVT, lane);
       }
     }
     else
@@ -1194,6 +1215,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     }
 
     // ---- column-sum parts (lane per part, G accumulators) and row constants (thread per (species, state)) --------------
+    fetch_T(tile + gridDim.x);
     {
       const int ncsp = dm.jp_ncsp, ncs = dm.jp_ncs;
       // parts first, on whole warps, so that the row jobs start on a warp boundary
@@ -1254,6 +1276,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     TL_MARK(8)
     __syncthreads();
     // ---- temperature row (:58-98, 142-168; flamelet_kernels.cpp:1290-1320) ----------------------------------------------------
+    finish_T();
     for (int item = tid; item < ns * G; item += nt)
     {
       const int c = item / G, g = item - c * G;
