@@ -683,6 +683,7 @@ __global__ void __launch_bounds__(64) k_btddod_solve(int nsys, const double *d_f
             }
           }
         }
+        __syncwarp(); // every lane has gathered its right-hand side from v (the shuffles above order this already)
 #pragma unroll
         for (int h = 0; h < RPW; ++h)
         {
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
         // columns apart, which for an odd block size puts their eight rows in disjoint banks. All loads of a pair of
         // j are issued before the first fma (two accumulators).
         const int cpart = 8 * (part & 1) + 4 * (part >> 1);
-        const double *cb = cur + (size_t)cpart * bs + rr, *vb = vin + cpart;
+        const double *cb = cur + rr;
         double a0 = 0., a1 = 0.;
         for (int j = 0; j < bs; j += 32)
         {
@@ -893,10 +894,10 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
 #pragma unroll
           for (int u = 0; u < 8; ++u)
           {
-            const int cj = j + 16 * (u >> 2) + (u & 3);
-            const int cc = cj + cpart < bs ? cj : 0; // (a column past the end re-reads a valid one with weight zero)
+            const int c = cpart + j + 16 * (u >> 2) + (u & 3);
+            const int cc = c < bs ? c : 0; // (a column past the end re-reads column 0 with weight zero)
             mm[u] = lds_f64(cb + (size_t)cc * bs);
-            ww[u] = lds_f64(vb + cc);
+            ww[u] = lds_f64(vin + cc);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)

@@ -165,8 +165,11 @@ __device__ double warp_max_real_eigenvalue(double *a, double *vec, const int n, 
         if (s == 0.)
           s = anorm;
         if (fabs(EA(l, l - 1)) + s == s)
-        {
-          EA(l, l - 1) = 0.; // every lane writes the same value
+        { // (uniform: every lane evaluates the same test on the same values)
+          __syncwarp();
+          if (lane == 0)
+            EA(l, l - 1) = 0.;
+          __syncwarp();
           break;
         }
       }
