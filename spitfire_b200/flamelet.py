@@ -277,6 +277,7 @@ class _BatchOps(object):
     # only proposes the update of an iteration that converges on the true residual, and the inverse-based back sweep is
     # 3-4x shorter than the pivoted triangular solves (griffon_b200.h, gb_btddod_full_*_inv_batch).
     explicit_inverse_solves = True
+    _rows32 = (None, None)  # last (int64 rows, int32 copy) pair handed to the solve kernel
 
     def factor_store(self, F):
         """zeroed arrays for the factors of F systems: (J, L, pivots[, Dinv])"""
@@ -318,12 +319,17 @@ class _BatchOps(object):
         """solve with the factors of the members `rows` (positions in the factor arrays; default all)"""
         torch = self.torch
         n = rhs.shape[0]
-        x = torch.zeros_like(rhs)
         if self.on_device and len(fact) == 4:
             # the kernel addresses the members' factors in place (no gather of ~8 MB per member)
+            x = torch.empty_like(rhs)
+            if rows is not None:
+                if self._rows32[0] is not rows:
+                    self._rows32 = (rows, rows.to(torch.int32))
+                rows = self._rows32[1]
             self.gmod.btddod_full_solve_inv(fact[0], fact[1], fact[3], rhs.contiguous(), self.nzi, self.ns, x, n_systems=n,
-                                            system_rows=None if rows is None else rows.to(torch.int32))
+                                            system_rows=rows)
             return x
+        x = torch.zeros_like(rhs)
         if rows is not None:
             fact = tuple(a.index_select(0, rows) for a in fact)
         J, L, piv = fact[:3]

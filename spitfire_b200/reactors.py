@@ -366,6 +366,7 @@ def _borrow_linear_algebra():
     for name in ('factorize', 'solve', 'add_to_block_diagonal', 'factor_store', 'factorize_into'):
         setattr(_ReactorBatchOps, name, getattr(_BatchOps, name))
     _ReactorBatchOps.explicit_inverse_solves = _BatchOps.explicit_inverse_solves
+    _ReactorBatchOps._rows32 = (None, None)
 
 
 class HomogeneousReactorBatch(object):

@@ -31,7 +31,7 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
                     transient_tolerance=1.e-10, maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12,
                     max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
                     fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
-                    explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False):
+                    explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False, dense_limit=148):
     """advance every member of `ops` (flamelet._BatchOps) from q0 [F, ndof] until `stop(t, q, residual, nsteps)` (all
     [F]-shaped tensors; returns a bool tensor) holds for it and it has taken at least minimum_time_step_count steps.
     Returns per member the lists of saved times and states (numpy), initial state included, and a `failed` flag
@@ -69,8 +69,12 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
     def dev_vec(a):
         return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
 
+    wcache = [None, None]
+
     def wnorm(x, widx):
-        return (x * w.index_select(0, widx)).abs().amax(dim=1)
+        if wcache[0] is not widx:  # (the active set's weights are gathered once per step, not once per norm)
+            wcache[0], wcache[1] = widx, w.index_select(0, widx)
+        return (x * wcache[1]).abs().amax(dim=1)
 
     while True:
         idx_h = np.nonzero(going)[0]
@@ -110,18 +114,34 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             f = k[-1].clone()
             res = dta[:, None] * (_G * f + explicit) - (x - qa)
             conv = np.zeros(n, dtype=bool)
+            conv_d = None
             for it in range(max_nonlinear_iter):
                 l_h = np.nonzero(~conv)[0]
                 if l_h.size == 0:
                     break
                 g_h = idx_h[l_h]
-                if l_h.size == n:
+                if l_h.size != n and n <= dense_limit and ops.on_device:
+                    # Small batches are latency-bound: a kernel over all n members costs what a kernel over the
+                    # unconverged ones costs, so the iteration runs on everybody and the converged members simply keep
+                    # their values (no gathers, no index uploads; the unconverged members see the same arithmetic).
+                    if conv_d is None:
+                        conv_d = torch.as_tensor(conv, device=dev)
+                    dx = ops.solve(factors, res, rows=None if all_active else idx)
+                    xn = x - dx
+                    fn = ops.rhs(xn, idx, key=key_all)
+                    rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
+                    keep = conv_d[:, None]
+                    x, f, res = torch.where(keep, x, xn), torch.where(keep, f, fn), torch.where(keep, res, rn)
+                    conv_d = conv_d | (wnorm(rn, idx) < nonlinear_solve_tolerance)
+                    conv = conv_d.cpu().numpy()
+                elif l_h.size == n:
                     dx = ops.solve(factors, res, rows=None if all_active else idx)
                     xn = x - dx
                     fn = ops.rhs(xn, idx, key=key_all)
                     rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
                     x, f, res = xn, fn, rn
-                    conv = (wnorm(rn, idx) < nonlinear_solve_tolerance).cpu().numpy()
+                    conv_d = wnorm(rn, idx) < nonlinear_solve_tolerance
+                    conv = conv_d.cpu().numpy()
                 else:
                     loc, gl = dev_idx(l_h), dev_idx(g_h)
                     dx = ops.solve(factors, res.index_select(0, loc), rows=gl)
@@ -131,6 +151,7 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
                         (xn - qa.index_select(0, loc))
                     x[loc], f[loc], res[loc] = xn, fn, rn
                     conv[l_h] = (wnorm(rn, gl) < nonlinear_solve_tolerance).cpu().numpy()
+                    conv_d = None
             nl_ok &= conv
             qs = x
             k.append(f)
