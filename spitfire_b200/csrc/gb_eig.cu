@@ -384,6 +384,7 @@ cudaError_t launch_block_max_real_eig(int nblocks, const double *base, long stri
     attr = smem;
   }
   k_block_max_real_eig<<<nblocks, 32, smem, s>>>(nblocks, base, stride_f, per_f, n, out);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -394,6 +395,7 @@ cudaError_t launch_expand_expeig(int nblocks, int n, const double *maxre, double
   const size_t tot = (size_t)nblocks * n;
   const int grid = (int)std::min<size_t>((tot + 255) / 256, 148 * 8);
   k_expand_expeig<<<grid, 256, 0, s>>>(nblocks, n, maxre, diffterm, out);
+  count_launch();
   return cudaGetLastError();
 }
 

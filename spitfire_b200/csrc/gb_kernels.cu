@@ -29,6 +29,7 @@ namespace gb
 {
 
 static std::atomic<long> g_launches{0};
+void count_launch() { ++g_launches; } // kernels launched from other translation units (gb_eig.cu)
 extern std::atomic<long> g_btddod_launches; // gb_btddod.cu
 extern std::atomic<long> g_jac_launches;    // gb_jac.cu
 long kernel_launch_count() { return g_launches.load() + g_btddod_launches.load() + g_jac_launches.load(); }

@@ -75,6 +75,7 @@ cudaError_t launch_block_max_real_eig(int nblocks, const double *base, long stri
 // out[b * n + q] = max(maxre[b] - diffterm, 0)
 cudaError_t launch_expand_expeig(int nblocks, int n, const double *maxre, double diffterm, double *out, cudaStream_t s);
 long kernel_launch_count();
+void count_launch();
 #ifdef GB_JAC_TIMELINE
 int debug_jac_timeline(long long *out);
 int debug_bt_timeline(long long *out);
