@@ -585,38 +585,55 @@ __global__ void k_thermo(const DeviceMech dm, int what, int n, const double *aux
 }
 
 // flamelet pre-pass: cp at every interior point (flamelet_kernels.cpp:1062-1070), max T per flamelet (:1049-1058),
-// cp of the two boundary streams (:1076-1086). One thread per grid point.
-__global__ void k_flamelet_prepass(const DeviceMech dm, int F, int nzi, const double *state, const double *oxy,
-                                   const double *fuel, double *cp_grid, double *maxT, double *cp_bc)
+// cp of the two boundary streams (:1076-1086). One WARP per job: jobs [0, F*nzi) are the grid points, the next two the
+// streams, the last F the per-flamelet maxima. The species heat capacities of a point are evaluated by the lanes in
+// parallel; the two sums that the reference forms in species order (Y_ns = 1 - sum Y_j, cp = sum Y_i cp_i) are then
+// accumulated by lane 0 in that order from shared memory, so the value is bit-identical to the serial evaluation
+// while the latency drops from ns dependent polynomial evaluations to one.
+__global__ void __launch_bounds__(128) k_flamelet_prepass(const DeviceMech dm, int F, int nzi, const double *state,
+                                                          const double *oxy, const double *fuel, double *cp_grid,
+                                                          double *maxT, double *cp_bc)
 {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ns = dm.ns;
-  auto cp_of = [&](const double *st) {
+  extern __shared__ double pp_smem[]; // [warps per block][ns] products Y_i cp_i
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int job = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int ns = dm.ns, npts = F * nzi;
+  if (job < npts + 2)
+  {
+    const double *st = job < npts ? state + (size_t)job * ns : (job == npts ? oxy : fuel);
+    double *prod = pp_smem + (size_t)wib * ns;
     const double t = st[0], logT = log(t), invT = 1. / t;
-    double yl = 1.;
-    for (int j = 0; j < ns - 1; ++j)
-      yl -= st[1 + j];
-    double cp = 0.;
-    for (int i = 0; i < ns; ++i)
+    for (int i = lane; i < ns; i += 32)
+      prod[i] = species_thermo<false>(dm, i, t, logT, invT).cp; // cp_i for now
+    __syncwarp();
+    if (lane == 0)
     {
-      const double yi = (i < ns - 1) ? st[1 + i] : yl;
-      cp += yi * species_thermo<false>(dm, i, t, logT, invT).cp;
+      double yl = 1.;
+      for (int j = 0; j < ns - 1; ++j)
+        yl -= st[1 + j];
+      double cp = 0.;
+      for (int i = 0; i < ns; ++i)
+      {
+        const double yi = (i < ns - 1) ? st[1 + i] : yl;
+        cp += yi * prod[i];
+      }
+      if (job < npts)
+        cp_grid[job] = cp;
+      else
+        cp_bc[job - npts] = cp;
     }
-    return cp;
-  };
-  if (s < F * nzi)
-    cp_grid[s] = cp_of(state + (size_t)s * ns);
-  if (s == 0)
-  {
-    cp_bc[0] = cp_of(oxy);
-    cp_bc[1] = cp_of(fuel);
   }
-  if (s < F)
+  else if (job < npts + 2 + F)
   {
-    double m = -1;
-    for (int i = 0; i < nzi; ++i)
-      m = fmax(m, state[((size_t)s * nzi + i) * ns]);
-    maxT[s] = m;
+    const int f = job - npts - 2;
+    double m = -1.;
+    for (int i = lane; i < nzi; i += 32)
+      m = fmax(m, state[((size_t)f * nzi + i) * ns]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0)
+      maxT[f] = m;
   }
 }
 
@@ -719,10 +736,10 @@ cudaError_t launch_flamelet_offdiag(const DeviceMech &dm, int F, const FlameletD
 cudaError_t launch_flamelet_prepass(const DeviceMech &dm, int F, const double *state, const FlameletDev &fl,
                                     double *cp_grid, double *maxT, double *cp_bc, cudaStream_t s)
 {
-  const int n = std::max(F * fl.nzi, 1);
-  const int threads = 128;
-  k_flamelet_prepass<<<(n + threads - 1) / threads, threads, 0, s>>>(dm, F, fl.nzi, state, fl.oxy, fl.fuel, cp_grid,
-                                                                     maxT, cp_bc);
+  const int jobs = F * fl.nzi + 2 + F; // one warp each
+  const int threads = 128, wpb = threads / 32;
+  k_flamelet_prepass<<<(jobs + wpb - 1) / wpb, threads, sizeof(double) * wpb * dm.ns, s>>>(dm, F, fl.nzi, state, fl.oxy,
+                                                                                          fl.fuel, cp_grid, maxT, cp_bc);
   ++g_launches;
   return cudaGetLastError();
 }
