@@ -689,7 +689,11 @@ cudaError_t launch_rates(const ChemArgs &a_in, cudaStream_t s)
 {
   ChemArgs a = a_in;
   const int maxsm = 227 * 1024;
-  int G = env_int("GB_RATES_G", 31);
+  // tile size: 31 states per CTA for large batches; small batches (a few flamelets) are spread over all SMs with
+  // smaller tiles, whose latency is lower (GRI, 1008 states: 72 us with 7-state tiles against 115 us with 31)
+  int G = env_int("GB_RATES_G", 0);
+  if (G <= 0)
+    G = std::min(31, std::max(7, (a.n + sm_count() - 1) / sm_count()));
   while (G > 1 && rates_smem(a.dm, G | 1) > (size_t)maxsm)
     G -= 2;
   if (rates_smem(a.dm, G | 1) > (size_t)maxsm)
