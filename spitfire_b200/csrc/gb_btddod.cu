@@ -149,7 +149,7 @@ __device__ void lu_inverse_smem(const double *A, int bs, int ld, const int *piv,
 // group. The inverse of the factorised block (dgetrs on the identity, btddod_matrix_kernels.cpp:48-53) needs no barrier
 // at all: every group solves for its own column in (the same) registers, the substitution value travelling through
 // the group by shuffle.
-// Measured per GRI block (tools: -DGB_JAC_TIMELINE, tests/dev_bt.py): LU 99 k cycles (1.9 k per step: update 0.5-0.7 k,
+// Measured per GRI block (tools: -DGB_JAC_TIMELINE, tools/dev/dev_bt.py): LU 99 k cycles (1.9 k per step: update 0.5-0.7 k,
 // pivot search + publication 0.7-0.9 k, barrier 0.4 k), inverse 51 k, rest 5 k. A barrier-free dataflow variant (column
 // groups spin on a "column k published" flag) was tried and is 7 % SLOWER: the step's own dependent chain, not the
 // barrier, is the limit, and spinning groups take issue slots from it.

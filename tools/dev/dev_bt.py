@@ -1,6 +1,7 @@
 """dev: time / profile the block-Thomas kernels on a GRI-3.0 128-point flamelet Jacobian (not a test)"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import numpy as np, torch
 from common import build_mech
 from spitfire_b200.flamelet import Flamelet, FlameletSpec, FlameletBatch

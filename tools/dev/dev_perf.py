@@ -1,6 +1,7 @@
 """dev: time k_jac / k_rates on the synthetic batches (not a test)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import torch
 from common import build_mech
 from spitfire_b200.synthetic import synthetic_states

@@ -1,5 +1,6 @@
 import sys, numpy as np, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import torch
 from common import build_mech
 from spitfire_b200.synthetic import synthetic_states

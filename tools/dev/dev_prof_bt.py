@@ -1,6 +1,7 @@
 """dev: one GRI-3.0 128-point flamelet batch through jac_and_eig / factorize_inv / solve_inv, for ncu captures (not a test)"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import torch
 from common import build_mech
 from spitfire_b200.flamelet import Flamelet, FlameletSpec, FlameletBatch

@@ -1,7 +1,8 @@
 """dev: one small call of every kernel, for compute-sanitizer (memcheck / racecheck / synccheck) runs:
-    compute-sanitizer --tool racecheck python tests/dev_sanitize.py [mechanism]"""
+    compute-sanitizer --tool racecheck python tools/dev/dev_sanitize.py [mechanism]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import numpy as np, torch
 from common import build_mech
 from spitfire_b200 import griffon
