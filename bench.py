@@ -128,6 +128,34 @@ def run_reference_arm(args):
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: keep this rank's threads -- and with them, by first touch, its pinned host buffers -- on the NUMA
+    node its GPU hangs off, so that the end-to-end leg (6 GB device->host per step and rank) does not cross the socket
+    interconnect. Best effort: returns the node, or None if the topology is not visible or the cpuset forbids it."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), 'pci_domain_id', 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), 'pci_device_id', 0)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node' % (dom, bus, dev)
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def workload_config(args, n_states):
     return {'workload': f'BASELINE config 3: GRI-3.0 methane/air batched isobaric reactor RHS+analytical Jacobian '
                         f'({args.mech}, closed adiabatic, 1 atm)',
@@ -264,6 +292,7 @@ def run_gpu_arm(args):
     from spitfire_b200.synthetic import synthetic_states
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     mech = ChemicalMechanismSpec(mech_data=load_mech_data(args.mech))
@@ -354,6 +383,7 @@ def run_gpu_arm(args):
                     'result_check': check},
             'gpu_launches': int(launches),
             'library_build': library,
+            'numa_node': numa,
             'clocks': clocks,
             'build': load_build_info(),
         }
