@@ -124,3 +124,17 @@ def test_batched_jac_and_eig_matches_oracle():
     assert eo.max() > 0.
     assert err <= 1e-8
     assert np.abs(Jg - Jo).max() <= 1e-9 * np.abs(Jo).max()
+
+
+def test_size_limits():
+    """the matrix lives in shared memory: n = 169 is the largest size, n = 170 is refused (not silently truncated)"""
+    import torch
+    from spitfire_b200 import griffon
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((2, 169, 169))
+    got, ref = gpu_max_real(A), lapack_max_real(A)
+    assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref))
+    big = torch.zeros((1, 170 * 170), dtype=torch.float64, device='cuda')
+    out = torch.zeros(1, dtype=torch.float64, device='cuda')
+    with pytest.raises(griffon.GriffonB200Error):
+        griffon.max_real_eigenvalue(big, 170, out, 1)

@@ -134,3 +134,27 @@ def test_inverse_based_solve_shapes(bs, nb):
     assert np.all(np.isfinite(a))
     assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b))
     assert np.max(np.abs(mv.cpu().numpy() - rhs)) <= 1e-11 * np.max(np.abs(rhs))
+
+
+def test_inverse_based_solve_addresses_a_subset_of_the_factors_in_place():
+    """system_rows: right-hand sides k = 0..m-1 are solved with the factors of systems rows[k] of a larger batch"""
+    import torch
+    from spitfire_b200 import griffon
+    rng = np.random.default_rng(7)
+    F, bs, nb = 6, 11, 9
+    nelem = bs * (nb * bs + 2 * (nb - 1))
+    A = rng.normal(size=(F, nelem))
+    A[:, :nb * bs * bs].reshape(F, nb, bs, bs)[...] += 2. * bs * np.eye(bs)
+    rhs = rng.normal(size=(F, nb * bs))
+    dA = torch.from_numpy(A).cuda()
+    z = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt, device='cuda')
+    dL, dI, dP = z(F, nb * bs * bs), z(F, nb * bs * bs), z(F, nb * bs, dt=torch.int32)
+    griffon.btddod_full_factorize_inv(dA, nb, bs, dL, dP, dI, n_systems=F)
+    dR = torch.from_numpy(rhs).cuda()
+    full = torch.zeros_like(dR)
+    griffon.btddod_full_solve_inv(dA, dL, dI, dR, nb, bs, full, n_systems=F)
+    rows = torch.tensor([4, 1, 5], dtype=torch.int32, device='cuda')
+    sub = torch.zeros((3, nb * bs), dtype=torch.float64, device='cuda')
+    griffon.btddod_full_solve_inv(dA, dL, dI, dR[rows.long()].contiguous(), nb, bs, sub, n_systems=3, system_rows=rows)
+    torch.cuda.synchronize()
+    assert torch.equal(sub, full[rows.long()])

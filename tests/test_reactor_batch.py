@@ -99,3 +99,32 @@ def test_reactor_batch_gri_ignition_delays_on_gpu():
     serial = HomogeneousReactor(m, mix, 'isobaric', 'adiabatic', 'closed').compute_ignition_delay()
     print('GRI ignition delay at', T0[k], 'K:', tau[k], 'serial', serial)
     assert abs(tau[k] - serial) <= 1e-4 * serial
+
+
+@pytest.mark.parametrize('heat,mass', [('isothermal', 'closed'), ('adiabatic', 'open'), ('diathermal', 'open')])
+def test_reactor_batch_other_configurations_on_host(heat, mass):
+    """open (constant feed), isothermal and diathermal reactors: the batch follows the serial class member by member"""
+    from spitfire_b200.reactors import HomogeneousReactor, HomogeneousReactorBatch
+    m, mix, _ = _template(ORACLE)
+    feed = m.copy_stream(mix)
+    feed.TP = 1400., 101325.
+    kw = dict()
+    if mass == 'open':
+        kw.update(mixing_tau=1.e-4, feed_temperature=1400., feed_mass_fractions=feed.Y)
+    if heat == 'diathermal':
+        kw.update(convection_temperature=350., radiation_temperature=300., convection_coefficient=10.,
+                  radiative_emissivity=0.5, shape_dimension_dict={'shape': 'sphere', 'char. length': 0.02})
+
+    def make(T):
+        mix.TP = T, 101325.
+        return HomogeneousReactor(m, mix, 'isobaric', heat, mass, **kw)
+
+    T0 = [1150., 1250.]
+    b = HomogeneousReactorBatch(make(1200.), T0, np.tile(mix.Y, (2, 1)))
+    times, states, failed = b.integrate_to_time(2.e-4, save_each_step=True)
+    assert not np.any(failed)
+    for k, T in enumerate(T0):
+        lib = make(T).integrate(stop_criteria=lambda t, q, r, n: t >= 2.e-4)
+        assert lib.time_values.size == times[k].size, (heat, mass, lib.time_values.size, times[k].size)
+        assert np.allclose(lib.time_values, times[k], rtol=1e-4, atol=1e-14)
+        assert np.allclose(lib['temperature'], states[k][:, 0], rtol=1e-4)
