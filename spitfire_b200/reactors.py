@@ -424,7 +424,23 @@ class HomogeneousReactorBatch(object):
 
     def compute_ignition_delay(self, delta_temperature_ignition=400., minimum_allowable_residual=1.e-12, **kwargs):
         """time at which each member's temperature has risen by delta_temperature_ignition (reactors.py:724-779); NaN for
-        a member whose residual falls below minimum_allowable_residual first (the serial class raises for it)."""
+        a member whose residual falls below minimum_allowable_residual first (the serial class raises for it).
+        Under torchrun (spitfire_b200.parallel initialised) the members are dealt block-cyclically to the ranks, every
+        rank integrates its share on its own GPU and the delays are exchanged once at the end (no data-path
+        collective: the reactors are independent)."""
+        from . import parallel
+        if parallel.world_size() > 1 and not getattr(self, '_is_share', False):
+            mine = parallel.my_share(list(range(self.n_reactors)))
+            local = dict()
+            if mine:
+                Y = np.hstack((self._initial_states[mine, 1:], 1. - self._initial_states[mine, 1:].sum(axis=1, keepdims=True)))
+                share = HomogeneousReactorBatch(self._r, self._initial_states[mine, 0], Y)
+                share._initial_states = np.ascontiguousarray(self._initial_states[mine])  # (exactly the caller's states)
+                share._is_share = True
+                tau = share.compute_ignition_delay(delta_temperature_ignition, minimum_allowable_residual, **kwargs)
+                local = {int(k): float(t) for k, t in zip(mine, tau)}
+            merged = parallel.gather_dicts(local)
+            return np.array([merged[k] for k in range(self.n_reactors)])
         T0 = self.ops.torch.as_tensor(self._initial_states[:, 0]).to(self.ops.device)
 
         def stop(t, q, residual, nsteps):

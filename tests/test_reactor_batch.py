@@ -128,3 +128,25 @@ def test_reactor_batch_other_configurations_on_host(heat, mass):
         assert lib.time_values.size == times[k].size, (heat, mass, lib.time_values.size, times[k].size)
         assert np.allclose(lib.time_values, times[k], rtol=1e-4, atol=1e-14)
         assert np.allclose(lib['temperature'], states[k][:, 0], rtol=1e-4)
+
+
+def test_two_rank_gloo_ignition_table(tmp_path):
+    """the members of a batch are dealt to the ranks of torch.distributed (gloo on CPU here, NCCL on GPU boxes); the
+    merged delays equal the single-process ones"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / 'tau.npz'
+    port = 31500 + os.getpid() % 2000
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', str(port), os.path.join(root, 'tests', 'dist_ignition_worker.py'), ORACLE,
+           str(out)]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    d = np.load(out)
+    assert int(d['world']) == 2
+    from spitfire_b200.reactors import HomogeneousReactorBatch
+    m, mix, r = _template(ORACLE)
+    single = HomogeneousReactorBatch(r, d['T0'], np.tile(mix.Y, (d['T0'].size, 1))).compute_ignition_delay()
+    assert np.array_equal(d['tau'], single)
+    assert np.all(np.diff(d['tau']) < 0.)
