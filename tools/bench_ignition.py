@@ -1,7 +1,7 @@
 """Ignition-delay table: N isobaric GRI-3.0 methane/air reactors (phi = 1, 1 atm, T0 in [1100, 1900] K) integrated
 together on one B200 (HomogeneousReactorBatch). Prints one JSON line.
 
-    python tools/bench_ignition.py [--n 4096] [--mech methane-gri30] [--serial K]
+    python tools/bench_ignition.py [--reactors 4096] [--mech methane-gri30] [--serial K]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_ignition.py   # ranks share the table
 
 --serial K: also time K members with the serial HomogeneousReactor on the same backend (one state per C-ABI call)."""
@@ -23,7 +23,7 @@ from spitfire_b200.reactors import HomogeneousReactor, HomogeneousReactorBatch  
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=4096)
+    ap.add_argument('--reactors', dest='n', type=int, default=4096)
     ap.add_argument('--mech', default='methane-gri30')
     ap.add_argument('--backend', default='gpu')
     ap.add_argument('--serial', type=int, default=0)
