@@ -238,6 +238,10 @@ int gb_btddod_scale_and_add_diagonal_host(int n_systems, double *matrix, double 
 long gb_kernel_launch_count(void);
 /* name of the build (arch, flags), for logs */
 const char *gb_build_info(void);
+/* FP64 vector peak of the current device, measured with a dependent-free DFMA (kind 0) or DMUL+DADD (kind 1)
+ * micro-benchmark: Tflop/s (2 flops per multiply-add) and thread-level FP64 instructions per clock and SM.
+ * bench.py's second roofline bound. No reference counterpart. */
+int gb_measure_fp64_peak(int kind, double *out_tflops, double *out_inst_per_clk_sm);
 
 #ifdef __cplusplus
 }

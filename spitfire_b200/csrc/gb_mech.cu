@@ -172,13 +172,6 @@ int commit(HostMech &m)
     set_error("too many species");
     return GB_ERR_UNSUPPORTED;
   }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-  {
-    cudaGetLastError();
-    set_error("no CUDA device is usable; the B200 Griffon path has no CPU fallback");
-    return GB_ERR_CUDA;
-  }
 
   const int last = ns - 1;
   std::vector<int> flags(nr), sum_stoich(nr), sum_rc(nr), sum_pd(nr), n_rc(nr), n_pd(nr), n_net(nr), n_sp(nr);
@@ -366,6 +359,14 @@ int commit(HostMech &m)
       return rc;
   }
 
+  // (everything above is pure host work, so GB_PLAN_VERBOSE=1 shows the plan without a device)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+  {
+    cudaGetLastError();
+    set_error("no CUDA device is usable; the B200 Griffon path has no CPU fallback");
+    return GB_ERR_CUDA;
+  }
   std::vector<double> cpc = m.cpc;
   Blob b;
   std::vector<double> netmw(ns);

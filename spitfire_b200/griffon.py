@@ -68,6 +68,7 @@ def load_library():
     sig('gb_mech_commit', I, [P])
     sig('gb_kernel_launch_count', L, [])
     sig('gb_build_info', C.c_char_p, [])
+    sig('gb_measure_fp64_peak', I, [I, dp, dp])
     sig('gb_thermo_batch', I, [P, I, I, V, V, V, V, V])
     sig('gb_thermo_host', I, [P, I, I, V, V, V, V])
     sig('gb_production_rates_batch', I, [P, I, V, V, V, V, V])
@@ -109,6 +110,13 @@ def check(rc, what):
 
 def kernel_launch_count():
     return load_library().gb_kernel_launch_count()
+
+
+def measure_fp64_peak(kind=0):
+    """(Tflop/s, FP64 thread instructions per clock and SM) of the device's FP64 pipe: kind 0 = DFMA, 1 = DMUL+DADD"""
+    tf, ipc = C.c_double(0.), C.c_double(0.)
+    check(load_library().gb_measure_fp64_peak(int(kind), C.byref(tf), C.byref(ipc)), 'measure_fp64_peak')
+    return tf.value, ipc.value
 
 
 def _is_torch(x):
