@@ -64,7 +64,7 @@ int gb_mech_add_const_cp(gb_mech *m, const char *species, double Tmin, double Tm
 int gb_mech_add_nasa7_cp(gb_mech *m, const char *species, double Tmin, double Tmid, double Tmax,
                          const double *low7, const double *high7); /* chemistry_setup.cpp:102           */
 int gb_mech_add_nasa9_cp(gb_mech *m, const char *species, double Tmin, double Tmax, int n_coeffs,
-                         const double *coeffs);                 /* chemistry_setup.cpp:132 (NASA9: GB_ERR_UNSUPPORTED at finalize) */
+                         const double *coeffs);                 /* chemistry_setup.cpp:132; coeffs = {nregions, (Tlo, Thi, a0..a8) * nregions} */
 /* One generic adder covers mechanism_add_reaction_{simple,three_body,Lindemann,Troe}[_with_special_orders]
  * (chemistry_setup.cpp:156-345). Unused groups are passed with n = 0 / NULL. Ea is Ea/Ru (K), as the
  * reference's Python passes it (mechanism.py:185). troe4 = [A, T3, T1, T2] zero padded (griffon.pyx:410-416). */

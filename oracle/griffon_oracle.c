@@ -13,7 +13,7 @@
  * /root/reference/src/spitfire/griffon/). Third-party arithmetic: LAPACK dgetrf/dgetrs/dgeev
  * (blas_lapack_kernels.h:84-180), taken -- like the reference build here -- from SciPy's bundled OpenBLAS.
  *
- * Not restated (out of the hot path): NASA9 thermo, the inexact no-TBAF sensitivities
+ * Not restated (out of the hot path): the inexact no-TBAF sensitivities
  * (option 1 is mapped to the exact option 0), isochoric reactors, 2-D flamelets, block-Jacobi/GS helpers.
  */
 #include "griffon_oracle.h"
@@ -71,7 +71,8 @@ struct go_mech
   double p_ref, T_ref, Ru;
   int nr, cap_r;
   rxn_t *rx;
-  int unsupported; /* set when a NASA9 species is added */
+  int unsupported;
+  double **c9; /* NASA9: per species {nregions, (Tlo, Thi, a0..a8 [a2.. times R]) * nregions}, chemistry_setup.cpp:132-152 */
 };
 
 const char *go_kind(void) { return "port"; }
@@ -113,6 +114,10 @@ void go_mech_destroy(go_mech *m)
   free(m->tmin);
   free(m->tmax);
   free(m->cptype);
+  if (m->c9)
+    for (int i = 0; i < m->ns; ++i)
+      free(m->c9[i]);
+  free(m->c9);
   free(m->rx);
   free(m);
 }
@@ -228,6 +233,11 @@ int go_mech_resize_heat_capacity_data(go_mech *m) /* :79 */
   m->tmin = (double *)calloc(m->ns > 0 ? m->ns : 1, sizeof(double));
   m->tmax = (double *)calloc(m->ns > 0 ? m->ns : 1, sizeof(double));
   m->cptype = (int *)calloc(m->ns > 0 ? m->ns : 1, sizeof(int));
+  if (m->c9)
+    for (int i = 0; i < m->ns; ++i)
+      free(m->c9[i]);
+  free(m->c9);
+  m->c9 = (double **)calloc(m->ns > 0 ? m->ns : 1, sizeof(double *));
   return 0;
 }
 
@@ -274,11 +284,42 @@ int go_mech_add_nasa7_cp(go_mech *m, const char *s, double Tmin, double Tmid, do
   return 0;
 }
 
-int go_mech_add_nasa9_cp(go_mech *m, const char *s, double Tmin, double Tmax, int n, const double *c)
+int go_mech_add_nasa9_cp(go_mech *m, const char *s, double Tmin, double Tmax, int n, const double *c) /* :132-152 */
 {
-  (void)s, (void)Tmin, (void)Tmax, (void)n, (void)c;
-  m->unsupported = 1; /* NASA9 is outside the restated path */
-  return -4;
+  const int i = species_index(m, s);
+  if (i < 0 || !m->cpc || n < 1)
+    return -1;
+  const int nregions = (int)c[0];
+  if (n < 1 + 11 * nregions)
+    return -1;
+  m->cptype[i] = CP_NASA9;
+  m->tmin[i] = Tmin;
+  m->tmax[i] = Tmax;
+  free(m->c9[i]);
+  m->c9[i] = (double *)calloc((size_t)n, sizeof(double));
+  const double R = m->Ru;
+  m->c9[i][0] = c[0];
+  for (int k = 0; k < nregions; ++k)
+    for (int j = 0; j < 11; ++j)
+      m->c9[i][1 + k * 11 + j] = (j < 2 ? 1.0 : R) * c[1 + k * 11 + j];
+  return 0;
+}
+
+/* NASA9 polynomial pieces as written at the cited lines; a = region coefficients a0..a8 */
+static double n9_cp(const double *a, double t, double invT)
+{ /* thermodynamics_kernels.cpp:99, 106, 118 */
+  return invT * (a[1] + invT * a[0]) + a[2] + t * (a[3] + t * (a[4] + t * (a[5] + t * a[6])));
+}
+static double n9_h_over_t(const double *a, double t, double invT, double logT)
+{ /* :314, 324, 337 (the factor invMW * T is applied by the caller) */
+  return invT * (a[7] + logT * a[1] - a[0] * invT) + a[2] +
+         t * (0.5 * a[3] + t * (0.3333333333333333 * a[4] + t * (0.25 * a[5] + t * 0.2 * a[6])));
+}
+static double n9_gibbs(const double *a, double T, double invT, double logT)
+{ /* chemistry_kernels.cpp:83, rates_sensitivities_exact.cpp:110 */
+  return a[7] - 0.5 * a[0] * invT + a[1] * (logT + 1.0) -
+         T * (a[2] * (logT - 1.0) + a[8] +
+              T * (0.5 * a[3] + T * (0.1666666666666666 * a[4] + T * (0.0833333333333333 * a[5] + T * 0.05 * a[6]))));
 }
 
 /* ReactionRateData::finalize, chemistry_setup.cpp:460-732 */
@@ -617,6 +658,27 @@ static void cp_mix_and_species(const go_mech *m, double t, const double *y, doub
       else
         out_cpi[i] = iw * (c[1] + maxT * (2. * c[2] + maxT * (6. * c[3] + maxT * (12. * c[4] + 20. * maxT * c[5]))));
     }
+    else if (m->cptype[i] == CP_NASA9)
+    { /* :91-124: frozen outside [Tmin, Tmax]; inside, the region with Tlo <= t < Thi (t == Tmax matches none) */
+      const double *c9 = m->c9[i];
+      const int nregions = (int)c9[0];
+      if (t < minT)
+        out_cpi[i] = iw * n9_cp(c9 + 3, minT, 1. / minT);
+      else if (t > maxT)
+        out_cpi[i] = iw * n9_cp(c9 + 1 + (nregions - 1) * 11 + 2, maxT, 1. / maxT);
+      else
+      {
+        int found = 0;
+        for (int k = 0; k < nregions && !found; ++k)
+          if (t >= c9[1 + k * 11] && t < c9[1 + k * 11 + 1])
+          {
+            out_cpi[i] = iw * n9_cp(c9 + 1 + k * 11 + 2, t, 1. / t);
+            found = 1;
+          }
+        if (!found)
+          continue;
+      }
+    }
     else
       continue;
     *out_cpmix += yi * out_cpi[i];
@@ -681,6 +743,29 @@ void go_cp_sens_T(const go_mech *m, double t, const double *y, double *out_mix, 
         *out_mix += 0.;
       }
     }
+    else if (m->cptype[i] == CP_NASA9)
+    { /* :229-253 */
+      const double *c9 = m->c9[i];
+      const int nregions = (int)c9[0];
+      if (t < minT || t > maxT)
+      {
+        out_spec[i] = 0.;
+        *out_mix += 0.;
+      }
+      else
+      {
+        const double invT = 1. / t;
+        for (int k = 0; k < nregions; ++k)
+          if (t >= c9[1 + k * 11] && t < c9[1 + k * 11 + 1])
+          {
+            const double *a = c9 + 1 + k * 11 + 2;
+            out_spec[i] = iw * (-invT * invT * (a[1] + invT * 2.0 * a[0]) + a[3] +
+                                t * (2.0 * a[4] + t * (3.0 * a[5] + t * 4.0 * a[6])));
+            *out_mix += y[i] * out_spec[i];
+            break;
+          }
+      }
+    }
   }
 }
 
@@ -714,6 +799,37 @@ void go_species_enthalpies(const go_mech *m, double temp, double *out) /* :262-3
                                        maxT * (4. * 3. * c[4] * temp - 2. * 2. * c[3] +
                                                maxT * (5. * 4. * c[5] * temp - 3. * 3. * c[4] +
                                                        maxT * -4. * 4. * c[5])))));
+    }
+    else if (m->cptype[i] == CP_NASA9)
+    { /* :305-347: linear extension with the frozen cp outside [Tmin, Tmax] */
+      const double *c9 = m->c9[i];
+      const int nregions = (int)c9[0];
+      if (temp < minT)
+      {
+        const double invT = 1. / minT, logT = log(minT);
+        const double *a = c9 + 3;
+        const double hmin = iw * minT * n9_h_over_t(a, minT, invT, logT);
+        const double cpmin = iw * n9_cp(a, minT, invT);
+        out[i] = hmin + cpmin * (temp - minT);
+      }
+      else if (temp > maxT)
+      {
+        const double invT = 1. / maxT, logT = log(maxT);
+        const double *a = c9 + 1 + (nregions - 1) * 11 + 2;
+        const double hmax = iw * maxT * n9_h_over_t(a, maxT, invT, logT);
+        const double cpmax = iw * n9_cp(a, maxT, invT);
+        out[i] = hmax + cpmax * (temp - maxT);
+      }
+      else
+      {
+        const double invT = 1. / temp, logT = log(temp);
+        for (int k = 0; k < nregions; ++k)
+          if (temp >= c9[1 + k * 11] && temp < c9[1 + k * 11 + 1])
+          {
+            out[i] = iw * temp * n9_h_over_t(c9 + 1 + k * 11 + 2, temp, invT, logT);
+            break;
+          }
+      }
     }
   }
 }
@@ -760,6 +876,18 @@ static void species_gibbs(const go_mech *m, double T, double logT, double *g)
     }
     else if (m->cptype[n] == CP_CONST)
       g[n] = c[1] + c[3] * (T - c[0]) - T * (c[2] + c[3] * (logT - log(c[0])));
+    else if (m->cptype[n] == CP_NASA9)
+    { /* :74-88: strictly inside a region, Tlo < T < Thi (otherwise the reference leaves the value unset; 0 here) */
+      const double *c9 = m->c9[n];
+      const int nregions = (int)c9[0];
+      g[n] = 0.;
+      for (int k = 0; k < nregions; ++k)
+        if (T < c9[1 + k * 11 + 1] && T > c9[1 + k * 11])
+        {
+          g[n] = n9_gibbs(c9 + 1 + k * 11 + 2, T, 1. / T, logT);
+          break;
+        }
+    }
     else
       g[n] = 0.;
   }
@@ -1096,6 +1224,20 @@ static void prod_rates_sens_exact(const go_mech *m, double T, double rho, double
     {
       specG[n] = c[1] + c[3] * (T - c[0]) - T * (c[2] + c[3] * (logT - log(c[0])));
       dBdTSpec[n] = invT * (Msp[n] * invRu * (c[3] - invT * (c[3] * c[0] - c[1])) - 1);
+    }
+    else if (m->cptype[n] == CP_NASA9)
+    { /* :101-116: the first region with T < Thi, else the last one */
+      const double *c9 = m->c9[n];
+      const int nregions = (int)c9[0];
+      for (int k = 0; k < nregions; ++k)
+        if (T < c9[1 + k * 11 + 1] || k == nregions - 1)
+        {
+          const double *a = c9 + 1 + k * 11 + 2;
+          specG[n] = n9_gibbs(a, T, invT, logT);
+          dBdTSpec[n] = invRu * (invT * (a[2] - Ru + invT * (a[7] + a[1] * logT - invT * a[0])) + 0.5 * a[3] +
+                                 T * (a[4] * 0.3333333333333333 + T * (0.25 * a[5] + T * 0.2 * a[6])));
+          break;
+        }
     }
     else
       dBdTSpec[n] = 0.;

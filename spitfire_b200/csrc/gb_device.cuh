@@ -88,6 +88,68 @@ __device__ __forceinline__ SpeciesThermo species_thermo(const DeviceMech &dm, in
       o.dcp = 0.;
     }
   }
+  else if (type == CP_NASA9)
+  {
+    // NASA9, several temperature regions. cp, dcp/dT: thermodynamics_kernels.cpp:91-124, 229-253 (frozen outside
+    // [Tmin, Tmax]); h: :305-347 (linear extension); Gibbs and dB/dT: rates_sensitivities_exact.cpp:101-116 (the first
+    // region with T < Thi, else the last one -- chemistry_kernels.cpp:74-88 picks the same region whenever T lies
+    // strictly inside one and leaves the value unset otherwise).
+    const double *c9 = dm.n9 + dm.n9_off[i];
+    const int nreg = (int)c9[0];
+    const double minT = dm.tmin[i], maxT = dm.tmax[i];
+    int kg = nreg - 1;
+    for (int k = 0; k < nreg - 1; ++k)
+      if (T < c9[1 + k * 11 + 1])
+      {
+        kg = k;
+        break;
+      }
+    {
+      const double *a = c9 + 1 + kg * 11 + 2;
+      o.g = a[7] - 0.5 * a[0] * invT + a[1] * (logT + 1.0) -
+            T * (a[2] * (logT - 1.0) + a[8] +
+                 T * (0.5 * a[3] + T * (0.1666666666666666 * a[4] + T * (0.0833333333333333 * a[5] + T * 0.05 * a[6]))));
+      if (JAC)
+      {
+        const double invRu = dm.invRu, Ru = dm.RuR;
+        o.dB = invRu * (invT * (a[2] - Ru + invT * (a[7] + a[1] * logT - invT * a[0])) + 0.5 * a[3] +
+                        T * (a[4] * 0.3333333333333333 + T * (0.25 * a[5] + T * 0.2 * a[6])));
+      }
+      else
+        o.dB = 0.;
+    }
+    auto cp_of = [](const double *a, double t, double it) {
+      return it * (a[1] + it * a[0]) + a[2] + t * (a[3] + t * (a[4] + t * (a[5] + t * a[6])));
+    };
+    auto h_over_t = [](const double *a, double t, double it, double lt) {
+      return it * (a[7] + lt * a[1] - a[0] * it) + a[2] +
+             t * (0.5 * a[3] + t * (0.3333333333333333 * a[4] + t * (0.25 * a[5] + t * 0.2 * a[6])));
+    };
+    if (T < minT || T > maxT)
+    {
+      const double tb = T < minT ? minT : maxT;
+      const double *a = c9 + 1 + (T < minT ? 0 : nreg - 1) * 11 + 2;
+      const double itb = 1. / tb, ltb = log(tb);
+      const double hb = iw * tb * h_over_t(a, tb, itb, ltb);
+      o.cp = iw * cp_of(a, tb, itb);
+      o.h = hb + o.cp * (T - tb);
+      o.dcp = 0.;
+    }
+    else
+    {
+      int kr = nreg - 1; // (T == Tmax matches no region in the reference; the last one is used here)
+      for (int k = 0; k < nreg; ++k)
+        if (T >= c9[1 + k * 11] && T < c9[1 + k * 11 + 1])
+        {
+          kr = k;
+          break;
+        }
+      const double *a = c9 + 1 + kr * 11 + 2;
+      o.cp = iw * cp_of(a, T, invT);
+      o.h = iw * T * h_over_t(a, T, invT, logT);
+      o.dcp = iw * (-invT * invT * (a[1] + invT * 2.0 * a[0]) + a[3] + T * (2.0 * a[4] + T * (3.0 * a[5] + T * 4.0 * a[6])));
+    }
+  }
   else
   { // CP_CONST: c = {T0, h0, s0, cp}
     o.cp = iw * c[3];

@@ -156,13 +156,8 @@ int commit(HostMech &m)
     set_error("heat capacity data was never set (mechanism_resize_heat_capacity_data)");
     return GB_ERR_STATE;
   }
-  if (m.has_nasa9)
-  {
-    set_error("NASA9 thermo is not supported by the B200 path yet");
-    return GB_ERR_UNSUPPORTED;
-  }
   for (int i = 0; i < ns; ++i)
-    if (m.cptype[i] != CP_CONST && m.cptype[i] != CP_NASA7)
+    if (m.cptype[i] != CP_CONST && m.cptype[i] != CP_NASA7 && m.cptype[i] != CP_NASA9)
     {
       set_error("species " + m.species[i] + " has no heat capacity model");
       return GB_ERR_STATE;
@@ -375,6 +370,12 @@ int commit(HostMech &m)
   const size_t o_netmw = b.add(netmw);
   const size_t o_mw = b.add(m.mw), o_invmw = b.add(m.invmw), o_tmin = b.add(m.tmin), o_tmax = b.add(m.tmax);
   const size_t o_cpc = b.add(cpc), o_cptype = b.add(m.cptype);
+  std::vector<int> n9_off = m.n9_off;
+  n9_off.resize(ns, -1);
+  std::vector<double> n9 = m.n9;
+  if (n9.empty())
+    n9.push_back(0.);
+  const size_t o_n9off = b.add(n9_off), o_n9 = b.add(n9);
   const size_t o_flags = b.add(flags), o_kfA = b.add(kfA), o_kfb = b.add(kfb), o_kfE = b.add(kfE), o_kpA = b.add(kpA),
                o_kpb = b.add(kpb), o_kpE = b.add(kpE), o_troe = b.add(troe), o_base = b.add(base_eff);
   const size_t o_ss = b.add(sum_stoich), o_src = b.add(sum_rc), o_spd = b.add(sum_pd);
@@ -407,6 +408,7 @@ int commit(HostMech &m)
   d.mw = at<double>(base, o_mw), d.invmw = at<double>(base, o_invmw), d.netmw = at<double>(base, o_netmw);
   d.tmin = at<double>(base, o_tmin), d.tmax = at<double>(base, o_tmax);
   d.cpc = at<double>(base, o_cpc), d.cptype = at<int>(base, o_cptype);
+  d.n9_off = at<int>(base, o_n9off), d.n9 = at<double>(base, o_n9);
   d.flags = at<int>(base, o_flags);
   d.kfA = at<double>(base, o_kfA), d.kfb = at<double>(base, o_kfb), d.kfE = at<double>(base, o_kfE);
   d.kpA = at<double>(base, o_kpA), d.kpb = at<double>(base, o_kpb), d.kpE = at<double>(base, o_kpE);
@@ -605,12 +607,30 @@ extern "C"
     c[9] /= 2., c[10] /= 6., c[11] /= 12., c[12] /= 20.;
     return GB_OK;
   }
-  int gb_mech_add_nasa9_cp(gb_mech *m, const char *s, double, double, int, const double *)
+  int gb_mech_add_nasa9_cp(gb_mech *m, const char *s, double Tmin, double Tmax, int n, const double *c)
   {
     GB_TOUCH(m);
-    if (species_or_error(m, s) < 0)
+    const int i = species_or_error(m, s);
+    if (i < 0)
       return GB_ERR_ARG;
-    m->h.has_nasa9 = true; // reported as GB_ERR_UNSUPPORTED when the mechanism is committed
+    const int nregions = (n >= 1 && c) ? (int)c[0] : 0;
+    if (nregions < 1 || n < 1 + 11 * nregions)
+    {
+      gb::set_error("NASA9 coefficient list must be {nregions, (Tlo, Thi, a0..a8) * nregions}");
+      return GB_ERR_ARG;
+    }
+    HostMech &h = m->h;
+    h.cptype[i] = gb::CP_NASA9;
+    h.tmin[i] = Tmin, h.tmax[i] = Tmax;
+    h.has_nasa9 = true;
+    // chemistry_setup.cpp:132-152: region bounds as given, a0..a8 times R
+    if ((int)h.n9_off.size() != (int)h.species.size())
+      h.n9_off.assign(h.species.size(), -1);
+    h.n9_off[i] = (int)h.n9.size();
+    h.n9.push_back(c[0]);
+    for (int k = 0; k < nregions; ++k)
+      for (int j = 0; j < 11; ++j)
+        h.n9.push_back((j < 2 ? 1.0 : h.Ru) * c[1 + k * 11 + j]);
     return GB_OK;
   }
 

@@ -65,6 +65,8 @@ struct DeviceMech
   const double *netmw;                    // [ns] 1/invmw: the molecular weight the net factors -nu*M use (chemistry_setup.cpp:538)
   const double *cpc;                      // [ns][NCP]
   const int *cptype;                      // [ns]
+  const int *n9_off;                      // [ns] NASA9: offset of the species' block in n9, -1 otherwise
+  const double *n9;                       // {nregions, (Tlo, Thi, a0..a8 [times R]) * nregions} per NASA9 species
   // reactions, SoA [nr]
   const int *flags;
   const double *kfA, *kfb, *kfE, *kpA, *kpb, *kpE, *troe /*[nr][4]*/, *base_eff;
@@ -149,6 +151,8 @@ struct HostMech
   std::vector<double> cpc; // [ns][NCP]
   bool heat_capacity_sized = false;
   bool has_nasa9 = false;
+  std::vector<int> n9_off;   // per species offset into n9 (-1: not NASA9)
+  std::vector<double> n9;
   double p_ref = 101325., T_ref = 298.15, Ru = 8314.46261815324;
   std::vector<HostReaction> reactions;
 

@@ -126,6 +126,14 @@ def equilibrate(stream, XY='HP', max_iterations=400, tolerance=1.e-10):
             abs(dlnT) <= tolerance and np.max(np.abs(b0 - (A * n).sum(axis=1))) <= tolerance * np.max(b0)
         if conv and lam == 1.:
             break
+    else:
+        # Cantera's equilibrate raises when it fails; a stalled iteration must not feed a flamelet initial condition or
+        # an equilibrium library silently
+        raise RuntimeError(
+            f'equilibrate({XY!r}) did not converge in {max_iterations} iterations: T = {T:.2f} K, '
+            f'max |n dln n| / sum n = {np.max(n * np.abs(dlnnj)) / np.sum(n):.3e}, |dln n| = {abs(dlnn):.3e}, '
+            f'|dln T| = {abs(dlnT):.3e}, element balance error = '
+            f'{np.max(np.abs(b0 - (A * n).sum(axis=1))) / np.max(b0):.3e} (tolerance {tolerance:.1e})')
     Y = np.zeros(ns)
     Y[possible] = n * mw
     Y /= np.sum(Y)

@@ -3,13 +3,16 @@ Structured tabulated-chemistry containers: `Dimension` and `Library`.
 
 Mirror of the reference's `spitfire.chemistry.library` (reference: src/spitfire/chemistry/library.py:19-452): named
 N-D property arrays on a tensor grid of named dimensions, slicing into sub-libraries, and pickle persistence with the
-same state dictionary (`dimensions`, `dim_ordering`, `properties`, `extra_attributes`), so libraries written by
-either code base can be read by the other. This is the output format of the flamelet sweeps; it holds no numerics.
+same state dictionary (`dimensions`, `dim_ordering`, `properties`, `extra_attributes`). A pickle names the class by
+its module path, so a file written by one code base loads in the other only through a module alias
+(`sys.modules['spitfire.chemistry.library'] = spitfire_b200.library`, and likewise for the mechanism class held in
+`extra_attributes['mech_spec']`); the state dictionaries themselves are interchangeable. This is the output format of
+the flamelet sweeps; it holds no numerics.
 """
 import os
 import pickle
 import shutil
-from copy import deepcopy
+from copy import copy, deepcopy
 
 import numpy as np
 
@@ -252,9 +255,13 @@ class Library(object):
 
     @classmethod
     def copy(cls, library):
-        return deepcopy(library)
+        """shallow copy: new Library and Dimension objects that share the arrays (library.py:282-285)"""
+        return copy(library)
 
-    deepcopy = copy
+    @classmethod
+    def deepcopy(cls, library):
+        """deep copy (library.py:287-290)"""
+        return deepcopy(library)
 
     @classmethod
     def squeeze(cls, library):

@@ -188,10 +188,12 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             cnt = setup_count[ga_h]
             okn = nl_ok[a_h]
             by_count = cnt == maximum_steps_per_jacobian
-            by_fail = ~by_count & ~okn
+            # a Newton solve that ran out of iterations reports slow convergence (nonlinear.py:259-268), so it takes the
+            # `nlslowness` branch and the slow-solve factor; fail_factor is for steps that are rejected outright (below)
+            by_slow = ~by_count & ~okn
             by_size = ~by_count & okn & ((dnew > d * grow_limit) | (dnew < d * shrink_limit))
-            dnew = np.where(by_fail, dnew * fail_factor, dnew)
-            refresh[ga_h] = by_count | by_fail | by_size
+            dnew = np.where(by_slow, dnew * slow_factor, dnew)
+            refresh[ga_h] = by_count | by_slow | by_size
             setup_count[ga_h] = np.where(by_count, 0, cnt)
             dt[ga_h] = dnew
             if save_each_step:

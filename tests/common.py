@@ -18,10 +18,21 @@ def golden_mech_names():
 
 
 def load_mech_data(name):
-    with open(os.path.join(GOLDEN, 'mech', name + '.json')) as f:
+    """`name#k` is the single-reaction mechanism made of reaction k of `name` -- how the reference's own rate tests use
+    reaction_test_mechanism.yaml (tests/griffon/test_reaction_rates.py:127-180: one Solution per reaction)"""
+    base, _, k = name.partition('#')
+    with open(os.path.join(GOLDEN, 'mech', base + '.json')) as f:
         md = json.load(f)
     # JSON turns the reaction tuples into lists; that is all mech_data_to_extracted needs
+    if k:
+        md['reactions'] = [md['reactions'][int(k)]]
     return md
+
+
+def single_reaction_cases(name='reaction_test_mechanism'):
+    """the reference's 16 one-reaction cases (elementary / non-elementary orders below, across and above one / the five
+    rate-constant forms, irreversible and reversible / third-body, Lindemann, Troe), test_reaction_rates.py:127-143"""
+    return [f'{name}#{k}' for k in range(len(load_mech_data(name)['reactions']))]
 
 
 def has_nasa9(md):

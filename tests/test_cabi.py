@@ -92,9 +92,13 @@ def test_host_side_flamelet_helpers_match_oracle():
         assert np.array_equal(a, b)
 
 
-def test_nasa9_is_reported_unsupported():
+def test_nasa9_mechanism_is_accepted_and_malformed_coefficients_are_refused():
+    """NASA9 species are packed for the device (parity: tests/test_gpu_parity.py); a coefficient list that is not
+    {nregions, (Tlo, Thi, a0..a8) * nregions} is an argument error, never a silent path"""
     md = load_mech_data('old_xmls_nasa9_air_h2')
     from spitfire_b200.mechanism import ChemicalMechanismSpec
-    m = ChemicalMechanismSpec(mech_data=md)  # building is fine
+    m = ChemicalMechanismSpec(mech_data=md)
+    g = m.griffon
+    name = m.species_names[0]
     with pytest.raises(GriffonB200Error):
-        m.griffon.commit()  # either "NASA9 not supported" or, with no device, the CUDA error -- never a silent path
+        g.mechanism_add_nasa9_cp(name, 200., 6000., [2., 200., 1000., 1., 2., 3.])

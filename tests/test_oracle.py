@@ -9,10 +9,11 @@ Gold-file pins that need the host solver loops live in test_reactor_host.py / te
 import numpy as np
 import pytest
 
-from common import build_mech, golden_mech_names, has_nasa9, load_mech_data, oracle_available
+from common import (build_mech, golden_mech_names, has_nasa9, load_mech_data, oracle_available,
+                    single_reaction_cases)
 from cases import FLAGS, assemble_dense, block_thomas_all, call_all, flamelet_all, flamelet_case, random_case
 
-MECHS = [n for n in golden_mech_names() if not has_nasa9(load_mech_data(n)) and n != 'reaction_test_mechanism']
+MECHS = golden_mech_names() + single_reaction_cases()
 need_ref = pytest.mark.skipif(not oracle_available('reference'), reason='oracle/_ref not built (no /root/reference)')
 
 
