@@ -121,6 +121,7 @@ extern "C"
 #ifdef GB_JAC_TIMELINE
   int gb_debug_jac_timeline(long long *out /* [16*32] */) { return gb::debug_jac_timeline(out); }
   int gb_debug_bt_timeline(long long *out /* [8] */) { return gb::debug_bt_timeline(out); }
+  int gb_debug_jac4_timeline(long long *out /* [16*32] */) { return gb::debug_jac4_timeline(out); }
 #endif
   const char *gb_build_info(void) { return "griffon_b200 sm_100a fp64, nvcc " GB_STR(__CUDACC_VER_MAJOR__) "." GB_STR(__CUDACC_VER_MINOR__) GB_FLAGS; }
 

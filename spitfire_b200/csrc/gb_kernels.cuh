@@ -63,6 +63,9 @@ struct ChemArgs
 // launches; return cudaError_t of the launch
 cudaError_t launch_rates(const ChemArgs &a, cudaStream_t s);
 cudaError_t launch_jac(const ChemArgs &a, cudaStream_t s);
+// gb_jac4.cu: warp-specialised reactor-Jacobian kernel for large mechanisms (launch_jac dispatches to it)
+bool jac4_applicable(const ChemArgs &a);
+cudaError_t launch_jac4(const ChemArgs &a, cudaStream_t s);
 cudaError_t launch_thermo(const DeviceMech &dm, int what, int n, const double *aux, const double *T, const double *y,
                           double *out, cudaStream_t s);
 // flamelet pre-pass: cp_grid[F][nzi], maxT[F], cp_bc[2]
@@ -78,6 +81,7 @@ long kernel_launch_count();
 void count_launch();
 #ifdef GB_JAC_TIMELINE
 int debug_jac_timeline(long long *out);
+int debug_jac4_timeline(long long *out);
 int debug_bt_timeline(long long *out);
 #endif
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/griffon_b200.h"
@@ -354,6 +355,29 @@ int commit(HostMech &m)
       return rc;
   }
 
+  // schedule of the warp-specialised reactor-Jacobian kernel (k_jac4): used when the mechanism is large enough to fill
+  // its CTA and the working set of a four-state tile fits in shared memory
+  JacPlan4Host j4;
+  bool have_j4 = false;
+  {
+    int threads = 768, nprod = 4;
+    if (const char *e = std::getenv("GB_JAC4_THREADS"))
+      threads = std::max(128, std::min(1024, (std::atoi(e) / 32) * 32));
+    if (const char *e = std::getenv("GB_JAC4_PRODUCERS"))
+      nprod = std::max(2, std::min(threads / 32 - 1, std::atoi(e)));
+    int min_nr = 100;
+    if (const char *e = std::getenv("GB_JAC4_MIN_REACTIONS"))
+      min_nr = std::atoi(e);
+    if (!std::getenv("GB_JAC4_OFF") && nr >= min_nr && ns <= 250 &&
+        build_jac4_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, threads / 32 - nprod, nprod,
+                        j4) == GB_OK &&
+        jac4_smem_bytes(ns, j4) <= (size_t)227 * 1024)
+      have_j4 = true;
+    if (std::getenv("GB_PLAN_VERBOSE"))
+      fprintf(stderr, "[gb plan4] %s, shared memory %zu bytes\n", have_j4 ? "enabled" : "not used",
+              j4.threads ? jac4_smem_bytes(ns, j4) : (size_t)0);
+  }
+
   // (everything above is pure host work, so GB_PLAN_VERBOSE=1 shows the plan without a device)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -391,6 +415,7 @@ int commit(HostMech &m)
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
   const size_t o_jpprm = b.add(jp.prm), o_jpitems = b.add(jp.items), o_jpemap = b.add(jp.emap),
                o_jptab = b.add(jp.tab);
+  const size_t o_j4items = b.add(j4.items), o_j4rdest = b.add(j4.rdest), o_j4tab = b.add(j4.tab);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -442,6 +467,13 @@ int commit(HostMech &m)
   d.jp_G = jp.G, d.jp_threads = jp.threads, d.jp_rec_rows = jp.rec_rows, d.jp_rows = jp.rows;
   d.jp_nfix = (int)jp.fix.size() / 3, d.jp_ncs = jp.ncs, d.jp_ncsp = jp.ncsp, d.jp_t0base = jp.t0base;
   d.jp_c0base = jp.c0base, d.jp_zrow = jp.zrow, d.jp_smem = (int)jac_smem_bytes(ns, jp);
+  d.j4_items = at<unsigned int>(base, o_j4items), d.j4_rdest = at<unsigned int>(base, o_j4rdest);
+  d.j4_tab = at<int>(base, o_j4tab);
+  d.j4_tab_words = (int)j4.tab.size();
+  d.j4_t_wg = j4.t_wg, d.j4_t_groups = j4.t_groups, d.j4_t_fgroups = j4.t_fgroups, d.j4_t_wr = j4.t_wr;
+  d.j4_t_rounds = j4.t_rounds, d.j4_t_wfix = j4.t_wfix, d.j4_t_cfxoff = j4.t_cfxoff, d.j4_t_cfx = j4.t_cfx;
+  d.j4_threads = have_j4 ? j4.threads : 0, d.j4_ncons = j4.ncons, d.j4_rec_rows = j4.rec_rows, d.j4_nF = j4.nF;
+  d.j4_nfg = j4.nfg, d.j4_bufsz = j4.bufsz, d.j4_nwx = j4.nwx, d.j4_smem = have_j4 ? (int)jac4_smem_bytes(ns, j4) : 0;
   m.committed = true;
   return GB_OK;
 }

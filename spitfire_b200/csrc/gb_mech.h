@@ -116,6 +116,11 @@ struct DeviceMech
   int jp_tab_words, jp_t_wg, jp_t_groups, jp_t_wr, jp_t_rounds, jp_t_rdest, jp_t_fix, jp_t_rowsrc, jp_t_csparts,
       jp_t_cspfirst, jp_t_csitems, jp_t_rspec;
   int jp_G, jp_threads, jp_rec_rows, jp_rows, jp_nfix, jp_ncs, jp_ncsp, jp_t0base, jp_c0base, jp_zrow, jp_smem;
+  // ---- schedule of k_jac4 (gb_plan4.cu, gb_jac4.cu); j4_threads == 0: not available for this mechanism ----
+  const unsigned int *j4_items, *j4_rdest;
+  const int *j4_tab;
+  int j4_tab_words, j4_t_wg, j4_t_groups, j4_t_fgroups, j4_t_wr, j4_t_rounds, j4_t_wfix, j4_t_cfxoff, j4_t_cfx;
+  int j4_threads, j4_ncons, j4_rec_rows, j4_nF, j4_nfg, j4_bufsz, j4_nwx, j4_smem;
 };
 
 constexpr int JP_FAST_WORDS = 12; // fast-path parameter record, 8-byte words
@@ -137,6 +142,31 @@ struct JacPlanHost
   int rec_rows = 0, rows = 0, ncs = 0, ncsp = 0, t0base = 0, c0base = 0, zrow = 0;
   // statistics (printed with GB_PLAN_VERBOSE=1)
   int n_fast = 0, n_struct = 0, n_generic = 0, n_dest = 0, n_parts = 0, n_items = 0, n_steps = 0, max_rounds = 0;
+};
+
+// what both Jacobian plans share: classification of the reactions by code path, packed parameter records, record rows
+// and the logical destinations (gb_plan.cu)
+struct PlanCommon
+{
+  std::vector<char> fast, last_involved, kind; // kind: 0 fast, 1 structured, 2 generic
+  std::vector<int> hdr_of, rec_off, prm_off, fidx;
+  int rec_rows = 0, n_falloff = 0;
+  std::vector<unsigned long long> prm;
+  // logical destinations: [0, ns*(ns-1)) R[i][k] at k*ns + i; then 5*ns row scalars q*ns + i (sums of nu * {q, dq/drho,
+  // dq/dT, a, b}); items = record row (16) | nu (int8) << 16, ascending reaction order
+  std::vector<std::vector<unsigned int>> dest;
+};
+
+// schedule of k_jac4 (gb_plan4.cu)
+struct JacPlan4Host
+{
+  int ncons = 0, nprod = 0, threads = 0;
+  int rec_rows = 0, nF = 0, nfg = 0, bufsz = 0, nwx = 0;
+  std::vector<unsigned int> items; // [round][step pair][lane][2]: record row | sign << 31
+  std::vector<unsigned int> rdest; // [round][lane]: destination code | species << 16
+  std::vector<int> tab;            // small tables, copied to shared memory
+  int t_wg = 0, t_groups = 0, t_fgroups = 0, t_wr = 0, t_rounds = 0, t_wfix = 0, t_cfxoff = 0, t_cfx = 0;
+  int n_fast = 0, n_struct = 0, n_generic = 0, n_parts = 0, n_items = 0, n_steps = 0;
 };
 
 struct HostMech
@@ -174,6 +204,16 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
                    const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
                    const std::vector<int> &tb_off, int G, int threads, JacPlanHost &out);
 size_t jac_smem_bytes(int ns, const JacPlanHost &p);
+int build_jac4_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
+                    const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
+                    const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
+                    const std::vector<int> &tb_off, int ncons, int nprod, JacPlan4Host &out);
+size_t jac4_smem_bytes(int ns, const JacPlan4Host &p);
+struct HostMech;
+int build_plan_common(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
+                      const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
+                      const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
+                      const std::vector<int> &tb_off, PlanCommon &out);
 
 // returns 0 or a negative GB_ERR_* code; message in gb::last_error
 int finalize_reaction(const HostMech &m, HostReaction &x);

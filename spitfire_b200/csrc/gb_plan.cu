@@ -38,26 +38,24 @@ size_t jac_smem_bytes(int ns, const JacPlanHost &p)
          sizeof(unsigned short) * (size_t)(ns + 1) * (ns - 1) + 16;
 }
 
-int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
-                   const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
-                   const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
-                   const std::vector<int> &tb_off, int G, int threads, JacPlanHost &out)
+int build_plan_common(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
+                      const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
+                      const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
+                      const std::vector<int> &tb_off, PlanCommon &out)
 {
   const int ns = (int)m.species.size(), nr = (int)m.reactions.size(), last = ns - 1;
-  out = JacPlanHost();
-  out.G = G;
-  out.threads = threads;
-  const int nwarps = threads / 32, LPR = 32 / G, RMAX = 32 / G;
+  out = PlanCommon();
   auto dbits = [](double v) {
     unsigned long long u;
     std::memcpy(&u, &v, 8);
     return u;
   };
-
   // ---- classification, records, parameter blob -----------------------------------------------------------------------
-  std::vector<char> fast(nr, 0), last_involved(nr, 0), kind(nr, 2);
-  std::vector<int> hdr_of(nr, JP_HDR_GEN);
-  std::vector<int> rec_off(nr, 0), prm_off(nr, 0);
+  std::vector<char> &fast = out.fast, &last_involved = out.last_involved, &kind = out.kind;
+  std::vector<int> &hdr_of = out.hdr_of, &rec_off = out.rec_off, &prm_off = out.prm_off;
+  fast.assign(nr, 0), last_involved.assign(nr, 0), kind.assign(nr, 2);
+  hdr_of.assign(nr, JP_HDR_GEN), rec_off.assign(nr, 0), prm_off.assign(nr, 0);
+  out.fidx.assign(nr, -1);
   int rec_rows = 0;
   for (int r = 0; r < nr; ++r)
   {
@@ -200,7 +198,10 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
       }
       for (int i = 0; i < 6; i += 2)
         out.prm.push_back((unsigned long long)ne[i] | ((unsigned long long)ne[i + 1] << 32));
-      out.prm.push_back(0ull);
+      // w11: index of the reaction among the structured third-body / falloff reactions (k_jac4 evaluates their
+      // factors ahead of the reaction phase, falloff_task in gb_react.cuh)
+      out.fidx[r] = x.type != RT_SIMPLE ? out.n_falloff++ : -1;
+      out.prm.push_back((unsigned long long)(unsigned int)std::max(0, out.fidx[r]));
       if (x.type != RT_SIMPLE)
       {
         out.prm.push_back(dbits(x.base_eff));
@@ -265,6 +266,67 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
   }
   for (int k = 0; k < 66; ++k)
     out.prm.push_back(0ull); // the group prefetch touches up to 512 bytes past the start of the last record
+
+  // ---- logical destinations and their items ----------------------------------------------------------------------------------
+  // [0, ns*(ns-1))       R[i][k], logical id k*ns + i
+  // [rbase, rbase+5*ns)  row scalars q*ns + i, q = 0..4: sums of nu * {q, dq/drho, dq/dT, a, b}
+  const int yend = ns * (ns - 1), rbase = yend, nlogical = rbase + 5 * ns;
+  std::vector<std::vector<unsigned int>> &dest = out.dest;
+  dest.assign(nlogical, std::vector<unsigned int>());
+  for (int r = 0; r < nr; ++r)
+  {
+    const HostReaction &x = m.reactions[r];
+    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r], hdr = hdr_of[r];
+    const bool tbtype = x.type != RT_SIMPLE;
+    for (int k = 0; k < x.n_net; ++k)
+    {
+      const int row = x.net_idx[k], nu = x.net_st[k];
+      if (nu < -128 || nu > 127)
+      {
+        set_error("net stoichiometric coefficient outside [-128, 127]");
+        return GB_ERR_UNSUPPORTED;
+      }
+      auto item = [&](int rec) { return (unsigned int)rec | ((unsigned int)(nu & 255) << 16); };
+      for (int q = 0; q < 3; ++q)
+        dest[rbase + q * ns + row].push_back(item(base + q));
+      if (tbtype && hdr == JP_HDR_GEN)
+        dest[rbase + 3 * ns + row].push_back(item(base + 3));
+      if (last_involved[r] && hdr == JP_HDR_GEN)
+        dest[rbase + 4 * ns + row].push_back(item(base + 4));
+      for (int q = 0; q < nsl; ++q)
+        dest[(int)slot_species[slot_off[r] + q] * ns + row].push_back(item(base + hdr + q));
+    }
+  }
+
+  return GB_OK;
+}
+
+int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::vector<int> &slot_off,
+                   const std::vector<short> &slot_species, const std::vector<signed char> &rc_slot,
+                   const std::vector<signed char> &pd_slot, const std::vector<signed char> &tb_slot,
+                   const std::vector<int> &tb_off, int G, int threads, JacPlanHost &out)
+{
+  const int ns = (int)m.species.size(), nr = (int)m.reactions.size(), last = ns - 1;
+  out = JacPlanHost();
+  out.G = G;
+  out.threads = threads;
+  const int nwarps = threads / 32, LPR = 32 / G, RMAX = 32 / G;
+
+  PlanCommon pc;
+  {
+    const int rc = build_plan_common(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, pc);
+    if (rc != GB_OK)
+      return rc;
+  }
+  const std::vector<char> &fast = pc.fast, &last_involved = pc.last_involved, &kind = pc.kind;
+  const std::vector<int> &hdr_of = pc.hdr_of, &rec_off = pc.rec_off, &prm_off = pc.prm_off;
+  const int rec_rows = pc.rec_rows;
+  out.rec_rows = rec_rows;
+  out.prm = pc.prm;
+  (void)last_involved;
+  (void)hdr_of;
+  (void)rec_off;
+  (void)last;
 
   // ---- reaction groups --------------------------------------------------------------------------------------------------
   {
@@ -365,35 +427,9 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     }
   }
 
-  // ---- logical destinations and their items ----------------------------------------------------------------------------------
-  // [0, ns*(ns-1))       R[i][k], logical id k*ns + i
-  // [rbase, rbase+5*ns)  row scalars q*ns + i, q = 0..4: sums of nu * {q, dq/drho, dq/dT, a, b}
+  // ---- logical destinations and their items (build_plan_common) --------------------------------------------------------
   const int yend = ns * (ns - 1), rbase = yend, nlogical = rbase + 5 * ns;
-  std::vector<std::vector<unsigned int>> dest(nlogical);
-  for (int r = 0; r < nr; ++r)
-  {
-    const HostReaction &x = m.reactions[r];
-    const int base = rec_off[r], nsl = slot_off[r + 1] - slot_off[r], hdr = hdr_of[r];
-    const bool tbtype = x.type != RT_SIMPLE;
-    for (int k = 0; k < x.n_net; ++k)
-    {
-      const int row = x.net_idx[k], nu = x.net_st[k];
-      if (nu < -128 || nu > 127)
-      {
-        set_error("net stoichiometric coefficient outside [-128, 127]");
-        return GB_ERR_UNSUPPORTED;
-      }
-      auto item = [&](int rec) { return (unsigned int)rec | ((unsigned int)(nu & 255) << 16); };
-      for (int q = 0; q < 3; ++q)
-        dest[rbase + q * ns + row].push_back(item(base + q));
-      if (tbtype && hdr == JP_HDR_GEN)
-        dest[rbase + 3 * ns + row].push_back(item(base + 3));
-      if (last_involved[r] && hdr == JP_HDR_GEN)
-        dest[rbase + 4 * ns + row].push_back(item(base + 4));
-      for (int q = 0; q < nsl; ++q)
-        dest[(int)slot_species[slot_off[r] + q] * ns + row].push_back(item(base + hdr + q));
-    }
-  }
+  const std::vector<std::vector<unsigned int>> &dest = pc.dest;
 
   // ---- rows of the gathered-sum array -----------------------------------------------------------------------------------------
   std::vector<int> row_of(nlogical, -1);
