@@ -63,7 +63,7 @@ def build(force=False, parity=True, out=LIB, verbose=True, defines=()):
 
 
 if __name__ == '__main__':
-    if '--timeline' in sys.argv:  # debug build: per-warp phase timeline of k_jac (tools/timeline.py)
+    if "--timeline" in sys.argv:  # debug build: per-warp phase timeline of k_jac (tools/timeline.py)
         build(force=True, out=os.path.join(HERE, 'libgriffon_b200_tl.so'), defines=('GB_JAC_TIMELINE',))
     elif '--fma' in sys.argv:
         build(force=True, parity=False, out=os.path.join(HERE, 'libgriffon_b200_fma.so'))

@@ -55,6 +55,22 @@ enum TScalar : int
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned int addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds_v2f64(unsigned int addr, double &x, double &y)
+{
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts_f64(unsigned int addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2f64(unsigned int addr, double x, double y)
+{
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+constexpr int JT_MAXM = 8; // rows per lane of the transform phase held in registers: mechanisms up to 64 species
 
 #ifdef GB_JAC_TIMELINE
 __device__ long long g_jac4_timeline[16 * 32];
@@ -88,7 +104,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
 {
   constexpr int G = G4;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const DeviceMech &dm = a.dm;
   const int ns = dm.ns, nsm1 = ns - 1, nsns = ns * ns;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,9 +115,9 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
   const int bufsz = dm.j4_bufsz;
   double *const sdcp = bufs + 2 * bufsz;
   double *const su = sdcp + ns * G, *const snm = su + ns, *const sim = snm + ns;
-  double *const sWX = sim + ns + (ns & 1);
+  double *const sWX = sim + ns + ((4 - (3 * ns) % 4) & 3); // 32-byte aligned rows from here on
   double *const sc2 = sWX + (size_t)dm.j4_nwx * G, *const sc3 = sc2 + ns * G, *const sS = sc3 + ns * G;
-  double *const sR = sS + 8 * G;
+  double *const sR = sS + 16 * G;
   double *const sJ = sR + (size_t)dm.j4_rec_rows * G;
   int *const stab = (int *)(sJ + (size_t)G * nsns);
 
@@ -137,8 +153,10 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
       s.sc = B.sc, s.sy = B.sy, s.sC = B.sC, s.sg = B.sg, s.sdb = B.sdb, s.sh = B.sh, s.scp = B.scp, s.sdcp = sdcp;
       s.su = su, s.snm = snm, s.sim = sim, s.sR = sR, s.sTH = nullptr, s.semap = nullptr, s.sF = B.sF;
       const int tile0 = tile * G, gcount = min(G, a.n - tile0);
+      TL4(11)
       if (kt >= 2)
         nbar_sync(BAR_EMPTY0 + b, NT);
+      TL4(12)
       // ---- load (states past the end of the batch replicate the tile's first state; they are never written) -------
       for (int item = ptid; item < G * ns; item += npt)
       {
@@ -201,6 +219,7 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
         }
       }
       nbar_sync(BAR_PROD, npt);
+      TL4(13)
       // ---- concentrations; mixture cp, dcp/dT and the open-reactor terms in species order (last producer warp) ------
       for (int item = ptid; item < ns * G; item += npt)
       {
@@ -243,6 +262,7 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
           SMG(s.sc, J_YCP, g) = ycp;
         }
       }
+      TL4(14)
       // ---- third-body / falloff factors: 8 reactions x 4 states per task -----------------------------------------------
       for (int fg = pw; fg < dm.j4_nfg; fg += nprod)
       {
@@ -250,6 +270,7 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
         if (off >= 0)
           falloff_task<G>(dm, dm.jp_prm + off, lane & 3, s);
       }
+      TL4(15)
       nbar_arrive(BAR_FULL0 + b, NT);
     }
     return;
@@ -260,6 +281,8 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
   const int *t_rounds = stab + dm.j4_t_rounds, *t_wfix = stab + dm.j4_t_wfix, *t_cfxoff = stab + dm.j4_t_cfxoff;
   const int *t_cfx = stab + dm.j4_t_cfx;
   const int nwrow = 5 * ns; // row-scalar rows of sWX; extra parts follow
+  const unsigned int sJ_u32 = smem_u32(sJ), sR_u32 = smem_u32(sR), sWX_u32 = smem_u32(sWX);
+  const unsigned int jstride = 8u * (unsigned int)nsns; // bytes between the blocks of two states
   int kt = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kt)
   {
@@ -270,15 +293,6 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
     s.su = su, s.snm = snm, s.sim = sim, s.sR = sR, s.sTH = nullptr, s.semap = nullptr, s.sF = B.sF;
     const int tile0 = tile * G, gcount = min(G, a.n - tile0);
     TL4(0)
-    // ---- the previous tile's bulk copy must have finished reading the Jacobian tile ---------------------------------------
-    if (tid == 0)
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    nbar_sync(BAR_CONS, nct);
-    {
-      double2 *z = reinterpret_cast<double2 *>(sJ);
-      for (int i = tid; i < G * nsns / 2; i += nct)
-        z[i] = make_double2(0., 0.);
-    }
     TL4(1)
     nbar_sync(BAR_FULL0 + b, NT);
     TL4(2)
@@ -320,22 +334,38 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
       }
     }
     TL4(3)
+    // the previous tile's bulk copy must have finished reading the Jacobian tile before the gather writes into it
+    if (tid == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     nbar_sync(BAR_CONS, nct);
     TL4(4)
     // ---- gather: lane per destination part, four accumulators, results straight into the Jacobian tile ---------
     {
+      // structural zeros of R (entries without a destination) are written here: nobody else touches them
+      for (int z = tid; z < dm.j4_nzero; z += nct)
+      {
+        const unsigned int addr = sJ_u32 + 8u * (unsigned int)__ldg(dm.j4_zlist + z);
+        sts_f64(addr, 0.);
+        sts_f64(addr + jstride, 0.);
+        sts_f64(addr + 2 * jstride, 0.);
+        sts_f64(addr + 3 * jstride, 0.);
+      }
       const int r0 = t_wr[warp], r1 = t_wr[warp + 1];
-      const int rot = lane & 1;
+      const unsigned int rot16 = (lane & 1) * 16u;
+      // the rounds of a warp are contiguous in the item stream: items are fetched three step pairs ahead (they come
+      // from L2: what is left of L1 next to 225 KB of shared memory does not hold the plan)
       const uint2 *__restrict__ it =
           reinterpret_cast<const uint2 *>(dm.j4_items) + (r1 > r0 ? t_rounds[2 * r0] / 2 : 0) + lane;
-      uint2 cur = __ldg(it), nxt = __ldg(it + 32);
-      it += 64;
+      uint2 cur = __ldg(it), n1 = __ldg(it + 32), n2 = __ldg(it + 64);
+      it += 96;
+      unsigned int rd = r1 > r0 ? __ldg(dm.j4_rdest + (size_t)r0 * 32 + lane) : 0xffffu;
       for (int r = r0; r < r1; ++r)
       {
         const int L = t_rounds[2 * r + 1];
-        const unsigned int rd = __ldg(dm.j4_rdest + (size_t)r * 32 + lane);
-        const int code = (int)(rd & 0xffffu);
+        const unsigned int code = rd & 0xffffu;
         const double nm = snm[rd >> 16];
+        if (r + 1 < r1)
+          rd = __ldg(dm.j4_rdest + (size_t)(r + 1) * 32 + lane);
         const int nm_hi = __double2hiint(nm), nm_lo = __double2loint(nm);
         double acc0 = 0., acc1 = 0., acc2 = 0., acc3 = 0.; // slots: states 2*rot, 2*rot+1, 2*(rot^1), 2*(rot^1)+1
         for (int k = 0; k < L; k += 2)
@@ -347,31 +377,35 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
           {
             const unsigned int u = q == 0 ? cur.x : cur.y;
             // factor -nu*M_i of the reference's `wsens += factor * dq` (rates_sensitivities_exact.cpp:1014-1026);
-            // |nu| > 1 arrives as repeated items
+            // |nu| > 1 arrives as repeated items. Item = byte offset of the record row | sign << 31
             const double c = __hiloint2double(nm_hi ^ (int)(u & 0x80000000u), nm_lo);
-            const double2 *p = reinterpret_cast<const double2 *>(sR + (size_t)(u & 0xffffu) * G);
-            const double2 x = p[rot], y = p[rot ^ 1];
-            acc0 = fma(c, x.x, acc0);
-            acc1 = fma(c, x.y, acc1);
-            acc2 = fma(c, y.x, acc2);
-            acc3 = fma(c, y.y, acc3);
+            const unsigned int addr = sR_u32 + (u & 0x7fffffffu) + rot16;
+            double x0, x1, y0, y1;
+            lds_v2f64(addr, x0, x1);
+            lds_v2f64(addr ^ 16u, y0, y1);
+            acc0 = fma(c, x0, acc0);
+            acc1 = fma(c, x1, acc1);
+            acc2 = fma(c, y0, acc2);
+            acc3 = fma(c, y1, acc3);
           }
-          cur = nxt;
-          nxt = nn;
+          cur = n1;
+          n1 = n2;
+          n2 = nn;
         }
-        if (code < nsns)
+        if (code < (unsigned int)nsns)
         {
-          double *p = sJ + code;
-          p[(size_t)(2 * rot) * nsns] = acc0;
-          p[(size_t)(2 * rot + 1) * nsns] = acc1;
-          p[(size_t)(2 * (rot ^ 1)) * nsns] = acc2;
-          p[(size_t)(2 * (rot ^ 1) + 1) * nsns] = acc3;
+          const unsigned int addr = sJ_u32 + 8u * code + (rot16 >> 3) * jstride; // state 2*rot
+          sts_f64(addr, acc0);
+          sts_f64(addr + jstride, acc1);
+          const unsigned int addr2 = sJ_u32 + 8u * code + (2u - (rot16 >> 3)) * jstride; // state 2*(rot^1)
+          sts_f64(addr2, acc2);
+          sts_f64(addr2 + jstride, acc3);
         }
-        else if (code != 0xffff)
+        else if (code != 0xffffu)
         {
-          double2 *p = reinterpret_cast<double2 *>(sWX + (size_t)(code - nsns) * G);
-          p[rot] = make_double2(acc0, acc1);
-          p[rot ^ 1] = make_double2(acc2, acc3);
+          const unsigned int addr = sWX_u32 + 32u * (code - (unsigned int)nsns) + rot16;
+          sts_v2f64(addr, acc0, acc1);
+          sts_v2f64(addr ^ 16u, acc2, acc3);
         }
       }
     }
@@ -382,90 +416,50 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
     {
       // row scalar q of species i: the gathered value plus its extra parts in part order
       auto wval = [&](int q, int i, int g) {
-        double v = sWX[(size_t)(q * ns + i) * G + g];
+        double v = sWX[(q * ns + i) * G + g];
         const int fx = t_wfix[q * ns + i];
-        for (int p = 0; p < (fx & 255); ++p)
-          v += sWX[(size_t)(nwrow + (fx >> 8) + p) * G + g];
+        if (fx)
+          for (int p = 0; p < (fx & 255); ++p)
+            v += sWX[(nwrow + (fx >> 8) + p) * G + g];
         return v;
       };
-      if (warp == ncons - 1)
+      // (q, g) pairs dealt to the warps, lanes along the species: sum_i h_i * {W, Wrho, WT, A, B}_i and sum_i cp_i * W_i,
+      // the inner products of isobaric_reactor_kernels.cpp:74-92 (pairwise instead of sequential summation)
+      for (int pr = warp; pr < 6 * G; pr += ncons)
       {
-        // lanes (q, g): sum_i h_i * {W, Wrho, WT, A, B}_i and sum_i cp_i * W_i in species order, the inner products of
-        // isobaric_reactor_kernels.cpp:74-92
-        const int q = lane >> 2, g = lane & 3;
+        const int q = pr >> 2, g = pr & 3;
+        const double *wsrc = q == 5 ? s.scp : s.sh;
+        const int qq = q == 5 ? 0 : q;
         double acc = 0.;
-        if (q < 6)
-        {
-          const double *wsrc = q == 5 ? s.scp : s.sh;
-          const int qq = q == 5 ? 0 : q;
-          for (int i = 0; i < ns; ++i)
-            acc = fma(SMG(wsrc, i, g), wval(qq, i, g), acc);
-        }
-        const double SW = __shfl_sync(0xffffffffu, acc, g), SWr = __shfl_sync(0xffffffffu, acc, 4 + g);
-        const double SWT = __shfl_sync(0xffffffffu, acc, 8 + g), SA = __shfl_sync(0xffffffffu, acc, 12 + g);
-        const double SB = __shfl_sync(0xffffffffu, acc, 16 + g), wcp = __shfl_sync(0xffffffffu, acc, 20 + g);
-        if (lane < G)
-        { // chem_jac_isobaric :58-98, mass_jac_isobaric :100-140, heat_jac_isobaric :142-168, transform :319-343
-          const double rho = SMG(s.sc, J_RHO, g), cp = SMG(s.sc, J_CP, g), T = SMG(s.sc, J_T, g);
-          const double cpsensT = SMG(s.sc, J_DCP, g);
-          const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
-          const double rhs0c = -SW * invRhoCp;
-          double rhs0 = rhs0c;
-          double P0rho = -invRhoCp * SWr - invRho * rhs0c;
-          double P0T = -invRhoCp * (SWT + wcp) - rhs0c * cpsensT * invCp;
-          double cextra = 0.;
-          if (open)
-          {
-            const double m0 = SMG(s.sc, J_M0, g);
-            P0T += -invCp * (cpsensT * m0 + invTau * SMG(s.sc, J_YCP, g));
-            cextra += -m0 * invCp;
-            rhs0 += m0;
-          }
-          if (a.rx.heat_option == 2)
-          {
-            const double Ts = a.rx.T_surf;
-            const double rate = a.rx.SoV / (rho * cp) *
-                                (a.rx.h_conv * (a.rx.T_inf - T) + a.rx.eps_rad * 5.67e-8 * (Ts * Ts * Ts * Ts - T * T * T * T));
-            P0rho += -rate / rho;
-            P0T += -invCp * cpsensT * rate - a.rx.SoV * invRhoCp * (a.rx.h_conv + 4. * a.rx.eps_rad * 5.67e-8 * T * T * T);
-            cextra += -invCp * rate;
-            rhs0 += rate;
-          }
-          const double roT = rho * SMG(s.sc, J_INVT, g), nRM = -rho * SMG(s.sc, J_MMW, g);
-          sJ[(size_t)g * nsns] = isothermal ? 0. : P0T - roT * P0rho;
-          if (g < gcount)
-            a.out0[(size_t)(tile0 + g) * ns] = isothermal ? 0. : rhs0;
-          SMG(sS, TS_INVRHO, g) = invRho;
-          SMG(sS, TS_INVRHOCP, g) = invRhoCp;
-          SMG(sS, TS_KY, g) = -rhs0c * invCp + cextra;
-          SMG(sS, TS_SA, g) = SA;
-          SMG(sS, TS_SB, g) = SB;
-          SMG(sS, TS_NRM, g) = nRM;
-          SMG(sS, TS_P0RHO, g) = P0rho;
-        }
+        for (int i = lane; i < ns; i += 32)
+          acc = fma(wsrc[i * G + g], wval(qq, i, g), acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (lane == 0)
+          sS[(8 + q) * G + g] = acc;
       }
-      else
-      {
-        for (int item = tid; item < ns * G; item += nct - 32)
-        { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
-          const int i = item / G, g = item - i * G;
-          const double invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
-          const double w = wval(0, i, g), wr = wval(1, i, g), wT = wval(2, i, g);
-          const double nmA = wval(3, i, g), nmB = wval(4, i, g);
-          const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
-          const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
-          SMG(sc2, i, g) = invRho * nmA + nRM * prho;
-          SMG(sc3, i, g) = invRho * nmB;
-          if (i < nsm1)
-          {
-            sJ[(size_t)g * nsns + 1 + i] = wT * invRho - roT * prho; // J[1+i, 0]
-            if (g < gcount)
-            { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
-              double v = w * invRho;
-              if (open)
-                v += (a.rx.y_in[i] - SMG(s.sy, i, g)) * invTau;
-              a.out0[(size_t)(tile0 + g) * ns + 1 + i] = v;
-            }
+      for (int item = tid; item < ns * G; item += nct)
+      { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
+        const int i = item >> 2, g = item & 3;
+        const double invRho = s.sc[J_IRHO * G + g], rho = s.sc[J_RHO * G + g];
+        const double w = wval(0, i, g), wr = wval(1, i, g), wT = wval(2, i, g);
+        const double nmA = wval(3, i, g), nmB = wval(4, i, g);
+        const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
+        const double nRM = -rho * s.sc[J_MMW * G + g], roT = rho / s.sc[J_T * G + g];
+        sc2[item] = invRho * nmA + nRM * prho;
+        sc3[item] = invRho * nmB;
+        if (i < nsm1)
+        {
+          sJ[g * nsns + 1 + i] = wT * invRho - roT * prho; // J[1+i, 0]
+          if (g < gcount)
+          { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
+            double v = w * invRho;
+            if (open)
+              v += (a.rx.y_in[i] - s.sy[item]) * invTau;
+            a.out0[(size_t)(tile0 + g) * ns + 1 + i] = v;
           }
         }
       }
@@ -473,15 +467,72 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
     TL4(7)
     nbar_sync(BAR_CONS, nct);
     TL4(8)
-    // ---- transform in place, one column per warp pass: lanes (j, g) own the rows j, j+8, ... of state g -----------------
+    // ---- transform in place, one column per warp pass: lanes (j, g) own the rows j, j+8, ... of state g. Row 0 of a
+    // column temporarily holds the row of the last species (it only enters the temperature row) and receives the
+    // column's inner product sum_i h_i R[i][k]; the temperature row is finished after the next barrier. -----------
     {
+      if (warp == ncons - 1 && lane < G)
+      { // chem_jac_isobaric :58-98, mass_jac_isobaric :100-140, heat_jac_isobaric :142-168, transform :319-343
+        const int g = lane;
+        const double SW = sS[8 * G + g], SWr = sS[9 * G + g], SWT = sS[10 * G + g], SA = sS[11 * G + g];
+        const double SB = sS[12 * G + g], wcp = sS[13 * G + g];
+        const double rho = SMG(s.sc, J_RHO, g), cp = SMG(s.sc, J_CP, g), T = SMG(s.sc, J_T, g);
+        const double cpsensT = SMG(s.sc, J_DCP, g);
+        const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
+        const double rhs0c = -SW * invRhoCp;
+        double rhs0 = rhs0c;
+        double P0rho = -invRhoCp * SWr - invRho * rhs0c;
+        double P0T = -invRhoCp * (SWT + wcp) - rhs0c * cpsensT * invCp;
+        double cextra = 0.;
+        if (open)
+        {
+          const double m0 = SMG(s.sc, J_M0, g);
+          P0T += -invCp * (cpsensT * m0 + invTau * SMG(s.sc, J_YCP, g));
+          cextra += -m0 * invCp;
+          rhs0 += m0;
+        }
+        if (a.rx.heat_option == 2)
+        {
+          const double Ts = a.rx.T_surf;
+          const double rate = a.rx.SoV / (rho * cp) *
+                              (a.rx.h_conv * (a.rx.T_inf - T) + a.rx.eps_rad * 5.67e-8 * (Ts * Ts * Ts * Ts - T * T * T * T));
+          P0rho += -rate / rho;
+          P0T += -invCp * cpsensT * rate - a.rx.SoV * invRhoCp * (a.rx.h_conv + 4. * a.rx.eps_rad * 5.67e-8 * T * T * T);
+          cextra += -invCp * rate;
+          rhs0 += rate;
+        }
+        const double roT = rho * SMG(s.sc, J_INVT, g), nRM = -rho * SMG(s.sc, J_MMW, g);
+        sJ[g * nsns] = isothermal ? 0. : P0T - roT * P0rho;
+        if (g < gcount)
+          a.out0[(size_t)(tile0 + g) * ns] = isothermal ? 0. : rhs0;
+        SMG(sS, TS_INVRHOCP, g) = invRhoCp;
+        SMG(sS, TS_KY, g) = -rhs0c * invCp + cextra;
+        SMG(sS, TS_SA, g) = SA;
+        SMG(sS, TS_SB, g) = SB;
+        SMG(sS, TS_NRM, g) = nRM;
+        SMG(sS, TS_P0RHO, g) = P0rho;
+      }
       const int j = lane >> 2, g = lane & 3;
-      const double c1 = SMG(sS, TS_INVRHO, g);
-      double *const Jg = sJ + (size_t)g * nsns;
+      const double c1 = s.sc[J_IRHO * G + g];
+      // this lane's rows: r = j + 8 m; their h, c2, c3 stay in registers for all columns of the tile
+      double hr[JT_MAXM], c2r[JT_MAXM], c3r[JT_MAXM];
+      const int mall = ns >= 8 ? (ns - 8) / 8 + 1 : 0; // iterations in which every lane has a row
+      const bool tail = j + 8 * mall < ns;
+#pragma unroll
+      for (int m = 0; m < JT_MAXM; ++m)
+      {
+        const int r = j + 8 * m;
+        hr[m] = c2r[m] = c3r[m] = 0.;
+        if (r < ns)
+        {
+          const int sp = r ? r - 1 : nsm1;
+          hr[m] = s.sh[sp * G + g], c2r[m] = sc2[sp * G + g], c3r[m] = sc3[sp * G + g];
+        }
+      }
+      const unsigned int lane_u32 = sJ_u32 + 8u * (unsigned int)(g * nsns + j);
       for (int c = 1 + warp; c < ns; c += ncons)
       {
-        const int k = c - 1;
-        const double uk = su[k];
+        const double uk = su[c - 1];
         // split destinations of this column: add the extra parts in part order
         {
           const int f0 = t_cfxoff[c], f1 = t_cfxoff[c + 1];
@@ -489,48 +540,58 @@ __global__ void __launch_bounds__(NT, 1) k_jac4(const ChemArgs a)
           {
             for (int f = f0 + j; f < f1; f += 8)
             {
-              double *p = Jg + c * ns + t_cfx[3 * f];
+              double *p = sJ + g * nsns + c * ns + t_cfx[3 * f];
               double v = *p;
               const int first = t_cfx[3 * f + 1], np = t_cfx[3 * f + 2];
               for (int q = 0; q < np; ++q)
-                v += sWX[(size_t)(nwrow + first + q) * G + g];
+                v += sWX[(nwrow + first + q) * G + g];
               *p = v;
             }
             __syncwarp();
           }
         }
+        const unsigned int col = lane_u32 + 8u * (unsigned int)(c * ns);
         double acc = 0.;
-        for (int r = j; r < ns; r += 8)
+#pragma unroll
+        for (int m = 0; m < JT_MAXM; ++m)
         {
-          double *p = Jg + c * ns + r;
-          const double v = *p;
-          const int sp = r ? r - 1 : nsm1; // row 0 temporarily holds the row of the last species
-          acc = fma(SMG(s.sh, sp, g), v, acc);
-          if (r)
+          if (m < mall || (m == mall && tail))
           {
-            double o = fma(c1, v, fma(uk, SMG(sc2, sp, g), SMG(sc3, sp, g)));
-            if (r == c && open)
-              o += -invTau;
-            *p = o;
+            const double v = lds_f64(col + 64u * m);
+            acc = fma(hr[m], v, acc);
+            if (m > 0 || j > 0)
+            {
+              double o = fma(c1, v, fma(uk, c2r[m], c3r[m]));
+              if (open && j + 8 * m == c)
+                o += -invTau;
+              sts_f64(col + 64u * m, o);
+            }
           }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (j == 0)
-        { // temperature row, isobaric_reactor_kernels.cpp:74-98 with the transform :319-343
-          double v = 0.;
-          if (!isothermal)
-          {
-            const double sum = acc + uk * SMG(sS, TS_SA, g) + SMG(sS, TS_SB, g);
-            const double pY = -sum * SMG(sS, TS_INVRHOCP, g) + SMG(sS, TS_KY, g) * (SMG(s.scp, k, g) - SMG(s.scp, nsm1, g));
-            v = pY + SMG(sS, TS_NRM, g) * uk * SMG(sS, TS_P0RHO, g);
-          }
-          Jg[c * ns] = v;
-        }
+          sts_f64(col, acc);
       }
     }
     TL4(9)
+    nbar_sync(BAR_CONS, nct);
+    // ---- temperature row, isobaric_reactor_kernels.cpp:74-98 with the transform :319-343 ------------------------------------
+    for (int item = tid; item < (ns - 1) * G; item += nct)
+    {
+      const int k = item >> 2, g = item & 3;
+      double *p = sJ + g * nsns + (k + 1) * ns;
+      double v = 0.;
+      if (!isothermal)
+      {
+        const double uk = su[k];
+        const double sum = *p + uk * SMG(sS, TS_SA, g) + SMG(sS, TS_SB, g);
+        const double pY = -sum * SMG(sS, TS_INVRHOCP, g) + SMG(sS, TS_KY, g) * (s.scp[k * G + g] - s.scp[nsm1 * G + g]);
+        v = pY + SMG(sS, TS_NRM, g) * uk * SMG(sS, TS_P0RHO, g);
+      }
+      *p = v;
+    }
     if (tile + 2 * (int)gridDim.x < ntiles)
       nbar_arrive(BAR_EMPTY0 + b, NT);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -602,8 +663,12 @@ cudaError_t launch_jac4(const ChemArgs &a, cudaStream_t s)
   {
   case 512:
     return launch_jac4_nt<512>(a, s);
+  case 640:
+    return launch_jac4_nt<640>(a, s);
   case 768:
     return launch_jac4_nt<768>(a, s);
+  case 896:
+    return launch_jac4_nt<896>(a, s);
   case 1024:
     return launch_jac4_nt<1024>(a, s);
   default:

@@ -368,7 +368,9 @@ int commit(HostMech &m)
     int min_nr = 100;
     if (const char *e = std::getenv("GB_JAC4_MIN_REACTIONS"))
       min_nr = std::atoi(e);
-    if (!std::getenv("GB_JAC4_OFF") && nr >= min_nr && ns <= 250 &&
+    // opt-in while it is slower than k_jac (GB_JAC4=1): see profiles/r02_kjac4_*.txt
+    const char *on = std::getenv("GB_JAC4");
+    if (on && std::atoi(on) != 0 && nr >= min_nr && ns <= 250 &&
         build_jac4_plan(m, flags, slot_off, slot_species, rc_slot, pd_slot, tb_slot, tb_off, threads / 32 - nprod, nprod,
                         j4) == GB_OK &&
         jac4_smem_bytes(ns, j4) <= (size_t)227 * 1024)
@@ -415,7 +417,7 @@ int commit(HostMech &m)
                o_rowstmw = b.add(row_stmw), o_roworder = b.add(row_order);
   const size_t o_jpprm = b.add(jp.prm), o_jpitems = b.add(jp.items), o_jpemap = b.add(jp.emap),
                o_jptab = b.add(jp.tab);
-  const size_t o_j4items = b.add(j4.items), o_j4rdest = b.add(j4.rdest), o_j4tab = b.add(j4.tab);
+  const size_t o_j4items = b.add(j4.items), o_j4rdest = b.add(j4.rdest), o_j4tab = b.add(j4.tab), o_j4z = b.add(j4.zlist);
 
   release_device(m);
   if (cudaMalloc(&m.d_blob, b.bytes.size()) != cudaSuccess ||
@@ -471,7 +473,8 @@ int commit(HostMech &m)
   d.j4_tab = at<int>(base, o_j4tab);
   d.j4_tab_words = (int)j4.tab.size();
   d.j4_t_wg = j4.t_wg, d.j4_t_groups = j4.t_groups, d.j4_t_fgroups = j4.t_fgroups, d.j4_t_wr = j4.t_wr;
-  d.j4_t_rounds = j4.t_rounds, d.j4_t_wfix = j4.t_wfix, d.j4_t_cfxoff = j4.t_cfxoff, d.j4_t_cfx = j4.t_cfx;
+  d.j4_t_rounds = j4.t_rounds, d.j4_t_wfix = j4.t_wfix, d.j4_t_cfxoff = j4.t_cfxoff, d.j4_t_cfx = j4.t_cfx, d.j4_nzero = j4.nzero;
+  d.j4_zlist = at<unsigned short>(base, o_j4z);
   d.j4_threads = have_j4 ? j4.threads : 0, d.j4_ncons = j4.ncons, d.j4_rec_rows = j4.rec_rows, d.j4_nF = j4.nF;
   d.j4_nfg = j4.nfg, d.j4_bufsz = j4.bufsz, d.j4_nwx = j4.nwx, d.j4_smem = have_j4 ? (int)jac4_smem_bytes(ns, j4) : 0;
   m.committed = true;

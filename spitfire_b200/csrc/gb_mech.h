@@ -119,7 +119,8 @@ struct DeviceMech
   // ---- schedule of k_jac4 (gb_plan4.cu, gb_jac4.cu); j4_threads == 0: not available for this mechanism ----
   const unsigned int *j4_items, *j4_rdest;
   const int *j4_tab;
-  int j4_tab_words, j4_t_wg, j4_t_groups, j4_t_fgroups, j4_t_wr, j4_t_rounds, j4_t_wfix, j4_t_cfxoff, j4_t_cfx;
+  int j4_tab_words, j4_t_wg, j4_t_groups, j4_t_fgroups, j4_t_wr, j4_t_rounds, j4_t_wfix, j4_t_cfxoff, j4_t_cfx, j4_nzero;
+  const unsigned short *j4_zlist;
   int j4_threads, j4_ncons, j4_rec_rows, j4_nF, j4_nfg, j4_bufsz, j4_nwx, j4_smem;
 };
 
@@ -165,7 +166,8 @@ struct JacPlan4Host
   std::vector<unsigned int> items; // [round][step pair][lane][2]: record row | sign << 31
   std::vector<unsigned int> rdest; // [round][lane]: destination code | species << 16
   std::vector<int> tab;            // small tables, copied to shared memory
-  int t_wg = 0, t_groups = 0, t_fgroups = 0, t_wr = 0, t_rounds = 0, t_wfix = 0, t_cfxoff = 0, t_cfx = 0;
+  int t_wg = 0, t_groups = 0, t_fgroups = 0, t_wr = 0, t_rounds = 0, t_wfix = 0, t_cfxoff = 0, t_cfx = 0, nzero = 0;
+  std::vector<unsigned short> zlist; // entries (c*ns + r) without a destination
   int n_fast = 0, n_struct = 0, n_generic = 0, n_parts = 0, n_items = 0, n_steps = 0;
 };
 

@@ -29,9 +29,9 @@ size_t jac4_smem_bytes(int ns, const JacPlan4Host &p)
   const size_t G = 4;
   size_t doubles = 2 * (size_t)p.bufsz;                      // double-buffered producer output
   doubles += (size_t)ns * G;                                 // dcp_i/dT (producer scratch)
-  doubles += 3 * (size_t)ns + (ns & 1);                      // u, -M, 1/M
+  doubles += 3 * (size_t)ns + ((4 - (3 * ns) % 4) & 3);       // u, -M, 1/M (padded: 32-byte aligned rows follow)
   doubles += (size_t)p.nwx * G;                              // row scalars + extra parts
-  doubles += 2 * (size_t)ns * G + 8 * G;                     // c2, c3, per-state scalars of the transform
+  doubles += 2 * (size_t)ns * G + 16 * G;                     // c2, c3, per-state scalars of the transform
   doubles += (size_t)p.rec_rows * G;                         // reaction records
   doubles += G * (size_t)ns * ns;                            // Jacobian tile
   return doubles * sizeof(double) + sizeof(int) * p.tab.size() + 16;
@@ -190,7 +190,7 @@ int build_jac4_plan(const HostMech &m, const std::vector<int> &flags, const std:
     for (unsigned int it : d)
     {
       const int nu = (int)(signed char)((it >> 16) & 255);
-      const unsigned int w = (it & 0xffffu) | (nu < 0 ? 0x80000000u : 0u);
+      const unsigned int w = ((it & 0xffffu) * 32u) | (nu < 0 ? 0x80000000u : 0u); // byte offset of the row | sign
       for (int k = 0; k < std::abs(nu); ++k)
         ex.push_back(w);
     }
@@ -276,7 +276,7 @@ int build_jac4_plan(const HostMech &m, const std::vector<int> &flags, const std:
           for (int l = 0; l < 32; ++l)
             for (int q = 0; q < 2; ++q)
             {
-              unsigned int it = (unsigned int)zrow;
+              unsigned int it = (unsigned int)zrow * 32u;
               if (l < (int)rd.p.size() && k + q < (int)parts[rd.p[l]].items.size())
                 it = parts[rd.p[l]].items[k + q];
               out.items.push_back(it);
@@ -295,8 +295,8 @@ int build_jac4_plan(const HostMech &m, const std::vector<int> &flags, const std:
       }
     }
     wr_off[ncons] = (int)rounds.size() / 2;
-    for (int k = 0; k < 64 * 4; ++k)
-      out.items.push_back((unsigned int)zrow); // the item prefetch runs up to two blocks past the end
+    for (int k = 0; k < 64 * 6; ++k)
+      out.items.push_back((unsigned int)zrow * 32u); // the item prefetch runs up to three blocks past the end
     if (getenv("GB_PLAN_VERBOSE"))
     {
       fprintf(stderr, "[gb plan4] rec_rows=%d parts=%d items=%d steps*32=%d rounds=%d extra parts=%d; warp steps:", out.rec_rows,
@@ -360,6 +360,18 @@ int build_jac4_plan(const HostMech &m, const std::vector<int> &flags, const std:
     cfx_flat.push_back(0);
     out.t_cfxoff = add(cfx_off);
     out.t_cfx = add(cfx_flat);
+    // entries of the columns 1..ns-1 without a destination: structural zeros, written by the gather phase
+    {
+      std::vector<char> has((size_t)nsns, 0);
+      for (int lg = 0; lg < yend; ++lg)
+        if (!pc.dest[lg].empty())
+          has[code_of(lg)] = 1;
+      for (int e = ns; e < nsns; ++e)
+        if (!has[e])
+          out.zlist.push_back((unsigned short)e);
+      out.nzero = (int)out.zlist.size();
+      out.zlist.push_back(0);
+    }
     if (out.tab.size() & 1)
       out.tab.push_back(0);
   }
