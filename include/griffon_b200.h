@@ -139,6 +139,22 @@ int gb_reactor_jac_isobaric_host(gb_mech *m, int n, const double *state, const g
                                  int rates_sensitivity_option, int sensitivity_transform_option, double *out_rhs,
                                  double *out_jac);
 
+/* ---- isochoric reactor (griffon.pyx:831-866; isochoric_reactor_kernels.cpp:192-335) ------------------------- */
+/* state [n*(ns+1)] = [rho, T, Y_0..Y_{ns-2}] per state; out_rhs [n*(ns+1)]; out_jac [n*(ns+1)^2], per state
+ * column-major in the primitive variables (row i, col j at i + j*(ns+1)). `prm->pressure` is not read; the inflow
+ * density replaces it (reactor_rhs_isochoric's inflowDensity). rates_sensitivity_option as for the isobaric call.
+ * Work arrays live in the handle (scratch slots): one stream at a time per handle. */
+int gb_reactor_rhs_isochoric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                   double inflow_density, double *out_rhs, void *stream);
+int gb_reactor_rhs_isochoric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                  double inflow_density, double *out_rhs);
+int gb_reactor_jac_isochoric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                   double inflow_density, int rates_sensitivity_option, double *out_rhs,
+                                   double *out_jac, void *stream);
+int gb_reactor_jac_isochoric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                  double inflow_density, int rates_sensitivity_option, double *out_rhs,
+                                  double *out_jac);
+
 /* ---- flamelet (griffon.pyx:556-679; flamelet_kernels.cpp:31-90, 1039-1409) -------------------------------- */
 /* Host-side setup helpers (cold; run once per Flamelet) */
 int gb_flamelet_stencils(const gb_mech *m, const double *dz, int nzi, const double *dissipation_rate,

@@ -1907,6 +1907,212 @@ void go_reactor_jac_isobaric(const go_mech *m, const double *state, double p, do
   free(P);
 }
 
+/* ----------------------------------------------------------------------------------------------------------------
+ * isochoric reactor -- isochoric_reactor_kernels.cpp. State [rho, T, Y_0..Y_{ns-2}], Jacobian (ns+1) x (ns+1)
+ * column-major in the primitive variables themselves (no transform).
+ * -------------------------------------------------------------------------------------------------------------- */
+static void cv_mix_and_species(const go_mech *m, double T, const double *y, double mmw, double *cv,
+                               double *cvi) /* thermodynamics_kernels.cpp:169-181 */
+{
+  cp_mix_and_species(m, T, y, cv, cvi);
+  *cv -= m->Ru / mmw;
+  for (int i = 0; i < m->ns; ++i)
+    cvi[i] -= m->Ru * m->invmw[i];
+}
+
+static void species_energies(const go_mech *m, double T, double *e) /* thermodynamics_kernels.cpp:353-364 */
+{
+  go_species_enthalpies(m, T, e);
+  const double RT = m->Ru * T;
+  for (int i = 0; i < m->ns; ++i)
+    e[i] -= RT * m->invmw[i];
+}
+
+static void chem_rhs_isochoric(const go_mech *m, double rho, double cv, const double *e, const double *w,
+                               double *out_rhs) /* :19-30 */
+{
+  const int ns = m->ns;
+  out_rhs[0] = 0.;
+  out_rhs[1] = -inner_product(ns, w, e) / (rho * cv);
+  const double invRho = 1. / rho;
+  for (int i = 0; i < ns - 1; ++i)
+    out_rhs[2 + i] = w[i] * invRho;
+}
+
+static double heat_rhs_isochoric(double T, double rho, double cv, double Tf, double Ts, double hConv, double epsRad,
+                                 double SoV) /* :32-38 */
+{
+  return SoV / (rho * cv) * (hConv * (Tf - T) + epsRad * 5.67e-8 * (Ts * Ts * Ts * Ts - T * T * T * T));
+}
+
+static void mass_rhs_isochoric(const go_mech *m, const double *y, const double *e, const double *ein, double rho,
+                               double rhoin, double cv, const double *yin, double tau, double *out_rhs) /* :40-62 */
+{
+  const int ns = m->ns;
+  out_rhs[1] = (ein[ns - 1] - e[ns - 1]) * yin[ns - 1];
+  for (int i = 0; i < ns - 1; ++i)
+  {
+    out_rhs[1] += (ein[i] - e[i]) * yin[i];
+    out_rhs[2 + i] = yin[i] - y[i];
+  }
+  const double invRho = 1. / rho;
+  const double invTau = 1. / tau;
+  out_rhs[0] = (rhoin - rho) * invTau;
+  out_rhs[1] /= cv;
+  for (int i = 1; i < ns + 1; ++i)
+    out_rhs[i] *= invTau * rhoin * invRho;
+}
+
+static void chem_jac_isochoric(const go_mech *m, double rho, double cv, const double *cvi, double cvsensT,
+                               const double *e, const double *w, const double *wsens, double *out_rhs,
+                               double *J) /* :64-110 */
+{
+  const int ns = m->ns, n1 = ns + 1;
+  chem_rhs_isochoric(m, rho, cv, e, w, out_rhs);
+  const double invRho = 1. / rho;
+  const double invCv = 1. / cv;
+  const double invRhoCv = 1. / (rho * cv);
+  J[0] = 0.;
+  J[1] = -invRhoCv * inner_product(ns, wsens, e) - invRho * out_rhs[1];
+  for (int i = 0; i < ns - 1; ++i)
+    J[2 + i] = invRho * (wsens[i] - invRho * w[i]);
+  J[n1] = 0.;
+  J[n1 + 1] = -invCv * (invRho * (inner_product(ns, &wsens[n1], e) + inner_product(ns, w, cvi)) + out_rhs[1] * cvsensT);
+  for (int i = 0; i < ns - 1; ++i)
+    J[n1 + 2 + i] = invRho * wsens[n1 + i];
+  const double cvn = cvi[ns - 1];
+  for (int k = 0; k < ns - 1; ++k)
+  {
+    const int fr = (2 + k) * n1;
+    J[fr] = 0.;
+    J[fr + 1] = -invRhoCv * inner_product(ns, &wsens[fr], e) - out_rhs[1] * (cvi[k] - cvn) * invCv;
+    for (int i = 0; i < ns - 1; ++i)
+      J[fr + 2 + i] = invRho * wsens[fr + i];
+  }
+}
+
+static void mass_jac_isochoric(const go_mech *m, const double *y, double rho, double rhoin, double cv, double cvsensT,
+                               const double *cvi, const double *e, const double *ein, const double *yin, double tau,
+                               double *out_rhs, double *J) /* :112-160 */
+{
+  const int ns = m->ns, n1 = ns + 1;
+  mass_rhs_isochoric(m, y, e, ein, rho, rhoin, cv, yin, tau, out_rhs);
+  const double invRho = 1. / rho;
+  const double invCv = 1. / cv;
+  const double invTau = 1. / tau;
+  J[0] = -invTau;
+  for (int i = 0; i < ns; ++i)
+    J[1 + i] = -invRho * out_rhs[1 + i];
+  J[n1] = 0.;
+  J[n1 + 1] = -invCv * (invTau * invRho * (rhoin * inner_product(ns, yin, cvi)) + cvsensT * out_rhs[1]);
+  for (int i = 0; i < ns - 1; ++i)
+    J[n1 + 2 + i] = 0.;
+  const double cvn = cvi[ns - 1];
+  for (int k = 0; k < ns - 1; ++k)
+  {
+    const int fr = (2 + k) * n1;
+    J[fr] = 0.;
+    J[fr + 1] = -invCv * out_rhs[1] * (cvi[k] - cvn);
+    for (int i = 0; i < ns - 1; ++i)
+      J[fr + 2 + i] = 0.;
+    J[fr + 2 + k] = -invTau * rhoin / rho;
+  }
+}
+
+static void heat_jac_isochoric(const go_mech *m, double T, double rho, double cv, double cvsensT, const double *cvi,
+                               double Tc, double Tr, double hc, double eps, double SoV, double *rate,
+                               double *PJ) /* :162-190 */
+{
+  const int ns = m->ns;
+  *rate = heat_rhs_isochoric(T, rho, cv, Tc, Tr, hc, eps, SoV);
+  const double invRhoCv = 1. / (rho * cv);
+  const double invCv = 1. / cv;
+  PJ[0] = -*rate / rho;
+  PJ[1] = -invCv * cvsensT * *rate - SoV * invRhoCv * (hc + 4. * eps * 5.67e-8 * T * T * T);
+  const double cvn = cvi[ns - 1];
+  for (int k = 0; k < ns - 1; ++k)
+    PJ[2 + k] = invCv * *rate * (cvn - cvi[k]);
+}
+
+void go_reactor_rhs_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                              double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                              int heat_option, int open, double *out_rhs) /* :192-246 */
+{
+  const int ns = m->ns;
+  double cv, cvi[ns], e[ns], w[ns], y[ns];
+  const double rho = state[0], T = state[1];
+  extract_y(m, &state[2], y);
+  const double mmw = go_mixture_molecular_weight(m, y);
+  cv_mix_and_species(m, T, y, mmw, &cv, cvi);
+  species_energies(m, T, e);
+  production_rates_mmw(m, T, rho, mmw, y, w);
+  chem_rhs_isochoric(m, rho, cv, e, w, out_rhs);
+  if (open)
+  {
+    double massRhs[ns + 1], ein[ns];
+    species_energies(m, T_in, ein);
+    mass_rhs_isochoric(m, y, e, ein, rho, rho_in, cv, y_in, tau, massRhs);
+    for (int i = 0; i < ns + 1; ++i)
+      out_rhs[i] += massRhs[i];
+  }
+  switch (heat_option)
+  {
+  case 1:
+    out_rhs[1] = 0.;
+    break;
+  case 2:
+    out_rhs[1] += heat_rhs_isochoric(T, rho, cv, T_inf, T_surf, h_conv, eps_rad, SoV);
+    break;
+  }
+}
+
+void go_reactor_jac_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                              double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                              int heat_option, int open, int rates_sens_option, double *out_rhs,
+                              double *out_jac) /* :248-335 */
+{
+  (void)rates_sens_option;
+  const int ns = m->ns, n1 = ns + 1;
+  double cv, cvsensT, heatRate;
+  double cvi[ns], cvisensT[ns], e[ns], w[ns], y[ns], heatPJ[ns + 1];
+  double *wsens = (double *)malloc(sizeof(double) * n1 * n1);
+  const double rho = state[0], T = state[1];
+  extract_y(m, &state[2], y);
+  const double mmw = go_mixture_molecular_weight(m, y);
+  cv_mix_and_species(m, T, y, mmw, &cv, cvi);
+  go_cp_sens_T(m, T, y, &cvsensT, cvisensT); /* cv_sens_T = cp_sens_T, combustion_kernels.h:542-545 */
+  species_energies(m, T, e);
+  prod_rates_sens_exact(m, T, rho, mmw, y, w, wsens);
+  chem_jac_isochoric(m, rho, cv, cvi, cvsensT, e, w, wsens, out_rhs, out_jac);
+  if (open)
+  {
+    double massRhs[ns + 1], ein[ns];
+    double *mJ = (double *)malloc(sizeof(double) * n1 * n1);
+    species_energies(m, T_in, ein);
+    mass_jac_isochoric(m, y, rho, rho_in, cv, cvsensT, cvi, e, ein, y_in, tau, massRhs, mJ);
+    for (int i = 0; i < ns + 1; ++i)
+      out_rhs[i] += massRhs[i];
+    for (int i = 0; i < n1 * n1; ++i)
+      out_jac[i] += mJ[i];
+    free(mJ);
+  }
+  switch (heat_option)
+  {
+  case 1:
+    for (int k = 0; k < n1; ++k)
+      out_jac[k * n1 + 1] = 0.;
+    out_rhs[1] = 0.;
+    break;
+  case 2:
+    heat_jac_isochoric(m, T, rho, cv, cvsensT, cvi, T_inf, T_surf, h_conv, eps_rad, SoV, &heatRate, heatPJ);
+    out_rhs[1] += heatRate;
+    for (int k = 0; k < n1; ++k)
+      out_jac[k * n1 + 1] += heatPJ[k];
+    break;
+  }
+  free(wsens);
+}
+
 void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rates_sens_option,
                                   double *out_rhs, double *out_jac)
 {

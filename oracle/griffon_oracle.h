@@ -78,6 +78,13 @@ void go_reactor_jac_isobaric(const go_mech *m, const double *state, double p, do
 
 /* convenience for timing the CPU path without Python overhead: a plain loop of the single-state call over n states
  * (state [n][ns], out_rhs [n][ns], out_jac [n][ns*ns]); closed adiabatic reactor */
+/* isochoric reactor (isochoric_reactor_kernels.cpp:192-335): state [rho, T, Y_0..Y_{ns-2}], rhs [ns+1], jac [(ns+1)^2] */
+void go_reactor_rhs_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                              double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                              int heat_option, int open, double *out_rhs);
+void go_reactor_jac_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                              double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                              int heat_option, int open, int rates_sens_option, double *out_rhs, double *out_jac);
 void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rates_sens_option,
                                   double *out_rhs, double *out_jac);
 void go_reactor_rhs_isobaric_many(const go_mech *m, int n, const double *state, double p, double *out_rhs);

@@ -55,6 +55,8 @@ def _load(kind):
     sig('go_reactor_rhs_isobaric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, dp])
     sig('go_reactor_jac_isobaric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, I, I, dp, dp])
     sig('go_reactor_jac_isobaric_many', None, [P, I, dp, D, I, dp, dp])
+    sig('go_reactor_rhs_isochoric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, dp])
+    sig('go_reactor_jac_isochoric', None, [P, dp, D, D, dp, D, D, D, D, D, D, I, I, I, dp, dp])
     sig('go_reactor_rhs_isobaric_many', None, [P, I, dp, D, dp])
     sig('go_flamelet_stencils', None, [P, dp, I, dp, dp, dp, dp, dp, dp, dp])
     sig('go_flamelet_jac_indices', None, [P, I, ip, ip])
@@ -156,6 +158,18 @@ class OracleKernels(MechanismSetters):
 
     def reactor_rhs_isobaric_many(self, state, p, out_rhs):
         self._lib.go_reactor_rhs_isobaric_many(self._h, state.shape[0], dptr(state), p, dptr(out_rhs))
+
+    # isochoric reactor -- griffon.pyx:831-866 (state [rho, T, Y_0..Y_{ns-2}])
+    def reactor_rhs_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                              open_, out_rhs):
+        self._lib.go_reactor_rhs_isochoric(self._h, dptr(state), rho_in, T_in, dptr(y_in), tau, T_inf, T_surf, h_conv,
+                                           eps_rad, SoV, int(heat_option), int(bool(open_)), dptr(out_rhs))
+
+    def reactor_jac_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                              open_, rates_sens_option, out_rhs, out_jac):
+        self._lib.go_reactor_jac_isochoric(self._h, dptr(state), rho_in, T_in, dptr(y_in), tau, T_inf, T_surf, h_conv,
+                                           eps_rad, SoV, int(heat_option), int(bool(open_)), int(rates_sens_option),
+                                           dptr(out_rhs), dptr(out_jac))
 
     # flamelet -- griffon.pyx:556-679 (Python order: T_conv, T_rad, h_conv, h_rad)
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):

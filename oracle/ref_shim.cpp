@@ -259,6 +259,21 @@ extern "C"
                                rso, sto, out_rhs, out_jac);
   }
 
+  void go_reactor_rhs_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                                double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                                int heat_option, int open, double *out_rhs)
+  {
+    m->ck.reactor_rhs_isochoric(state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                                open != 0, out_rhs);
+  }
+  void go_reactor_jac_isochoric(const go_mech *m, const double *state, double rho_in, double T_in, const double *y_in,
+                                double tau, double T_inf, double T_surf, double h_conv, double eps_rad, double SoV,
+                                int heat_option, int open, int rso, double *out_rhs, double *out_jac)
+  {
+    m->ck.reactor_jac_isochoric(state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                                open != 0, rso, out_rhs, out_jac);
+  }
+
   void go_reactor_jac_isobaric_many(const go_mech *m, int n, const double *state, double p, int rso, double *out_rhs,
                                     double *out_jac)
   {

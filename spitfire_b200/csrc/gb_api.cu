@@ -367,6 +367,139 @@ extern "C"
   }
 }
 
+// ---- isochoric reactor ---------------------------------------------------------------------------------------------
+namespace gb
+{
+cudaError_t launch_iso_split(int ns, int n, const double *state, double *rho, double *T, double *y, cudaStream_t s);
+cudaError_t launch_iso_assemble(const DeviceMech &dm, int n, const double *state, const double *y, const double *w,
+                                const double *wsens, const ReactorDev &rx, double rho_in, double *out_rhs,
+                                double *out_jac, cudaStream_t s);
+} // namespace gb
+
+namespace
+{
+// rates (and, with out_jac, exact sensitivities) of the batch through the kernels of the isobaric path, then the
+// isochoric assembly. Work arrays live in the handle's scratch slots 4 and 5 (a handle serves one stream at a time).
+int isochoric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm, double rho_in, double *out_rhs,
+                    double *out_jac, void *stream)
+{
+  const int ns = m->h.dm.ns;
+  cudaStream_t st = (cudaStream_t)stream;
+  void *p_work, *p_sens = nullptr;
+  RC(scratch(m, 4, sizeof(double) * (size_t)n * (2 + 2 * (size_t)ns), &p_work));
+  if (out_jac)
+    RC(scratch(m, 5, sizeof(double) * (size_t)n * (ns + 1) * (ns + 1), &p_sens));
+  double *rho = (double *)p_work, *T = rho + n, *y = T + n, *w = y + (size_t)n * ns;
+  CK(gb::launch_iso_split(ns, n, state, rho, T, y, st));
+  ChemArgs a{};
+  a.dm = m->h.dm;
+  a.mode = MODE_PRODRATES;
+  a.n = n;
+  a.in_T = T, a.in_rho = rho, a.in_y = y;
+  a.out0 = w;
+  CK(launch_rates(a, st));
+  if (out_jac)
+  {
+    a.mode = MODE_SENS;
+    a.out0 = nullptr;
+    a.out1 = (double *)p_sens;
+    CK(launch_jac(a, st));
+  }
+  const ReactorDev rx = reactor_dev(prm, prm->inflow_y);
+  CK(gb::launch_iso_assemble(m->h.dm, n, state, y, w, (const double *)p_sens, rx, rho_in, out_rhs, out_jac, st));
+  return GB_OK;
+}
+} // namespace
+
+extern "C"
+{
+  int gb_reactor_rhs_isochoric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                     double inflow_density, double *out_rhs, void *stream)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    return isochoric_batch(m, n, state, prm, inflow_density, out_rhs, nullptr, stream);
+  }
+
+  int gb_reactor_jac_isochoric_batch(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                     double inflow_density, int rates_sensitivity_option, double *out_rhs,
+                                     double *out_jac, void *stream)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if ((n > 0 && !out_jac) || rates_sensitivity_option < 0 || rates_sensitivity_option > 2)
+    {
+      set_error("bad isochoric Jacobian arguments");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return GB_OK;
+    return isochoric_batch(m, n, state, prm, inflow_density, out_rhs, out_jac, stream);
+  }
+
+  static int stage_isochoric(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                             gb_reactor_params *dprm, double **d_state)
+  {
+    const int ns = m->h.dm.ns;
+    void *p_state, *p_yin;
+    RC(scratch(m, 0, sizeof(double) * (size_t)n * (ns + 1), &p_state));
+    RC(scratch(m, 1, sizeof(double) * ns, &p_yin));
+    CK(cudaMemcpy(p_state, state, sizeof(double) * (size_t)n * (ns + 1), cudaMemcpyHostToDevice));
+    *dprm = *prm;
+    if (prm->open)
+    {
+      CK(cudaMemcpy(p_yin, prm->inflow_y, sizeof(double) * ns, cudaMemcpyHostToDevice));
+      dprm->inflow_y = (const double *)p_yin;
+    }
+    else
+      dprm->inflow_y = nullptr;
+    *d_state = (double *)p_state;
+    return GB_OK;
+  }
+
+  int gb_reactor_rhs_isochoric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                    double inflow_density, double *out_rhs)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    gb_reactor_params dprm;
+    double *d_state;
+    RC(stage_isochoric(m, n, state, prm, &dprm, &d_state));
+    void *d_rhs;
+    RC(scratch(m, 2, sizeof(double) * (size_t)n * (ns + 1), &d_rhs));
+    RC(gb_reactor_rhs_isochoric_batch(m, n, d_state, &dprm, inflow_density, (double *)d_rhs, nullptr));
+    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * (size_t)n * (ns + 1), cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+
+  int gb_reactor_jac_isochoric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
+                                    double inflow_density, int rates_sensitivity_option, double *out_rhs,
+                                    double *out_jac)
+  {
+    RC(ready(m));
+    RC(check_reactor(m, n, state, prm, out_rhs));
+    if (n == 0)
+      return GB_OK;
+    const int ns = m->h.dm.ns;
+    gb_reactor_params dprm;
+    double *d_state;
+    RC(stage_isochoric(m, n, state, prm, &dprm, &d_state));
+    void *d_rhs, *d_jac;
+    RC(scratch(m, 2, sizeof(double) * (size_t)n * (ns + 1), &d_rhs));
+    RC(scratch(m, 3, sizeof(double) * (size_t)n * (ns + 1) * (ns + 1), &d_jac));
+    RC(gb_reactor_jac_isochoric_batch(m, n, d_state, &dprm, inflow_density, rates_sensitivity_option, (double *)d_rhs,
+                                      (double *)d_jac, nullptr));
+    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * (size_t)n * (ns + 1), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * (ns + 1) * (ns + 1), cudaMemcpyDeviceToHost));
+    return GB_OK;
+  }
+}
+
 // ---- flamelet ------------------------------------------------------------------------------------------------------
 namespace
 {

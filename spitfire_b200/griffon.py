@@ -80,6 +80,10 @@ def load_library():
     sig('gb_reactor_rhs_isobaric_host', I, [P, I, V, RP, V])
     sig('gb_reactor_jac_isobaric_batch', I, [P, I, V, RP, I, I, V, V, V])
     sig('gb_reactor_jac_isobaric_host', I, [P, I, V, RP, I, I, V, V])
+    sig('gb_reactor_rhs_isochoric_batch', I, [P, I, V, RP, D, V, V])
+    sig('gb_reactor_rhs_isochoric_host', I, [P, I, V, RP, D, V])
+    sig('gb_reactor_jac_isochoric_batch', I, [P, I, V, RP, D, I, V, V, V])
+    sig('gb_reactor_jac_isochoric_host', I, [P, I, V, RP, D, I, V, V])
     sig('gb_flamelet_stencils', I, [P, dp, I, dp, dp, dp, dp, dp, dp, dp])
     sig('gb_flamelet_jac_indices', I, [P, I, ip, ip])
     FP = C.POINTER(FlameletParams)
@@ -313,6 +317,47 @@ class PyCombustionKernels(MechanismSetters):
             check(self._lib.gb_reactor_jac_isobaric_host(self._h, n, _addr(state), C.byref(prm),
                                                          int(rates_sens_option), int(sens_transform_option),
                                                          _addr(out_rhs), _addr(out_jac)), 'reactor_jac_isobaric')
+
+    # ---- isochoric reactor (griffon.pyx:831-866): state [rho, T, Y_0..Y_{ns-2}], Jacobian (ns+1) x (ns+1) -------------
+    def reactor_rhs_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                              open_, out_rhs):
+        prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        check(self._lib.gb_reactor_rhs_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
+                                                      _addr(out_rhs)), 'reactor_rhs_isochoric')
+
+    def reactor_jac_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
+                              open_, rates_sens_option, out_rhs, out_jac):
+        prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        check(self._lib.gb_reactor_jac_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
+                                                      int(rates_sens_option), _addr(out_rhs), _addr(out_jac)),
+              'reactor_jac_isochoric')
+
+    def reactor_rhs_isochoric_batch(self, state, out_rhs, rho_in=0., T_in=0., y_in=None, tau=0., T_inf=0., T_surf=0.,
+                                    h_conv=0., eps_rad=0., SoV=0., heat_option=0, open_=False):
+        """state [n, ns+1] -> out_rhs [n, ns+1]; torch CUDA tensors (async) or numpy arrays (sync)"""
+        n = state.shape[0]
+        prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        if _on_device(state, out_rhs):
+            check(self._lib.gb_reactor_rhs_isochoric_batch(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+                                                           _addr(out_rhs), _stream()), 'reactor_rhs_isochoric_batch')
+        else:
+            check(self._lib.gb_reactor_rhs_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+                                                          _addr(out_rhs)), 'reactor_rhs_isochoric')
+
+    def reactor_jac_isochoric_batch(self, state, out_rhs, out_jac, rho_in=0., T_in=0., y_in=None, tau=0., T_inf=0.,
+                                    T_surf=0., h_conv=0., eps_rad=0., SoV=0., heat_option=0, open_=False,
+                                    rates_sens_option=0):
+        """state [n, ns+1] -> out_rhs [n, ns+1], out_jac [n, (ns+1)^2] (column-major per state)"""
+        n = state.shape[0]
+        prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
+        if _on_device(state, out_rhs, out_jac):
+            check(self._lib.gb_reactor_jac_isochoric_batch(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+                                                           int(rates_sens_option), _addr(out_rhs), _addr(out_jac),
+                                                           _stream()), 'reactor_jac_isochoric_batch')
+        else:
+            check(self._lib.gb_reactor_jac_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+                                                          int(rates_sens_option), _addr(out_rhs), _addr(out_jac)),
+                  'reactor_jac_isochoric')
 
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):

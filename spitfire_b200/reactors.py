@@ -1,10 +1,9 @@
 """
 Zero-dimensional homogeneous reactors on the B200 Griffon path: `HomogeneousReactor` with the reference's constructor
-and `integrate*` signatures (reactors.py:27-794) for the **isobaric** configurations (adiabatic / isothermal /
-diathermal, closed / open) -- the part of the reference class that is on the hot path of SURVEY.md section 8. The
-isochoric configuration is out of scope and raises.
+and `integrate*` signatures (reactors.py:27-794): isobaric and isochoric configurations, adiabatic / isothermal /
+diathermal, closed / open.
 
-The right-hand side and the analytical Jacobian come from `gb_reactor_{rhs,jac}_isobaric_*` through
+The right-hand side and the analytical Jacobian come from `gb_reactor_{rhs,jac}_{isobaric,isochoric}_*` through
 spitfire_b200.griffon; the dense ns x ns linear algebra of one reactor stays with SciPy's LAPACK on the host exactly
 as in the reference (reactors.py:340-356), the time integration with spitfire_b200.time.
 For many reactors at once use `PyCombustionKernels.reactor_{rhs,jac}_isobaric_batch` directly (bench.py).
@@ -64,9 +63,6 @@ class HomogeneousReactor(object):
         self._check(heat_transfer, 'heat transfer', self._heat_transfers)
         self._check(mass_transfer, 'mass transfer', self._mass_transfers)
         self._configuration = self._configuration_dict[configuration.lower()]
-        if self._configuration != 'isobaric':
-            raise NotImplementedError('spitfire_b200 provides the isobaric reactor; the isochoric configuration is '
-                                      'outside the B200 hot path (SURVEY.md section 8(f))')
         self._heat_transfer = heat_transfer.lower()
         self._mass_transfer = mass_transfer.lower()
 
@@ -99,17 +95,22 @@ class HomogeneousReactor(object):
         else:
             self._mixing_tau, self._feed_temperature = 0., 0.
             self._feed_mass_fractions = np.zeros(1)  # never dereferenced when closed (reactors.py:226)
-        self._feed_density = feed_density
+        if self._mass_transfer == 'open' and self._configuration == 'isochoric':
+            self._feed_density = self._need(feed_density, 'feed_density', 'mass transfer is set to open')
+        else:
+            self._feed_density = 0. if feed_density is None else feed_density
 
         # parameters may be constants or functions of time (reactors.py:246-271)
         self._timevar = {a: callable(getattr(self, a)) for a in
                          ('_convection_temperature', '_radiation_temperature', '_convection_coefficient',
-                          '_radiative_emissivity', '_mixing_tau', '_feed_temperature', '_feed_mass_fractions')}
+                          '_radiative_emissivity', '_mixing_tau', '_feed_temperature', '_feed_mass_fractions',
+                          '_feed_density')}
         at0 = lambda a: getattr(self, a)(0.) if self._timevar[a] else getattr(self, a)
         self._tc_value, self._tr_value = at0('_convection_temperature'), at0('_radiation_temperature')
         self._cc_value, self._re_value = at0('_convection_coefficient'), at0('_radiative_emissivity')
         self._tau_value, self._tf_value = at0('_mixing_tau'), at0('_feed_temperature')
         self._yf_value = at0('_feed_mass_fractions')
+        self._rf_value = at0('_feed_density')
 
         self._rates_sensitivity_option = {'dense': 0, 'no-TBAF': 1, 'sparse': 2}[rates_sensitivity_type]
         self._sensitivity_transform_option = {'exact': 0}[sensitivity_transform_type]
@@ -128,9 +129,15 @@ class HomogeneousReactor(object):
         self._current_time = np.copy(initial_time)
         self._n_species = mech_spec.n_species
         self._n_reactions = mech_spec.n_reactions
-        self._n_equations = self._n_species  # [T, Y_0..Y_{ns-2}]
-        self._temperature_index = 0
-        self._initial_state = np.hstack((self._initial_temperature, self._initial_mass_fractions[:-1]))
+        if self._configuration == 'isobaric':
+            self._n_equations = self._n_species  # [T, Y_0..Y_{ns-2}]
+            self._temperature_index = 0
+            self._initial_state = np.hstack((self._initial_temperature, self._initial_mass_fractions[:-1]))
+        else:
+            self._n_equations = self._n_species + 1  # [rho, T, Y_0..Y_{ns-2}] (reactors.py:313-318)
+            self._temperature_index = 1
+            self._initial_state = np.hstack((float(initial_mixture.density), self._initial_temperature,
+                                             self._initial_mass_fractions[:-1]))
         self._current_state = np.copy(self._initial_state)
         self._variable_scales = np.ones(self._n_equations)
         self._variable_scales[self._temperature_index] = 1.e3
@@ -174,10 +181,19 @@ class HomogeneousReactor(object):
             self._tf_value = self._feed_temperature(t)
         if v['_feed_mass_fractions']:
             self._yf_value = self._feed_mass_fractions(t)
+        if v['_feed_density']:
+            self._rf_value = self._feed_density(t)
 
     def _rhs(self, t, state):
         k = np.zeros(self._n_equations)
         self._update_parameters(t)
+        if self._configuration == 'isochoric':
+            self._griffon.reactor_rhs_isochoric(np.ascontiguousarray(state), self._rf_value, self._tf_value,
+                                                np.ascontiguousarray(self._yf_value, dtype=np.float64),
+                                                self._tau_value, self._tc_value, self._tr_value, self._cc_value,
+                                                self._re_value, self._surface_area_to_volume,
+                                                self._heat_transfer_option, self._is_open, k)
+            return k
         self._griffon.reactor_rhs_isobaric(np.ascontiguousarray(state), self._initial_pressure, self._tf_value,
                                            np.ascontiguousarray(self._yf_value, dtype=np.float64), self._tau_value,
                                            self._tc_value, self._tr_value, self._cc_value, self._re_value,
@@ -187,6 +203,14 @@ class HomogeneousReactor(object):
     def _jac(self, state):
         k = np.zeros(self._n_equations)
         j = np.zeros(self._n_equations * self._n_equations)
+        if self._configuration == 'isochoric':
+            self._griffon.reactor_jac_isochoric(np.ascontiguousarray(state), self._rf_value, self._tf_value,
+                                                np.ascontiguousarray(self._yf_value, dtype=np.float64),
+                                                self._tau_value, self._tc_value, self._tr_value, self._cc_value,
+                                                self._re_value, self._surface_area_to_volume,
+                                                self._heat_transfer_option, self._is_open,
+                                                self._rates_sensitivity_option, k, j)
+            return j.reshape((self._n_equations, self._n_equations), order='F')
         self._griffon.reactor_jac_isobaric(np.ascontiguousarray(state), self._initial_pressure, self._tf_value,
                                            np.ascontiguousarray(self._yf_value, dtype=np.float64), self._tau_value,
                                            self._tc_value, self._tr_value, self._cc_value, self._re_value,
@@ -252,18 +276,26 @@ class HomogeneousReactor(object):
             t, states = output
         self._current_state = np.copy(states[-1, :])
         self._current_time = np.copy(t[-1])
-        self._current_temperature = float(states[-1, 0])
+        ti = self._temperature_index
+        self._current_temperature = float(states[-1, ti])
         lib = Library(Dimension('time', t))
-        lib['temperature'] = np.array(states[:, 0])
-        lib['pressure'] = self._initial_pressure + np.zeros_like(lib['temperature'])
+        if self._configuration == 'isobaric':
+            lib['temperature'] = np.array(states[:, 0])
+            lib['pressure'] = self._initial_pressure + np.zeros_like(lib['temperature'])
+        else:  # reactors.py:637-645
+            lib['density'] = np.array(states[:, 0])
+            lib['temperature'] = np.array(states[:, 1])
         names = self._mechanism.species_names
         last = np.ones_like(lib['temperature'])
         lib['mass fraction ' + names[-1]] = last
         for i, s in enumerate(names[:-1]):
-            lib['mass fraction ' + s] = np.array(states[:, 1 + i])
-            last = last - states[:, 1 + i]
+            lib['mass fraction ' + s] = np.array(states[:, ti + 1 + i])
+            last = last - states[:, ti + 1 + i]
         lib['mass fraction ' + names[-1]] = last
         self._current_mass_fractions = np.array([lib['mass fraction ' + s][-1] for s in names])
+        if self._configuration == 'isochoric':
+            mw = np.asarray(self._mechanism.molecular_weights, dtype=np.float64)
+            self._current_pressure = float(states[-1, 0] * states[-1, 1] / np.sum(self._current_mass_fractions / mw))
         lib.extra_attributes['mech_spec'] = self._mechanism
         return lib
 
@@ -335,30 +367,48 @@ class _ReactorBatchOps(object):
     def rhs(self, q, idx=None, key=None):
         torch = self.torch
         out = torch.empty_like(q)
+        iso = self.r._configuration == 'isochoric'
         if self.on_device:
-            self.g.reactor_rhs_isobaric_batch(q.contiguous(), self._args[0], out, **self._kw)
+            if iso:
+                self.g.reactor_rhs_isochoric_batch(q.contiguous(), out, rho_in=self.r._rf_value, **self._kw)
+            else:
+                self.g.reactor_rhs_isobaric_batch(q.contiguous(), self._args[0], out, **self._kw)
         else:
             qn, on = q.numpy(), out.numpy()
             for k in range(q.shape[0]):
-                self.g.reactor_rhs_isobaric(np.ascontiguousarray(qn[k]), *self._host, on[k])
+                if iso:
+                    self.g.reactor_rhs_isochoric(np.ascontiguousarray(qn[k]), self.r._rf_value, *self._host[1:], on[k])
+                else:
+                    self.g.reactor_rhs_isobaric(np.ascontiguousarray(qn[k]), *self._host, on[k])
         return out
 
     def jac(self, q, idx=None, key=None):
         torch = self.torch
         n = q.shape[0]
         rhs = torch.empty_like(q)
+        iso = self.r._configuration == 'isochoric'
         if self.on_device:
             J = torch.empty((n, self.nelem), dtype=torch.float64, device=self.device)
-            self.g.reactor_jac_isobaric_batch(q.contiguous(), self._args[0], rhs, J,
-                                              rates_sens_option=self.r._rates_sensitivity_option,
-                                              sens_transform_option=self.r._sensitivity_transform_option, **self._kw)
+            if iso:
+                self.g.reactor_jac_isochoric_batch(q.contiguous(), rhs, J, rho_in=self.r._rf_value,
+                                                   rates_sens_option=self.r._rates_sensitivity_option, **self._kw)
+            else:
+                self.g.reactor_jac_isobaric_batch(q.contiguous(), self._args[0], rhs, J,
+                                                  rates_sens_option=self.r._rates_sensitivity_option,
+                                                  sens_transform_option=self.r._sensitivity_transform_option,
+                                                  **self._kw)
         else:
             J = torch.zeros((n, self.nelem), dtype=torch.float64)
             qn, rn, Jn = q.numpy(), rhs.numpy(), J.numpy()
             for k in range(n):
-                self.g.reactor_jac_isobaric(np.ascontiguousarray(qn[k]), *self._host, self.r._rates_sensitivity_option,
-                                            self.r._sensitivity_transform_option, rn[k], Jn[k])
-        return J  # column-major ns x ns per reactor = one BTDDOD block
+                if iso:
+                    self.g.reactor_jac_isochoric(np.ascontiguousarray(qn[k]), self.r._rf_value, *self._host[1:],
+                                                 self.r._rates_sensitivity_option, rn[k], Jn[k])
+                else:
+                    self.g.reactor_jac_isobaric(np.ascontiguousarray(qn[k]), *self._host,
+                                                self.r._rates_sensitivity_option,
+                                                self.r._sensitivity_transform_option, rn[k], Jn[k])
+        return J  # column-major n_equations x n_equations per reactor = one BTDDOD block
 
 
 def _borrow_linear_algebra():
@@ -370,7 +420,8 @@ def _borrow_linear_algebra():
 
 
 class HomogeneousReactorBatch(object):
-    """N isobaric reactors integrated together on the GPU ("many ignition reactors at once").
+    """N reactors (isobaric or isochoric) integrated together on the GPU ("many ignition
+    reactors at once"). Isochoric members start at the template's pressure: rho_i = p M_i / (R T_i).
 
     Same model and integrator as `HomogeneousReactor` (ESDIRK64, PI step control, Newton with the Jacobian refreshed
     every `maximum_steps_per_jacobian` steps, negative mass fractions clipped after each step); every member keeps its
@@ -390,7 +441,14 @@ class HomogeneousReactorBatch(object):
         Y = np.atleast_2d(np.asarray(mass_fractions, dtype=np.float64))
         if Y.shape != (T.size, template._n_species):
             raise ValueError('mass_fractions must be [n_reactors, n_species]')
-        self._initial_states = np.ascontiguousarray(np.hstack((T[:, None], Y[:, :-1])))
+        self._ti = template._temperature_index
+        if template._configuration == 'isochoric':
+            m = template._mechanism
+            mw = np.asarray(m.molecular_weights, dtype=np.float64)
+            rho = template._initial_pressure / (m.gas_constant * T * np.sum(Y / mw[None, :], axis=1))
+            self._initial_states = np.ascontiguousarray(np.hstack((rho[:, None], T[:, None], Y[:, :-1])))
+        else:
+            self._initial_states = np.ascontiguousarray(np.hstack((T[:, None], Y[:, :-1])))
         if not hasattr(_ReactorBatchOps, 'factorize'):
             _borrow_linear_algebra()
         self.ops = _ReactorBatchOps(template, T.size)
@@ -433,20 +491,23 @@ class HomogeneousReactorBatch(object):
             mine = parallel.my_share(list(range(self.n_reactors)))
             local = dict()
             if mine:
-                Y = np.hstack((self._initial_states[mine, 1:], 1. - self._initial_states[mine, 1:].sum(axis=1, keepdims=True)))
-                share = HomogeneousReactorBatch(self._r, self._initial_states[mine, 0], Y)
+                ti = self._ti
+                Y = np.hstack((self._initial_states[mine, ti + 1:],
+                               1. - self._initial_states[mine, ti + 1:].sum(axis=1, keepdims=True)))
+                share = HomogeneousReactorBatch(self._r, self._initial_states[mine, ti], Y)
                 share._initial_states = np.ascontiguousarray(self._initial_states[mine])  # (exactly the caller's states)
                 share._is_share = True
                 tau = share.compute_ignition_delay(delta_temperature_ignition, minimum_allowable_residual, **kwargs)
                 local = {int(k): float(t) for k, t in zip(mine, tau)}
             merged = parallel.gather_dicts(local)
             return np.array([merged[k] for k in range(self.n_reactors)])
-        T0 = self.ops.torch.as_tensor(self._initial_states[:, 0]).to(self.ops.device)
+        ti = self._ti
+        T0 = self.ops.torch.as_tensor(self._initial_states[:, ti]).to(self.ops.device)
 
         def stop(t, q, residual, nsteps):
-            return ((q[:, 0] - T0) > delta_temperature_ignition) | (residual <= minimum_allowable_residual)
+            return ((q[:, ti] - T0) > delta_temperature_ignition) | (residual <= minimum_allowable_residual)
 
         times, states, failed = self.integrate(stop, **kwargs)
         tau = np.array([th[-1] for th in times])
-        ignited = np.array([qs[-1][0] for qs in states]) - self._initial_states[:, 0] > delta_temperature_ignition
+        ignited = np.array([qs[-1][ti] for qs in states]) - self._initial_states[:, ti] > delta_temperature_ignition
         return np.where(ignited & ~np.asarray(failed), tau, np.nan)

@@ -217,6 +217,37 @@ def test_open_isothermal_diathermal_reactor(name):
         assert_parity(j, ref_j, f'{name} open jac heat={heat_option}')
 
 
+@pytest.mark.parametrize('name', ['h2-burke', 'methane-gri30', 'old_xmls_rev_lindemann_withN_withNTB',
+                                  'old_xmls_nasa9_air_h2'])
+def test_isochoric_reactor(name):
+    """reactor_{rhs,jac}_isochoric (isochoric_reactor_kernels.cpp:192-335): state [rho, T, Y], (ns+1)^2 Jacobian;
+    closed and open, the three heat-transfer options; batch entry points and the single-state method names"""
+    mg, mo = build_mech(name, 'gpu'), build_mech(name, ORACLE)
+    ns = mg.n_species
+    rng = np.random.default_rng(6)
+    n = 40
+    y = rng.dirichlet(np.ones(ns) * 0.5, n)
+    state = np.ascontiguousarray(np.hstack([rng.uniform(0.05, 4., (n, 1)), rng.uniform(500., 2500., (n, 1)), y[:, :-1]]))
+    yin = rng.dirichlet(np.ones(ns))
+    for open_ in (False, True):
+        for heat_option in (0, 1, 2):
+            args = (1.3, 900., yin, 1e-3, 400., 500., 10., 0.3, 2.5, heat_option, open_)
+            ref_r, ref_jr, ref_j = np.zeros((n, ns + 1)), np.zeros((n, ns + 1)), np.zeros((n, (ns + 1) ** 2))
+            for i in range(n):
+                mo.griffon.reactor_rhs_isochoric(state[i], *args, ref_r[i])
+                mo.griffon.reactor_jac_isochoric(state[i], *args, 0, ref_jr[i], ref_j[i])
+            r, jr, j = np.zeros((n, ns + 1)), np.zeros((n, ns + 1)), np.zeros((n, (ns + 1) ** 2))
+            mg.griffon.reactor_rhs_isochoric_batch(state, r, *args)
+            mg.griffon.reactor_jac_isochoric_batch(state, jr, j, *args, 0)
+            what = f'{name} isochoric open={open_} heat={heat_option}'
+            assert_parity(r, ref_r, what + ' rhs')
+            assert_parity(jr, ref_jr, what + ' jac-rhs')
+            assert_parity(j, ref_j, what + ' jac')
+            r1, j1 = np.zeros(ns + 1), np.zeros((ns + 1) ** 2)
+            mg.griffon.reactor_jac_isochoric(state[3], *args, 0, r1, j1)
+            assert np.array_equal(r1, jr[3]) and np.array_equal(j1, j[3])
+
+
 def test_single_state_api_is_the_batch_path():
     """the reference's single-state method names are batch-of-one calls of the same kernels"""
     mg, mo = build_mech('h2-burke', 'gpu'), build_mech('h2-burke', ORACLE)

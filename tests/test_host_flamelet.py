@@ -81,9 +81,12 @@ def test_library_slice_round_trip():
     assert np.array_equal(f2.mixfrac_grid, f.mixfrac_grid)
 
 
+@pytest.mark.parametrize('configuration', ['isobaric', 'isochoric'])
 @pytest.mark.parametrize('heat_transfer', ['adiabatic', 'isothermal'])
-def test_homogeneous_reactor_matches_reference_gold(heat_transfer):
-    """BASELINE config 1 (H2/air isobaric ignition) through HomogeneousReactor + ESDIRK64 with the oracle kernels"""
+def test_homogeneous_reactor_matches_reference_gold(heat_transfer, configuration):
+    """BASELINE config 1 (H2/air ignition) through HomogeneousReactor + ESDIRK64 with the oracle kernels: the four
+    configurations of the reference's closed_reactors regression test (tests/reactor/closed_reactors/test.py)"""
     from reactor_cases import compare_with_gold, run
-    m, lib = run(ORACLE, heat_transfer)
-    print(heat_transfer, 'steps', lib.time_values.size, 'max rel err T', compare_with_gold(m, lib, heat_transfer))
+    m, lib = run(ORACLE, heat_transfer, configuration)
+    print(configuration, heat_transfer, 'steps', lib.time_values.size, 'max rel err T',
+          compare_with_gold(m, lib, heat_transfer, configuration=configuration))

@@ -37,6 +37,30 @@ def test_port_is_bit_identical_to_reference(name):
 
 
 @need_ref
+@pytest.mark.parametrize('name', ['h2-burke', 'methane-gri30', 'old_xmls_nasa9_air_h2',
+                                  'old_xmls_rev_troe4_withN_withNTB', 'old_xmls_irr_elementary_noN_noT_generalstoich'])
+def test_port_isochoric_reactor_bit_identical_to_reference(name):
+    """isochoric_reactor_kernels.cpp:192-335: closed/open, adiabatic/isothermal/diathermal"""
+    a, b = build_mech(name, 'reference'), build_mech(name, 'port')
+    ns = a.n_species
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        y = rng.dirichlet(np.ones(ns) * 0.5)
+        state = np.concatenate([[rng.uniform(0.05, 5.), rng.uniform(300., 3000.)], y[:-1]])
+        yin = rng.dirichlet(np.ones(ns))
+        for heat in (0, 1, 2):
+            for open_ in (False, True):
+                args = (state, 1.1, 350., yin, 1e-3, 400., 500., 10., 0.3, 2.0, heat, open_)
+                r = [np.zeros(ns + 1) for _ in range(4)]
+                j = [np.zeros((ns + 1) ** 2) for _ in range(2)]
+                a.griffon.reactor_rhs_isochoric(*args, r[0])
+                b.griffon.reactor_rhs_isochoric(*args, r[1])
+                a.griffon.reactor_jac_isochoric(*args, 0, r[2], j[0])
+                b.griffon.reactor_jac_isochoric(*args, 0, r[3], j[1])
+                assert np.array_equal(r[0], r[1]) and np.array_equal(r[2], r[3]) and np.array_equal(j[0], j[1])
+
+
+@need_ref
 @pytest.mark.parametrize('name,nz', [('h2-burke', 34), ('methane-gri30', 16), ('old_xmls_rev_troe4_withN_withNTB', 12)])
 def test_port_flamelet_and_block_thomas_bit_identical_to_reference(name, nz):
     a, b = build_mech(name, 'reference'), build_mech(name, 'port')

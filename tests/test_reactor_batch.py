@@ -150,3 +150,31 @@ def test_two_rank_gloo_ignition_table(tmp_path):
     single = HomogeneousReactorBatch(r, d['T0'], np.tile(mix.Y, (d['T0'].size, 1))).compute_ignition_delay()
     assert np.array_equal(d['tau'], single)
     assert np.all(np.diff(d['tau']) < 0.)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('configuration', ['isobaric', 'isochoric'])
+@pytest.mark.parametrize('heat_transfer', ['adiabatic', 'isothermal'])
+def test_closed_reactor_gold_on_gpu(heat_transfer, configuration):
+    """the four configurations of the reference's closed_reactors regression test (tests/reactor/closed_reactors),
+    HomogeneousReactor on the CUDA kernels"""
+    from reactor_cases import compare_with_gold, run
+    m, lib = run('gpu', heat_transfer, configuration)
+    compare_with_gold(m, lib, heat_transfer, configuration=configuration)
+
+
+@pytest.mark.gpu
+def test_isochoric_reactor_batch_matches_serial_on_gpu():
+    from spitfire_b200.reactors import HomogeneousReactor, HomogeneousReactorBatch
+    m = build_mech('h2-burke', 'gpu')
+    air = m.stream(stp_air=True)
+    fuel = m.stream('X', 'H2:1')
+    mix = m.mix_for_equivalence_ratio(1.0, fuel, air)
+    mix.TP = 1200., 101325.
+    r = HomogeneousReactor(m, mix, 'isochoric', 'adiabatic', 'closed')
+    b = HomogeneousReactorBatch(r, T0S, np.tile(mix.Y, (len(T0S), 1)))
+    tau = b.compute_ignition_delay()
+    for k, T0 in enumerate(T0S):
+        mix.TP = T0, 101325.
+        t1 = HomogeneousReactor(m, mix, 'isochoric', 'adiabatic', 'closed').compute_ignition_delay()
+        assert abs(tau[k] - t1) <= 1e-4 * t1, (T0, tau[k], t1)
