@@ -359,6 +359,26 @@ class PyCombustionKernels(MechanismSetters):
                                                           int(rates_sens_option), _addr(out_rhs), _addr(out_jac)),
                   'reactor_jac_isochoric')
 
+    # ---- methods of the reference class that are not on the B200 path (griffon.pyx:870-987): callable, raise clearly ----
+    def _not_on_path(self, name):
+        raise GriffonB200Error(f'{name} is not part of the B200 Griffon hot path (SURVEY.md section 8: two-dimensional '
+                               f'flamelets are out of scope); there is no CPU fallback')
+
+    def flamelet2d_rhs(self, *args, **kwargs):
+        self._not_on_path('flamelet2d_rhs')
+
+    def flamelet2d_factored_block_diag_jacobian(self, *args, **kwargs):
+        self._not_on_path('flamelet2d_factored_block_diag_jacobian')
+
+    def flamelet2d_offdiag_matvec(self, *args, **kwargs):
+        self._not_on_path('flamelet2d_offdiag_matvec')
+
+    def flamelet2d_matvec(self, *args, **kwargs):
+        self._not_on_path('flamelet2d_matvec')
+
+    def flamelet2d_block_diag_solve(self, *args, **kwargs):
+        self._not_on_path('flamelet2d_block_diag_solve')
+
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):
         check(self._lib.gb_flamelet_stencils(self._h, dptr(dz), int(nzi), dptr(chi), dptr(inv_lewis),
@@ -500,3 +520,22 @@ def py_btddod_scale_and_add_diagonal(in_out_matrix_values, matrix_scale, diagona
         _on_device(in_out_matrix_values, diagonal),
         int(n_systems), _addr(in_out_matrix_values), float(matrix_scale), _addr(diagonal), float(diag_scale),
         int(num_blocks), int(block_size))
+
+
+# ---- module functions of the reference that are not on the B200 path (griffon.pyx:1019-1105): the block-Jacobi /
+# Gauss-Seidel helpers of the 2-D flamelet solver. Callable, raise clearly. ---------------------------------------------
+def _btddod_not_on_path(name):
+    def f(*args, **kwargs):
+        raise GriffonB200Error(f'{name} is not part of the B200 Griffon hot path (SURVEY.md section 8: the flamelet '
+                               f'Newton / ESDIRK loops use py_btddod_full_factorize / py_btddod_full_solve); there is no '
+                               f'CPU fallback')
+    f.__name__ = name
+    return f
+
+
+py_btddod_blockdiag_matvec = _btddod_not_on_path('py_btddod_blockdiag_matvec')
+py_btddod_blockdiag_factorize = _btddod_not_on_path('py_btddod_blockdiag_factorize')
+py_btddod_blockdiag_solve = _btddod_not_on_path('py_btddod_blockdiag_solve')
+py_btddod_lowerfulltriangle_solve = _btddod_not_on_path('py_btddod_lowerfulltriangle_solve')
+py_btddod_upperfulltriangle_solve = _btddod_not_on_path('py_btddod_upperfulltriangle_solve')
+py_btddod_scale_and_add_scaled_block_diagonal = _btddod_not_on_path('py_btddod_scale_and_add_scaled_block_diagonal')

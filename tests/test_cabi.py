@@ -102,3 +102,23 @@ def test_nasa9_mechanism_is_accepted_and_malformed_coefficients_are_refused():
     name = m.species_names[0]
     with pytest.raises(GriffonB200Error):
         g.mechanism_add_nasa9_cp(name, 200., 6000., [2., 200., 1000., 1., 2., 3.])
+
+
+def test_reference_names_outside_the_path_are_callable_and_raise():
+    """griffon.pyx:870-987, 1019-1105: the 2-D flamelet methods and the block-Jacobi helpers exist and raise
+    GriffonB200Error ("keep them callable ... or raise clearly")"""
+    import pytest
+    from spitfire_b200 import griffon
+    for name in ('flamelet2d_rhs', 'flamelet2d_factored_block_diag_jacobian', 'flamelet2d_offdiag_matvec',
+                 'flamelet2d_matvec', 'flamelet2d_block_diag_solve'):
+        f = getattr(griffon.PyCombustionKernels, name)
+        with pytest.raises(griffon.GriffonB200Error):
+            f(object.__new__(griffon.PyCombustionKernels))
+    for name in ('py_btddod_blockdiag_matvec', 'py_btddod_blockdiag_factorize', 'py_btddod_blockdiag_solve',
+                 'py_btddod_lowerfulltriangle_solve', 'py_btddod_upperfulltriangle_solve',
+                 'py_btddod_scale_and_add_scaled_block_diagonal'):
+        with pytest.raises(griffon.GriffonB200Error):
+            getattr(griffon, name)()
+    for name in ('reactor_rhs_isochoric', 'reactor_jac_isochoric', 'reactor_rhs_isochoric_batch',
+                 'reactor_jac_isochoric_batch'):
+        assert callable(getattr(griffon.PyCombustionKernels, name))
