@@ -27,6 +27,11 @@ import sys
 import threading
 import time
 
+# one thread per process on the host side: the CPU arm runs one process per core (OPENBLAS_NUM_THREADS=1)
+os.environ.setdefault('OMP_NUM_THREADS', '1')
+os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+os.environ.setdefault('MKL_NUM_THREADS', '1')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -52,7 +57,7 @@ def host_cores():
 
 # ---- CPU arm (the only place bench.py executes oracle/) ------------------------------------------------------------
 def _cpu_worker(args):
-    kind, mech_name, fuel, lo, n, reps = args
+    kind, mech_name, fuel, lo, n, reps, keep = args
     from oracle.oracle import OracleKernels
     from spitfire_b200.mechanism import ChemicalMechanismSpec
     from spitfire_b200.synthetic import synthetic_states
@@ -67,7 +72,8 @@ def _cpu_worker(args):
         t0 = time.perf_counter()
         m.griffon.reactor_jac_isobaric_many(state, PRESSURE, 0, rhs, jac)
         times.append(time.perf_counter() - t0)
-    return times
+    # the first `keep` states' outputs go back to the parent: they check the GPU results of the same states (parity)
+    return times, (rhs[:keep].copy(), jac[:keep].copy()) if keep else None
 
 
 class CpuArm(object):
@@ -80,16 +86,23 @@ class CpuArm(object):
         self.mech_name, self.fuel = mech_name, fuel
         self.cores = host_cores()
         self.per_core = per_core_states
+        # load the library in the parent first: the forked workers inherit the mapping, and the driver's record of the
+        # shared objects this process loaded then shows which CPU implementation was timed
+        oracle._load(self.kind)
+        self.lib_path = oracle.lib_path(self.kind)
         import multiprocessing as mp
         self.pool = mp.get_context('fork').Pool(self.cores)
+        self.reference_outputs = None
 
     def run(self, reps):
         """returns the list over `reps` of wall seconds for cores*per_core states (all cores busy concurrently)"""
-        jobs = [(self.kind, self.mech_name, self.fuel, c * self.per_core, self.per_core, reps)
-                for c in range(self.cores)]
+        jobs = [(self.kind, self.mech_name, self.fuel, c * self.per_core, self.per_core, reps,
+                 min(self.per_core, 1024) if c == 0 else 0) for c in range(self.cores)]
         t0 = time.perf_counter()
-        per_worker = self.pool.map(_cpu_worker, jobs)
+        res = self.pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
+        per_worker = [r[0] for r in res]
+        self.reference_outputs = res[0][1]
         # per repetition the slowest worker bounds the throughput
         step_times = [max(w[k] for w in per_worker) for k in range(reps)]
         return step_times, wall
@@ -102,6 +115,87 @@ class CpuArm(object):
     def sample(self):
         return (f'{self.cores * self.per_core} states of the workload per step ({self.per_core} per core), single-state '
                 f'reactor_jac_isobaric looped in C, one process per core')
+
+
+def _oracle_mech(name, kind):
+    from oracle.oracle import OracleKernels
+    from spitfire_b200.mechanism import ChemicalMechanismSpec
+    return ChemicalMechanismSpec(mech_data=load_mech_data(name), griffon_factory=lambda: OracleKernels(kind))
+
+
+def _gri_flamelet_specs(m):
+    from spitfire_b200.flamelet import FlameletSpec
+    air = m.stream(stp_air=True)
+    fuel = m.stream('TPX', (300., PRESSURE, 'CH4:1'))
+    return FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128)
+
+
+def library_fields(lib):
+    names = ['temperature'] + [k for k in lib.props if k.startswith('mass fraction ')]
+    return names
+
+
+def library_parity(lib, ref):
+    """largest difference of the temperature and mass-fraction fields of two libraries of equal shape, each field
+    relative to its own largest reference value"""
+    if list(lib.shape) != list(ref.shape):
+        return {'error': f'shape {list(lib.shape)} vs {list(ref.shape)}'}
+    worst, worst_name = 0., None
+    for k in library_fields(ref):
+        a, b = np.asarray(lib[k]), np.asarray(ref[k])
+        scale = float(np.max(np.abs(b)))
+        if scale <= 1e-12:  # (species that never form, e.g. AR in CH4/air: rounding noise around zero)
+            continue
+        e = float(np.max(np.abs(a - b))) / scale
+        if e > worst:
+            worst, worst_name = e, k
+    eT = float(np.max(np.abs(np.asarray(lib['temperature']) - np.asarray(ref['temperature'])) /
+                      np.asarray(ref['temperature'])))
+    return {'T_max_rel': eT, 'fields_max_rel_to_field_scale': worst, 'worst_field': worst_name,
+            'n_fields': len(library_fields(ref))}
+
+
+def cpu_library_sample(args, kind, cores):
+    """CPU baseline of the secondary metric on a bounded sample of BASELINE configs 4-5: every `stride`-th dissipation
+    rate of the configuration, the SAME host code driving the reference's CPU kernels, the heat-loss expansions in a
+    process pool over the dissipation rates (the reference's num_procs mode, tabulation.py:542-568)."""
+    from spitfire_b200 import tabulation as tab
+    m = _oracle_mech('methane-gri30', kind)
+    chis = np.logspace(-3, 2, args.library_chi)[::args.library_cpu_stride]
+    t0 = time.perf_counter()
+    ad = tab.build_adiabatic_slfm_library(_gri_flamelet_specs(m), diss_rate_values=chis, verbose=False)
+    t_ad = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    na = tab.build_nonadiabatic_defect_transient_slfm_library(_gri_flamelet_specs(m), diss_rate_values=chis,
+                                                              verbose=False, n_defect_st=16, num_procs=cores)
+    t_na = time.perf_counter() - t0
+    return {'chis': chis, 'adiabatic': ad, 'nonadiabatic': na,
+            'report': {'kind': kind, 'cores': cores,
+                       'sample': f'every {args.library_cpu_stride}th chi_st of the configuration '
+                                 f'({chis.size} requested, {ad.shape[1]} burn), same host code on the reference CPU '
+                                 f'kernels; reference-order chain, heat-loss expansions in a pool of {cores} processes',
+                       'adiabatic_slfm_s': t_ad, 'nonadiabatic_defect_slfm_s': t_na,
+                       'adiabatic_shape': list(ad.shape), 'nonadiabatic_shape': list(na.shape)}}
+
+
+def config1_ignition(backend):
+    """BASELINE config 1: H2/air phi = 1, 1200 K, 1 atm, closed adiabatic isobaric reactor, integrate_to_steady with
+    defaults, against the reference's gold trajectory (tests/reactor/closed_reactors, rtol 1e-4)"""
+    from reactor_cases import compare_with_gold
+    from spitfire_b200.reactors import HomogeneousReactor
+    from common import build_mech
+    m = build_mech('h2-burke', backend)
+    air = m.stream(stp_air=True)
+    fuel = m.stream('X', 'H2:1')
+    mix = m.mix_for_equivalence_ratio(1.0, fuel, air)
+    mix.TP = 1200., 101325.
+    r = HomogeneousReactor(m, mix, 'isobaric', 'adiabatic', 'closed')
+    t0 = time.perf_counter()
+    lib = r.integrate_to_steady()
+    wall = time.perf_counter() - t0
+    err = compare_with_gold(m, lib, 'adiabatic')
+    return {'wall_s': wall, 'steps': int(lib.time_values.size), 'gold_T_max_rel': err, 'gold_rtol': 1e-4,
+            'T_end': float(lib['temperature'][-1])}
 
 
 def run_reference_arm(args):
@@ -120,7 +214,9 @@ def run_reference_arm(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, n_states=n),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.sample,
+                         'library': os.path.relpath(arm.lib_path, ROOT),
+                         'note': 'a rate: the sample is a prefix of the same seeded workload, not the whole batch'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -236,33 +332,44 @@ def ncu_traffic_per_launch(mech, n_states):
     return float(e['dram_bytes']) / float(e['states']) * n_states
 
 
-def time_library_builds(args, world):
+def time_library_builds(args, world, cpu_sample=None):
     """secondary metric of BASELINE.json, "SLFM library build wall time": BASELINE configs 4 and 5 (GRI-3.0, CH4 300 K /
     air 300 K, 1 atm, 128-point clustered grid, chi_st in logspace(-3, 2, 64), 16 enthalpy defects) through the
-    repo's public builders, heat-loss trajectories dealt to the ranks. Every rank must call this (one gather)."""
+    repo's public builders, heat-loss trajectories dealt to the ranks. Every rank must call this (one gather).
+    cpu_sample (N = 1): the CPU leg's libraries of a sub-sampled configuration; the same sample is rebuilt on the GPU
+    and compared field by field (`parity`)."""
     from spitfire_b200 import tabulation as tab
-    from spitfire_b200.flamelet import FlameletSpec
     from spitfire_b200.mechanism import ChemicalMechanismSpec
     m = ChemicalMechanismSpec(mech_data=load_mech_data('methane-gri30'))
-    air = m.stream(stp_air=True)
-    fuel = m.stream('TPX', (300., PRESSURE, 'CH4:1'))
     chis = np.logspace(-3, 2, args.library_chi)
     out = {'config': f'GRI-3.0 CH4/air 300 K 1 atm, {args.library_chi} chi_st in logspace(-3,2), 128-point grid',
-           'n_gpus': world}
+           'n_gpus': world, 'wave': 8}
     t0 = time.perf_counter()
-    lib = tab.build_adiabatic_slfm_library(FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128),
-                                           diss_rate_values=chis, verbose=False, wave=8)
+    lib = tab.build_adiabatic_slfm_library(_gri_flamelet_specs(m), diss_rate_values=chis, verbose=False, wave=8)
     out['adiabatic_slfm_s'] = time.perf_counter() - t0
     out['adiabatic_shape'] = list(lib.shape)
     t0 = time.perf_counter()
     lib = tab.build_nonadiabatic_defect_transient_slfm_library(
-        FlameletSpec(mech_spec=m, oxy_stream=air, fuel_stream=fuel, grid_points=128), diss_rate_values=chis,
-        verbose=False, n_defect_st=16, wave=8)
+        _gri_flamelet_specs(m), diss_rate_values=chis, verbose=False, n_defect_st=16, wave=8)
     out['nonadiabatic_defect_slfm_s'] = time.perf_counter() - t0
     out['nonadiabatic_shape'] = list(lib.shape)
     out['T_max'] = float(lib['temperature'].max())
-    out['cpu_reference_note'] = ('reference CPU path, 1 core (SURVEY.md section 6 probe): ~0.07 s per adiabatic '
-                                 'continuation step, 7 s first/last member, 13.8 s per heat-loss trajectory')
+    if cpu_sample is not None:
+        sc = cpu_sample['chis']
+        same = {}
+        for wave in (1, 8):
+            t0 = time.perf_counter()
+            ad = tab.build_adiabatic_slfm_library(_gri_flamelet_specs(m), diss_rate_values=sc, verbose=False, wave=wave)
+            t_ad = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            na = tab.build_nonadiabatic_defect_transient_slfm_library(
+                _gri_flamelet_specs(m), diss_rate_values=sc, verbose=False, n_defect_st=16, wave=wave)
+            t_na = time.perf_counter() - t0
+            same[f'wave{wave}'] = {'adiabatic_slfm_s': t_ad, 'nonadiabatic_defect_slfm_s': t_na,
+                                   'parity_adiabatic': library_parity(ad, cpu_sample['adiabatic']),
+                                   'parity_nonadiabatic': library_parity(na, cpu_sample['nonadiabatic'])}
+        out['cpu_baseline'] = cpu_sample['report']
+        out['gpu_same_sample'] = same
     return out
 
 
@@ -271,8 +378,8 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
-    # CPU baseline first, before any CUDA context exists in this process (fork-safe); rank 0 at N=1 only
-    cpu_baseline = None
+    # CPU legs first, before any CUDA context exists in this process (fork-safe); rank 0 at N=1 only
+    cpu_baseline, cpu_ref_out, cpu_lib, config1 = None, None, None, {}
     if world == 1 and not args.no_cpu_baseline:
         try:
             arm = CpuArm(args.mech, args.fuel, args.cpu_states_per_core)
@@ -280,10 +387,17 @@ def run_gpu_arm(args):
             arm.close()
             n_cpu = arm.cores * arm.per_core
             cpu_baseline = {'value': n_cpu / st[-1], 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind,
-                            'sample': arm.sample}
+                            'sample': arm.sample, 'library': os.path.relpath(arm.lib_path, ROOT)}
+            cpu_ref_out = arm.reference_outputs
+            if args.library_chi > 0:
+                cpu_lib = cpu_library_sample(args, arm.kind, arm.cores)
+            config1['cpu_reference'] = dict(config1_ignition(arm.kind), kind=arm.kind, cores=1)
         except Exception as e:  # the checker is optional for the measurement itself
-            cpu_baseline = {'value': None, 'unit': UNIT, 'cores': host_cores(), 'kind': 'unavailable',
-                            'sample': f'failed: {e}'}
+            if cpu_baseline is None:
+                cpu_baseline = {'value': None, 'unit': UNIT, 'cores': host_cores(), 'kind': 'unavailable',
+                                'sample': f'failed: {e!r}'[:300]}
+            else:
+                cpu_baseline['secondary_failed'] = repr(e)[:300]
 
     import torch
     import torch.distributed as dist
@@ -331,10 +445,11 @@ def run_gpu_arm(args):
     clocks = sampler.stop()
 
     # ---- end to end through the host-buffer entry point: pinned host state in, rhs + jac back to the host ----------
-    e2e_states = min(n, args.e2e_states)
-    h_state = torch.from_numpy(state_np[:e2e_states]).pin_memory()
-    h_rhs = torch.empty((e2e_states, ns), dtype=torch.float64).pin_memory()
-    h_jac = torch.empty((e2e_states, ns * ns), dtype=torch.float64).pin_memory()
+    e2e_states = min(n, args.e2e_states if (world > 1 or args.e2e_states_set) else n)
+    h_state = torch.empty((e2e_states, ns), dtype=torch.float64, pin_memory=True)
+    h_state.copy_(torch.from_numpy(state_np[:e2e_states]))
+    h_rhs = torch.empty((e2e_states, ns), dtype=torch.float64, pin_memory=True)
+    h_jac = torch.empty((e2e_states, ns * ns), dtype=torch.float64, pin_memory=True)
     hs, hr, hj = h_state.numpy(), h_rhs.numpy(), h_jac.numpy()
     g.reactor_jac_isobaric_batch(hs, PRESSURE, hr, hj)
     barrier()
@@ -346,6 +461,53 @@ def run_gpu_arm(args):
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
     check = float(hr[0, 0])  # read of the step's result on the host
 
+    # ---- parity of the timed kernel on the states the CPU leg evaluated (same seeded inputs) ------------------------
+    parity = None
+    if cpu_ref_out is not None:
+        from cases import error_stats
+        k = cpu_ref_out[0].shape[0]
+        parity = {'states': int(k), 'against': cpu_baseline['kind'],
+                  'rhs': error_stats(d_rhs[:k].cpu().numpy(), cpu_ref_out[0]),
+                  'jac': error_stats(d_jac[:k].cpu().numpy(), cpu_ref_out[1]),
+                  'e2e_equals_device': bool(np.array_equal(hj[:k], d_jac[:k].cpu().numpy()) and
+                                            np.array_equal(hr[:k], d_rhs[:k].cpu().numpy()))}
+    # ---- second roofline bound: FP64 pipe, measured on this device ---------------------------------------
+    fp64_peak = None
+    if rank == 0:
+        try:
+            fp64_peak = griffon.measure_fp64_peak(0)[0]
+        except Exception:
+            fp64_peak = None
+    # ---- BASELINE config 2 (H2, 1M states) and config 1 (one ignition through the public reactor class) -------------
+    config2 = None
+    if rank == 0 and not args.no_extra_configs and args.mech != 'h2-burke':
+        try:
+            del h_jac, hj
+            mh = ChemicalMechanismSpec(mech_data=load_mech_data('h2-burke'))
+            gh, nh = mh.griffon, mh.n_species
+            sh, _ = synthetic_states(mh.species_names, n, 'H2', seed=20241017)
+            dsh = torch.from_numpy(sh).cuda()
+            drh = torch.empty((n, nh), dtype=torch.float64, device='cuda')
+            djh = torch.empty((n, nh * nh), dtype=torch.float64, device='cuda')
+            for _ in range(3):
+                gh.reactor_jac_isobaric_batch(dsh, PRESSURE, drh, djh)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                gh.reactor_jac_isobaric_batch(dsh, PRESSURE, drh, djh)
+            e1.record()
+            torch.cuda.synchronize()
+            msh = e0.elapsed_time(e1) / args.steps
+            bh = 8 * (nh * nh + 2 * nh)
+            config2 = {'workload': 'BASELINE config 2: h2-burke, 1 atm, closed adiabatic', 'states': n,
+                       'value': n / (msh * 1e-3), 'unit': UNIT, 'ms_per_step': msh,
+                       'hbm_gbs': bh * n / (msh * 1e-3) / 1e9}
+            del dsh, drh, djh
+            config1['gpu'] = config1_ignition('gpu')
+        except Exception as e:
+            config2 = {'error': repr(e)[:300]}
+
     t_ms = torch.tensor([total_ms / args.steps, e2e_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -356,7 +518,7 @@ def run_gpu_arm(args):
             if world > 1:
                 from spitfire_b200 import parallel  # the builders find the process group bench.py initialised
                 assert parallel.world_size() == world
-            library = time_library_builds(args, world)
+            library = time_library_builds(args, world, cpu_lib)
         except Exception as e:  # the headline line must survive a failure of the secondary metric
             library = {'error': repr(e)[:300]}
     if rank == 0:
@@ -365,15 +527,26 @@ def run_gpu_arm(args):
         bytes_per_state = 8 * (ns * ns + 2 * ns)  # ns in, ns + ns^2 out
         kernel_ms = float(np.mean(step_ms))
         achieved = bytes_per_state * n / (kernel_ms * 1e-3) / 1e9
+        # the kernel is measured against both roofs, HBM (8*(ns^2+2ns) bytes per state) and the FP64 pipe
+        # (flop model of the sparse-exact formulation, transcendental calls not counted); the larger fraction is the bound
+        flops_per_state = {'methane-gri30': 0.093e6, 'h2-burke': 5.7e3}.get(args.mech)
+        hbm_frac = achieved / peak
+        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': hbm_frac,
+                    'traffic': ncu_traffic_per_launch(args.mech, n), 'kernel': 'k_jac',
+                    'algorithmic_bytes_per_launch': bytes_per_state * n, 'kernel_ms': kernel_ms,
+                    'peak_source': peak_src}
+        if fp64_peak and flops_per_state:
+            tf = flops_per_state * n / (kernel_ms * 1e-3) / 1e12
+            roofline['fp64'] = {'achieved': tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf / fp64_peak,
+                                'flops_per_state': flops_per_state,
+                                'peak_source': 'measured now (gb_measure_fp64_peak: dependent-free DFMA, all SMs)'}
+            roofline['frac_max_of_both'] = max(hbm_frac, tf / fp64_peak)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args, n),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': ncu_traffic_per_launch(args.mech, n), 'kernel': 'k_jac',
-                         'algorithmic_bytes_per_launch': bytes_per_state * n, 'kernel_ms': kernel_ms,
-                         'peak_source': peak_src},
+            'roofline': roofline,
             'cpu_baseline': cpu_baseline,
             'e2e': {'value': world * e2e_states / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': int(8 * e2e_states * ns),
@@ -382,6 +555,9 @@ def run_gpu_arm(args):
                     'api': 'PyCombustionKernels.reactor_jac_isobaric_batch(numpy) -> gb_reactor_jac_isobaric_host',
                     'result_check': check},
             'gpu_launches': int(launches),
+            'parity': parity,
+            'config1_h2_ignition': config1 or None,
+            'config2_h2_states': config2,
             'library_build': library,
             'numa_node': numa,
             'clocks': clocks,
@@ -406,13 +582,20 @@ def main():
     ap.add_argument('--mech', default='methane-gri30')
     ap.add_argument('--fuel', default=None)
     ap.add_argument('--states', type=int, default=1 << 20)
-    ap.add_argument('--e2e-states', type=int, default=1 << 18)
+    ap.add_argument('--e2e-states', type=int, default=None,
+                    help='states per end-to-end step (default: the whole batch at N = 1, 262144 per rank at N > 1)')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-states-per-core', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-configs', action='store_true', help='skip the BASELINE config 1 / 2 extras')
+    ap.add_argument('--library-cpu-stride', type=int, default=4,
+                    help='the CPU leg of the library metric builds every stride-th dissipation rate')
     ap.add_argument('--library-chi', type=int, default=64,
                     help='dissipation rates of the SLFM library builds timed as the secondary metric (0 = skip)')
     args = ap.parse_args()
+    args.e2e_states_set = args.e2e_states is not None
+    if args.e2e_states is None:
+        args.e2e_states = 1 << 18
     if args.fuel is None:
         args.fuel = 'H2' if args.mech.startswith('h2') else 'CH4'
     if args.impl == 'reference':

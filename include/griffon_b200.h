@@ -239,6 +239,13 @@ int gb_btddod_full_factorize_inv_batch(int n_systems, double *d_factors, int num
 int gb_btddod_full_solve_inv_batch(int n_systems, const double *d_factors, const double *l_values, const double *dinv,
                                    const double *rhs, int num_blocks, int block_size, double *out_solution,
                                    const int *system_rows, void *stream);
+/* Extension: the same elimination by explicit inverses only -- Gauss-Jordan with partial pivoting on every
+ * D'_i = D_i - L_i diag(sup_{i-1}), L_i = diag(sub_{i-1}) D'_{i-1}^{-1} (btddod_matrix_kernels.cpp:48-75) -- for solvers
+ * that apply the result through gb_btddod_full_solve_inv_batch alone (pass `matrix` as its d_factors: only the
+ * super-diagonal is read from it). `matrix` is NOT overwritten; no LU factors or pivots are produced. About 5x
+ * shorter latency chain per system than factorize_inv (one barrier and bs, not ~3 bs, dependent steps per block). */
+int gb_btddod_full_invert_batch(int n_systems, const double *matrix, int num_blocks, int block_size,
+                                double *out_l_values, double *out_dinv, void *stream);
 int gb_btddod_full_factorize_host(int n_systems, double *d_factors, int num_blocks, int block_size,
                                   double *out_l_values, int *out_d_pivots);
 int gb_btddod_full_solve_host(int n_systems, const double *d_factors, const double *l_values, const int *d_pivots,
@@ -248,6 +255,36 @@ int gb_btddod_full_matvec_host(int n_systems, const double *matrix, const double
 int gb_btddod_scale_and_add_diagonal_host(int n_systems, double *matrix, double matrix_scale,
                                           const double *diagonal, double diag_scale, int num_blocks,
                                           int block_size);
+
+/* ---- vector kernels of the batched implicit integrator (host solver loops) ---------------------
+ * Replace, for a batch of independent members on the device, the numpy expressions of the reference's ESDIRK stage loop
+ * (time/methods.py:502-612), SimpleNewtonSolver (time/nonlinear.py:185-268) and the embedded error estimate for the
+ * PI controller (time/stepcontrol.py:84-101). Members are the rows of [n][ndof] device arrays; the arithmetic follows
+ * the reference's expressions operation by operation. No reference C++ counterpart (the reference does this in numpy).
+ *
+ * stage begin: explicit = coef[nk-1]*k[nk-1] + ... + coef[0]*k[0] (accumulated from j = nk-1 down, methods.py:560-575),
+ *              res = dt*(gamma*f + explicit) - (x - q) (nonlinear.py:204), conv[m] = 0.
+ *              k: HOST array of nk (<= 6) device pointers, coef: HOST array. */
+int gb_esdirk_stage_begin_batch(int n, int ndof, int nk, const double *const *k, const double *coef, double gamma,
+                                const double *dt, const double *x, const double *q, const double *f,
+                                double *explicit_out, double *res_out, int *conv, void *stream);
+/* xn = conv ? x : x - dx; also resets *n_unconverged (device int) for the tail kernel of the same iteration */
+int gb_newton_update_batch(int n, int ndof, const double *x, const double *dx, const int *conv, double *xn,
+                           int *n_unconverged, void *stream);
+/* rn = dt*(gamma*fn + explicit) - (xn - q); members with conv == 0 take (xn, fn, rn) as their new (x, f, res) and set
+ * conv when max|rn*weights| < tolerance (nonlinear.py:236-257); *n_unconverged counts the members still iterating.
+ * host_count (may be NULL): if given, the count is copied there and the stream is synchronised -- the one integer
+ * the host loop branches on. */
+int gb_newton_tail_batch(int n, int ndof, const double *fn, const double *xn, const double *explicit_, const double *q,
+                         const double *dt, double gamma, const double *weights, double tolerance, double *x, double *f,
+                         double *res, int *conv, int *n_unconverged, int *host_count, void *stream);
+/* dq = dt*(b[0]*k[0] + ... + b[nk-1]*k[nk-1]), dqh likewise with bh (methods.py:598-610); stats [3][n]:
+ * max|(dq - dqh)*weights| (error estimate), max|dq*weights|, 1/0 = every dq finite / not. k, b, bh: HOST arrays. */
+int gb_esdirk_finish_batch(int n, int ndof, int nk, const double *const *k, const double *b, const double *bh,
+                           const double *dt, const double *weights, double *dq, double *stats, void *stream);
+/* q <- q + dq (clipped at zero if clip_negative) for the members with accept[m] != 0, in place */
+int gb_accept_step_batch(int n, int ndof, const double *dq, const int *accept, int clip_negative, double *q,
+                         void *stream);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

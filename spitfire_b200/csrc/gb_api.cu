@@ -2,7 +2,9 @@
 // kernel launches, and the *_host variants that stage host buffers through device scratch owned by the handle.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -344,6 +346,56 @@ extern "C"
     return GB_OK;
   }
 
+  // Pipeline resources of the host entry points: three streams (host->device, kernels, device->host) and the events
+  // that order the two halves of the double-buffered device staging area. Process-wide, created on first use; the
+  // *_host entry points are synchronous, so one set serves every handle of the calling thread's device.
+  struct HostPipe
+  {
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int device = -1;
+  };
+  static int host_pipe(HostPipe **out)
+  {
+    static HostPipe pipes[16];
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16)
+    {
+      set_error("device ordinal out of range for the host pipeline");
+      return GB_ERR_CUDA;
+    }
+    HostPipe &p = pipes[dev];
+    if (p.device != dev)
+    {
+      CK(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b)
+      {
+        CK(cudaEventCreateWithFlags(&p.ev_in[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p.ev_k[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p.ev_out[b], cudaEventDisableTiming));
+      }
+      p.device = dev;
+    }
+    *out = &p;
+    return GB_OK;
+  }
+
+  // states per chunk of the pipelined host path: about 256 MB of Jacobian per chunk, a whole number of waves of
+  // 8-state tiles over 148 SMs; batches of up to two chunks take the serial path (nothing to overlap)
+  static int host_chunk_states(int ns)
+  {
+    const size_t per = sizeof(double) * (size_t)ns * ns;
+    size_t c = ((size_t)256 << 20) / per;
+    const size_t wave = 8 * 148;
+    c = std::max<size_t>(wave, c / wave * wave);
+    if (const char *e = getenv("GB_HOST_CHUNK"))
+      c = std::max(1, atoi(e));
+    return (int)std::min<size_t>(c, (size_t)1 << 30);
+  }
+
   int gb_reactor_jac_isobaric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
                                    int rates_sensitivity_option, int sensitivity_transform_option, double *out_rhs,
                                    double *out_jac)
@@ -353,17 +405,75 @@ extern "C"
     if (n == 0)
       return GB_OK;
     const int ns = m->h.dm.ns;
-    gb_reactor_params dprm;
-    double *d_state;
-    RC(stage_reactor(m, n, state, prm, &dprm, &d_state));
-    void *d_rhs, *d_jac;
-    RC(scratch(m, 2, sizeof(double) * n * ns, &d_rhs));
-    RC(scratch(m, 3, sizeof(double) * (size_t)n * ns * ns, &d_jac));
-    RC(gb_reactor_jac_isobaric_batch(m, n, d_state, &dprm, rates_sensitivity_option, sensitivity_transform_option,
-                                     (double *)d_rhs, (double *)d_jac, nullptr));
-    CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * ns * ns, cudaMemcpyDeviceToHost));
-    return GB_OK;
+    const int chunk = host_chunk_states(ns);
+    if (n <= 2 * chunk)
+    { // small batch: copy in, one launch, copy out
+      gb_reactor_params dprm;
+      double *d_state;
+      RC(stage_reactor(m, n, state, prm, &dprm, &d_state));
+      void *d_rhs, *d_jac;
+      RC(scratch(m, 2, sizeof(double) * n * ns, &d_rhs));
+      RC(scratch(m, 3, sizeof(double) * (size_t)n * ns * ns, &d_jac));
+      RC(gb_reactor_jac_isobaric_batch(m, n, d_state, &dprm, rates_sensitivity_option, sensitivity_transform_option,
+                                       (double *)d_rhs, (double *)d_jac, nullptr));
+      CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * ns * ns, cudaMemcpyDeviceToHost));
+      return GB_OK;
+    }
+    // Large batch: chunks flow through a double-buffered staging area on three streams, so the device->host copy of
+    // chunk c (the 8*ns^2 bytes per state that bound this entry point) overlaps the kernel of chunk c+1 and the
+    // host->device copy of chunk c+2. Pinned host buffers make the copies asynchronous; pageable ones still work
+    // (the runtime stages them), only without overlap.
+    HostPipe *pp;
+    RC(host_pipe(&pp));
+    HostPipe &P = *pp;
+    void *p_state, *p_yin, *p_rhs, *p_jac;
+    const size_t sb = sizeof(double) * (size_t)chunk * ns, jb = sizeof(double) * (size_t)chunk * ns * ns;
+    RC(scratch(m, 0, 2 * sb, &p_state));
+    RC(scratch(m, 1, sizeof(double) * ns, &p_yin));
+    RC(scratch(m, 2, 2 * sb, &p_rhs));
+    RC(scratch(m, 3, 2 * jb, &p_jac));
+    gb_reactor_params dprm = *prm;
+    if (prm->open)
+    {
+      CK(cudaMemcpy(p_yin, prm->inflow_y, sizeof(double) * ns, cudaMemcpyHostToDevice));
+      dprm.inflow_y = (const double *)p_yin;
+    }
+    else
+      dprm.inflow_y = nullptr;
+    CK(cudaDeviceSynchronize()); // earlier work on the handle's buffers (legacy stream) is done
+    int rc = GB_OK;
+    const int nchunks = (n + chunk - 1) / chunk;
+    for (int c = 0; c < nchunks && rc == GB_OK; ++c)
+    {
+      const int b = c & 1, lo = c * chunk, cnt = std::min(chunk, n - lo);
+      double *d_state = (double *)p_state + (size_t)b * chunk * ns, *d_rhs = (double *)p_rhs + (size_t)b * chunk * ns;
+      double *d_jac = (double *)p_jac + (size_t)b * chunk * ns * ns;
+      if (c >= 2)
+      { // buffer b is free once chunk c-2 has left the device (its kernel, which read d_state, finished before that)
+        CK(cudaStreamWaitEvent(P.s_in, P.ev_out[b], 0));
+        CK(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));
+      }
+      CK(cudaMemcpyAsync(d_state, state + (size_t)lo * ns, sizeof(double) * (size_t)cnt * ns, cudaMemcpyHostToDevice,
+                         P.s_in));
+      CK(cudaEventRecord(P.ev_in[b], P.s_in));
+      CK(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
+      rc = gb_reactor_jac_isobaric_batch(m, cnt, d_state, &dprm, rates_sensitivity_option,
+                                         sensitivity_transform_option, d_rhs, d_jac, P.s_k);
+      if (rc != GB_OK)
+        break;
+      CK(cudaEventRecord(P.ev_k[b], P.s_k));
+      CK(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
+      CK(cudaMemcpyAsync(out_rhs + (size_t)lo * ns, d_rhs, sizeof(double) * (size_t)cnt * ns, cudaMemcpyDeviceToHost,
+                         P.s_out));
+      CK(cudaMemcpyAsync(out_jac + (size_t)lo * ns * ns, d_jac, sizeof(double) * (size_t)cnt * ns * ns,
+                         cudaMemcpyDeviceToHost, P.s_out));
+      CK(cudaEventRecord(P.ev_out[b], P.s_out));
+    }
+    CK(cudaStreamSynchronize(P.s_in));
+    CK(cudaStreamSynchronize(P.s_k));
+    CK(cudaStreamSynchronize(P.s_out));
+    return rc;
   }
 }
 

@@ -759,6 +759,24 @@ __device__ __forceinline__ double lds_f64(const double *p)
   asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(smem_u32(p)));
   return v;
 }
+__device__ __forceinline__ double lds32_f64(unsigned int a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds32_v2f64(unsigned int a)
+{
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(const double *p)
+{
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
+  return v;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group()
 {
@@ -776,7 +794,7 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm); // [SI_STAGES] "block landed" barriers
   double *ring = sm + 8;
   double *v0 = ring + (size_t)SI_STAGES * bufsz; // [2][bsp] ping-pong vector
-  const int bsp = (bs + 1) & ~1;
+  const int bsp = (bs + 63) & ~63; // padded with zeros to whole groups of 64 columns (the dot product does not mask)
   double *yv = v0 + 2 * bsp;                     // [nb*bs] right-hand side, overwritten with y_i (if `staged`: it fits)
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
   const int sub = lane & 7, part = lane >> 3;
@@ -788,6 +806,19 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
   }
   __syncthreads();
   int gs0 = 0; // blocks streamed by this CTA before the current system (ring slot and barrier phase follow from it)
+  // byte offsets, inside a block, of the sixteen matrix entries this thread multiplies in the fast path (bs <= 64):
+  // the same for every step, kept in registers so that a step's loads are plain 32-bit shared addresses
+  unsigned int mofs[16];
+  {
+    const int cp0 = 8 * (part & 1) + 4 * (part >> 1);
+    const int r0 = warp * 8 + sub;
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+    {
+      const int c = cp0 + 16 * (u >> 2) + (u & 3);
+      mofs[u] = (unsigned int)(((c < bs ? c : 0) * bs + (r0 < bs ? r0 : 0)) * 8);
+    }
+  }
 
   for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
   {
@@ -803,33 +834,43 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     // Block s lands at ring[(gs0+s) % STAGES] + (1 if its source address is an odd multiple of 8 bytes): one TMA bulk
     // copy of the 16-byte aligned span that lies inside the block's neighbourhood (a single SM cannot keep enough
     // LDGSTS requests in flight to stream 22 KB per step), plus the odd last element, if any, by an 8-byte cp.async.
+    // parity (in units of 8 bytes) of the address of block s: decides the one-element shift of its ring slot
+    const unsigned int parL = (unsigned int)(reinterpret_cast<size_t>(Lv) >> 3) & 1u;
+    const unsigned int parD = (unsigned int)(reinterpret_cast<size_t>(Di) >> 3) & 1u;
+    auto par_of = [&](int s) {
+      return s < nb - 1 ? (parL + (unsigned int)(s + 1) * (unsigned int)nb2) & 1u
+                        : (parD + (unsigned int)(nstream - 1 - s) * (unsigned int)nb2) & 1u;
+    };
     auto fetch = [&](int s) {
-      if (s < nstream)
+      if (s < nstream && warp == SI_THREADS / 32 - 1)
       {
         const double *src = src_of(s);
         const int g = gs0 + s;
         double *dst = ring + (size_t)(g % SI_STAGES) * bufsz;
         const int off = (int)((reinterpret_cast<size_t>(src) >> 3) & 1);
         const int span = nb2 + off, n16 = span >> 1; // elements from src - off
-        if (tid == 0)
+        // (issued from the last warp: it owns rows 56..63, so for block sizes up to 56 it has no dot product to start
+        // and the ~350 cycles of address arithmetic and issue stay off the critical path of the sweep)
+        if (tid == SI_THREADS - 32)
         {
           mbar_expect_tx(bars + g % SI_STAGES, (unsigned int)n16 * 16u);
           bulk_g2s(dst, src - off, (unsigned int)n16 * 16u, bars + g % SI_STAGES);
         }
-        if ((span & 1) && tid == 32)
+        if ((span & 1) && tid == SI_THREADS - 31)
           cp_async8(dst + 2 * n16, src - off + 2 * n16);
       }
       cp_async_commit(); // (an empty group keeps the group count in step)
     };
-    auto buf_of = [&](int s) {
-      return ring + (size_t)((gs0 + s) % SI_STAGES) * bufsz + (int)((reinterpret_cast<size_t>(src_of(s)) >> 3) & 1);
-    };
+    auto buf_of = [&](int s) { return ring + (unsigned int)((gs0 + s) % SI_STAGES) * (unsigned int)bufsz + par_of(s); };
     __syncthreads(); // the previous system is done with the shared arrays
     if (staged)
       for (int e = tid; e < nb * bs; e += SI_THREADS)
         yv[e] = b[e];
     for (int s = 0; s < SI_STAGES - 1; ++s)
       fetch(s);
+    for (int j = tid; j < 2 * bsp; j += SI_THREADS)
+      if (j % bsp >= bs)
+        v0[j] = 0.; // the padding of both vectors stays zero for the whole sweep
     for (int j = tid; j < bs; j += SI_THREADS)
     {
       v0[j] = b[j];
@@ -887,34 +928,66 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
         // j are issued before the first fma (two accumulators).
         const int cpart = 8 * (part & 1) + 4 * (part >> 1);
         const double *cb = cur + rr;
-        double a0 = 0., a1 = 0.;
-        for (int j = 0; j < bs; j += 32)
+        double acc;
+        if (bs <= 64)
         {
-          double mm[8], ww[8];
+          // All sixteen matrix entries and the sixteen vector entries (four 16-byte loads per pair of groups) are
+          // requested before the first fma; four accumulators of depth four. Columns past the end re-read column 0
+          // against the zero padding of the vector.
+          double mm[16];
+          double2 wv[8];
+          const unsigned int cur32 = smem_u32(cur), vin32 = smem_u32(vin) + (unsigned int)cpart * 8u;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < 16; ++u)
+            mm[u] = lds32_f64(cur32 + mofs[u]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
           {
-            const int c = cpart + j + 16 * (u >> 2) + (u & 3);
-            const int cc = c < bs ? c : 0; // (a column past the end re-reads column 0 with weight zero)
-            mm[u] = lds_f64(cb + (size_t)cc * bs);
-            ww[u] = lds_f64(vin + cc);
+            wv[2 * q] = lds32_v2f64(vin32 + 128u * q);
+            wv[2 * q + 1] = lds32_v2f64(vin32 + 128u * q + 16u);
           }
+          // (the accumulators depend on the LAST loads, so that the in-order issue cannot stall on the first fma
+          // before every load is in flight)
+          double a0 = fma(mm[15], 0., 0.), a1 = fma(wv[7].y, 0., 0.), a2 = 0., a3 = 0.;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (j + 16 * (u >> 2) + (u & 3) + cpart >= bs)
-              ww[u] = 0.;
-          // (the accumulators are made to depend on the LAST load, so that the in-order issue cannot stall on the
-          // first fma before every load of the batch is in flight)
-          a0 = fma(mm[7], 0., a0);
-          a1 = fma(ww[7], 0., a1);
-#pragma unroll
-          for (int u = 0; u < 8; u += 2)
+          for (int q = 0; q < 4; ++q)
           {
-            a0 = fma(mm[u], ww[u], a0);
-            a1 = fma(mm[u + 1], ww[u + 1], a1);
+            a0 = fma(mm[4 * q], wv[2 * q].x, a0);
+            a1 = fma(mm[4 * q + 1], wv[2 * q].y, a1);
+            a2 = fma(mm[4 * q + 2], wv[2 * q + 1].x, a2);
+            a3 = fma(mm[4 * q + 3], wv[2 * q + 1].y, a3);
           }
+          acc = (a0 + a1) + (a2 + a3);
         }
-        double acc = a0 + a1;
+        else
+        {
+          double a0 = 0., a1 = 0.;
+          for (int j = 0; j < bs; j += 32)
+          {
+            double mm[8], ww[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+            {
+              const int c = cpart + j + 16 * (u >> 2) + (u & 3);
+              const int cc = c < bs ? c : 0; // (a column past the end re-reads column 0 with weight zero)
+              mm[u] = lds_f64(cb + (size_t)cc * bs);
+              ww[u] = lds_f64(vin + cc);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (j + 16 * (u >> 2) + (u & 3) + cpart >= bs)
+                ww[u] = 0.;
+            a0 = fma(mm[7], 0., a0);
+            a1 = fma(ww[7], 0., a1);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2)
+            {
+              a0 = fma(mm[u], ww[u], a0);
+              a1 = fma(mm[u + 1], ww[u + 1], a1);
+            }
+          }
+          acc = a0 + a1;
+        }
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
 #ifdef GB_JAC_TIMELINE
@@ -1075,7 +1148,7 @@ extern "C"
     int rc = bt_check(n, nb, bs);
     if (rc != GB_OK || n == 0)
       return rc;
-    const size_t base = sizeof(double) * ((size_t)SI_STAGES * (((size_t)bs * bs + 3) & ~(size_t)1) + 2 * (((size_t)bs + 1) & ~(size_t)1)) + 64 + 16;
+    const size_t base = sizeof(double) * ((size_t)SI_STAGES * (((size_t)bs * bs + 3) & ~(size_t)1) + 2 * (((size_t)bs + 63) & ~(size_t)63)) + 64 + 16;
     const size_t with_rhs = base + sizeof(double) * (size_t)nb * bs;
     if (base > (size_t)227 * 1024)
     {

@@ -1,0 +1,282 @@
+// gb_btinv.cu -- k_btddod_invert: block-Thomas elimination of BTDDOD systems by explicit inverses, FP64, sm_100a.
+//
+// Extension of the block-Thomas path (btddod_matrix_kernels.cpp:19-80) for the Newton / PsiTC / ESDIRK loops that run
+// on the device: those loops only ever apply the factorisation through gb_btddod_full_solve_inv_batch, whose forward
+// sweep needs L_i = diag(sub_{i-1}) D'_{i-1}^{-1} and whose back sweep needs D'_i^{-1}, with
+//     D'_0 = D_0,   D'_i = D_i - L_i diag(sup_{i-1})                 (btddod_matrix_kernels.cpp:48-75)
+// so the LU factors and pivot vectors of the reference's layout are never read. This kernel therefore skips dgetrf +
+// dgetrs-on-the-identity (two dependent sweeps of ~3 bs steps per block) and inverts every D'_i in place with
+// Gauss-Jordan elimination and partial pivoting: bs steps per block, ONE block barrier per step.
+//
+// The block recurrence is sequential, so a system is a latency chain of nb * bs elimination steps; the design goal is
+// the shortest possible step:
+//   * one CTA of 8 warps per system; the block lives in REGISTERS, thread (warp w, lane l) owns rows l + 32a and
+//     columns w + 8b -- 14 doubles for a 53 x 53 block;
+//   * implicit pivoting: rows are never exchanged. The pivot of step k is the largest entry of column k among the rows
+//     not used yet; the warp that owns column k finds it with three redux.sync on the bit pattern of |a| and
+//     publishes the pivot row index, the reciprocal pivot and the column (one 8-byte store per lane) -- the only
+//     shared-memory traffic of a step; the other warps pick the pivot row out of their own registers by shuffle;
+//   * the row / column permutation is undone once per block when the inverse goes to shared memory in its true
+//     layout, from where it is stored (coalesced) and folded into the next block's D'.
+// The original matrix is NOT overwritten (the reference's factorisation is in place; here the Jacobian survives).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+
+#include "../../include/griffon_b200.h"
+#include "gb_kernels.cuh"
+#include "gb_mech.h"
+
+namespace gb
+{
+extern std::atomic<long> g_btddod_launches;
+
+namespace
+{
+constexpr int IW = 8;        // warps per CTA
+constexpr int INT_ = IW * 32; // threads per CTA
+
+#ifdef GB_JAC_TIMELINE
+__device__ long long g_inv_timeline[8];
+#endif
+
+// reciprocal by MUFU.RCP64H and three Newton steps (the last one on the residual): within an ulp of 1/x for normal x,
+// without the range checks and the slow path of the IEEE division (the pivot's reciprocal sits on the critical path of
+// every elimination step). 0 -> inf and non-finite x behave as in a plain division for the purposes of this kernel
+// (the block is singular: the result is non-finite either way).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.);
+  r = fma(r, e, r);
+  return r;
+}
+
+// R rows per lane (bs <= 32 R), C column slots per warp (bs <= 8 C)
+template <int R, int C>
+__global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *__restrict__ mats, int nb, int bs,
+                                                        double *__restrict__ l_values, double *__restrict__ dinv)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb2 = bs * bs;
+  double *sInv = sm;                        // [bs*bs] inverse of the previous block, true column-major layout
+  double *sf = sInv + nb2 + (nb2 & 1);      // [2][64 R... ] published pivot column, ping-pong
+  const int fstride = 32 * R;
+  double *srinv = sf + 2 * fstride;         // [2] reciprocal pivot
+  int *sp = reinterpret_cast<int *>(srinv + 2);  // [2] pivot row of the step
+  int *sperm = sp + 2;                      // [bs] pivot row of step k
+  int *sinvp = sperm + 32 * R;              // [bs] step at which row r was the pivot
+  const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
+
+  for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
+  {
+    const double *M = mats + (size_t)sys * mat_stride;
+    const double *subd = M + (size_t)nb * nb2, *supd = subd + (size_t)(nb - 1) * bs;
+    double *Lv = l_values + (size_t)sys * nb * nb2;
+    double *Di = dinv + (size_t)sys * nb * nb2;
+    double S[R][C], Dn[R][C];
+    auto load_block = [&](int i, double (&dst)[R][C]) {
+      const double *D = M + (size_t)i * nb2;
+#pragma unroll
+      for (int b = 0; b < C; ++b)
+      {
+        const int col = warp + IW * b;
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          const int row = lane + 32 * a;
+          dst[a][b] = (row < bs && col < bs) ? __ldg(D + (size_t)col * bs + row) : 0.;
+        }
+      }
+    };
+    load_block(0, Dn);
+    __syncthreads(); // the previous system is done with the shared arrays
+    for (int i = 0; i < nb; ++i)
+    {
+      // ---- D'_i: the first block as it is; then D_i - (sub o Dinv_{i-1}) o sup, L_i on the way (:48-75) --------------
+#pragma unroll
+      for (int b = 0; b < C; ++b)
+      {
+        const int col = warp + IW * b;
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          const int row = lane + 32 * a;
+          double v = Dn[a][b];
+          if (i > 0 && row < bs && col < bs)
+          {
+            const double l = __ldg(subd + (size_t)(i - 1) * bs + row) * sInv[(size_t)col * bs + row];
+            Lv[(size_t)i * nb2 + (size_t)col * bs + row] = l;
+            v = v - l * __ldg(supd + (size_t)(i - 1) * bs + col);
+          }
+          else if (i == 0 && row < bs && col < bs)
+            Lv[(size_t)col * bs + row] = 0.; // (block 0 of l_values is never read; defined for reproducibility)
+          S[a][b] = v;
+        }
+      }
+      if (i + 1 < nb)
+        load_block(i + 1, Dn); // lands during the elimination
+      // ---- Gauss-Jordan with implicit partial pivoting -----------------------------------------------------------
+      unsigned int used = 0; // bit a: my row lane + 32a has been a pivot
+#pragma unroll
+      for (int bk = 0; bk < C; ++bk)
+      {
+        for (int wk = 0; wk < IW; ++wk)
+        {
+          const int k = wk + IW * bk;
+          if (k >= bs)
+            break;
+          const int buf = k & 1;
+          if (warp == wk)
+          {
+            // Row of maximum modulus among the unused rows, compared on the upper 32 bits of |a| (sign-free exponent
+            // and 20 mantissa bits: entries within 1e-6 of each other may tie, the lowest lane wins -- harmless for
+            // the stability of the elimination and it takes one redux.sync instead of three): key = bits + 1, 0 for rows
+            // out of play.
+            unsigned int key = 0u;
+            int krow = 0;
+            double kval = 0.;
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+            {
+              const int row = lane + 32 * a;
+              if (row < bs && !((used >> a) & 1u))
+              {
+                const unsigned int kk = (unsigned int)__double2hiint(fabs(S[a][bk])) + 1u;
+                if (kk > key)
+                  key = kk, krow = row, kval = S[a][bk];
+              }
+            }
+            const unsigned int m1 = __reduce_max_sync(0xffffffffu, key);
+            const int src = __ffs(__ballot_sync(0xffffffffu, key == m1)) - 1;
+            const int p = __shfl_sync(0xffffffffu, krow, src);
+            const double pv = __shfl_sync(0xffffffffu, kval, src);
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+              sf[buf * fstride + lane + 32 * a] = S[a][bk];
+            if (lane == 0)
+            {
+              srinv[buf] = fast_rcp(pv);
+              sp[buf] = p;
+              sperm[k] = p;
+              sinvp[p] = k;
+            }
+          }
+          __syncthreads();
+          const int p = sp[buf];
+          const double rinv = srinv[buf];
+          double colk[R];
+#pragma unroll
+          for (int a = 0; a < R; ++a)
+            colk[a] = sf[buf * fstride + lane + 32 * a];
+          const int pa = p >> 5, pl = p & 31;
+          const bool mine_p = lane == pl;
+          if (mine_p)
+            used |= 1u << pa;
+#pragma unroll
+          for (int b = 0; b < C; ++b)
+          {
+            double sel = S[0][b];
+#pragma unroll
+            for (int a = 1; a < R; ++a)
+              if (pa == a)
+                sel = S[a][b];
+            const double prs = __shfl_sync(0xffffffffu, sel, pl) * rinv; // scaled pivot-row entry of my column
+            const bool is_k = (b == bk) && (warp == wk);
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+            {
+              const bool prow = mine_p && pa == a;
+              if (is_k)
+                S[a][b] = prow ? rinv : -(colk[a] * rinv);
+              else
+                S[a][b] = prow ? prs : fma(-colk[a], prs, S[a][b]);
+            }
+          }
+        }
+      }
+      __syncthreads(); // sperm / sinvp complete; everybody is done reading sInv of the previous block
+      // ---- undo the permutation: S[r][m] is entry (step of r, pivot row of step m) of the inverse -----------------------
+#pragma unroll
+      for (int b = 0; b < C; ++b)
+      {
+        const int m = warp + IW * b;
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          const int r = lane + 32 * a;
+          if (r < bs && m < bs)
+            sInv[(size_t)sperm[m] * bs + sinvp[r]] = S[a][b];
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < nb2; e += INT_)
+        Di[(size_t)i * nb2 + e] = sInv[e];
+    }
+  }
+}
+
+int inv_fail(cudaError_t e, const char *what)
+{
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  cudaGetLastError();
+  return GB_ERR_CUDA;
+}
+
+template <int R, int C>
+int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, double *dinv, cudaStream_t st)
+{
+  const size_t nb2 = (size_t)bs * bs;
+  const size_t smem = sizeof(double) * (nb2 + (nb2 & 1) + 2 * 32 * R + 2) + sizeof(int) * (2 + 2 * 32 * R) + 16;
+  cudaError_t e = cudaFuncSetAttribute(k_btddod_invert<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return inv_fail(e, "k_btddod_invert attribute");
+  int dev = 0, sms = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / smem));
+  const int grid = std::min(n, sms * per_sm);
+  k_btddod_invert<R, C><<<grid, INT_, smem, st>>>(n, mats, nb, bs, l_values, dinv);
+  ++g_btddod_launches;
+  e = cudaGetLastError();
+  return e == cudaSuccess ? GB_OK : inv_fail(e, "k_btddod_invert");
+}
+} // namespace
+} // namespace gb
+
+using namespace gb;
+
+extern "C" int gb_btddod_full_invert_batch(int n, const double *matrix, int nb, int bs, double *out_l_values,
+                                           double *out_dinv, void *stream)
+{
+  if (n < 0 || nb < 1 || bs < 1 || (n > 0 && (!matrix || !out_l_values || !out_dinv)))
+  {
+    set_error("gb_btddod_full_invert_batch: bad dimensions or null array");
+    return GB_ERR_ARG;
+  }
+  if (n == 0)
+    return GB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bs <= 16)
+    return launch_invert<1, 2>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  if (bs <= 32)
+    return launch_invert<1, 4>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  if (bs <= 56)
+    return launch_invert<2, 7>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  if (bs <= 64)
+    return launch_invert<2, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  if (bs <= 96)
+    return launch_invert<3, 12>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  if (bs <= 128)
+    return launch_invert<4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+  set_error("gb_btddod_full_invert_batch: block size above 128 is not supported");
+  return GB_ERR_UNSUPPORTED;
+}

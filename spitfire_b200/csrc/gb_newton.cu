@@ -1,0 +1,318 @@
+// gb_newton.cu -- vector kernels of the batched implicit time integrator (host solver loops).
+//
+// The reference advances one flamelet at a time with numpy expressions: the ESDIRK stage loop of
+// KennedyCarpenterS6P4Q3.single_step (time/methods.py:502-612), SimpleNewtonSolver (time/nonlinear.py:185-268: residual
+// dt*(gamma*f(x) + explicit) - (x - q_n), update x <- x - solve(residual), weighted infinity norm against the
+// tolerance) and the embedded error estimate handed to the PI controller (time/stepcontrol.py:84-101). For a batch of
+// F independent members on the device those expressions are a dozen eager tensor operations and one host
+// synchronisation per Newton iteration; here each of them is ONE kernel over all members, the convergence flags stay
+// on the device and the host only reads one integer (the number of members still iterating).
+//
+// Members are the rows of [n][ndof] arrays (row stride ndof). One CTA per member: a GRI-3.0 flamelet row is 6678
+// doubles, a batch has at most a few hundred members, so every kernel is a single wave of CTAs that each stream
+// ~0.4 MB through one SM -- launch-latency sized, which is the point. The arithmetic follows the reference's
+// expressions operation by operation (the library is compiled without FMA contraction), so a member of the batch
+// sees exactly the numbers the serial code would produce for it.
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "../../include/griffon_b200.h"
+#include "gb_kernels.cuh"
+#include "gb_mech.h"
+
+namespace gb
+{
+extern std::atomic<long> g_btddod_launches; // (shared launch counter of the solver-side kernels, gb_btddod.cu)
+
+namespace
+{
+constexpr int NT = 512;
+constexpr int MAXK = 6;
+
+struct KPtrs
+{
+  const double *k[MAXK];
+  double c[MAXK];
+  double c2[MAXK];
+};
+
+// explicit = c[nk-1]*k[nk-1]; then for j = nk-2 .. 0: explicit = explicit + c[j]*k[j]   (methods.py:560-575)
+// res = dt*(gamma*f + explicit) - (x - q)                                               (nonlinear.py:204)
+__global__ void __launch_bounds__(NT) k_stage_begin(int ndof, int nk, KPtrs kp, double gamma, const double *__restrict__ dt,
+                                                    const double *__restrict__ x, const double *__restrict__ q,
+                                                    const double *__restrict__ f, double *__restrict__ expl,
+                                                    double *__restrict__ res, int *__restrict__ conv)
+{
+  const int m = blockIdx.x;
+  const size_t base = (size_t)m * ndof;
+  const double h = dt[m];
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    double e = kp.c[nk - 1] * kp.k[nk - 1][base + i];
+    for (int j = nk - 2; j >= 0; --j)
+      e = e + kp.c[j] * kp.k[j][base + i];
+    expl[base + i] = e;
+    res[base + i] = h * (gamma * f[base + i] + e) - (x[base + i] - q[base + i]);
+  }
+  if (threadIdx.x == 0)
+    conv[m] = 0;
+}
+
+// xn = x - dx for the members still iterating, xn = x for the converged ones; resets the unconverged counter that the
+// tail kernel of the same iteration accumulates
+__global__ void __launch_bounds__(NT) k_newton_update(int ndof, const double *__restrict__ x, const double *__restrict__ dx,
+                                                      const int *__restrict__ conv, double *__restrict__ xn,
+                                                      int *__restrict__ n_unconverged)
+{
+  const int m = blockIdx.x;
+  const size_t base = (size_t)m * ndof;
+  const bool done = conv[m] != 0;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+    xn[base + i] = done ? x[base + i] : x[base + i] - dx[base + i];
+  if (m == 0 && threadIdx.x == 0)
+    *n_unconverged = 0;
+}
+
+__device__ __forceinline__ void block_max_nan(double &v, int &bad)
+{
+  __shared__ double sv[NT / 32];
+  __shared__ int sb[NT / 32];
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  __syncthreads(); // (the arrays may still be read from a previous call)
+  if ((threadIdx.x & 31) == 0)
+    sv[threadIdx.x >> 5] = v, sb[threadIdx.x >> 5] = bad;
+  __syncthreads();
+  v = sv[0], bad = sb[0];
+  for (int w = 1; w < NT / 32; ++w)
+    v = fmax(v, sv[w]), bad |= sb[w];
+}
+
+// rn = dt*(gamma*fn + explicit) - (xn - q); members still iterating take (xn, fn, rn) as their new (x, f, res);
+// conv |= max|rn*w| < tol (a NaN anywhere in rn leaves the member unconverged, as the comparison does in the reference)
+__global__ void __launch_bounds__(NT) k_newton_tail(int ndof, const double *__restrict__ fn, const double *__restrict__ xn,
+                                                    const double *__restrict__ expl, const double *__restrict__ q,
+                                                    const double *__restrict__ dt, double gamma,
+                                                    const double *__restrict__ w, double tol, double *__restrict__ x,
+                                                    double *__restrict__ f, double *__restrict__ res, int *__restrict__ conv,
+                                                    int *__restrict__ n_unconverged)
+{
+  const int m = blockIdx.x;
+  const size_t base = (size_t)m * ndof;
+  const bool done = conv[m] != 0;
+  if (done)
+    return; // (uniform over the CTA) a converged member keeps its values
+  const double h = dt[m];
+  double nrm = 0.;
+  int bad = 0;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    const double fi = fn[base + i], xi = xn[base + i];
+    const double r = h * (gamma * fi + expl[base + i]) - (xi - q[base + i]);
+    x[base + i] = xi;
+    f[base + i] = fi;
+    res[base + i] = r;
+    const double a = fabs(r * w[base + i]);
+    bad |= (a != a);
+    nrm = fmax(nrm, a);
+  }
+  block_max_nan(nrm, bad);
+  if (threadIdx.x == 0)
+  {
+    const bool ok = !bad && nrm < tol;
+    if (ok)
+      conv[m] = 1;
+    else
+      atomicAdd(n_unconverged, 1);
+  }
+}
+
+// dq = dt*(b0*k0 + b1*k1 + ... ), dqh likewise with bh (left to right, methods.py:598-610); stats[0][m] = max|(dq-dqh)*w|
+// (the error estimate of the PI controller), stats[1][m] = max|dq*w|, stats[2][m] = 1 if every dq is finite else 0
+__global__ void __launch_bounds__(NT) k_esdirk_finish(int ndof, int n, int nk, KPtrs kp, const double *__restrict__ dt,
+                                                      const double *__restrict__ w, double *__restrict__ dq,
+                                                      double *__restrict__ stats)
+{
+  const int m = blockIdx.x;
+  const size_t base = (size_t)m * ndof;
+  const double h = dt[m];
+  double e_err = 0., e_dq = 0.;
+  int nan_err = 0, nan_dq = 0, nonfinite = 0;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    double s = kp.c[0] * kp.k[0][base + i], sh = kp.c2[0] * kp.k[0][base + i];
+    for (int j = 1; j < nk; ++j)
+    {
+      s = s + kp.c[j] * kp.k[j][base + i];
+      sh = sh + kp.c2[j] * kp.k[j][base + i];
+    }
+    const double d = h * s, dh = h * sh;
+    dq[base + i] = d;
+    const double wi = w[base + i];
+    const double a = fabs((d - dh) * wi), b = fabs(d * wi);
+    nan_err |= (a != a);
+    nan_dq |= (b != b);
+    nonfinite |= !isfinite(d);
+    e_err = fmax(e_err, a);
+    e_dq = fmax(e_dq, b);
+  }
+  block_max_nan(e_err, nan_err);
+  block_max_nan(e_dq, nan_dq);
+  double dummy = 0.;
+  block_max_nan(dummy, nonfinite);
+  if (threadIdx.x == 0)
+  {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    stats[m] = nan_err ? qnan : e_err;
+    stats[n + m] = nan_dq ? qnan : e_dq;
+    stats[2 * n + m] = nonfinite ? 0. : 1.;
+  }
+}
+
+// q <- max(q + dq, 0) (or q + dq) for the accepted members, in place (integrator.py:598-612 with the flamelet's
+// clip-negative post-step); members with accept[m] == 0 keep their state
+__global__ void __launch_bounds__(NT) k_accept_step(int ndof, const double *__restrict__ dq, const int *__restrict__ accept,
+                                                    int clip, double *__restrict__ q)
+{
+  const int m = blockIdx.x;
+  if (!accept[m])
+    return;
+  const size_t base = (size_t)m * ndof;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    double v = q[base + i] + dq[base + i];
+    if (clip && v < 0.)
+      v = 0.;
+    q[base + i] = v;
+  }
+}
+
+int check_n(int n, int ndof)
+{
+  if (n < 0 || ndof <= 0)
+  {
+    set_error("batched integrator kernels: n >= 0 and ndof > 0 required");
+    return GB_ERR_ARG;
+  }
+  return GB_OK;
+}
+int cuda_rc(const char *what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return GB_ERR_CUDA;
+  }
+  return GB_OK;
+}
+} // namespace
+} // namespace gb
+
+using namespace gb;
+
+extern "C"
+{
+  int gb_esdirk_stage_begin_batch(int n, int ndof, int nk, const double *const *k, const double *coef, double gamma,
+                                  const double *dt, const double *x, const double *q, const double *f,
+                                  double *explicit_out, double *res_out, int *conv, void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (nk < 1 || nk > MAXK || !k || !coef || !dt || !x || !q || !f || !explicit_out || !res_out || !conv)
+    {
+      set_error("gb_esdirk_stage_begin_batch: 1 <= nk <= 6 and non-null arrays required");
+      return GB_ERR_ARG;
+    }
+    KPtrs kp{};
+    for (int j = 0; j < nk; ++j)
+      kp.k[j] = k[j], kp.c[j] = coef[j];
+    k_stage_begin<<<n, NT, 0, (cudaStream_t)stream>>>(ndof, nk, kp, gamma, dt, x, q, f, explicit_out, res_out, conv);
+    ++g_btddod_launches;
+    return cuda_rc("k_stage_begin");
+  }
+
+  int gb_newton_update_batch(int n, int ndof, const double *x, const double *dx, const int *conv, double *xn,
+                             int *n_unconverged, void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (!x || !dx || !conv || !xn || !n_unconverged)
+    {
+      set_error("gb_newton_update_batch: null array");
+      return GB_ERR_ARG;
+    }
+    k_newton_update<<<n, NT, 0, (cudaStream_t)stream>>>(ndof, x, dx, conv, xn, n_unconverged);
+    ++g_btddod_launches;
+    return cuda_rc("k_newton_update");
+  }
+
+  int gb_newton_tail_batch(int n, int ndof, const double *fn, const double *xn, const double *explicit_, const double *q,
+                           const double *dt, double gamma, const double *weights, double tolerance, double *x, double *f,
+                           double *res, int *conv, int *n_unconverged, int *host_count, void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (!fn || !xn || !explicit_ || !q || !dt || !weights || !x || !f || !res || !conv || !n_unconverged)
+    {
+      set_error("gb_newton_tail_batch: null array");
+      return GB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_newton_tail<<<n, NT, 0, st>>>(ndof, fn, xn, explicit_, q, dt, gamma, weights, tolerance, x, f, res, conv,
+                                    n_unconverged);
+    ++g_btddod_launches;
+    rc = cuda_rc("k_newton_tail");
+    if (rc != GB_OK)
+      return rc;
+    if (host_count)
+    { // synchronous read of the one integer the host loop branches on
+      if (cudaMemcpyAsync(host_count, n_unconverged, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        return cuda_rc("gb_newton_tail_batch: count read-back");
+    }
+    return GB_OK;
+  }
+
+  int gb_esdirk_finish_batch(int n, int ndof, int nk, const double *const *k, const double *b, const double *bh,
+                             const double *dt, const double *weights, double *dq, double *stats, void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (nk < 1 || nk > MAXK || !k || !b || !bh || !dt || !weights || !dq || !stats)
+    {
+      set_error("gb_esdirk_finish_batch: 1 <= nk <= 6 and non-null arrays required");
+      return GB_ERR_ARG;
+    }
+    KPtrs kp{};
+    for (int j = 0; j < nk; ++j)
+      kp.k[j] = k[j], kp.c[j] = b[j], kp.c2[j] = bh[j];
+    k_esdirk_finish<<<n, NT, 0, (cudaStream_t)stream>>>(ndof, n, nk, kp, dt, weights, dq, stats);
+    ++g_btddod_launches;
+    return cuda_rc("k_esdirk_finish");
+  }
+
+  int gb_accept_step_batch(int n, int ndof, const double *dq, const int *accept, int clip_negative, double *q,
+                           void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (!dq || !accept || !q)
+    {
+      set_error("gb_accept_step_batch: null array");
+      return GB_ERR_ARG;
+    }
+    k_accept_step<<<n, NT, 0, (cudaStream_t)stream>>>(ndof, dq, accept, clip_negative, q);
+    ++g_btddod_launches;
+    return cuda_rc("k_accept_step");
+  }
+}

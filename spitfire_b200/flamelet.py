@@ -277,6 +277,7 @@ class _BatchOps(object):
     # only proposes the update of an iteration that converges on the true residual, and the inverse-based back sweep is
     # 3-4x shorter than the pivoted triangular solves (griffon_b200.h, gb_btddod_full_*_inv_batch).
     explicit_inverse_solves = True
+    gauss_jordan_inverses = True  # k_btddod_invert instead of LU + dgetrs-on-identity (gb_btinv.cu)
     _rows32 = (None, None)  # last (int64 rows, int32 copy) pair handed to the solve kernel
 
     def factor_store(self, F):
@@ -305,7 +306,11 @@ class _BatchOps(object):
         piv = torch.zeros((n, self.ndof), dtype=torch.int32, device=self.device)
         if self.on_device and with_inverse:
             Dinv = torch.empty((n, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device)
-            self.gmod.btddod_full_factorize_inv(J, self.nzi, self.ns, L, piv, Dinv, n_systems=n)
+            if getattr(self, 'gauss_jordan_inverses', True):
+                # the solvers only ever apply these factors through solve_inv: inverses alone, by the short-chain kernel
+                self.gmod.btddod_full_invert(J, self.nzi, self.ns, L, Dinv, n_systems=n)
+            else:
+                self.gmod.btddod_full_factorize_inv(J, self.nzi, self.ns, L, piv, Dinv, n_systems=n)
             return J, L, piv, Dinv
         if self.on_device:
             self.gmod.py_btddod_full_factorize(J, self.nzi, self.ns, L, piv, n_systems=n)

@@ -95,9 +95,16 @@ def load_library():
     sig('gb_btddod_full_solve_batch', I, [I, V, V, V, V, I, I, V, V])
     sig('gb_btddod_full_factorize_inv_batch', I, [I, V, I, I, V, V, V, V])
     sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V, V])
+    sig('gb_btddod_full_invert_batch', I, [I, V, I, I, V, V, V])
     sig('gb_max_real_eigenvalue_batch', I, [I, I, V, V, V])
     sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
     sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
+    PP = C.POINTER(C.c_void_p)
+    sig('gb_esdirk_stage_begin_batch', I, [I, I, I, PP, dp, D, V, V, V, V, V, V, V, V])
+    sig('gb_newton_update_batch', I, [I, I, V, V, V, V, V, V])
+    sig('gb_newton_tail_batch', I, [I, I, V, V, V, V, V, D, V, D, V, V, V, V, V, ip, V])
+    sig('gb_esdirk_finish_batch', I, [I, I, I, PP, dp, dp, V, V, V, V, V])
+    sig('gb_accept_step_batch', I, [I, I, V, V, I, V, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
     sig('gb_btddod_full_matvec_host', I, [I, V, V, I, I, V])
@@ -498,6 +505,14 @@ def max_real_eigenvalue(blocks, n, out, n_blocks):
           'gb_max_real_eigenvalue_batch')
 
 
+def btddod_full_invert(matrix, num_blocks, block_size, out_l_values, out_dinv, n_systems=1):
+    """extension (device arrays only): block-Thomas elimination by Gauss-Jordan inverses; `matrix` is left intact and
+    serves as the d_factors argument of btddod_full_solve_inv"""
+    check(load_library().gb_btddod_full_invert_batch(int(n_systems), _addr(matrix), int(num_blocks), int(block_size),
+                                                     _addr(out_l_values), _addr(out_dinv), _stream()),
+          'gb_btddod_full_invert_batch')
+
+
 def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1,
                           system_rows=None):
     """extension (device arrays only): block-Thomas solve whose back sweep multiplies by the stored inverses.
@@ -507,6 +522,60 @@ def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size
                                                         _addr(out_solution),
                                                         None if system_rows is None else _addr(system_rows, np.int32), _stream()),
           'gb_btddod_full_solve_inv_batch')
+
+
+# ---- vector kernels of the batched implicit integrator (device tensors; griffon_b200.h) ----------------------------
+def _kptrs(ks):
+    arr = (C.c_void_p * len(ks))(*[k.data_ptr() for k in ks])
+    return arr
+
+
+def _hvec(v):
+    return (C.c_double * len(v))(*[float(x) for x in v])
+
+
+def esdirk_stage_begin(ks, coefs, gamma, dt, x, q, f, explicit_out, res_out, conv):
+    """explicit = sum_j coefs[j]*ks[j] (from the last term down), res = dt*(gamma*f + explicit) - (x - q), conv = 0"""
+    n, ndof = x.shape
+    check(load_library().gb_esdirk_stage_begin_batch(int(n), int(ndof), len(ks), _kptrs(ks), _hvec(coefs), float(gamma),
+                                                     _addr(dt), _addr(x), _addr(q), _addr(f), _addr(explicit_out),
+                                                     _addr(res_out), _addr(conv, np.int32), _stream()),
+          'gb_esdirk_stage_begin_batch')
+
+
+def newton_update(x, dx, conv, xn, n_unconverged):
+    n, ndof = x.shape
+    check(load_library().gb_newton_update_batch(int(n), int(ndof), _addr(x), _addr(dx), _addr(conv, np.int32), _addr(xn),
+                                                _addr(n_unconverged, np.int32), _stream()), 'gb_newton_update_batch')
+
+
+_host_count = C.c_int(0)
+
+
+def newton_tail(fn, xn, explicit, q, dt, gamma, weights, tolerance, x, f, res, conv, n_unconverged, read_count=True):
+    """the fused residual / select / norm / convergence kernel; returns the number of members still iterating (after
+    a stream synchronisation) when read_count, else None"""
+    n, ndof = x.shape
+    check(load_library().gb_newton_tail_batch(int(n), int(ndof), _addr(fn), _addr(xn), _addr(explicit), _addr(q),
+                                              _addr(dt), float(gamma), _addr(weights), float(tolerance), _addr(x),
+                                              _addr(f), _addr(res), _addr(conv, np.int32),
+                                              _addr(n_unconverged, np.int32),
+                                              C.byref(_host_count) if read_count else None, _stream()),
+          'gb_newton_tail_batch')
+    return _host_count.value if read_count else None
+
+
+def esdirk_finish(ks, b, bh, dt, weights, dq, stats):
+    n, ndof = dq.shape
+    check(load_library().gb_esdirk_finish_batch(int(n), int(ndof), len(ks), _kptrs(ks), _hvec(b), _hvec(bh), _addr(dt),
+                                                _addr(weights), _addr(dq), _addr(stats), _stream()),
+          'gb_esdirk_finish_batch')
+
+
+def accept_step(dq, accept, clip_negative, q):
+    n, ndof = dq.shape
+    check(load_library().gb_accept_step_batch(int(n), int(ndof), _addr(dq), _addr(accept, np.int32),
+                                              int(bool(clip_negative)), _addr(q), _stream()), 'gb_accept_step_batch')
 
 
 def py_btddod_full_matvec(matrix_values, vec, num_blocks, block_size, out_matvec, n_systems=1):

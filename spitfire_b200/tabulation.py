@@ -9,7 +9,8 @@ sub-sampling rules as the reference. What is different is how the flamelets are 
     the last converged member (the reference's chain is W = 1, the default, and is followed step for step then);
   * the per-chi_st heat-loss expansions of the non-adiabatic builders -- the reference's `Pool.starmap` units -- are
     dealt to the ranks of torch.distributed (one process per GPU) and gathered once at the end
-    (spitfire_b200.parallel); `num_procs` is accepted and ignored;
+    (spitfire_b200.parallel); `num_procs` > 1 forks a process pool over the dissipation rates as the reference does, but
+    only for a host-side Griffon object (the injected CPU checker) -- on the device it is ignored;
   * specific enthalpies come from Griffon's `enthalpy_mix` instead of a Cantera SolutionArray (analysis.py:77-98);
   * the structured-defect interpolation (a Python triple loop over chi, property and grid point in the reference,
     tabulation.py:629-654) is done with array operations.
@@ -352,6 +353,27 @@ def _expand_enthalpy_defect_dimension_steady(chi_st, managed_dict, flamelet_spec
         print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
 
 
+_pool_job = None
+
+
+def _pool_expand(chi_st):
+    expand, flamelet_specs, table_dict, h_stoich_spacing, integration_args, solver_verbose = _pool_job
+    try:  # one thread per worker: the pool already uses every core
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    out = dict()
+    expand(chi_st, out, copy.copy(flamelet_specs), table_dict, h_stoich_spacing, False, integration_args, solver_verbose)
+    return out
+
+
+def _griffon_on_device(flamelet_specs):
+    from spitfire_b200 import griffon as gmod
+    specs = flamelet_specs if not isinstance(flamelet_specs, dict) else FlameletSpec(**flamelet_specs)
+    return isinstance(specs.mech_spec.griffon, gmod.PyCombustionKernels)
+
+
 def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion='transient',
                                                          diss_rate_values=np.logspace(-3, 2, 16),
                                                          diss_rate_ref='stoichiometric', verbose=True,
@@ -370,7 +392,23 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
     cput0 = perf_counter()
     local = dict()
     mine = parallel.my_share(list(table_dict.keys()))
-    if heat_loss_expansion == 'transient' and batch_expansions and len(mine) > 1:
+    on_device = _griffon_on_device(flamelet_specs)
+    if num_procs > 1 and not on_device and len(mine) > 1:
+        # the reference's own parallel mode (tabulation.py:542-568): a process pool over the dissipation rates, results
+        # collected in a shared dictionary. Only meaningful for a host Griffon object (the CPU checker injected through
+        # ChemicalMechanismSpec(griffon_factory=...)); on the device the rank's trajectories advance as one batch.
+        # The workers are forked, so they inherit the specification (with its Griffon object) instead of unpickling it.
+        import multiprocessing as mp
+        global _pool_job
+        _pool_job = (expand, flamelet_specs, table_dict, h_stoich_spacing, integration_args, solver_verbose)
+        ctx = mp.get_context('fork')
+        try:
+            with ctx.Pool(processes=min(int(num_procs), len(mine))) as pool:
+                for part in pool.map(_pool_expand, mine, chunksize=1):
+                    local.update(part)
+        finally:
+            _pool_job = None
+    elif heat_loss_expansion == 'transient' and batch_expansions and len(mine) > 1:
         _expand_enthalpy_defect_dimension_transient_batch(mine, local, flamelet_specs, table_dict, h_stoich_spacing,
                                                           verbose, integration_args, solver_verbose)
     else:

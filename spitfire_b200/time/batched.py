@@ -27,11 +27,17 @@ _BH = [4586570599. / 29645900160., 0., 178811875. / 945068544., 814220225. / 115
        61727. / 225920.]
 
 
+# the device-resident stage loop (csrc/gb_newton.cu) is used for device batches of up to dense_limit members; False falls
+# back to the eager tensor loop (kept for larger batches, where the iteration runs on the unconverged members only)
+FUSED_NEWTON = True
+
+
 def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, minimum_time_step_count=40,
                     transient_tolerance=1.e-10, maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12,
                     max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
                     fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
-                    explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False, dense_limit=148):
+                    explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False, dense_limit=148,
+                    fused_newton=None):
     """advance every member of `ops` (flamelet._BatchOps) from q0 [F, ndof] until `stop(t, q, residual, nsteps)` (all
     [F]-shaped tensors; returns a bool tensor) holds for it and it has taken at least minimum_time_step_count steps.
     Returns per member the lists of saved times and states (numpy), initial state included, and a `failed` flag
@@ -102,64 +108,100 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
         factors = (J, L, piv, Dinv) if use_inv else (J, L, piv)
         key_all = tuple(idx_h.tolist())
         # ---- one ESDIRK64 step for every active member --------------------------------------------------------------------
-        k = [ops.rhs(qa, idx, key=key_all)]
-        qs = qa
-        nl_ok = np.ones(n, dtype=bool)
-        for s in range(1, 6):
-            explicit = _A[s][s - 1] * k[s - 1]
-            for j in range(s - 2, -1, -1):
-                explicit = explicit + _A[s][j] * k[j]
-            # Newton with the lagged projector: x -= solve(res); res = dt*(gamma*f(x) + explicit) - (x - q_n)
-            x = qs.clone()
-            f = k[-1].clone()
-            res = dta[:, None] * (_G * f + explicit) - (x - qa)
-            conv = np.zeros(n, dtype=bool)
-            conv_d = None
-            for it in range(max_nonlinear_iter):
-                l_h = np.nonzero(~conv)[0]
-                if l_h.size == 0:
-                    break
-                g_h = idx_h[l_h]
-                if l_h.size != n and n <= dense_limit and ops.on_device:
-                    # Small batches are latency-bound: a kernel over all n members costs what a kernel over the
-                    # unconverged ones costs, so the iteration runs on everybody and the converged members simply keep
-                    # their values (no gathers, no index uploads; the unconverged members see the same arithmetic).
-                    if conv_d is None:
-                        conv_d = torch.as_tensor(conv, device=dev)
-                    dx = ops.solve(factors, res, rows=None if all_active else idx)
-                    xn = x - dx
+        fused = bool(ops.on_device) and n <= dense_limit and (FUSED_NEWTON if fused_newton is None else fused_newton)
+        if fused:
+            # Device-resident stage loop (griffon_b200.h, "vector kernels of the batched implicit integrator"): one kernel
+            # forms the explicit part and the first residual, and every Newton iteration is solve -> update -> rhs -> one
+            # fused kernel (residual, select, weighted norm, convergence flags); the host reads one integer per iteration.
+            gm = ops.gmod
+            wa = w if all_active else w.index_select(0, idx)
+            k = [ops.rhs(qa, idx, key=key_all)]
+            qs = qa
+            conv_i = torch.zeros(n, dtype=torch.int32, device=dev)
+            left_d = torch.zeros(1, dtype=torch.int32, device=dev)
+            expl, res = torch.empty_like(qa), torch.empty_like(qa)
+            nl_ok = np.ones(n, dtype=bool)
+            rows = None if all_active else idx
+            for s in range(1, 6):
+                x, f = qs.clone(), k[-1].clone()
+                gm.esdirk_stage_begin(k[:s], _A[s][:s], _G, dta, x, qa, f, expl, res, conv_i)
+                left = n
+                for it in range(max_nonlinear_iter):
+                    dx = ops.solve(factors, res, rows=rows)
+                    xn = torch.empty_like(x)
+                    gm.newton_update(x, dx, conv_i, xn, left_d)
                     fn = ops.rhs(xn, idx, key=key_all)
-                    rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
-                    keep = conv_d[:, None]
-                    x, f, res = torch.where(keep, x, xn), torch.where(keep, f, fn), torch.where(keep, res, rn)
-                    conv_d = conv_d | (wnorm(rn, idx) < nonlinear_solve_tolerance)
-                    conv = conv_d.cpu().numpy()
-                elif l_h.size == n:
-                    dx = ops.solve(factors, res, rows=None if all_active else idx)
-                    xn = x - dx
-                    fn = ops.rhs(xn, idx, key=key_all)
-                    rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
-                    x, f, res = xn, fn, rn
-                    conv_d = wnorm(rn, idx) < nonlinear_solve_tolerance
-                    conv = conv_d.cpu().numpy()
-                else:
-                    loc, gl = dev_idx(l_h), dev_idx(g_h)
-                    dx = ops.solve(factors, res.index_select(0, loc), rows=gl)
-                    xn = x.index_select(0, loc) - dx
-                    fn = ops.rhs(xn, gl, key=tuple(g_h.tolist()))
-                    rn = dta.index_select(0, loc)[:, None] * (_G * fn + explicit.index_select(0, loc)) - \
-                        (xn - qa.index_select(0, loc))
-                    x[loc], f[loc], res[loc] = xn, fn, rn
-                    conv[l_h] = (wnorm(rn, gl) < nonlinear_solve_tolerance).cpu().numpy()
-                    conv_d = None
-            nl_ok &= conv
-            qs = x
-            k.append(f)
-        dq = dta[:, None] * (_B[0] * k[0] + _B[1] * k[1] + _B[2] * k[2] + _B[3] * k[3] + _B[4] * k[4] + _B[5] * k[5])
-        dqh = dta[:, None] * (_BH[0] * k[0] + _BH[1] * k[1] + _BH[2] * k[2] + _BH[3] * k[3] + _BH[4] * k[4] +
-                              _BH[5] * k[5])
-        stats = torch.stack([wnorm(dq - dqh, idx), wnorm(dq, idx), torch.isfinite(dq).all(dim=1).to(torch.float64)])
-        stats = stats.cpu().numpy()
+                    left = gm.newton_tail(fn, xn, expl, qa, dta, _G, wa, nonlinear_solve_tolerance, x, f, res, conv_i,
+                                          left_d)
+                    if left == 0:
+                        break
+                if left:
+                    nl_ok &= conv_i.cpu().numpy().astype(bool)
+                qs = x
+                k.append(f)
+            dq = torch.empty_like(qa)
+            stats = torch.empty((3, n), dtype=torch.float64, device=dev)
+            gm.esdirk_finish(k, _B, _BH, dta, wa, dq, stats)
+            stats = stats.cpu().numpy()
+        else:
+            k = [ops.rhs(qa, idx, key=key_all)]
+            qs = qa
+            nl_ok = np.ones(n, dtype=bool)
+            for s in range(1, 6):
+                explicit = _A[s][s - 1] * k[s - 1]
+                for j in range(s - 2, -1, -1):
+                    explicit = explicit + _A[s][j] * k[j]
+                # Newton with the lagged projector: x -= solve(res); res = dt*(gamma*f(x) + explicit) - (x - q_n)
+                x = qs.clone()
+                f = k[-1].clone()
+                res = dta[:, None] * (_G * f + explicit) - (x - qa)
+                conv = np.zeros(n, dtype=bool)
+                conv_d = None
+                for it in range(max_nonlinear_iter):
+                    l_h = np.nonzero(~conv)[0]
+                    if l_h.size == 0:
+                        break
+                    g_h = idx_h[l_h]
+                    if l_h.size != n and n <= dense_limit and ops.on_device:
+                        # Small batches are latency-bound: a kernel over all n members costs what a kernel over the
+                        # unconverged ones costs, so the iteration runs on everybody and the converged members simply keep
+                        # their values (no gathers, no index uploads; the unconverged members see the same arithmetic).
+                        if conv_d is None:
+                            conv_d = torch.as_tensor(conv, device=dev)
+                        dx = ops.solve(factors, res, rows=None if all_active else idx)
+                        xn = x - dx
+                        fn = ops.rhs(xn, idx, key=key_all)
+                        rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
+                        keep = conv_d[:, None]
+                        x, f, res = torch.where(keep, x, xn), torch.where(keep, f, fn), torch.where(keep, res, rn)
+                        conv_d = conv_d | (wnorm(rn, idx) < nonlinear_solve_tolerance)
+                        conv = conv_d.cpu().numpy()
+                    elif l_h.size == n:
+                        dx = ops.solve(factors, res, rows=None if all_active else idx)
+                        xn = x - dx
+                        fn = ops.rhs(xn, idx, key=key_all)
+                        rn = dta[:, None] * (_G * fn + explicit) - (xn - qa)
+                        x, f, res = xn, fn, rn
+                        conv_d = wnorm(rn, idx) < nonlinear_solve_tolerance
+                        conv = conv_d.cpu().numpy()
+                    else:
+                        loc, gl = dev_idx(l_h), dev_idx(g_h)
+                        dx = ops.solve(factors, res.index_select(0, loc), rows=gl)
+                        xn = x.index_select(0, loc) - dx
+                        fn = ops.rhs(xn, gl, key=tuple(g_h.tolist()))
+                        rn = dta.index_select(0, loc)[:, None] * (_G * fn + explicit.index_select(0, loc)) - \
+                            (xn - qa.index_select(0, loc))
+                        x[loc], f[loc], res[loc] = xn, fn, rn
+                        conv[l_h] = (wnorm(rn, gl) < nonlinear_solve_tolerance).cpu().numpy()
+                        conv_d = None
+                nl_ok &= conv
+                qs = x
+                k.append(f)
+            dq = dta[:, None] * (_B[0] * k[0] + _B[1] * k[1] + _B[2] * k[2] + _B[3] * k[3] + _B[4] * k[4] + _B[5] * k[5])
+            dqh = dta[:, None] * (_BH[0] * k[0] + _BH[1] * k[1] + _BH[2] * k[2] + _BH[3] * k[3] + _BH[4] * k[4] +
+                                  _BH[5] * k[5])
+            stats = torch.stack([wnorm(dq - dqh, idx), wnorm(dq, idx), torch.isfinite(dq).all(dim=1).to(torch.float64)])
+            stats = stats.cpu().numpy()
         err, ok = stats[0], stats[2] > 0.5
         with np.errstate(all='ignore'):
             residual = stats[1] / dta_h

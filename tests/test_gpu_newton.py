@@ -1,0 +1,109 @@
+"""vector kernels of the batched implicit integrator (csrc/gb_newton.cu) against the tensor expressions they replace --
+the numpy expressions of the reference's stage loop (time/methods.py:502-612), Newton solver (time/nonlinear.py:185-268)
+and error estimate -- evaluated with eager torch operations in the same order: bit-identical."""
+import numpy as np
+import pytest
+
+from spitfire_b200.time import batched
+
+
+def _rand(torch, *shape, seed=0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,ndof', [(1, 53), (7, 374), (56, 6678)])
+def test_stage_kernels_equal_the_tensor_expressions(n, ndof):
+    import torch
+    from spitfire_b200 import griffon as gm
+    G = batched._G
+    ks = [_rand(torch, n, ndof, seed=10 + j) for j in range(6)]
+    q, x = _rand(torch, n, ndof, seed=1), _rand(torch, n, ndof, seed=2)
+    dt = torch.rand(n, dtype=torch.float64).cuda() * 1e-3 + 1e-6
+    w = torch.rand(n, ndof, dtype=torch.float64).cuda() + 0.5
+    for s in range(1, 6):
+        explicit = batched._A[s][s - 1] * ks[s - 1]
+        for j in range(s - 2, -1, -1):
+            explicit = explicit + batched._A[s][j] * ks[j]
+        f = ks[s - 1]
+        res = dt[:, None] * (G * f + explicit) - (x - q)
+        e2, r2 = torch.empty_like(q), torch.empty_like(q)
+        conv = torch.ones(n, dtype=torch.int32, device='cuda')
+        gm.esdirk_stage_begin(ks[:s], batched._A[s][:s], G, dt, x, q, f, e2, r2, conv)
+        assert torch.equal(e2, explicit) and torch.equal(r2, res) and int(conv.sum()) == 0
+    # Newton update + tail with a mix of converged and iterating members
+    conv = torch.zeros(n, dtype=torch.int32, device='cuda')
+    conv[::3] = 1
+    dx = _rand(torch, n, ndof, seed=3) * 1e-3
+    cnt = torch.full((1,), 99, dtype=torch.int32, device='cuda')
+    xn = torch.empty_like(x)
+    gm.newton_update(x, dx, conv, xn, cnt)
+    keep = conv.bool()[:, None]
+    assert torch.equal(xn, torch.where(keep, x, x - dx)) and int(cnt) == 0
+    fn = _rand(torch, n, ndof, seed=4)
+    rn = dt[:, None] * (G * fn + explicit) - (xn - q)
+    norms = (rn * w).abs().amax(dim=1)
+    tol = float(norms.median()) if n > 1 else float(norms[0]) * 2.
+    x0, f0, r0 = x.clone(), f.clone(), res.clone()
+    x1, f1, r1 = x.clone(), f.clone(), res.clone()
+    conv1 = conv.clone()
+    left = gm.newton_tail(fn, xn, explicit, q, dt, G, w, tol, x1, f1, r1, conv1, cnt)
+    assert torch.equal(x1, torch.where(keep, x0, xn)) and torch.equal(f1, torch.where(keep, f0, fn))
+    assert torch.equal(r1, torch.where(keep, r0, rn))
+    want = conv.bool() | (norms < tol)
+    assert torch.equal(conv1.bool(), want) and left == int((~want).sum())
+    # a NaN in a member's residual leaves it unconverged
+    fn2 = fn.clone()
+    fn2[n - 1, ndof // 2] = float('nan')
+    conv2 = torch.zeros(n, dtype=torch.int32, device='cuda')
+    gm.newton_update(x, dx, conv2, xn, cnt)
+    left = gm.newton_tail(fn2, xn, explicit, q, dt, G, w, 1e300, x1, f1, r1, conv2, cnt)
+    assert left == 1 and int(conv2[n - 1]) == 0
+    # error estimate
+    dq = dt[:, None] * (batched._B[0] * ks[0] + batched._B[1] * ks[1] + batched._B[2] * ks[2] + batched._B[3] * ks[3] +
+                        batched._B[4] * ks[4] + batched._B[5] * ks[5])
+    dqh = dt[:, None] * (batched._BH[0] * ks[0] + batched._BH[1] * ks[1] + batched._BH[2] * ks[2] +
+                         batched._BH[3] * ks[3] + batched._BH[4] * ks[4] + batched._BH[5] * ks[5])
+    d2, stats = torch.empty_like(q), torch.empty((3, n), dtype=torch.float64, device='cuda')
+    gm.esdirk_finish(ks, batched._B, batched._BH, dt, w, d2, stats)
+    assert torch.equal(d2, dq)
+    assert torch.equal(stats[0], ((dq - dqh) * w).abs().amax(dim=1)) and torch.equal(stats[1], (dq * w).abs().amax(dim=1))
+    assert torch.equal(stats[2], torch.ones(n, dtype=torch.float64, device='cuda'))
+    ks[2][0, 1] = float('inf')
+    gm.esdirk_finish(ks, batched._B, batched._BH, dt, w, d2, stats)
+    assert float(stats[2, 0]) == 0. and (n == 1 or float(stats[2, 1]) == 1.)
+    # accepted step
+    acc = torch.zeros(n, dtype=torch.int32, device='cuda')
+    acc[::2] = 1
+    qq = q.clone()
+    gm.accept_step(dq, acc, True, qq)
+    want = torch.where(acc.bool()[:, None], torch.clamp(q + dq, min=0.), q)
+    assert torch.equal(qq, want)
+
+
+@pytest.mark.gpu
+def test_fused_stage_loop_reproduces_the_eager_one():
+    """the transient heat-loss trajectories of the H2 gold case: the device-resident stage loop and the eager tensor
+    loop take the same steps and give the same states, bit for bit"""
+    import slfm_cases
+    from spitfire_b200 import tabulation as tab
+    from spitfire_b200.flamelet import Flamelet, FlameletBatch, FlameletSpec
+    from spitfire_b200.time import batched as tb
+    specs = FlameletSpec(**slfm_cases.h2_specs('gpu'))
+    chis = np.logspace(0, 1, 4)
+    table, _, _ = tab.build_adiabatic_slfm_library(specs, chis, verbose=False, _return_intermediates=True)
+    out = []
+    for fused in (True, False):
+        fls = [Flamelet(tab._transient_heat_loss_specs(specs, table, c)) for c in table.keys()]
+        args = tab._transient_integration_args({'transient_tolerance': 1e-10}, False)
+        tb.FUSED_NEWTON = fused
+        try:
+            libs, failed = FlameletBatch(fls).integrate_for_heat_loss(**args)
+        finally:
+            tb.FUSED_NEWTON = True
+        assert not any(failed)
+        out.append(libs)
+    for a, b in zip(*out):
+        assert a.shape == b.shape
+        assert np.array_equal(a['temperature'], b['temperature'])

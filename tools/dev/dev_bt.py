@@ -18,8 +18,13 @@ def tm(fn, n=3):
     torch.cuda.synchronize(); return (time.time() - t0) / n * 1e3
 fact = ops.factorize(J.clone())
 print(f'F={F}: factorize {tm(lambda: ops.factorize(J.clone())):.3f} ms, solve {tm(lambda: ops.solve(fact, r)):.3f} ms')
+ops.gauss_jordan_inverses = False
 fact_inv = ops.factorize(J.clone(), with_inverse=True)
 print(f'F={F}: factorize_inv {tm(lambda: ops.factorize(J.clone(), with_inverse=True)):.3f} ms, solve_inv {tm(lambda: ops.solve(fact_inv, r)):.3f} ms, rhs {tm(lambda: ops.rhs(state)):.3f} ms, jac {tm(lambda: ops.jac(state)):.3f} ms')
+ops.gauss_jordan_inverses = True
+fact_gj = ops.factorize(J.clone(), with_inverse=True)
+xa, xb = ops.solve(fact_inv, r), ops.solve(fact_gj, r)
+print(f'F={F}: invert (Gauss-Jordan) {tm(lambda: ops.factorize(J, with_inverse=True)):.3f} ms; solution vs LU-based inverses: max rel diff {float((xa - xb).abs().max() / xa.abs().max()):.2e}')
 x = state.clone(); e = r.clone(); dta = torch.ones(F, device='cuda', dtype=torch.float64)
 def elem():
     rn = dta[:, None] * (0.25 * r + e) - (x - state)
