@@ -10,7 +10,16 @@
  * Conventions
  *  - plain pointers and sizes only; no C++/torch types cross this boundary.
  *  - all functions return int: 0 = ok, <0 = argument / state / CUDA error
- *    (text via gb_last_error()), >0 reserved. Nothing throws.
+ *    (text via gb_last_error()). The synchronous `*_host` entry points of the
+ *    reactor / flamelet right-hand sides and Jacobians return > 0 = the number
+ *    of members (states, flamelets) whose output holds an Inf or NaN; for the
+ *    asynchronous `*_batch` ones ask gb_count_nonfinite_members_batch. Nothing
+ *    throws.
+ *  - a gb_mech handle serves ONE stream and ONE host thread at a time: the
+ *    flamelet and isochoric entry points and every `*_host` one keep work
+ *    arrays in the handle (grown on demand with cudaMalloc, which synchronises
+ *    the device the first time a larger batch arrives). Use one handle per
+ *    stream / thread; handles are cheap (the tables are ~150 KB).
  *  - `*_batch` entry points take DEVICE pointers and a cudaStream_t passed as
  *    void* (NULL = default stream); they are asynchronous w.r.t. the host.
  *  - `*_host` entry points take HOST pointers, stage through device buffers
@@ -282,6 +291,13 @@ int gb_newton_tail_batch(int n, int ndof, const double *fn, const double *xn, co
  * max|(dq - dqh)*weights| (error estimate), max|dq*weights|, 1/0 = every dq finite / not. k, b, bh: HOST arrays. */
 int gb_esdirk_finish_batch(int n, int ndof, int nk, const double *const *k, const double *b, const double *bh,
                            const double *dt, const double *weights, double *dq, double *stats, void *stream);
+/* Status "> 0 = number of members with non-finite output" (SURVEY 8(b)): flags_out[m] (device, may be NULL) = 1 if row m of
+ * a [n][len_a] -- or of b [n][len_b], if given -- holds an Inf or NaN. Synchronises the stream and returns the number of
+ * such members (>= 0) or a negative error code. The asynchronous *_batch entry points cannot report it themselves; the
+ * synchronous *_host entry points of the reactor and flamelet right-hand sides / Jacobians return it as their status.
+ * Replaces the NaN / Inf scans the reference does in Python (flamelet.py:1435, 1443). */
+int gb_count_nonfinite_members_batch(int n, long len_a, const double *a, long len_b, const double *b, int *flags_out,
+                                     void *stream);
 /* q <- q + dq (clipped at zero if clip_negative) for the members with accept[m] != 0, in place */
 int gb_accept_step_batch(int n, int ndof, const double *dq, const int *accept, int clip_negative, double *q,
                          void *stream);

@@ -13,6 +13,13 @@
 #include "gb_kernels.cuh"
 #include "gb_mech.h"
 
+namespace gb
+{
+int nonfinite_reset(cudaStream_t st);
+int nonfinite_accumulate(int n, long la, const double *a, long lb, const double *b, int *flags, cudaStream_t st);
+int nonfinite_read(cudaStream_t st);
+} // namespace gb
+
 using namespace gb;
 
 #define GB_STR2(x) #x
@@ -342,8 +349,9 @@ extern "C"
     void *d_rhs;
     RC(scratch(m, 2, sizeof(double) * n * ns, &d_rhs));
     RC(gb_reactor_rhs_isobaric_batch(m, n, d_state, &dprm, (double *)d_rhs, nullptr));
+    const int bad = gb_count_nonfinite_members_batch(n, ns, (const double *)d_rhs, 0, nullptr, nullptr, nullptr);
     CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
-    return GB_OK;
+    return bad; // > 0: states whose right-hand side holds an Inf or NaN
   }
 
   // Pipeline resources of the host entry points: three streams (host->device, kernels, device->host) and the events
@@ -416,9 +424,11 @@ extern "C"
       RC(scratch(m, 3, sizeof(double) * (size_t)n * ns * ns, &d_jac));
       RC(gb_reactor_jac_isobaric_batch(m, n, d_state, &dprm, rates_sensitivity_option, sensitivity_transform_option,
                                        (double *)d_rhs, (double *)d_jac, nullptr));
+      const int bad = gb_count_nonfinite_members_batch(n, ns, (const double *)d_rhs, (long)ns * ns, (const double *)d_jac,
+                                                       nullptr, nullptr);
       CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * n * ns, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * ns * ns, cudaMemcpyDeviceToHost));
-      return GB_OK;
+      return bad; // > 0: states whose right-hand side or Jacobian holds an Inf or NaN
     }
     // Large batch: chunks flow through a double-buffered staging area on three streams, so the device->host copy of
     // chunk c (the 8*ns^2 bytes per state that bound this entry point) overlaps the kernel of chunk c+1 and the
@@ -442,6 +452,7 @@ extern "C"
     else
       dprm.inflow_y = nullptr;
     CK(cudaDeviceSynchronize()); // earlier work on the handle's buffers (legacy stream) is done
+    RC(gb::nonfinite_reset(P.s_k));
     int rc = GB_OK;
     const int nchunks = (n + chunk - 1) / chunk;
     for (int c = 0; c < nchunks && rc == GB_OK; ++c)
@@ -462,6 +473,9 @@ extern "C"
                                          sensitivity_transform_option, d_rhs, d_jac, P.s_k);
       if (rc != GB_OK)
         break;
+      rc = gb::nonfinite_accumulate(cnt, ns, d_rhs, (long)ns * ns, d_jac, nullptr, P.s_k);
+      if (rc != GB_OK)
+        break;
       CK(cudaEventRecord(P.ev_k[b], P.s_k));
       CK(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
       CK(cudaMemcpyAsync(out_rhs + (size_t)lo * ns, d_rhs, sizeof(double) * (size_t)cnt * ns, cudaMemcpyDeviceToHost,
@@ -471,9 +485,10 @@ extern "C"
       CK(cudaEventRecord(P.ev_out[b], P.s_out));
     }
     CK(cudaStreamSynchronize(P.s_in));
+    const int bad = rc == GB_OK ? gb::nonfinite_read(P.s_k) : rc;
     CK(cudaStreamSynchronize(P.s_k));
     CK(cudaStreamSynchronize(P.s_out));
-    return rc;
+    return bad; // > 0: states whose right-hand side or Jacobian holds an Inf or NaN
   }
 }
 
@@ -583,8 +598,9 @@ extern "C"
     void *d_rhs;
     RC(scratch(m, 2, sizeof(double) * (size_t)n * (ns + 1), &d_rhs));
     RC(gb_reactor_rhs_isochoric_batch(m, n, d_state, &dprm, inflow_density, (double *)d_rhs, nullptr));
+    const int bad = gb_count_nonfinite_members_batch(n, ns + 1, (const double *)d_rhs, 0, nullptr, nullptr, nullptr);
     CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * (size_t)n * (ns + 1), cudaMemcpyDeviceToHost));
-    return GB_OK;
+    return bad;
   }
 
   int gb_reactor_jac_isochoric_host(gb_mech *m, int n, const double *state, const gb_reactor_params *prm,
@@ -604,9 +620,11 @@ extern "C"
     RC(scratch(m, 3, sizeof(double) * (size_t)n * (ns + 1) * (ns + 1), &d_jac));
     RC(gb_reactor_jac_isochoric_batch(m, n, d_state, &dprm, inflow_density, rates_sensitivity_option, (double *)d_rhs,
                                       (double *)d_jac, nullptr));
+    const int bad = gb_count_nonfinite_members_batch(n, ns + 1, (const double *)d_rhs, (long)(ns + 1) * (ns + 1),
+                                                     (const double *)d_jac, nullptr, nullptr);
     CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * (size_t)n * (ns + 1), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * (size_t)n * (ns + 1) * (ns + 1), cudaMemcpyDeviceToHost));
-    return GB_OK;
+    return bad;
   }
 }
 
@@ -879,8 +897,10 @@ extern "C"
     RC(scratch(m, 2, sizeof(double) * nv, &d_rhs));
     CK(cudaMemcpy(d_state, state, sizeof(double) * nv, cudaMemcpyHostToDevice));
     RC(gb_flamelet_rhs_batch(m, F, (double *)d_state, &st.dp, (double *)d_rhs, nullptr));
+    const int bad = gb_count_nonfinite_members_batch(F, (long)prm->nzi * ns, (const double *)d_rhs, 0, nullptr, nullptr,
+                                                     nullptr);
     CK(cudaMemcpy(out_rhs, d_rhs, sizeof(double) * nv, cudaMemcpyDeviceToHost));
-    return GB_OK;
+    return bad; // > 0: flamelets whose right-hand side holds an Inf or NaN
   }
 
   int gb_flamelet_jacobian_host(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
@@ -905,9 +925,10 @@ extern "C"
     RC(gb_flamelet_jacobian_batch(m, F, (double *)d_state, &st.dp, compute_eigenvalues, diffterm, scale_and_offset,
                                   prefactor, rates_sensitivity_option, sensitivity_transform_option, (double *)d_eig,
                                   (double *)d_jac, nullptr));
+    const int bad = gb_count_nonfinite_members_batch(F, (long)(nj / F), (const double *)d_jac, 0, nullptr, nullptr, nullptr);
     CK(cudaMemcpy(out_jac, d_jac, sizeof(double) * nj, cudaMemcpyDeviceToHost));
     if (compute_eigenvalues && out_expeig)
       CK(cudaMemcpy(out_expeig, d_eig, sizeof(double) * nv, cudaMemcpyDeviceToHost));
-    return GB_OK;
+    return bad; // > 0: flamelets whose Jacobian holds an Inf or NaN
   }
 }

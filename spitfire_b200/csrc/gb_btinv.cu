@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <type_traits>
 
 #include "../../include/griffon_b200.h"
 #include "gb_kernels.cuh"
@@ -41,6 +42,16 @@ constexpr int INT_ = IW * 32; // threads per CTA
 #ifdef GB_JAC_TIMELINE
 __device__ long long g_inv_timeline[8];
 #endif
+
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+  if constexpr (I < N)
+  {
+    f(std::integral_constant<int, I>{});
+    static_for<N, I + 1>(f);
+  }
+}
 
 // reciprocal by MUFU.RCP64H and three Newton steps (the last one on the residual): within an ulp of 1/x for normal x,
 // without the range checks and the slow path of the IEEE division (the pivot's reciprocal sits on the critical path of
@@ -82,8 +93,9 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
     const double *subd = M + (size_t)nb * nb2, *supd = subd + (size_t)(nb - 1) * bs;
     double *Lv = l_values + (size_t)sys * nb * nb2;
     double *Di = dinv + (size_t)sys * nb * nb2;
-    double S[R][C], Dn[R][C];
-    auto load_block = [&](int i, double (&dst)[R][C]) {
+    double S[R][C], Dn[R][C], subn[R], supn[C];
+    // block i into registers, with the off-diagonal entries that turn it into D'_i (sub_{i-1} by row, sup_{i-1} by column)
+    auto load_block = [&](int i) {
       const double *D = M + (size_t)i * nb2;
 #pragma unroll
       for (int b = 0; b < C; ++b)
@@ -93,11 +105,15 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
         for (int a = 0; a < R; ++a)
         {
           const int row = lane + 32 * a;
-          dst[a][b] = (row < bs && col < bs) ? __ldg(D + (size_t)col * bs + row) : 0.;
+          Dn[a][b] = (row < bs && col < bs) ? __ldg(D + (size_t)col * bs + row) : 0.;
         }
+        supn[b] = (i > 0 && col < bs) ? __ldg(supd + (size_t)(i - 1) * bs + col) : 0.;
       }
+#pragma unroll
+      for (int a = 0; a < R; ++a)
+        subn[a] = (i > 0 && lane + 32 * a < bs) ? __ldg(subd + (size_t)(i - 1) * bs + lane + 32 * a) : 0.;
     };
-    load_block(0, Dn);
+    load_block(0);
     __syncthreads(); // the previous system is done with the shared arrays
     for (int i = 0; i < nb; ++i)
     {
@@ -113,9 +129,9 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
           double v = Dn[a][b];
           if (i > 0 && row < bs && col < bs)
           {
-            const double l = __ldg(subd + (size_t)(i - 1) * bs + row) * sInv[(size_t)col * bs + row];
+            const double l = subn[a] * sInv[(size_t)col * bs + row];
             Lv[(size_t)i * nb2 + (size_t)col * bs + row] = l;
-            v = v - l * __ldg(supd + (size_t)(i - 1) * bs + col);
+            v = v - l * supn[b];
           }
           else if (i == 0 && row < bs && col < bs)
             Lv[(size_t)col * bs + row] = 0.; // (block 0 of l_values is never read; defined for reproducibility)
@@ -123,86 +139,141 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
         }
       }
       if (i + 1 < nb)
-        load_block(i + 1, Dn); // lands during the elimination
-      // ---- Gauss-Jordan with implicit partial pivoting -----------------------------------------------------------
+        load_block(i + 1); // lands during the elimination
+      // ---- Gauss-Jordan with implicit partial pivoting ---------------------------------------------------------------
+      // Step k: the warp that owns column k ("owner") finds the pivot and publishes {pivot row, 1/pivot, column k};
+      // every warp then updates its columns. The owner of step k+1 runs ahead: as soon as step k's data is there it
+      // updates column k+1 alone, searches, publishes and ARRIVES at step k+1's named barrier without waiting, and
+      // only then finishes its other columns -- so the pivot search of the next step hides under the updates of this
+      // one. The other warps SYNC on that barrier when they get there. Two barrier ids and two publish buffers
+      // alternate; an owner keeps what it published in registers and never re-reads it.
       unsigned int used = 0; // bit a: my row lane + 32a has been a pivot
+      int p_cur = 0;
+      double r_cur = 0., c_cur[R];
 #pragma unroll
-      for (int bk = 0; bk < C; ++bk)
-      {
+      for (int a = 0; a < R; ++a)
+        c_cur[a] = 0.;
+      // pivot search on my column slot B (compile-time) for step k1, published into buffer k1 & 1
+      auto search_publish = [&](auto B, int k1, int &p_o, double &r_o, double (&c_o)[R]) {
+        constexpr int b1 = decltype(B)::value;
+        // Row of maximum modulus among the unused rows, compared on the upper 32 bits of |a| (sign-free exponent and
+        // 20 mantissa bits: entries within 1e-6 of each other may tie, the lowest lane wins -- harmless for the
+        // stability of the elimination, and one redux.sync instead of three): key = bits + 1, 0 for rows out of play.
+        unsigned int key = 0u;
+        int krow = 0;
+        double kval = 0.;
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          const int row = lane + 32 * a;
+          if (row < bs && !((used >> a) & 1u))
+          {
+            const unsigned int kk = (unsigned int)__double2hiint(fabs(S[a][b1])) + 1u;
+            if (kk > key)
+              key = kk, krow = row, kval = S[a][b1];
+          }
+        }
+        const unsigned int m1 = __reduce_max_sync(0xffffffffu, key);
+        const int src = __ffs(__ballot_sync(0xffffffffu, key == m1)) - 1;
+        p_o = __shfl_sync(0xffffffffu, krow, src);
+        const double pv = __shfl_sync(0xffffffffu, kval, src);
+        r_o = fast_rcp(pv);
+        const int buf1 = k1 & 1;
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          c_o[a] = S[a][b1];
+          sf[buf1 * fstride + lane + 32 * a] = c_o[a];
+        }
+        if (lane == 0)
+        {
+          srinv[buf1] = r_o;
+          sp[buf1] = p_o;
+          sperm[k1] = p_o;
+          sinvp[p_o] = k1;
+        }
+        // (bar.arrive orders the stores above before the barrier completes for the threads that bar.sync on it: the
+        // producer / consumer pattern of the PTX manual; an explicit fence here costs ~150 cycles on the critical path)
+        asm volatile("bar.arrive %0, %1;" ::"r"(1 + buf1), "r"(INT_) : "memory");
+      };
+      // one column slot of the step's update; kcol: this is column k itself (owner only)
+      auto update_col = [&](auto B, bool kcol, int pa, int pl, bool mine_p) {
+        constexpr int b = decltype(B)::value;
+        double sel = S[0][b];
+#pragma unroll
+        for (int a = 1; a < R; ++a)
+          if (pa == a)
+            sel = S[a][b];
+        const double prs = __shfl_sync(0xffffffffu, sel, pl) * r_cur; // scaled pivot-row entry of my column
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+        {
+          const bool prow = mine_p && pa == a;
+          if (kcol)
+            S[a][b] = prow ? r_cur : -(c_cur[a] * r_cur);
+          else
+            S[a][b] = prow ? prs : fma(-c_cur[a], prs, S[a][b]);
+        }
+      };
+      if (warp == 0)
+        search_publish(std::integral_constant<int, 0>{}, 0, p_cur, r_cur, c_cur);
+      static_for<C>([&](auto BK) {
+        constexpr int bk = decltype(BK)::value;
+        constexpr int bk1 = bk + 1 < C ? bk + 1 : bk;
         for (int wk = 0; wk < IW; ++wk)
         {
           const int k = wk + IW * bk;
           if (k >= bs)
             break;
           const int buf = k & 1;
-          if (warp == wk)
+          const bool own = warp == wk;
+          if (!own)
           {
-            // Row of maximum modulus among the unused rows, compared on the upper 32 bits of |a| (sign-free exponent
-            // and 20 mantissa bits: entries within 1e-6 of each other may tie, the lowest lane wins -- harmless for
-            // the stability of the elimination and it takes one redux.sync instead of three): key = bits + 1, 0 for rows
-            // out of play.
-            unsigned int key = 0u;
-            int krow = 0;
-            double kval = 0.;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + buf), "r"(INT_) : "memory");
+            p_cur = sp[buf];
+            r_cur = srinv[buf];
 #pragma unroll
             for (int a = 0; a < R; ++a)
-            {
-              const int row = lane + 32 * a;
-              if (row < bs && !((used >> a) & 1u))
-              {
-                const unsigned int kk = (unsigned int)__double2hiint(fabs(S[a][bk])) + 1u;
-                if (kk > key)
-                  key = kk, krow = row, kval = S[a][bk];
-              }
-            }
-            const unsigned int m1 = __reduce_max_sync(0xffffffffu, key);
-            const int src = __ffs(__ballot_sync(0xffffffffu, key == m1)) - 1;
-            const int p = __shfl_sync(0xffffffffu, krow, src);
-            const double pv = __shfl_sync(0xffffffffu, kval, src);
-#pragma unroll
-            for (int a = 0; a < R; ++a)
-              sf[buf * fstride + lane + 32 * a] = S[a][bk];
-            if (lane == 0)
-            {
-              srinv[buf] = fast_rcp(pv);
-              sp[buf] = p;
-              sperm[k] = p;
-              sinvp[p] = k;
-            }
+              c_cur[a] = sf[buf * fstride + lane + 32 * a];
           }
-          __syncthreads();
-          const int p = sp[buf];
-          const double rinv = srinv[buf];
-          double colk[R];
-#pragma unroll
-          for (int a = 0; a < R; ++a)
-            colk[a] = sf[buf * fstride + lane + 32 * a];
-          const int pa = p >> 5, pl = p & 31;
+          const int pa = p_cur >> 5, pl = p_cur & 31;
           const bool mine_p = lane == pl;
           if (mine_p)
             used |= 1u << pa;
+          // look-ahead: the owner of step k+1 brings its column k+1 up to date first and publishes
+          const bool own1 = (k + 1 < bs) && warp == ((wk + 1) & (IW - 1));
+          const bool ahead_same = own1 && wk < IW - 1;               // column k+1 sits in my slot bk
+          const bool ahead_next = own1 && wk == IW - 1 && bk + 1 < C; // ... in my slot bk + 1
+          int p_n = 0;
+          double r_n = 0., c_n[R];
 #pragma unroll
-          for (int b = 0; b < C; ++b)
+          for (int a = 0; a < R; ++a)
+            c_n[a] = 0.;
+          if (ahead_same)
           {
-            double sel = S[0][b];
-#pragma unroll
-            for (int a = 1; a < R; ++a)
-              if (pa == a)
-                sel = S[a][b];
-            const double prs = __shfl_sync(0xffffffffu, sel, pl) * rinv; // scaled pivot-row entry of my column
-            const bool is_k = (b == bk) && (warp == wk);
+            update_col(std::integral_constant<int, bk>{}, false, pa, pl, mine_p);
+            search_publish(std::integral_constant<int, bk>{}, k + 1, p_n, r_n, c_n);
+          }
+          if (ahead_next)
+          {
+            update_col(std::integral_constant<int, bk1>{}, false, pa, pl, mine_p);
+            search_publish(std::integral_constant<int, bk1>{}, k + 1, p_n, r_n, c_n);
+          }
+          static_for<C>([&](auto B) {
+            constexpr int b = decltype(B)::value;
+            if (!((ahead_same && b == bk) || (ahead_next && b == bk + 1)))
+              update_col(B, own && b == bk, pa, pl, mine_p);
+          });
+          if (own1)
+          {
+            p_cur = p_n;
+            r_cur = r_n;
 #pragma unroll
             for (int a = 0; a < R; ++a)
-            {
-              const bool prow = mine_p && pa == a;
-              if (is_k)
-                S[a][b] = prow ? rinv : -(colk[a] * rinv);
-              else
-                S[a][b] = prow ? prs : fma(-colk[a], prs, S[a][b]);
-            }
+              c_cur[a] = c_n[a];
           }
         }
-      }
+      });
       __syncthreads(); // sperm / sinvp complete; everybody is done reading sInv of the previous block
       // ---- undo the permutation: S[r][m] is entry (step of r, pivot row of step m) of the inverse -----------------------
 #pragma unroll

@@ -15,7 +15,9 @@
 // sees exactly the numbers the serial code would produce for it.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <string>
 
 #include "../../include/griffon_b200.h"
 #include "gb_kernels.cuh"
@@ -191,6 +193,47 @@ __global__ void __launch_bounds__(NT) k_accept_step(int ndof, const double *__re
   }
 }
 
+// flags[m] = member m of a (and b) holds a non-finite value; *count += 1 per such member. One warp per member.
+__global__ void __launch_bounds__(256) k_nonfinite_members(int n, long la, const double *__restrict__ a, long lb,
+                                                           const double *__restrict__ b, int *__restrict__ flags,
+                                                           int *__restrict__ count)
+{
+  const int lane = threadIdx.x & 31;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long m = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < n; m += nw)
+  {
+    int bad = 0;
+    const unsigned long long *pa = reinterpret_cast<const unsigned long long *>(a) + m * la;
+    for (long i = lane; i < la; i += 32)
+      bad |= ((pa[i] >> 52) & 0x7ffull) == 0x7ffull;
+    if (b)
+    {
+      const unsigned long long *pb = reinterpret_cast<const unsigned long long *>(b) + m * lb;
+      for (long i = lane; i < lb; i += 32)
+        bad |= ((pb[i] >> 52) & 0x7ffull) == 0x7ffull;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0)
+    {
+      if (flags)
+        flags[m] = bad;
+      if (bad)
+        atomicAdd(count, 1);
+    }
+  }
+}
+
+int *device_counter()
+{
+  static int *ctr[16] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16)
+    return nullptr;
+  if (!ctr[dev] && cudaMalloc(&ctr[dev], sizeof(int)) != cudaSuccess)
+    ctr[dev] = nullptr;
+  return ctr[dev];
+}
+
 int check_n(int n, int ndof)
 {
   if (n < 0 || ndof <= 0)
@@ -211,6 +254,40 @@ int cuda_rc(const char *what)
   return GB_OK;
 }
 } // namespace
+
+// the non-finite member count in three steps, so that a pipelined host entry point can accumulate over its chunks
+int nonfinite_reset(cudaStream_t st)
+{
+  int *ctr = device_counter();
+  if (!ctr || cudaMemsetAsync(ctr, 0, sizeof(int), st) != cudaSuccess)
+  {
+    set_error("non-finite count: no device counter");
+    return GB_ERR_CUDA;
+  }
+  return GB_OK;
+}
+int nonfinite_accumulate(int n, long la, const double *a, long lb, const double *b, int *flags, cudaStream_t st)
+{
+  int *ctr = device_counter();
+  if (!ctr)
+    return GB_ERR_CUDA;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<long>(((long)n + 7) / 8, (long)sms * 8);
+  k_nonfinite_members<<<grid, 256, 0, st>>>(n, la, a, lb, b, flags, ctr);
+  ++g_btddod_launches;
+  return cuda_rc("k_nonfinite_members");
+}
+int nonfinite_read(cudaStream_t st)
+{
+  int host = 0;
+  int *ctr = device_counter();
+  if (!ctr || cudaMemcpyAsync(&host, ctr, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return cuda_rc("non-finite count read-back");
+  return host;
+}
 } // namespace gb
 
 using namespace gb;
@@ -298,6 +375,26 @@ extern "C"
     k_esdirk_finish<<<n, NT, 0, (cudaStream_t)stream>>>(ndof, n, nk, kp, dt, weights, dq, stats);
     ++g_btddod_launches;
     return cuda_rc("k_esdirk_finish");
+  }
+
+  int gb_count_nonfinite_members_batch(int n, long len_a, const double *a, long len_b, const double *b, int *flags_out,
+                                       void *stream)
+  {
+    if (n < 0 || len_a <= 0 || (n > 0 && !a) || (b && len_b <= 0))
+    {
+      set_error("gb_count_nonfinite_members_batch: bad sizes or null array");
+      return GB_ERR_ARG;
+    }
+    if (n == 0)
+      return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = nonfinite_reset(st);
+    if (rc != GB_OK)
+      return rc;
+    rc = nonfinite_accumulate(n, len_a, a, len_b, b, flags_out, st);
+    if (rc != GB_OK)
+      return rc;
+    return nonfinite_read(st);
   }
 
   int gb_accept_step_batch(int n, int ndof, const double *dq, const int *accept, int clip_negative, double *q,

@@ -347,6 +347,16 @@ class _BatchOps(object):
                 self.g.btddod_full_solve(Jn[k], Ln[k], pn[k], np.ascontiguousarray(rn[k]), self.nzi, self.ns, xn[k])
         return x
 
+    def nonfinite_rows(self, a, b):
+        """bool [n]: the member's row of a or of b holds an Inf or NaN. On the device one kernel writes the flags
+        (gb_count_nonfinite_members_batch), on the host the tensor expressions do."""
+        torch = self.torch
+        if self.on_device:
+            flags = torch.empty(a.shape[0], dtype=torch.int32, device=self.device)
+            self.gmod.count_nonfinite_members(a.contiguous(), b.contiguous(), flags)
+            return flags.bool()
+        return ~torch.isfinite(a).all(dim=1) | ~torch.isfinite(b).all(dim=1)
+
     def add_to_block_diagonal(self, J, matrix_scale, diagonal, diag_scale):
         """J <- matrix_scale*J + diag_scale*diag(diagonal) for every system (btddod_scale_and_add_diagonal)"""
         n = J.shape[0]
@@ -417,11 +427,10 @@ class FlameletBatch(object):
                 ops.factorize_into(factors, ij, Jn)
                 need_jac[ij] = False
             dstate = ops.solve(factors, rhs.index_select(0, idx), rows=idx)
-            bad = ~torch.isfinite(dstate).all(dim=1)
             norm_old = self._norm(rhs.index_select(0, idx) * inv_scales.index_select(0, idx), norm_order)
             s_act = state.index_select(0, idx)
             rhs_new = ops.rhs(s_act + dstate, idx)
-            bad |= ~torch.isfinite(rhs_new).all(dim=1)
+            bad = ops.nonfinite_rows(dstate, rhs_new)  # (the reference's NaN / Inf scans, flamelet.py:1435, 1443)
             alpha = torch.ones(idx.numel(), dtype=torch.float64, device=dev)
             while True:
                 nrm = self._norm(rhs_new * inv_scales.index_select(0, idx), norm_order)
@@ -533,11 +542,10 @@ class FlameletBatch(object):
             jac_age[aged] += 1
             need_jac[idx] = (jac_age.index_select(0, idx) == jac_refresh_age) | (res.index_select(0, idx) > 1.e-2)
             dstate = ops.solve(factors, rhs.index_select(0, idx), rows=idx)
-            bad = ~torch.isfinite(dstate).all(dim=1)
             norm_old = self._norm(rhs.index_select(0, idx) * inv_scales.index_select(0, idx), norm_order)
             s_act = state.index_select(0, idx)
             rhs_new = ops.rhs(s_act + dstate, idx)
-            bad |= ~torch.isfinite(rhs_new).all(dim=1)
+            bad = ops.nonfinite_rows(dstate, rhs_new)  # (the reference's NaN / Inf scans, flamelet.py:1435, 1443)
             alpha = torch.ones(idx.numel(), dtype=torch.float64, device=dev)
             while True:
                 nrm = self._norm(rhs_new * inv_scales.index_select(0, idx), norm_order)

@@ -105,6 +105,7 @@ def load_library():
     sig('gb_newton_tail_batch', I, [I, I, V, V, V, V, V, D, V, D, V, V, V, V, V, ip, V])
     sig('gb_esdirk_finish_batch', I, [I, I, I, PP, dp, dp, V, V, V, V, V])
     sig('gb_accept_step_batch', I, [I, I, V, V, I, V, V])
+    sig('gb_count_nonfinite_members_batch', I, [I, L, V, L, V, V, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
     sig('gb_btddod_full_matvec_host', I, [I, V, V, I, I, V])
@@ -114,9 +115,12 @@ def load_library():
 
 
 def check(rc, what):
-    if rc != 0:
+    """raises on a negative status; a positive one is the number of members whose output holds an Inf or NaN
+    (griffon_b200.h: the synchronous *_host entry points report it) and is returned"""
+    if rc < 0:
         msg = load_library().gb_last_error()
         raise GriffonB200Error(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
+    return rc
 
 
 def kernel_launch_count():
@@ -287,13 +291,13 @@ class PyCombustionKernels(MechanismSetters):
     def reactor_rhs_isobaric(self, state, p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_,
                              out_rhs):
         prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
-        check(self._lib.gb_reactor_rhs_isobaric_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)),
+        return check(self._lib.gb_reactor_rhs_isobaric_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)),
               'reactor_rhs_isobaric')
 
     def reactor_jac_isobaric(self, state, p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_,
                              rates_sens_option, sens_transform_option, out_rhs, out_jac):
         prm = self._reactor_params(p, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
-        check(self._lib.gb_reactor_jac_isobaric_host(self._h, 1, _addr(state), C.byref(prm), int(rates_sens_option),
+        return check(self._lib.gb_reactor_jac_isobaric_host(self._h, 1, _addr(state), C.byref(prm), int(rates_sens_option),
                                                      int(sens_transform_option), _addr(out_rhs), _addr(out_jac)),
               'reactor_jac_isobaric')
 
@@ -306,7 +310,7 @@ class PyCombustionKernels(MechanismSetters):
             check(self._lib.gb_reactor_rhs_isobaric_batch(self._h, n, _addr(state), C.byref(prm), _addr(out_rhs),
                                                           _stream()), 'reactor_rhs_isobaric_batch')
         else:
-            check(self._lib.gb_reactor_rhs_isobaric_host(self._h, n, _addr(state), C.byref(prm), _addr(out_rhs)),
+            return check(self._lib.gb_reactor_rhs_isobaric_host(self._h, n, _addr(state), C.byref(prm), _addr(out_rhs)),
                   'reactor_rhs_isobaric')
 
     def reactor_jac_isobaric_batch(self, state, p, out_rhs, out_jac, T_in=0., y_in=None, tau=0., T_inf=0., T_surf=0.,
@@ -321,7 +325,7 @@ class PyCombustionKernels(MechanismSetters):
                                                           _addr(out_rhs), _addr(out_jac), _stream()),
                   'reactor_jac_isobaric_batch')
         else:
-            check(self._lib.gb_reactor_jac_isobaric_host(self._h, n, _addr(state), C.byref(prm),
+            return check(self._lib.gb_reactor_jac_isobaric_host(self._h, n, _addr(state), C.byref(prm),
                                                          int(rates_sens_option), int(sens_transform_option),
                                                          _addr(out_rhs), _addr(out_jac)), 'reactor_jac_isobaric')
 
@@ -329,13 +333,13 @@ class PyCombustionKernels(MechanismSetters):
     def reactor_rhs_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
                               open_, out_rhs):
         prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
-        check(self._lib.gb_reactor_rhs_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
+        return check(self._lib.gb_reactor_rhs_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
                                                       _addr(out_rhs)), 'reactor_rhs_isochoric')
 
     def reactor_jac_isochoric(self, state, rho_in, T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option,
                               open_, rates_sens_option, out_rhs, out_jac):
         prm = self._reactor_params(0., T_in, y_in, tau, T_inf, T_surf, h_conv, eps_rad, SoV, heat_option, open_)
-        check(self._lib.gb_reactor_jac_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
+        return check(self._lib.gb_reactor_jac_isochoric_host(self._h, 1, _addr(state), C.byref(prm), float(rho_in),
                                                       int(rates_sens_option), _addr(out_rhs), _addr(out_jac)),
               'reactor_jac_isochoric')
 
@@ -348,7 +352,7 @@ class PyCombustionKernels(MechanismSetters):
             check(self._lib.gb_reactor_rhs_isochoric_batch(self._h, n, _addr(state), C.byref(prm), float(rho_in),
                                                            _addr(out_rhs), _stream()), 'reactor_rhs_isochoric_batch')
         else:
-            check(self._lib.gb_reactor_rhs_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+            return check(self._lib.gb_reactor_rhs_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
                                                           _addr(out_rhs)), 'reactor_rhs_isochoric')
 
     def reactor_jac_isochoric_batch(self, state, out_rhs, out_jac, rho_in=0., T_in=0., y_in=None, tau=0., T_inf=0.,
@@ -362,7 +366,7 @@ class PyCombustionKernels(MechanismSetters):
                                                            int(rates_sens_option), _addr(out_rhs), _addr(out_jac),
                                                            _stream()), 'reactor_jac_isochoric_batch')
         else:
-            check(self._lib.gb_reactor_jac_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
+            return check(self._lib.gb_reactor_jac_isochoric_host(self._h, n, _addr(state), C.byref(prm), float(rho_in),
                                                           int(rates_sens_option), _addr(out_rhs), _addr(out_jac)),
                   'reactor_jac_isochoric')
 
@@ -426,7 +430,7 @@ class PyCombustionKernels(MechanismSetters):
         prm = self._flamelet_params(p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
                                     mcoeff, ncoeff, chi, include_enthalpy_flux, include_variable_cp,
                                     use_scaled_heat_loss)
-        check(self._lib.gb_flamelet_rhs_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)), 'flamelet_rhs')
+        return check(self._lib.gb_flamelet_rhs_host(self._h, 1, _addr(state), C.byref(prm), _addr(out_rhs)), 'flamelet_rhs')
 
     def flamelet_jacobian(self, state, p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
                           mcoeff, ncoeff, chi, compute_eigenvalues, diffterm, scale_and_offset, prefactor,
@@ -435,7 +439,7 @@ class PyCombustionKernels(MechanismSetters):
         prm = self._flamelet_params(p, oxy, fuel, adiabatic, T_conv, T_rad, h_conv, h_rad, nzi, cmajor, csub, csup,
                                     mcoeff, ncoeff, chi, include_enthalpy_flux, include_variable_cp,
                                     use_scaled_heat_loss)
-        check(self._lib.gb_flamelet_jacobian_host(self._h, 1, _addr(state), C.byref(prm),
+        return check(self._lib.gb_flamelet_jacobian_host(self._h, 1, _addr(state), C.byref(prm),
                                                   int(bool(compute_eigenvalues)), float(diffterm),
                                                   int(bool(scale_and_offset)), float(prefactor),
                                                   int(rates_sens_option), int(sens_transform_option),
@@ -447,7 +451,7 @@ class PyCombustionKernels(MechanismSetters):
             check(self._lib.gb_flamelet_rhs_batch(self._h, int(n_flamelets), _addr(state), C.byref(prm),
                                                   _addr(out_rhs), _stream()), 'flamelet_rhs_batch')
         else:
-            check(self._lib.gb_flamelet_rhs_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+            return check(self._lib.gb_flamelet_rhs_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
                                                  _addr(out_rhs)), 'flamelet_rhs')
 
     def flamelet_jacobian_batch(self, n_flamelets, state, prm, out_jac, compute_eigenvalues=False, diffterm=0.,
@@ -461,7 +465,7 @@ class PyCombustionKernels(MechanismSetters):
                                                        _addr(out_expeig), _addr(out_jac), _stream()),
                   'flamelet_jacobian_batch')
         else:
-            check(self._lib.gb_flamelet_jacobian_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
+            return check(self._lib.gb_flamelet_jacobian_host(self._h, int(n_flamelets), _addr(state), C.byref(prm),
                                                       int(bool(compute_eigenvalues)), float(diffterm),
                                                       int(bool(scale_and_offset)), float(prefactor),
                                                       int(rates_sens_option), int(sens_transform_option),
@@ -570,6 +574,15 @@ def esdirk_finish(ks, b, bh, dt, weights, dq, stats):
     check(load_library().gb_esdirk_finish_batch(int(n), int(ndof), len(ks), _kptrs(ks), _hvec(b), _hvec(bh), _addr(dt),
                                                 _addr(weights), _addr(dq), _addr(stats), _stream()),
           'gb_esdirk_finish_batch')
+
+
+def count_nonfinite_members(a, b=None, flags_out=None):
+    """number of rows of the device tensor a [n, la] (or of b [n, lb]) that hold an Inf or NaN; flags_out (int32 [n],
+    optional) receives the per-row flags. One kernel and one 4-byte read-back instead of isfinite / all / any passes."""
+    n = a.shape[0]
+    return check(load_library().gb_count_nonfinite_members_batch(
+        int(n), int(a.shape[1]), _addr(a), 0 if b is None else int(b.shape[1]), _addr(b),
+        None if flags_out is None else _addr(flags_out, np.int32), _stream()), 'gb_count_nonfinite_members_batch')
 
 
 def accept_step(dq, accept, clip_negative, q):

@@ -107,3 +107,33 @@ def test_fused_stage_loop_reproduces_the_eager_one():
     for a, b in zip(*out):
         assert a.shape == b.shape
         assert np.array_equal(a['temperature'], b['temperature'])
+
+
+@pytest.mark.gpu
+def test_nonfinite_member_count_and_host_status():
+    """'> 0 = number of members with non-finite output' -- as a call of its own on device arrays and as the
+    status of the synchronous host entry points"""
+    import torch
+    from common import build_mech
+    from spitfire_b200 import griffon as gm
+    a = torch.zeros((9, 53), dtype=torch.float64, device='cuda')
+    b = torch.ones((9, 2809), dtype=torch.float64, device='cuda')
+    flags = torch.full((9,), 7, dtype=torch.int32, device='cuda')
+    assert gm.count_nonfinite_members(a, b, flags) == 0 and int(flags.sum()) == 0
+    a[2, 52] = float('nan')
+    b[5, 0] = float('inf')
+    b[2, 100] = -float('inf')
+    assert gm.count_nonfinite_members(a, b, flags) == 2
+    assert flags.tolist() == [0, 0, 1, 0, 0, 1, 0, 0, 0]
+    assert gm.count_nonfinite_members(a) == 1
+    # host entry points: three states, one of them with a NaN temperature
+    m = build_mech('h2-burke', 'gpu')
+    ns = m.n_species
+    st = np.tile(np.concatenate([[1500.], np.full(ns - 1, 1. / ns)]), (3, 1))
+    st[1, 0] = np.nan
+    rhs, jac = np.zeros((3, ns)), np.zeros((3, ns * ns))
+    assert m.griffon.reactor_rhs_isobaric_batch(st, 101325., rhs) == 1
+    assert m.griffon.reactor_jac_isobaric_batch(st, 101325., rhs, jac) == 1
+    assert np.isnan(rhs[1]).any() and np.isfinite(rhs[[0, 2]]).all() and np.isfinite(jac[[0, 2]]).all()
+    st[1, 0] = 1400.
+    assert m.griffon.reactor_jac_isobaric_batch(st, 101325., rhs, jac) == 0
