@@ -291,6 +291,18 @@ int gb_newton_tail_batch(int n, int ndof, const double *fn, const double *xn, co
  * max|(dq - dqh)*weights| (error estimate), max|dq*weights|, 1/0 = every dq finite / not. k, b, bh: HOST arrays. */
 int gb_esdirk_finish_batch(int n, int ndof, int nk, const double *const *k, const double *b, const double *bh,
                            const double *dt, const double *weights, double *dq, double *stats, void *stream);
+/* The whole Newton loop of one implicit stage for F flamelets (time/nonlinear.py:185-268 for a batch): per iteration
+ * dx = solve_inv(factors, res); xn = x - dx; fn = flamelet_rhs(xn); gb_newton_tail_batch(...), until every member has
+ * converged or max_iterations is reached. Arguments as in gb_btddod_full_solve_inv_batch (num_blocks = prm->nzi,
+ * block_size = n_species), gb_flamelet_rhs_batch and gb_newton_tail_batch; work: 3*F*nzi*ns doubles. Synchronous.
+ * Returns the number of members that did not converge (>= 0) or a negative error code; *out_iterations (may be NULL)
+ * receives the number of iterations taken. The host cost of an iteration is four launches and one synchronisation. */
+int gb_flamelet_newton_stage_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                   const double *l_values, const double *dinv, const int *system_rows,
+                                   const double *explicit_, const double *q, const double *dt, double gamma,
+                                   const double *weights, double tolerance, int max_iterations, double *x, double *f,
+                                   double *res, int *conv, double *work, int *n_unconverged, int *out_iterations,
+                                   void *stream);
 /* Status "> 0 = number of members with non-finite output" (SURVEY 8(b)): flags_out[m] (device, may be NULL) = 1 if row m of
  * a [n][len_a] -- or of b [n][len_b], if given -- holds an Inf or NaN. Synchronises the stream and returns the number of
  * such members (>= 0) or a negative error code. The asynchronous *_batch entry points cannot report it themselves; the
@@ -311,6 +323,9 @@ const char *gb_build_info(void);
  * micro-benchmark: Tflop/s (2 flops per multiply-add) and thread-level FP64 instructions per clock and SM.
  * bench.py's second roofline bound. No reference counterpart. */
 int gb_measure_fp64_peak(int kind, double *out_tflops, double *out_inst_per_clk_sm);
+/* dependent-issue latency of the FP64 pipe: cycles per instruction of one warp running one dependent chain of DFMA
+ * (kind 2), DADD (3) or DMUL (4) -- the number every latency-bound kernel of this path is designed around */
+int gb_measure_fp64_latency(int kind, double *out_cycles);
 
 #ifdef __cplusplus
 }

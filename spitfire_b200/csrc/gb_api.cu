@@ -814,6 +814,44 @@ extern "C"
     return GB_OK;
   }
 
+  // The Newton loop of one implicit stage for F flamelets, entirely behind the C-ABI: per iteration the inverse-based
+  // block-Thomas solve, the update, the flamelet right-hand side and the fused residual / norm / convergence kernel
+  // are launched back to back and the host reads one integer. (time/nonlinear.py:185-268 restated for a batch; the
+  // host cost of an iteration is four launches and one synchronisation instead of a Python loop body.)
+  int gb_flamelet_newton_stage_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                     const double *l_values, const double *dinv, const int *system_rows,
+                                     const double *explicit_, const double *q, const double *dt, double gamma,
+                                     const double *weights, double tolerance, int max_iterations, double *x, double *f,
+                                     double *res, int *conv, double *work, int *n_unconverged, int *out_iterations,
+                                     void *stream)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, x, prm, f));
+    if (!d_factors || !l_values || !dinv || !explicit_ || !q || !dt || !weights || !res || !conv || !work || !n_unconverged)
+    {
+      set_error("gb_flamelet_newton_stage_batch: null array");
+      return GB_ERR_ARG;
+    }
+    if (out_iterations)
+      *out_iterations = 0;
+    if (F == 0)
+      return 0;
+    const int ns = m->h.dm.ns, nzi = prm->nzi, ndof = ns * nzi;
+    double *dx = work, *xn = dx + (size_t)F * ndof, *fn = xn + (size_t)F * ndof;
+    int left = F;
+    for (int it = 0; it < max_iterations && left > 0; ++it)
+    {
+      RC(gb_btddod_full_solve_inv_batch(F, d_factors, l_values, dinv, res, nzi, ns, dx, system_rows, stream));
+      RC(gb_newton_update_batch(F, ndof, x, dx, conv, xn, n_unconverged, stream));
+      RC(gb_flamelet_rhs_batch(m, F, xn, prm, fn, stream));
+      RC(gb_newton_tail_batch(F, ndof, fn, xn, explicit_, q, dt, gamma, weights, tolerance, x, f, res, conv,
+                              n_unconverged, &left, stream));
+      if (out_iterations)
+        *out_iterations = it + 1;
+    }
+    return left; // > 0: members that did not converge within max_iterations
+  }
+
   int gb_flamelet_jacobian_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
                                  int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
                                  int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,

@@ -53,21 +53,20 @@ __device__ __forceinline__ void static_for(F &&f)
   }
 }
 
-// reciprocal by MUFU.RCP64H and three Newton steps (the last one on the residual): within an ulp of 1/x for normal x,
+// reciprocal by MUFU.RCP64H and one cubic correction: within an ulp or two of 1/x for normal x,
 // without the range checks and the slow path of the IEEE division (the pivot's reciprocal sits on the critical path of
 // every elimination step). 0 -> inf and non-finite x behave as in a plain division for the purposes of this kernel
 // (the block is singular: the result is non-finite either way).
 __device__ __forceinline__ double fast_rcp(double x)
 {
+  // r0 = 1/x (1 + O(2^-23)); with e = 1 - x r0: 1/x = r0 (1 + e + e^2 + ...) -- the cubic step r0 (1 + e + e^2) leaves
+  // 2^-69 in three dependent FP64 operations (the FP64 pipe's dependent latency is what a pivot step pays for), and
+  // one more residual correction brings the result within an ulp
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.);
+  const double p = fma(e, e, e);
+  return fma(r, p, r);
 }
 
 // R rows per lane (bs <= 32 R), C column slots per warp (bs <= 8 C)
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
       // alternate; an owner keeps what it published in registers and never re-reads it.
       unsigned int used = 0; // bit a: my row lane + 32a has been a pivot
       int p_cur = 0;
-      double r_cur = 0., c_cur[R];
+      double r_cur = 0., c_cur[R], m_cur[R];
 #pragma unroll
       for (int a = 0; a < R; ++a)
         c_cur[a] = 0.;
@@ -204,15 +203,16 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
         for (int a = 1; a < R; ++a)
           if (pa == a)
             sel = S[a][b];
-        const double prs = __shfl_sync(0xffffffffu, sel, pl) * r_cur; // scaled pivot-row entry of my column
+        const double pr = __shfl_sync(0xffffffffu, sel, pl); // pivot-row entry of my column
 #pragma unroll
         for (int a = 0; a < R; ++a)
         {
           const bool prow = mine_p && pa == a;
+          // m_cur = -(column k entry * 1/pivot) does not wait for the shuffle: one FP64 operation after it
           if (kcol)
-            S[a][b] = prow ? r_cur : -(c_cur[a] * r_cur);
+            S[a][b] = prow ? r_cur : m_cur[a];
           else
-            S[a][b] = prow ? prs : fma(-c_cur[a], prs, S[a][b]);
+            S[a][b] = prow ? pr * r_cur : fma(m_cur[a], pr, S[a][b]);
         }
       };
       if (warp == 0)
@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
           const bool mine_p = lane == pl;
           if (mine_p)
             used |= 1u << pa;
+#pragma unroll
+          for (int a = 0; a < R; ++a)
+            m_cur[a] = -(c_cur[a] * r_cur);
           // look-ahead: the owner of step k+1 brings its column k+1 up to date first and publishes
           const bool own1 = (k + 1 < bs) && warp == ((wk + 1) & (IW - 1));
           const bool ahead_same = own1 && wk < IW - 1;               // column k+1 sits in my slot bk

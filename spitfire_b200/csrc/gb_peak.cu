@@ -36,7 +36,64 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     out[0] = sum; // never true: keeps the chains alive
 }
 
+// dependent-issue latency: ONE warp, one chain of dependent DFMA (kind 2), DADD (3) or DMUL (4); cycles per instruction
+template <int KIND>
+__global__ void k_fp64_latency(double *out, long long *cycles, int iters, double a, double b)
+{
+  double x = (double)threadIdx.x * 1e-3;
+  const long long t0 = clock64();
+#pragma unroll 16
+  for (int i = 0; i < iters; ++i)
+  {
+    if (KIND == 2)
+      x = fma(x, a, b);
+    else if (KIND == 3)
+      x = __dadd_rn(x, b);
+    else
+      x = __dmul_rn(x, a);
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0)
+    *cycles = t1 - t0;
+  if (x == 12345.678)
+    out[0] = x;
+}
+
 } // namespace gb
+
+extern "C" int gb_measure_fp64_latency(int kind, double *out_cycles)
+{
+  using namespace gb;
+  double *d = nullptr;
+  long long *c = nullptr, h = 0;
+  if (kind < 2 || kind > 4 || !out_cycles)
+  {
+    set_error("gb_measure_fp64_latency: kind 2 (DFMA), 3 (DADD) or 4 (DMUL)");
+    return GB_ERR_ARG;
+  }
+  if (cudaMalloc(&d, 8) != cudaSuccess || cudaMalloc(&c, 8) != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_error("no CUDA device");
+    return GB_ERR_CUDA;
+  }
+  const int iters = 1 << 16;
+  for (int rep = 0; rep < 2; ++rep)
+  {
+    if (kind == 2)
+      k_fp64_latency<2><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+    else if (kind == 3)
+      k_fp64_latency<3><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+    else
+      k_fp64_latency<4><<<1, 32>>>(d, c, iters, 0.999999, 1e-9);
+  }
+  const cudaError_t e = cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d), cudaFree(c);
+  if (e != cudaSuccess)
+    return GB_ERR_CUDA;
+  *out_cycles = (double)h / iters;
+  return GB_OK;
+}
 
 extern "C" int gb_measure_fp64_peak(int kind, double *out_tflops, double *out_inst_per_clk_sm)
 {

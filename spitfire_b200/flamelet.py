@@ -347,6 +347,19 @@ class _BatchOps(object):
                 self.g.btddod_full_solve(Jn[k], Ln[k], pn[k], np.ascontiguousarray(rn[k]), self.nzi, self.ns, xn[k])
         return x
 
+    def newton_stage(self, fact, rows, idx, key, explicit, q, dt, gamma, weights, tolerance, max_iterations, x, f, res,
+                     conv, work, counter):
+        """device path only: the Newton loop of one implicit stage in one C-ABI call; (members left, iterations)"""
+        prm, keep = self._params(idx, key)
+        if rows is not None:
+            if self._rows32[0] is not rows:
+                self._rows32 = (rows, rows.to(self.torch.int32))
+            rows = self._rows32[1]
+        out = self.g.flamelet_newton_stage_batch(x.shape[0], prm, fact[0], fact[1], fact[3], rows, explicit, q, dt, gamma,
+                                                 weights, tolerance, max_iterations, x, f, res, conv, work, counter)
+        del keep
+        return out
+
     def nonfinite_rows(self, a, b):
         """bool [n]: the member's row of a or of b holds an Inf or NaN. On the device one kernel writes the flags
         (gb_count_nonfinite_members_batch), on the host the tensor expressions do."""

@@ -69,6 +69,7 @@ def load_library():
     sig('gb_kernel_launch_count', L, [])
     sig('gb_build_info', C.c_char_p, [])
     sig('gb_measure_fp64_peak', I, [I, dp, dp])
+    sig('gb_measure_fp64_latency', I, [I, dp])
     sig('gb_thermo_batch', I, [P, I, I, V, V, V, V, V])
     sig('gb_thermo_host', I, [P, I, I, V, V, V, V])
     sig('gb_production_rates_batch', I, [P, I, V, V, V, V, V])
@@ -106,6 +107,7 @@ def load_library():
     sig('gb_esdirk_finish_batch', I, [I, I, I, PP, dp, dp, V, V, V, V, V])
     sig('gb_accept_step_batch', I, [I, I, V, V, I, V, V])
     sig('gb_count_nonfinite_members_batch', I, [I, L, V, L, V, V, V])
+    sig('gb_flamelet_newton_stage_batch', I, [P, I, FP, V, V, V, V, V, V, V, D, V, D, I, V, V, V, V, V, V, ip, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
     sig('gb_btddod_full_matvec_host', I, [I, V, V, I, I, V])
@@ -132,6 +134,13 @@ def measure_fp64_peak(kind=0):
     tf, ipc = C.c_double(0.), C.c_double(0.)
     check(load_library().gb_measure_fp64_peak(int(kind), C.byref(tf), C.byref(ipc)), 'measure_fp64_peak')
     return tf.value, ipc.value
+
+
+def measure_fp64_latency(kind=2):
+    """cycles per dependent FP64 instruction of a single warp: kind 2 = DFMA, 3 = DADD, 4 = DMUL"""
+    c = C.c_double(0.)
+    check(load_library().gb_measure_fp64_latency(int(kind), C.byref(c)), 'measure_fp64_latency')
+    return c.value
 
 
 def _is_torch(x):
@@ -389,6 +398,19 @@ class PyCombustionKernels(MechanismSetters):
 
     def flamelet2d_block_diag_solve(self, *args, **kwargs):
         self._not_on_path('flamelet2d_block_diag_solve')
+
+    def flamelet_newton_stage_batch(self, n_flamelets, prm, d_factors, l_values, dinv, system_rows, explicit, q, dt, gamma,
+                                    weights, tolerance, max_iterations, x, f, res, conv, work, n_unconverged):
+        """the Newton loop of one implicit stage on the device (griffon_b200.h: gb_flamelet_newton_stage_batch); returns
+        (members left unconverged, iterations taken)"""
+        its = C.c_int(0)
+        left = check(self._lib.gb_flamelet_newton_stage_batch(
+            self._h, int(n_flamelets), C.byref(prm), _addr(d_factors), _addr(l_values), _addr(dinv),
+            None if system_rows is None else _addr(system_rows, np.int32), _addr(explicit), _addr(q), _addr(dt),
+            float(gamma), _addr(weights), float(tolerance), int(max_iterations), _addr(x), _addr(f), _addr(res),
+            _addr(conv, np.int32), _addr(work), _addr(n_unconverged, np.int32), C.byref(its), _stream()),
+            'flamelet_newton_stage_batch')
+        return left, its.value
 
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):

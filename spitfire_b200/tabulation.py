@@ -302,55 +302,90 @@ def _expand_enthalpy_defect_dimension_steady(chi_st, managed_dict, flamelet_spec
                                              verbose, input_integration_args, solver_verbose):
     """quasi-steady heat loss at chi_st: continuation in the convection coefficient with an adaptive increment until
     the flamelet extinguishes (tabulation.py:408-519)"""
-    fs = copy.copy(flamelet_specs)
-    fs.initial_condition = table_dict[chi_st]['adiabatic_state']
-    fs.stoich_dissipation_rate = chi_st
-    fs.heat_transfer = 'nonadiabatic'
-    fs.scale_heat_loss_by_temp_range = False
-    fs.scale_convection_by_dissipation = False
-    fs.use_linear_ref_temp_profile = True
-    fs.radiative_emissivity = 0.
-    fs.convection_coefficient = 0.
-    flamelet = Flamelet(fs)
-    state_old = np.copy(flamelet.current_interior_state)
-    hval, dh, diff_target, hval_max = 0., 1.e-1, 1.e-1, 1.e10
-    solutions = [{p: table_dict[chi_st][p] for p in table_dict[chi_st] if p != 'adiabatic_state'}]
-    hvalues = [hval]
-    current_state = table_dict[chi_st]['adiabatic_state']
+    _expand_enthalpy_defect_dimension_steady_batch([chi_st], managed_dict, flamelet_specs, table_dict,
+                                                   h_stoich_spacing, verbose, input_integration_args, solver_verbose)
+
+
+def _expand_enthalpy_defect_dimension_steady_batch(chi_list, managed_dict, flamelet_specs, table_dict,
+                                                   h_stoich_spacing, verbose, input_integration_args, solver_verbose):
+    """the quasi-steady heat-loss continuations (tabulation.py:408-519) of several dissipation rates advanced together:
+    every member keeps its own convection coefficient, increment and extinction test -- the sequence of steady problems
+    it solves is the one the one-at-a-time path solves -- and each round's steady solves share their kernel launches
+    (FlameletBatch.compute_steady_state: Newton, then pseudo-transient continuation, then ESDIRK, member by member)."""
+    if not chi_list:
+        return
     cput0 = perf_counter()
-    first, extinguished = True, False
-    while first or (not extinguished and hval < hval_max):
-        hval += dh
-        first = False
-        fs.convection_coefficient = hval
-        fs.initial_condition = current_state
-        flamelet = Flamelet(fs)
-        g_library = flamelet.compute_steady_state(verbose=solver_verbose)
-        current_state = flamelet.current_interior_state
-        maxT = np.max(current_state)
-        diff_norm = np.max(np.abs(current_state - state_old) / (np.abs(current_state) + 1.e-4))
-        extinguished = maxT < (np.max([flamelet.oxy_stream.T, flamelet.fuel_stream.T]) + 10.)
-        state_old = np.copy(current_state)
-        dh *= np.min([np.max([np.sqrt(diff_target / diff_norm), 0.1]), 2.])
-        hvalues.append(hval)
-        solutions.append({p: g_library[p].ravel() for p in g_library.props})
-    z = flamelet.mixfrac_grid
-    steady_lib = Library(Dimension(_mixture_fraction_name, z),
-                         Dimension(_enthalpy_defect_name + _stoich_suffix, np.array(hvalues)))
-    steady_lib.extra_attributes['mech_spec'] = fs.mech_spec
-    props = [p for p in table_dict[chi_st] if p != 'adiabatic_state']
-    for p in props:
-        values = steady_lib.get_empty_dataset()
-        for ig, sol in enumerate(solutions):
-            values[:, ig] = sol[p].ravel()
-        steady_lib[p] = values
-    z_st = flamelet.mechanism.stoich_mixture_fraction(flamelet.fuel_stream, flamelet.oxy_stream)
-    h_zt = compute_specific_enthalpy(fs.mech_spec, steady_lib)['enthalpy']
-    indices = _subsample_by_stoich_enthalpy(z, z_st, h_zt.T, h_stoich_spacing, include_last=False)
-    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: steady_lib[q][:, i], steady_lib.props, h_zt.T,
-                           indices)
+    diff_target, hval_max = 1.e-1, 1.e10
+
+    class _Member(object):
+        pass
+
+    members = []
+    for chi_st in chi_list:
+        mb = _Member()
+        fs = copy.copy(flamelet_specs)
+        fs.initial_condition = table_dict[chi_st]['adiabatic_state']
+        fs.stoich_dissipation_rate = chi_st
+        fs.heat_transfer = 'nonadiabatic'
+        fs.scale_heat_loss_by_temp_range = False
+        fs.scale_convection_by_dissipation = False
+        fs.use_linear_ref_temp_profile = True
+        fs.radiative_emissivity = 0.
+        fs.convection_coefficient = 0.
+        mb.chi_st, mb.fs = chi_st, fs
+        mb.flamelet = Flamelet(fs)
+        mb.state_old = np.copy(mb.flamelet.current_interior_state)
+        mb.hval, mb.dh = 0., 1.e-1
+        mb.solutions = [{p: table_dict[chi_st][p] for p in table_dict[chi_st] if p != 'adiabatic_state'}]
+        mb.hvalues = [0.]
+        mb.current_state = table_dict[chi_st]['adiabatic_state']
+        mb.first, mb.extinguished = True, False
+        members.append(mb)
+    while True:
+        active = [mb for mb in members if mb.first or (not mb.extinguished and mb.hval < hval_max)]
+        if not active:
+            break
+        for mb in active:
+            mb.hval += mb.dh
+            mb.first = False
+            mb.fs.convection_coefficient = mb.hval
+            mb.fs.initial_condition = mb.current_state
+            mb.flamelet = Flamelet(mb.fs)
+        if len(active) == 1:
+            libs = [active[0].flamelet.compute_steady_state(verbose=solver_verbose)]
+        else:
+            FlameletBatch([mb.flamelet for mb in active]).compute_steady_state(verbose=solver_verbose)
+            libs = [mb.flamelet.make_library_from_interior_state(mb.flamelet.current_interior_state) for mb in active]
+        for mb, g_library in zip(active, libs):
+            flamelet = mb.flamelet
+            mb.current_state = flamelet.current_interior_state
+            maxT = np.max(mb.current_state)
+            diff_norm = np.max(np.abs(mb.current_state - mb.state_old) / (np.abs(mb.current_state) + 1.e-4))
+            mb.extinguished = maxT < (np.max([flamelet.oxy_stream.T, flamelet.fuel_stream.T]) + 10.)
+            mb.state_old = np.copy(mb.current_state)
+            mb.dh *= np.min([np.max([np.sqrt(diff_target / diff_norm), 0.1]), 2.])
+            mb.hvalues.append(mb.hval)
+            mb.solutions.append({p: g_library[p].ravel() for p in g_library.props})
+    for mb in members:
+        flamelet, fs, chi_st = mb.flamelet, mb.fs, mb.chi_st
+        z = flamelet.mixfrac_grid
+        steady_lib = Library(Dimension(_mixture_fraction_name, z),
+                             Dimension(_enthalpy_defect_name + _stoich_suffix, np.array(mb.hvalues)))
+        steady_lib.extra_attributes['mech_spec'] = fs.mech_spec
+        props = [p for p in table_dict[chi_st] if p != 'adiabatic_state']
+        for p in props:
+            values = steady_lib.get_empty_dataset()
+            for ig, sol in enumerate(mb.solutions):
+                values[:, ig] = sol[p].ravel()
+            steady_lib[p] = values
+        z_st = flamelet.mechanism.stoich_mixture_fraction(flamelet.fuel_stream, flamelet.oxy_stream)
+        h_zt = compute_specific_enthalpy(fs.mech_spec, steady_lib)['enthalpy']
+        indices = _subsample_by_stoich_enthalpy(z, z_st, h_zt.T, h_stoich_spacing, include_last=False)
+        _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: steady_lib[q][:, i], steady_lib.props, h_zt.T,
+                               indices)
     if verbose:
-        print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
+        print('{:} quasi-steady heat-loss continuations (chi_st {:8.1e} .. {:8.1e} 1/s) converged in {:6.2f} s'.format(
+            len(chi_list), min(chi_list), max(chi_list), perf_counter() - cput0), flush=True)
 
 
 _pool_job = None
@@ -411,6 +446,9 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
     elif heat_loss_expansion == 'transient' and batch_expansions and len(mine) > 1:
         _expand_enthalpy_defect_dimension_transient_batch(mine, local, flamelet_specs, table_dict, h_stoich_spacing,
                                                           verbose, integration_args, solver_verbose)
+    elif heat_loss_expansion == 'steady' and batch_expansions and len(mine) > 1:
+        _expand_enthalpy_defect_dimension_steady_batch(mine, local, flamelet_specs, table_dict, h_stoich_spacing,
+                                                       verbose, integration_args, solver_verbose)
     else:
         for chi_st in mine:
             expand(chi_st, local, flamelet_specs, table_dict, h_stoich_spacing, verbose, integration_args,
@@ -421,6 +459,26 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
         print('enthalpy defect dimension expanded in {:6.2f} s'.format(perf_counter() - cput0))
         print('-' * 82, flush=True)
     return merged
+
+
+def _interp_columns(x, xp, fp):
+    """np.interp(x, xp, fp[:, j]) for every column j at once (xp increasing, values held constant outside its range):
+    the bracketing interval and the abscissa differences are the same for all columns, so they are found once. Same
+    arithmetic as numpy's kernel -- slope = (fp[k+1] - fp[k]) / (xp[k+1] - xp[k]); slope * (x - xp[k]) + fp[k] -- hence
+    the same bits (tests/test_host_flamelet.py)."""
+    x, xp, fp = np.asarray(x, dtype=np.float64), np.asarray(xp, dtype=np.float64), np.asarray(fp, dtype=np.float64)
+    n = xp.size
+    if n == 1:
+        return np.repeat(fp[:1], x.size, axis=0)
+    k = np.clip(np.searchsorted(xp, x, side='right') - 1, 0, n - 2)
+    slope = (fp[k + 1] - fp[k]) / (xp[k + 1] - xp[k])[:, None]
+    out = slope * (x - xp[k])[:, None] + fp[k]
+    out[x <= xp[0]] = fp[0]
+    out[x >= xp[-1]] = fp[-1]
+    exact = np.nonzero(x == xp[np.clip(k + 1, 0, n - 1)])[0]  # (a knot hit from the left interval returns the knot value)
+    if exact.size:
+        out[exact] = fp[np.clip(k[exact] + 1, 0, n - 1)]
+    return out
 
 
 def _interpolate_to_structured_defect_dimension(unstructured_table, n_defect_stoich, verbose=False, extend=False):
@@ -442,10 +500,7 @@ def _interpolate_to_structured_defect_dimension(unstructured_table, n_defect_sto
         first = unstructured_table[(chi_st, g_sorted[0])]
         for q in first.keys():
             data = np.array([np.asarray(unstructured_table[(chi_st, g)][q], dtype=np.float64) for g in g_sorted])
-            nz = data.shape[1]
-            out = np.empty((defect_space.size, nz))
-            for iz in range(nz):
-                out[:, iz] = np.interp(defect_space, g_sorted, data[:, iz])
+            out = _interp_columns(defect_space, g_sorted, data)
             if extend and q in ('enthalpy', 'enthalpy_defect') and g_sorted.size > 1:
                 lo = defect_space < g_sorted[0]
                 slope = (data[1] - data[0]) / (g_sorted[1] - g_sorted[0])

@@ -30,6 +30,12 @@ _BH = [4586570599. / 29645900160., 0., 178811875. / 945068544., 814220225. / 115
 # the device-resident stage loop (csrc/gb_newton.cu) is used for device batches of up to dense_limit members; False falls
 # back to the eager tensor loop (kept for larger batches, where the iteration runs on the unconverged members only)
 FUSED_NEWTON = True
+# the Newton loop of a stage as ONE C-ABI call (gb_flamelet_newton_stage_batch) where the batch's operations offer it
+STAGE_CALL = True
+import os as _os
+if _os.environ.get('GB_NEWTON_MODE') in ('eager', 'fused', 'stage'):  # (A/B switch for tools/bench_slfm.py)
+    FUSED_NEWTON = _os.environ['GB_NEWTON_MODE'] != 'eager'
+    STAGE_CALL = _os.environ['GB_NEWTON_MODE'] == 'stage'
 
 
 def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, minimum_time_step_count=40,
@@ -122,11 +128,17 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             expl, res = torch.empty_like(qa), torch.empty_like(qa)
             nl_ok = np.ones(n, dtype=bool)
             rows = None if all_active else idx
+            stage_call = STAGE_CALL and use_inv and hasattr(ops, 'newton_stage')
+            work = torch.empty((3,) + tuple(qa.shape), dtype=torch.float64, device=dev) if stage_call else None
             for s in range(1, 6):
                 x, f = qs.clone(), k[-1].clone()
                 gm.esdirk_stage_begin(k[:s], _A[s][:s], _G, dta, x, qa, f, expl, res, conv_i)
                 left = n
-                for it in range(max_nonlinear_iter):
+                if stage_call:  # the whole Newton loop of the stage behind the C-ABI
+                    left, _ = ops.newton_stage(factors, rows, idx, key_all, expl, qa, dta, _G, wa,
+                                               nonlinear_solve_tolerance, max_nonlinear_iter, x, f, res, conv_i, work,
+                                               left_d)
+                for it in range(0 if stage_call else max_nonlinear_iter):
                     dx = ops.solve(factors, res, rows=rows)
                     xn = torch.empty_like(x)
                     gm.newton_update(x, dx, conv_i, xn, left_d)

@@ -90,3 +90,19 @@ def test_homogeneous_reactor_matches_reference_gold(heat_transfer, configuration
     m, lib = run(ORACLE, heat_transfer, configuration)
     print(configuration, heat_transfer, 'steps', lib.time_values.size, 'max rel err T',
           compare_with_gold(m, lib, heat_transfer, configuration=configuration))
+
+
+def test_structured_defect_interpolation_equals_numpy_interp_bit_for_bit():
+    """tabulation.py:629-654 interpolates every property at every grid point with its own `interp` object; the
+    column-wise restatement must return the same bits as np.interp"""
+    from spitfire_b200.tabulation import _interp_columns
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        n, nx, nc = rng.integers(1, 20), rng.integers(1, 40), rng.integers(1, 7)
+        xp = np.sort(rng.standard_normal(n))
+        if n > 1 and np.any(np.diff(xp) == 0):
+            continue
+        fp = rng.standard_normal((n, nc))
+        x = np.concatenate([rng.uniform(xp[0] - 1, xp[-1] + 1, nx), xp[rng.integers(0, n, 3)]])
+        ref = np.stack([np.interp(x, xp, fp[:, j]) for j in range(nc)], axis=1)
+        assert np.array_equal(_interp_columns(x, xp, fp), ref)
