@@ -843,9 +843,9 @@ class Flamelet(object):
             for i in range(neq):
                 state[:, i] = self._state_oxy[i] + (self._state_fuel[i] - self._state_oxy[i]) * z
         elif name == 'equilibrium':
-            for i in range(nzi):
-                q = mix(self._z[1 + i])
-                q.equilibrate('HP')
+            from spitfire_b200.equilibrium import equilibrate_many
+            qs = equilibrate_many([mix(self._z[1 + i]) for i in range(nzi)], 'HP')  # all grid points in one iteration
+            for i, q in enumerate(qs):
                 state[i, :] = np.hstack((q.T, q.Y[:-1]))
         elif name == 'Burke-Schumann':
             zst = m.stoich_mixture_fraction(fuel, oxy)

@@ -458,7 +458,7 @@ class HomogeneousReactorBatch(object):
 
     def integrate(self, stop, first_time_step=1.e-6, max_time_step=1.e6, minimum_time_step_count=40,
                   transient_tolerance=1.e-10, maximum_steps_per_jacobian=1, nonlinear_solve_tolerance=1.e-12,
-                  save_each_step=False, maximum_steps=100000, stop_ignores_minimum=False):
+                  save_each_step=False, maximum_steps=100000, stop_ignores_minimum=False, stop_at_time=None):
         """stop(t, states, residual, nsteps) -> bool tensor, all arguments tensors over the members.
         Returns (times, states, failed): per member arrays of the saved times / states (first and last only unless
         save_each_step)."""
@@ -470,15 +470,17 @@ class HomogeneousReactorBatch(object):
                                transient_tolerance=transient_tolerance,
                                maximum_steps_per_jacobian=maximum_steps_per_jacobian,
                                nonlinear_solve_tolerance=nonlinear_solve_tolerance, save_each_step=save_each_step,
-                               maximum_steps=maximum_steps, stop_ignores_minimum=stop_ignores_minimum)
+                               maximum_steps=maximum_steps, stop_ignores_minimum=stop_ignores_minimum,
+                               stop_at_time=stop_at_time)
 
     def integrate_to_steady(self, steady_tolerance=1.e-6, **kwargs):
         return self.integrate(lambda t, q, residual, nsteps: residual < steady_tolerance, stop_ignores_minimum=True,
                               **kwargs)
 
     def integrate_to_time(self, final_time, **kwargs):
-        """(the step that crosses final_time is not shortened, unlike odesolve's stop_at_time)"""
-        return self.integrate(lambda t, q, residual, nsteps: t >= final_time, **kwargs)
+        """every member lands on final_time exactly: the step that would cross it is shortened, as odesolve's
+        stop_at_time does (integrator.py:590-593)"""
+        return self.integrate(lambda t, q, residual, nsteps: t >= final_time, stop_at_time=float(final_time), **kwargs)
 
     def compute_ignition_delay(self, delta_temperature_ignition=400., minimum_allowable_residual=1.e-12, **kwargs):
         """time at which each member's temperature has risen by delta_temperature_ignition (reactors.py:724-779); NaN for

@@ -43,12 +43,14 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
                     max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
                     fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
                     explicit_inverse_solves=True, save_each_step=True, stop_ignores_minimum=False, dense_limit=148,
-                    fused_newton=None):
+                    fused_newton=None, stop_at_time=None):
     """advance every member of `ops` (flamelet._BatchOps) from q0 [F, ndof] until `stop(t, q, residual, nsteps)` (all
     [F]-shaped tensors; returns a bool tensor) holds for it and it has taken at least minimum_time_step_count steps.
     Returns per member the lists of saved times and states (numpy), initial state included, and a `failed` flag
     (non-finite update that the step-size reduction could not cure within maximum_steps). With save_each_step=False
-    only the initial and the final time / state of every member are returned (large batches of 0-D reactors)."""
+    only the initial and the final time / state of every member are returned (large batches of 0-D reactors).
+    stop_at_time: every member stops at this time exactly -- a step that would cross it is shortened, as odesolve does
+    (integrator.py:590-593, 633) -- in addition to `stop`."""
     torch = ops.torch
     dev = ops.device
     F = q0.shape[0]
@@ -72,7 +74,8 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
     Dinv = torch.zeros_like(L) if use_inv else None
     ones = torch.ones((F, ops.ndof), dtype=torch.float64, device=dev)
     t_hist = [[0.] for _ in range(F)]
-    q_hist = [[q0[f].cpu().numpy().copy()] for f in range(F)]
+    q0_h = q0.cpu().numpy()
+    q_hist = [[q0_h[f].copy()] for f in range(F)]
     residual_full = np.full(F, np.inf)
 
     def dev_idx(a):
@@ -96,6 +99,8 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
         idx = dev_idx(idx_h)
         all_active = n == F
         qa = q if all_active else q.index_select(0, idx)
+        if stop_at_time is not None:  # (the shortened step is the member's step size from here on, as in odesolve)
+            dt[idx_h] = np.where(t[idx_h] + dt[idx_h] > stop_at_time, stop_at_time - t[idx_h], dt[idx_h])
         dta_h = dt[idx_h]
         dta = dev_vec(dta_h)
         # ---- projector: prefactor*J - I with prefactor = gamma*dt, for the members flagged for a refresh ----------------
@@ -265,6 +270,8 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
         done = stop(dev_vec(t), q, dev_vec(residual_full), dev_idx(nsteps)).cpu().numpy()
         if not stop_ignores_minimum:  # (odesolve's stop_at_steady test is not subject to the minimum, integrator.py:633-640)
             done = done & (nsteps >= minimum_time_step_count)
+        if stop_at_time is not None:
+            done = done | (t >= stop_at_time)
         done = done | (attempts > maximum_steps)
         going = going & ~done
     failed = attempts > maximum_steps

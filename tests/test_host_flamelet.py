@@ -106,3 +106,22 @@ def test_structured_defect_interpolation_equals_numpy_interp_bit_for_bit():
         x = np.concatenate([rng.uniform(xp[0] - 1, xp[-1] + 1, nx), xp[rng.integers(0, n, 3)]])
         ref = np.stack([np.interp(x, xp, fp[:, j]) for j in range(nc)], axis=1)
         assert np.array_equal(_interp_columns(x, xp, fp), ref)
+
+
+def test_equilibrate_many_matches_the_one_at_a_time_solver():
+    """the flamelet's 'equilibrium' initial condition solves all grid points in one array iteration; every stream must
+    end where the single-stream Gibbs minimiser puts it (pure streams, trace mixtures and the interior)"""
+    from common import build_mech
+    from spitfire_b200.equilibrium import equilibrate_many
+    for name, fu in (('methane-gri30', 'CH4:1'), ('h2-burke', 'H2:1')):
+        m = build_mech(name, ORACLE)
+        air = m.stream(stp_air=True)
+        fuel = m.stream('TPX', (300., 101325., fu))
+        zs = np.concatenate([[0., 1e-6], np.linspace(0.01, 0.99, 25), [1 - 1e-6, 1.]])
+        mk = lambda z: m.mix_streams([(m.copy_stream(air), 1 - z), (m.copy_stream(fuel), z)], 'mass', 'HP')
+        a = [mk(z) for z in zs]
+        for q in a:
+            q.equilibrate('HP')
+        b = equilibrate_many([mk(z) for z in zs], 'HP')
+        for x, y in zip(a, b):
+            assert abs(x.T - y.T) <= 1e-11 * x.T and np.max(np.abs(x.Y - y.Y)) <= 1e-12

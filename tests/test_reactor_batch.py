@@ -124,7 +124,8 @@ def test_reactor_batch_other_configurations_on_host(heat, mass):
     times, states, failed = b.integrate_to_time(2.e-4, save_each_step=True)
     assert not np.any(failed)
     for k, T in enumerate(T0):
-        lib = make(T).integrate(stop_criteria=lambda t, q, r, n: t >= 2.e-4)
+        lib = make(T).integrate_to_time(2.e-4)
+        assert times[k][-1] == 2.e-4 and lib.time_values[-1] == 2.e-4  # both land on the final time exactly
         assert lib.time_values.size == times[k].size, (heat, mass, lib.time_values.size, times[k].size)
         assert np.allclose(lib.time_values, times[k], rtol=1e-4, atol=1e-14)
         assert np.allclose(lib['temperature'], states[k][:, 0], rtol=1e-4)
