@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
       // alternate; an owner keeps what it published in registers and never re-reads it.
       unsigned int used = 0; // bit a: my row lane + 32a has been a pivot
       int p_cur = 0;
-      double r_cur = 0., c_cur[R], m_cur[R];
+      double r_cur = 0., c_cur[R], m_cur[R], k_cur[R], rs[R];
 #pragma unroll
       for (int a = 0; a < R; ++a)
-        c_cur[a] = 0.;
+        c_cur[a] = 0., rs[a] = 1.;
       // pivot search on my column slot B (compile-time) for step k1, published into buffer k1 & 1
       auto search_publish = [&](auto B, int k1, int &p_o, double &r_o, double (&c_o)[R]) {
         constexpr int b1 = decltype(B)::value;
@@ -195,25 +195,22 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
         // producer / consumer pattern of the PTX manual; an explicit fence here costs ~150 cycles on the critical path)
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + buf1), "r"(INT_) : "memory");
       };
-      // one column slot of the step's update; kcol: this is column k itself (owner only)
-      auto update_col = [&](auto B, bool kcol, int pa, int pl, bool mine_p) {
+      // One column slot of the step's update; kcol: this is column k itself (owner only). Row scaling is DEFERRED: a
+      // pivot row keeps its values (and a 1 in slot k) and remembers the reciprocal of its pivot in rs; Gauss-Jordan
+      // is invariant under row scaling as long as every row is updated with ITS OWN entry of column k, which is what
+      // m_cur holds (0 for the pivot row itself), so the update is one fma per element for every row, and the rows are
+      // scaled once when the block is finished.
+      auto update_col = [&](auto B, bool kcol, int pa, int pl) {
         constexpr int b = decltype(B)::value;
         double sel = S[0][b];
 #pragma unroll
         for (int a = 1; a < R; ++a)
           if (pa == a)
             sel = S[a][b];
-        const double pr = __shfl_sync(0xffffffffu, sel, pl); // pivot-row entry of my column
+        const double pr = __shfl_sync(0xffffffffu, sel, pl) * r_cur; // scaled pivot-row entry of my column
 #pragma unroll
         for (int a = 0; a < R; ++a)
-        {
-          const bool prow = mine_p && pa == a;
-          // m_cur = -(column k entry * 1/pivot) does not wait for the shuffle: one FP64 operation after it
-          if (kcol)
-            S[a][b] = prow ? r_cur : m_cur[a];
-          else
-            S[a][b] = prow ? pr * r_cur : fma(m_cur[a], pr, S[a][b]);
-        }
+          S[a][b] = kcol ? k_cur[a] : fma(m_cur[a], pr, S[a][b]);
       };
       if (warp == 0)
         search_publish(std::integral_constant<int, 0>{}, 0, p_cur, r_cur, c_cur);
@@ -242,7 +239,13 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
             used |= 1u << pa;
 #pragma unroll
           for (int a = 0; a < R; ++a)
-            m_cur[a] = -(c_cur[a] * r_cur);
+          {
+            const bool prow = mine_p && pa == a;
+            m_cur[a] = prow ? 0. : -c_cur[a];
+            k_cur[a] = prow ? 1. : -(c_cur[a] * r_cur); // what slot k of my rows becomes
+            if (prow)
+              rs[a] = r_cur;
+          }
           // look-ahead: the owner of step k+1 brings its column k+1 up to date first and publishes
           const bool own1 = (k + 1 < bs) && warp == ((wk + 1) & (IW - 1));
           const bool ahead_same = own1 && wk < IW - 1;               // column k+1 sits in my slot bk
@@ -254,18 +257,18 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
             c_n[a] = 0.;
           if (ahead_same)
           {
-            update_col(std::integral_constant<int, bk>{}, false, pa, pl, mine_p);
+            update_col(std::integral_constant<int, bk>{}, false, pa, pl);
             search_publish(std::integral_constant<int, bk>{}, k + 1, p_n, r_n, c_n);
           }
           if (ahead_next)
           {
-            update_col(std::integral_constant<int, bk1>{}, false, pa, pl, mine_p);
+            update_col(std::integral_constant<int, bk1>{}, false, pa, pl);
             search_publish(std::integral_constant<int, bk1>{}, k + 1, p_n, r_n, c_n);
           }
           static_for<C>([&](auto B) {
             constexpr int b = decltype(B)::value;
             if (!((ahead_same && b == bk) || (ahead_next && b == bk + 1)))
-              update_col(B, own && b == bk, pa, pl, mine_p);
+              update_col(B, own && b == bk, pa, pl);
           });
           if (own1)
           {
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *
         {
           const int r = lane + 32 * a;
           if (r < bs && m < bs)
-            sInv[(size_t)sperm[m] * bs + sinvp[r]] = S[a][b];
+            sInv[(size_t)sperm[m] * bs + sinvp[r]] = S[a][b] * rs[a]; // (the deferred row scaling)
         }
       }
       __syncthreads();

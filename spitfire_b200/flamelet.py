@@ -14,8 +14,8 @@ Deviations from the reference, all on cold or fallback paths:
   * initial conditions 'equilibrium' / 'unreacted' / 'Burke-Schumann' use spitfire_b200.streams / equilibrium instead of
     Cantera (flamelet.py:525-586);
   * the explosive eigenvalues of the pseudo-transient solver (LAPACK dgeev per grid point inside Griffon in the
-    reference, flamelet_kernels.cpp:1329-1341) are taken with LAPACK on the host from the Jacobian blocks the device
-    produced (a device eigen-solver is the first "next" item of SURVEY 8(f)); they only set the pseudo-time step;
+    reference, flamelet_kernels.cpp:1329-1341) come from the device eigenvalue kernel (csrc/gb_eig.cu: balancing,
+    Hessenberg reduction, Francis QR per block) through the compute_eigenvalues branch of the flamelet Jacobian;
   * the SuperLU linear solver option is not provided (block Thomas only).
 """
 import numpy as np
