@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <string>
 #include <type_traits>
 
@@ -36,8 +37,6 @@ extern std::atomic<long> g_btddod_launches;
 
 namespace
 {
-constexpr int IW = 8;        // warps per CTA
-constexpr int INT_ = IW * 32; // threads per CTA
 
 #ifdef GB_JAC_TIMELINE
 __device__ long long g_inv_timeline[8];
@@ -69,11 +68,12 @@ __device__ __forceinline__ double fast_rcp(double x)
   return fma(r, p, r);
 }
 
-// R rows per lane (bs <= 32 R), C column slots per warp (bs <= 8 C)
-template <int R, int C>
-__global__ void __launch_bounds__(INT_) k_btddod_invert(int nsys, const double *__restrict__ mats, int nb, int bs,
+// IW warps per CTA (a power of two), R rows per lane (bs <= 32 R), C column slots per warp (bs <= IW C)
+template <int R, int C, int IW>
+__global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const double *__restrict__ mats, int nb, int bs,
                                                         double *__restrict__ l_values, double *__restrict__ dinv)
 {
+  constexpr int INT_ = IW * 32;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb2 = bs * bs;
@@ -308,12 +308,12 @@ int inv_fail(cudaError_t e, const char *what)
   return GB_ERR_CUDA;
 }
 
-template <int R, int C>
+template <int R, int C, int IW>
 int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, double *dinv, cudaStream_t st)
 {
   const size_t nb2 = (size_t)bs * bs;
   const size_t smem = sizeof(double) * (nb2 + (nb2 & 1) + 2 * 32 * R + 2) + sizeof(int) * (2 + 2 * 32 * R) + 16;
-  cudaError_t e = cudaFuncSetAttribute(k_btddod_invert<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_btddod_invert<R, C, IW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return inv_fail(e, "k_btddod_invert attribute");
   int dev = 0, sms = 1;
@@ -321,7 +321,7 @@ int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, d
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / smem));
   const int grid = std::min(n, sms * per_sm);
-  k_btddod_invert<R, C><<<grid, INT_, smem, st>>>(n, mats, nb, bs, l_values, dinv);
+  k_btddod_invert<R, C, IW><<<grid, IW * 32, smem, st>>>(n, mats, nb, bs, l_values, dinv);
   ++g_btddod_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? GB_OK : inv_fail(e, "k_btddod_invert");
@@ -342,18 +342,30 @@ extern "C" int gb_btddod_full_invert_batch(int n, const double *matrix, int nb, 
   if (n == 0)
     return GB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // warps per CTA: 8; GB_INVERT_WARPS=16 selects the variants with half the columns per thread (measured 3.24 ms
+  // against 3.01 ms per GRI-128 system: the step is bound by the owner-to-owner dependent chain, not by the width of
+  // a warp's update)
+  static int w16 = -1;
+  if (w16 < 0)
+  {
+    const char *e = getenv("GB_INVERT_WARPS");
+    w16 = (e && atoi(e) == 16) ? 1 : 0;
+  }
   if (bs <= 16)
-    return launch_invert<1, 2>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<1, 2, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   if (bs <= 32)
-    return launch_invert<1, 4>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<1, 2, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
+               : launch_invert<1, 4, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   if (bs <= 56)
-    return launch_invert<2, 7>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
+               : launch_invert<2, 7, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   if (bs <= 64)
-    return launch_invert<2, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
+               : launch_invert<2, 8, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   if (bs <= 96)
-    return launch_invert<3, 12>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<3, 6, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   if (bs <= 128)
-    return launch_invert<4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<4, 8, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
   set_error("gb_btddod_full_invert_batch: block size above 128 is not supported");
   return GB_ERR_UNSUPPORTED;
 }
