@@ -303,6 +303,28 @@ int gb_flamelet_newton_stage_batch(gb_mech *m, int F, const gb_flamelet_params *
                                    const double *weights, double tolerance, int max_iterations, double *x, double *f,
                                    double *res, int *conv, double *work, int *n_unconverged, int *out_iterations,
                                    void *stream);
+/* The Newton tail with a per-member stage machine: like gb_newton_tail_batch, but a member that converges (or has taken
+ * max_iterations) at its stage s stores K[s] = f and prepares stage s+1 itself (explicit part from tableau row s+1 and
+ * K[0..s], first residual), or sets done[m] after the last stage; nlfail[m] records a stage that ran out of
+ * iterations (nonlinear.py:259-268). K: [nstages][n][ndof]; tableau: HOST, nstages x nstages row-major (a[s][j]);
+ * stage / iters / nlfail / done: device int [n]; *n_left counts the members that are not done. The members of a batch
+ * then take the stages of a step independently of each other. */
+int gb_newton_tail_staged_batch(int n, int ndof, int nstages, const double *tableau, int max_iterations, const double *fn,
+                                const double *xn, const double *q, const double *dt, double gamma,
+                                const double *weights, double tolerance, double *x, double *f, double *res,
+                                double *explicit_, double *K, int *stage, int *iters, int *nlfail, int *done,
+                                int *n_left, int *host_count, void *stream);
+/* All implicit stages of one ESDIRK step for F flamelets (methods.py:502-612 for a batch): rounds of {solve_inv, update,
+ * flamelet rhs, staged tail} until every member is done. On entry: K[0] = f(q), (x, f) = (q, K[0]), explicit_ / res
+ * prepared for stage 1 (gb_esdirk_stage_begin_batch), stage[m] = 1, iters = nlfail = done = 0; work: 3*F*nzi*ns
+ * doubles. Synchronous; returns the number of members not done (0) or a negative error code; *out_rounds = rounds of
+ * kernels taken (the largest per-member sum of Newton iterations over the stages). */
+int gb_flamelet_esdirk_stages_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                    const double *l_values, const double *dinv, const int *system_rows, int nstages,
+                                    const double *tableau, const double *q, const double *dt, double gamma,
+                                    const double *weights, double tolerance, int max_iterations, double *x, double *f,
+                                    double *res, double *explicit_, double *K, int *stage, int *iters, int *nlfail,
+                                    int *done, double *work, int *n_left, int *out_rounds, void *stream);
 /* Status "> 0 = number of members with non-finite output" (SURVEY 8(b)): flags_out[m] (device, may be NULL) = 1 if row m of
  * a [n][len_a] -- or of b [n][len_b], if given -- holds an Inf or NaN. Synchronises the stream and returns the number of
  * such members (>= 0) or a negative error code. The asynchronous *_batch entry points cannot report it themselves; the

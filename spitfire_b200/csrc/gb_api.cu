@@ -852,6 +852,46 @@ extern "C"
     return left; // > 0: members that did not converge within max_iterations
   }
 
+  // All implicit stages of one ESDIRK step for F flamelets, the members walking through the stages independently (the
+  // stage machine of gb_newton_tail_staged_batch): rounds of {solve_inv, update, flamelet rhs, staged tail} until every
+  // member has finished its last stage. On entry stage[m] = first implicit stage (1), iters = nlfail = done = 0, K[0] =
+  // f(q), (x, f) = (q, K[0]), explicit / res prepared for stage 1 (gb_esdirk_stage_begin_batch).
+  int gb_flamelet_esdirk_stages_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                      const double *l_values, const double *dinv, const int *system_rows, int nstages,
+                                      const double *tableau, const double *q, const double *dt, double gamma,
+                                      const double *weights, double tolerance, int max_iterations, double *x, double *f,
+                                      double *res, double *explicit_, double *K, int *stage, int *iters, int *nlfail,
+                                      int *done, double *work, int *n_left, int *out_rounds, void *stream)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, x, prm, f));
+    if (!d_factors || !l_values || !dinv || !tableau || !q || !dt || !weights || !res || !explicit_ || !K || !stage ||
+        !iters || !nlfail || !done || !work || !n_left)
+    {
+      set_error("gb_flamelet_esdirk_stages_batch: null array");
+      return GB_ERR_ARG;
+    }
+    if (out_rounds)
+      *out_rounds = 0;
+    if (F == 0)
+      return 0;
+    const int ns = m->h.dm.ns, nzi = prm->nzi, ndof = ns * nzi;
+    double *dx = work, *xn = dx + (size_t)F * ndof, *fn = xn + (size_t)F * ndof;
+    int left = F;
+    const int max_rounds = (nstages - 1) * max_iterations;
+    for (int round = 0; round < max_rounds && left > 0; ++round)
+    {
+      RC(gb_btddod_full_solve_inv_batch(F, d_factors, l_values, dinv, res, nzi, ns, dx, system_rows, stream));
+      RC(gb_newton_update_batch(F, ndof, x, dx, done, xn, n_left, stream));
+      RC(gb_flamelet_rhs_batch(m, F, xn, prm, fn, stream));
+      RC(gb_newton_tail_staged_batch(F, ndof, nstages, tableau, max_iterations, fn, xn, q, dt, gamma, weights, tolerance,
+                                     x, f, res, explicit_, K, stage, iters, nlfail, done, n_left, &left, stream));
+      if (out_rounds)
+        *out_rounds = round + 1;
+    }
+    return left; // 0 once every member has finished its last stage
+  }
+
   int gb_flamelet_jacobian_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
                                  int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
                                  int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,

@@ -133,6 +133,86 @@ __global__ void __launch_bounds__(NT) k_newton_tail(int ndof, const double *__re
   }
 }
 
+// The Newton tail with a per-member STAGE MACHINE: a member that converges (or runs out of iterations) at stage s stores
+// its stage derivative K[s] = f, and, if stages remain, forms the explicit part and the first residual of stage s+1
+// right here -- so the members of a batch walk through the implicit stages of a step independently of each other and
+// a round of kernels (solve, update, rhs, this one) serves every member at whatever stage it is in. The number of
+// rounds of a step is then the largest per-member SUM of Newton iterations, not the sum over the stages of the largest
+// per-member count (measured on config 5: 6.4 k against 15.8 k iterations for the slowest member and the lock-step
+// batch). Each member's arithmetic is unchanged: same expressions, same order (methods.py:560-575, nonlinear.py:204-257).
+struct StageCoef
+{
+  double a[MAXK][MAXK]; // a[s][j], the Butcher tableau rows of the implicit stages
+};
+__global__ void __launch_bounds__(NT) k_newton_tail_staged(int n, int ndof, int nstages, StageCoef sc, int max_iter,
+                                                           const double *__restrict__ fn, const double *__restrict__ xn,
+                                                           const double *__restrict__ q, const double *__restrict__ dt,
+                                                           double gamma, const double *__restrict__ w, double tol,
+                                                           double *__restrict__ x, double *__restrict__ f,
+                                                           double *__restrict__ res, double *__restrict__ expl,
+                                                           double *__restrict__ K, int *__restrict__ stage,
+                                                           int *__restrict__ iters, int *__restrict__ nlfail,
+                                                           int *__restrict__ done, int *__restrict__ n_left)
+{
+  const int m = blockIdx.x;
+  if (done[m])
+    return;
+  const size_t base = (size_t)m * ndof, kstride = (size_t)n * ndof;
+  const double h = dt[m];
+  double nrm = 0.;
+  int bad = 0;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    const double fi = fn[base + i], xi = xn[base + i];
+    const double r = h * (gamma * fi + expl[base + i]) - (xi - q[base + i]);
+    x[base + i] = xi;
+    f[base + i] = fi;
+    res[base + i] = r;
+    const double a = fabs(r * w[base + i]);
+    bad |= (a != a);
+    nrm = fmax(nrm, a);
+  }
+  block_max_nan(nrm, bad);
+  const bool ok = !bad && nrm < tol;
+  const int it = iters[m] + 1, s = stage[m];
+  const bool stage_end = ok || it >= max_iter;
+  __syncthreads(); // (everybody has read iters / stage before thread 0 updates them)
+  if (!stage_end)
+  {
+    if (threadIdx.x == 0)
+    {
+      iters[m] = it;
+      atomicAdd(n_left, 1);
+    }
+    return;
+  }
+  const int s1 = s + 1;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    const double fi = f[base + i];
+    K[(size_t)s * kstride + base + i] = fi;
+    if (s1 < nstages)
+    {
+      double e = sc.a[s1][s1 - 1] * fi; // (K[s] = f, just stored)
+      for (int j = s1 - 2; j >= 0; --j)
+        e = e + sc.a[s1][j] * K[(size_t)j * kstride + base + i];
+      expl[base + i] = e;
+      res[base + i] = h * (gamma * fi + e) - (x[base + i] - q[base + i]);
+    }
+  }
+  if (threadIdx.x == 0)
+  {
+    if (!ok)
+      nlfail[m] = 1;
+    iters[m] = 0;
+    stage[m] = s1;
+    if (s1 < nstages)
+      atomicAdd(n_left, 1);
+    else
+      done[m] = 1;
+  }
+}
+
 // dq = dt*(b0*k0 + b1*k1 + ... ), dqh likewise with bh (left to right, methods.py:598-610); stats[0][m] = max|(dq-dqh)*w|
 // (the error estimate of the PI controller), stats[1][m] = max|dq*w|, stats[2][m] = 1 if every dq is finite else 0
 __global__ void __launch_bounds__(NT) k_esdirk_finish(int ndof, int n, int nk, KPtrs kp, const double *__restrict__ dt,
@@ -354,6 +434,41 @@ extern "C"
       if (cudaMemcpyAsync(host_count, n_unconverged, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaStreamSynchronize(st) != cudaSuccess)
         return cuda_rc("gb_newton_tail_batch: count read-back");
+    }
+    return GB_OK;
+  }
+
+  int gb_newton_tail_staged_batch(int n, int ndof, int nstages, const double *tableau, int max_iterations,
+                                  const double *fn, const double *xn, const double *q, const double *dt, double gamma,
+                                  const double *weights, double tolerance, double *x, double *f, double *res,
+                                  double *explicit_, double *K, int *stage, int *iters, int *nlfail, int *done,
+                                  int *n_left, int *host_count, void *stream)
+  {
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    if (nstages < 2 || nstages > MAXK || !tableau || !fn || !xn || !q || !dt || !weights || !x || !f || !res || !explicit_ ||
+        !K || !stage || !iters || !nlfail || !done || !n_left)
+    {
+      set_error("gb_newton_tail_staged_batch: 2 <= nstages <= 6 and non-null arrays required");
+      return GB_ERR_ARG;
+    }
+    StageCoef sc{};
+    for (int a = 0; a < nstages; ++a)
+      for (int b = 0; b < nstages; ++b)
+        sc.a[a][b] = tableau[a * nstages + b];
+    cudaStream_t st = (cudaStream_t)stream;
+    k_newton_tail_staged<<<n, NT, 0, st>>>(n, ndof, nstages, sc, max_iterations, fn, xn, q, dt, gamma, weights, tolerance,
+                                           x, f, res, explicit_, K, stage, iters, nlfail, done, n_left);
+    ++g_btddod_launches;
+    rc = cuda_rc("k_newton_tail_staged");
+    if (rc != GB_OK)
+      return rc;
+    if (host_count)
+    {
+      if (cudaMemcpyAsync(host_count, n_left, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        return cuda_rc("gb_newton_tail_staged_batch: count read-back");
     }
     return GB_OK;
   }

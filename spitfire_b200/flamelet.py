@@ -360,6 +360,21 @@ class _BatchOps(object):
         del keep
         return out
 
+    def esdirk_stages(self, fact, rows, idx, key, tableau, q, dt, gamma, weights, tolerance, max_iterations, x, f, res,
+                      explicit, K, stage, iters, nlfail, done, work, counter):
+        """device path only: every implicit stage of one step in one C-ABI call, the members taking the stages
+        independently of each other; (members not done, rounds of kernels)"""
+        prm, keep = self._params(idx, key)
+        if rows is not None:
+            if self._rows32[0] is not rows:
+                self._rows32 = (rows, rows.to(self.torch.int32))
+            rows = self._rows32[1]
+        out = self.g.flamelet_esdirk_stages_batch(x.shape[0], prm, fact[0], fact[1], fact[3], rows, tableau, q, dt, gamma,
+                                                  weights, tolerance, max_iterations, x, f, res, explicit, K, stage, iters,
+                                                  nlfail, done, work, counter)
+        del keep
+        return out
+
     def nonfinite_rows(self, a, b):
         """bool [n]: the member's row of a or of b holds an Inf or NaN. On the device one kernel writes the flags
         (gb_count_nonfinite_members_batch), on the host the tensor expressions do."""

@@ -107,6 +107,8 @@ def load_library():
     sig('gb_esdirk_finish_batch', I, [I, I, I, PP, dp, dp, V, V, V, V, V])
     sig('gb_accept_step_batch', I, [I, I, V, V, I, V, V])
     sig('gb_count_nonfinite_members_batch', I, [I, L, V, L, V, V, V])
+    sig('gb_newton_tail_staged_batch', I, [I, I, I, dp, I, V, V, V, V, D, V, D, V, V, V, V, V, V, V, V, V, V, ip, V])
+    sig('gb_flamelet_esdirk_stages_batch', I, [P, I, FP, V, V, V, V, I, dp, V, V, D, V, D, I, V, V, V, V, V, V, V, V, V, V, V, ip, V])
     sig('gb_flamelet_newton_stage_batch', I, [P, I, FP, V, V, V, V, V, V, V, D, V, D, I, V, V, V, V, V, V, ip, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
@@ -412,6 +414,24 @@ class PyCombustionKernels(MechanismSetters):
             'flamelet_newton_stage_batch')
         return left, its.value
 
+    def flamelet_esdirk_stages_batch(self, n_flamelets, prm, d_factors, l_values, dinv, system_rows, tableau, q, dt, gamma,
+                                     weights, tolerance, max_iterations, x, f, res, explicit, K, stage, iters, nlfail, done,
+                                     work, n_left):
+        """all implicit stages of one ESDIRK step, members independent of each other (griffon_b200.h:
+        gb_flamelet_esdirk_stages_batch); returns (members not done, rounds of kernels taken)"""
+        ns_ = len(tableau)
+        tab = (C.c_double * (ns_ * ns_))(*[float(tableau[a][b]) if b < len(tableau[a]) else 0. for a in range(ns_)
+                                           for b in range(ns_)])
+        rounds = C.c_int(0)
+        i32 = lambda a: _addr(a, np.int32)
+        left = check(self._lib.gb_flamelet_esdirk_stages_batch(
+            self._h, int(n_flamelets), C.byref(prm), _addr(d_factors), _addr(l_values), _addr(dinv),
+            None if system_rows is None else i32(system_rows), ns_, tab, _addr(q), _addr(dt), float(gamma),
+            _addr(weights), float(tolerance), int(max_iterations), _addr(x), _addr(f), _addr(res), _addr(explicit),
+            _addr(K), i32(stage), i32(iters), i32(nlfail), i32(done), _addr(work), i32(n_left), C.byref(rounds),
+            _stream()), 'flamelet_esdirk_stages_batch')
+        return left, rounds.value
+
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):
         check(self._lib.gb_flamelet_stencils(self._h, dptr(dz), int(nzi), dptr(chi), dptr(inv_lewis),
@@ -575,7 +595,16 @@ def newton_update(x, dx, conv, xn, n_unconverged):
                                                 _addr(n_unconverged, np.int32), _stream()), 'gb_newton_update_batch')
 
 
-_host_count = C.c_int(0)
+import threading as _threading
+
+_tls = _threading.local()  # (batches integrated concurrently from several host threads each read their own count)
+
+
+def _count_slot():
+    c = getattr(_tls, 'count', None)
+    if c is None:
+        c = _tls.count = C.c_int(0)
+    return c
 
 
 def newton_tail(fn, xn, explicit, q, dt, gamma, weights, tolerance, x, f, res, conv, n_unconverged, read_count=True):
@@ -586,9 +615,9 @@ def newton_tail(fn, xn, explicit, q, dt, gamma, weights, tolerance, x, f, res, c
                                               _addr(dt), float(gamma), _addr(weights), float(tolerance), _addr(x),
                                               _addr(f), _addr(res), _addr(conv, np.int32),
                                               _addr(n_unconverged, np.int32),
-                                              C.byref(_host_count) if read_count else None, _stream()),
+                                              C.byref(_count_slot()) if read_count else None, _stream()),
           'gb_newton_tail_batch')
-    return _host_count.value if read_count else None
+    return _count_slot().value if read_count else None
 
 
 def esdirk_finish(ks, b, bh, dt, weights, dq, stats):

@@ -274,6 +274,73 @@ def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_s
         print('chi_st = {:8.1e} 1/s converged in {:6.2f} s'.format(chi_st, perf_counter() - cput0), flush=True)
 
 
+# Concurrent sub-batches of a rank's heat-loss trajectories (see _integrate_heat_loss_in_groups). Measured on config 5
+# (56 trajectories, one B200): 1 group 15.3 s, 4 groups 19.2 s, 8 groups 22.6 s -- the rounds of the groups do not
+# overlap on the device, because a small flamelet batch is spread over all SMs on purpose (k_rates: one tile of a few
+# grid points per SM), so eight small batches cost eight times the latency of one. Off by default; the trajectories
+# are bit-identical either way (the GPU library tests were run with 8 groups).
+TRAJECTORY_GROUPS = 1  # None: chosen from the number of members (at most 8); 1: one lock-step batch
+
+
+def _trajectory_groups(flamelet_specs, n_members):
+    """how many independently advancing groups the heat-loss trajectories of a rank are split into (device path only)"""
+    import os
+    if not _griffon_on_device(flamelet_specs):
+        return 1
+    g = TRAJECTORY_GROUPS if TRAJECTORY_GROUPS is not None else os.environ.get('GB_TRAJECTORY_GROUPS')
+    g = int(g) if g is not None else min(8, n_members // 2)
+    return max(1, min(g, n_members))
+
+
+def _integrate_heat_loss_in_groups(chi_list, flamelet_specs, table_dict, integration_args, groups):
+    """The members of a lock-step batch wait for each other: every Newton iteration of a step is a round of
+    latency-bound kernels that serves all members, and a step takes as many rounds as its SLOWEST member needs -- a
+    different member at different times (measured on config 5: 15.8 k rounds for 56 members against 6.4 k Newton
+    iterations of the longest trajectory on its own). Here the members are dealt to `groups` smaller batches that
+    advance independently of each other: one host thread, one CUDA stream and one Griffon handle (its own work arrays)
+    per group; the kernels of different groups overlap on the device (a round occupies one SM per member), the C-ABI
+    calls release the interpreter lock. Every member's own arithmetic is unchanged, so the trajectories are the ones
+    the single batch computes, bit for bit."""
+    import threading
+
+    import torch
+    from spitfire_b200.mechanism import ChemicalMechanismSpec
+    m = flamelet_specs.mech_spec
+    parts = [list(range(g, len(chi_list), groups)) for g in range(groups)]
+    batches = []
+    for part in parts:  # (construction on the calling thread: it goes through the shared stream / mechanism objects)
+        fs = copy.copy(flamelet_specs)
+        fs.mech_spec = ChemicalMechanismSpec(mech_data=m.mech_data, griffon_factory=m._griffon_factory)
+        fls = [Flamelet(_transient_heat_loss_specs(fs, table_dict, chi_list[k])) for k in part]
+        batches.append((fls, FlameletBatch(fls)))
+    torch.cuda.synchronize()
+    device = torch.cuda.current_device()
+    results, errors = [None] * groups, [None] * groups
+
+    def work(g):
+        try:
+            torch.cuda.set_device(device)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                results[g] = batches[g][1].integrate_for_heat_loss(**integration_args)
+                torch.cuda.current_stream().synchronize()
+        except BaseException as e:  # re-raised on the calling thread
+            errors[g] = e
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in range(groups)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    flamelets, libs, failed = [None] * len(chi_list), [None] * len(chi_list), [None] * len(chi_list)
+    for g, part in enumerate(parts):
+        for j, k in enumerate(part):
+            flamelets[k], libs[k], failed[k] = batches[g][0][j], results[g][0][j], results[g][1][j]
+    return flamelets, libs, failed
+
+
 def _expand_enthalpy_defect_dimension_transient_batch(chi_list, managed_dict, flamelet_specs, table_dict,
                                                       h_stoich_spacing, verbose, input_integration_args,
                                                       solver_verbose):
@@ -283,9 +350,14 @@ def _expand_enthalpy_defect_dimension_transient_batch(chi_list, managed_dict, fl
     if not chi_list:
         return
     cput0 = perf_counter()
-    flamelets = [Flamelet(_transient_heat_loss_specs(flamelet_specs, table_dict, chi_st)) for chi_st in chi_list]
     integration_args = _transient_integration_args(input_integration_args, solver_verbose)
-    libs, failed = FlameletBatch(flamelets).integrate_for_heat_loss(**integration_args)
+    groups = _trajectory_groups(flamelet_specs, len(chi_list))
+    if groups > 1:
+        flamelets, libs, failed = _integrate_heat_loss_in_groups(chi_list, flamelet_specs, table_dict, integration_args,
+                                                                 groups)
+    else:
+        flamelets = [Flamelet(_transient_heat_loss_specs(flamelet_specs, table_dict, chi_st)) for chi_st in chi_list]
+        libs, failed = FlameletBatch(flamelets).integrate_for_heat_loss(**integration_args)
     for chi_st, fl, lib, bad in zip(chi_list, flamelets, libs, failed):
         if bad:
             _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict,

@@ -32,10 +32,18 @@ _BH = [4586570599. / 29645900160., 0., 178811875. / 945068544., 814220225. / 115
 FUSED_NEWTON = True
 # the Newton loop of a stage as ONE C-ABI call (gb_flamelet_newton_stage_batch) where the batch's operations offer it
 STAGE_CALL = True
+# ... and all implicit stages of a step as one call in which every member walks through the stages on its own
+# (gb_flamelet_esdirk_stages_batch): the rounds of kernels of a step are then the largest per-member sum of Newton
+# iterations instead of the sum over the stages of the largest per-member count
+# Measured on config 5 (56 trajectories): 15,792 rounds against 15,815 -- the member that is slowest in a step is slowest
+# at every stage of it, so nothing is gained within a step (the slowest member changes from step to step: the longest
+# trajectory on its own takes 6,447). Off by default; bit-identical to the stage-by-stage loop (tests/test_gpu_newton.py).
+ASYNC_STAGES = False
 import os as _os
-if _os.environ.get('GB_NEWTON_MODE') in ('eager', 'fused', 'stage'):  # (A/B switch for tools/bench_slfm.py)
+if _os.environ.get('GB_NEWTON_MODE') in ('eager', 'fused', 'stage', 'async'):  # (A/B switch for tools/bench_slfm.py)
     FUSED_NEWTON = _os.environ['GB_NEWTON_MODE'] != 'eager'
-    STAGE_CALL = _os.environ['GB_NEWTON_MODE'] == 'stage'
+    STAGE_CALL = _os.environ['GB_NEWTON_MODE'] in ('stage', 'async')
+    ASYNC_STAGES = _os.environ['GB_NEWTON_MODE'] == 'async'
 
 
 def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, minimum_time_step_count=40,
@@ -135,7 +143,22 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             rows = None if all_active else idx
             stage_call = STAGE_CALL and use_inv and hasattr(ops, 'newton_stage')
             work = torch.empty((3,) + tuple(qa.shape), dtype=torch.float64, device=dev) if stage_call else None
-            for s in range(1, 6):
+            async_stages = stage_call and ASYNC_STAGES and hasattr(ops, 'esdirk_stages')
+            if async_stages:
+                K = torch.empty((6,) + tuple(qa.shape), dtype=torch.float64, device=dev)
+                K[0].copy_(k[0])
+                x, f = qa.clone(), k[0].clone()
+                flags = torch.zeros((4, n), dtype=torch.int32, device=dev)  # stage, iterations, failed, done
+                flags[0].fill_(1)
+                gm.esdirk_stage_begin([K[0]], _A[1][:1], _G, dta, x, qa, f, expl, res, conv_i)
+                left, _ = ops.esdirk_stages(factors, rows, idx, key_all, _A, qa, dta, _G, wa, nonlinear_solve_tolerance,
+                                            max_nonlinear_iter, x, f, res, expl, K, flags[0], flags[1], flags[2],
+                                            flags[3], work, left_d)
+                if left:
+                    raise RuntimeError('batched ESDIRK: the stage loop ended with members that are not done')
+                nl_ok = ~(flags[2].cpu().numpy().astype(bool))
+                k = [K[j] for j in range(6)]
+            for s in range(1, 6 if not async_stages else 1):
                 x, f = qs.clone(), k[-1].clone()
                 gm.esdirk_stage_begin(k[:s], _A[s][:s], _G, dta, x, qa, f, expl, res, conv_i)
                 left = n

@@ -94,19 +94,24 @@ def test_fused_stage_loop_reproduces_the_eager_one():
     chis = np.logspace(0, 1, 4)
     table, _, _ = tab.build_adiabatic_slfm_library(specs, chis, verbose=False, _return_intermediates=True)
     out = []
-    for fused in (True, False):
+    # eager tensor loop / device kernels driven from Python / one C-ABI call per stage / one call per step with the
+    # members walking through the stages independently of each other
+    for fused, stage, asyn in ((False, False, False), (True, False, False), (True, True, False), (True, True, True)):
         fls = [Flamelet(tab._transient_heat_loss_specs(specs, table, c)) for c in table.keys()]
         args = tab._transient_integration_args({'transient_tolerance': 1e-10}, False)
-        tb.FUSED_NEWTON = fused
+        saved = tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES
+        tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES = fused, stage, asyn
         try:
             libs, failed = FlameletBatch(fls).integrate_for_heat_loss(**args)
         finally:
-            tb.FUSED_NEWTON = True
+            tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES = saved
         assert not any(failed)
         out.append(libs)
-    for a, b in zip(*out):
-        assert a.shape == b.shape
-        assert np.array_equal(a['temperature'], b['temperature'])
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert a.shape == b.shape
+            assert np.array_equal(a['temperature'], b['temperature'])
+            assert np.array_equal(a['mass fraction H2O'], b['mass fraction H2O'])
 
 
 @pytest.mark.gpu

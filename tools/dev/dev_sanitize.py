@@ -30,3 +30,35 @@ fact2 = ops.factorize(Jn.clone(), with_inverse=True); x2 = ops.solve(fact2, r)
 x3 = ops.solve(fact2, r[1:], rows=torch.tensor([1, 2], device='cuda'))
 mv = torch.zeros_like(r); griffon.py_btddod_full_matvec(Jn, x2, ops.nzi, ops.ns, mv, n_systems=3)
 torch.cuda.synchronize(); print('block thomas ok', float((x1 - x2).abs().max()), float((mv - r).abs().max()), float((x3 - x2[1:]).abs().max()))
+# ---- round-2 kernels: LU-based inverses against the Gauss-Jordan elimination, integrator vector kernels, non-finite scan,
+# the C-level Newton stage loop, isochoric reactor
+ops.gauss_jordan_inverses = False
+fact_lu = ops.factorize(Jn.clone(), with_inverse=True); x_lu = ops.solve(fact_lu, r)
+ops.gauss_jordan_inverses = True
+torch.cuda.synchronize(); print('invert ok', float((x_lu - x2).abs().max()))
+from spitfire_b200.time import batched
+F3, ndof = r.shape
+ks = [r.clone() * (1. + 0.1 * j) for j in range(6)]
+dt = torch.full((F3,), 1e-6, dtype=torch.float64, device='cuda')
+w = 1. / ops.scales
+expl, res = torch.empty_like(r), torch.empty_like(r)
+conv = torch.zeros(F3, dtype=torch.int32, device='cuda'); cnt = torch.zeros(1, dtype=torch.int32, device='cuda')
+x, fq = state.clone(), r.clone()
+griffon.esdirk_stage_begin(ks[:3], batched._A[3][:3], batched._G, dt, x, state, fq, expl, res, conv)
+dx = ops.solve(fact2, res); xn = torch.empty_like(x)
+griffon.newton_update(x, dx, conv, xn, cnt)
+fn = ops.rhs(xn)
+left = griffon.newton_tail(fn, xn, expl, state, dt, batched._G, w, 1e-12, x, fq, res, conv, cnt)
+dq = torch.empty_like(r); stats = torch.empty((3, F3), dtype=torch.float64, device='cuda')
+griffon.esdirk_finish(ks, batched._B, batched._BH, dt, w, dq, stats)
+acc = torch.ones(F3, dtype=torch.int32, device='cuda'); griffon.accept_step(dq, acc, True, x)
+nbad = griffon.count_nonfinite_members(x, dq)
+work = torch.empty((3, F3, ndof), dtype=torch.float64, device='cuda')
+conv.zero_()
+left2, its = ops.newton_stage(fact2, None, ops._all(), None, expl, state, dt, batched._G, w, 1e-12, 3, x, fq, res, conv, work, cnt)
+torch.cuda.synchronize(); print('integrator kernels ok', left, nbad, left2, its)
+iso = np.concatenate([np.full((N, 1), 0.3), st], axis=1)
+d_iso = torch.from_numpy(iso).cuda()
+d_r2 = torch.empty((N, ns + 1), dtype=torch.float64, device='cuda'); d_j2 = torch.empty((N, (ns + 1) ** 2), dtype=torch.float64, device='cuda')
+g.reactor_jac_isochoric_batch(d_iso, d_r2, d_j2)
+torch.cuda.synchronize(); print('isochoric ok', float(d_j2.abs().max()))
