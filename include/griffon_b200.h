@@ -325,6 +325,33 @@ int gb_flamelet_esdirk_stages_batch(gb_mech *m, int F, const gb_flamelet_params 
                                     const double *weights, double tolerance, int max_iterations, double *x, double *f,
                                     double *res, double *explicit_, double *K, int *stage, int *iters, int *nlfail,
                                     int *done, double *work, int *n_left, int *out_rounds, void *stream);
+/* The ASYNCHRONOUS batch integrator (spitfire_b200/time/batched.py: integrate_batch_async): the members of a batch
+ * advance independently of each other across steps. state[m]: 0 = not taking part (waiting for host control or new
+ * factors, or finished), 1 = BEGIN (this round's right-hand side is f(q): it becomes K[0] and the member enters stage 1),
+ * 2 = inside the implicit stages; a member that completes its last stage gets state 0 and stage == nstages.
+ * gb_async_round_kernels launches one kernel of a round: phase 0 update, 1 tail, 2 start (fn = int start flags, dx =
+ * step sizes, both device), 3 accept (fn = dq, dx = stats, max_iterations = clip flag).
+ * gb_flamelet_async_tick_batch does one "tick" on all F members: start the members flagged in host_start with the
+ * step sizes host_dt; rounds {solve_inv, update, flamelet rhs, tail} until a member has completed its stages, no member
+ * is active or max_rounds is reached (state / stage copied to host_state / host_stage after each round); then, if
+ * members completed, the embedded error estimate (b, bh: HOST arrays; dq, stats: device), q <- q + dq (clipped at zero
+ * if clip_negative) for the completed members whose update is finite, and host_stats [3][F], host_nlfail [F] and the
+ * rows of the completed members in host_q [F][ndof] are filled. Returns the rounds taken or a negative error code.
+ * newton_its[m] accumulates the member's Newton iterations; start_d / dtin_d: device work arrays of F ints / doubles. */
+int gb_async_round_kernels(int n, int ndof, int nstages, const double *tableau, int max_iterations, int phase,
+                           const double *fn, double *xn, const double *dx, const double *q, const double *dt,
+                           double gamma, const double *weights, double tolerance, double *x, double *f, double *res,
+                           double *explicit_, double *K, int *state, int *stage, int *iters, int *nlfail,
+                           int *newton_its, void *stream);
+int gb_flamelet_async_tick_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                 const double *l_values, const double *dinv, int nstages, const double *tableau,
+                                 const double *b, const double *bh, double *q, double *dt, double gamma,
+                                 const double *weights, double tolerance, int max_iterations, int clip_negative, double *x,
+                                 double *f, double *res, double *explicit_, double *K, int *state, int *stage, int *iters,
+                                 int *nlfail, int *newton_its, double *work, double *dq, double *stats, int *start_d,
+                                 double *dtin_d, int max_rounds, const int *host_start, const double *host_dt,
+                                 int *host_state, int *host_stage, double *host_stats, int *host_nlfail, double *host_q,
+                                 void *stream);
 /* Status "> 0 = number of members with non-finite output" (SURVEY 8(b)): flags_out[m] (device, may be NULL) = 1 if row m of
  * a [n][len_a] -- or of b [n][len_b], if given -- holds an Inf or NaN. Synchronises the stream and returns the number of
  * such members (>= 0) or a negative error code. The asynchronous *_batch entry points cannot report it themselves; the

@@ -892,6 +892,99 @@ extern "C"
     return left; // 0 once every member has finished its last stage
   }
 
+  // One "tick" of the asynchronous batch integrator for F flamelets, everything device-side in one call:
+  //   1. members flagged in host_start get state 1 (BEGIN) and their step size host_dt[m];
+  //   2. rounds {solve_inv, update, flamelet rhs, tail} for the members in state 1 or 2; after each round the state /
+  //      stage arrays are copied to the host; stop when a member has completed its stages (state 0, stage == nstages),
+  //      no member is active, or max_rounds rounds were taken;
+  //   3. if members completed: embedded error estimate (gb_esdirk_finish_batch), q <- q + dq for those whose update is
+  //      finite, and their statistics, Newton-failure flags and new states are copied to the host.
+  // Returns the number of rounds taken (>= 0) or a negative error code.
+  int gb_flamelet_async_tick_batch(gb_mech *m, int F, const gb_flamelet_params *prm, const double *d_factors,
+                                   const double *l_values, const double *dinv, int nstages, const double *tableau,
+                                   const double *b, const double *bh, double *q, double *dt, double gamma,
+                                   const double *weights, double tolerance, int max_iterations, int clip_negative,
+                                   double *x, double *f, double *res, double *explicit_, double *K, int *state, int *stage,
+                                   int *iters, int *nlfail, int *newton_its, double *work, double *dq, double *stats,
+                                   int *start_d, double *dtin_d, int max_rounds, const int *host_start,
+                                   const double *host_dt, int *host_state, int *host_stage, double *host_stats,
+                                   int *host_nlfail, double *host_q, void *stream)
+  {
+    RC(ready(m));
+    RC(check_flamelet(F, x, prm, f));
+    if (!d_factors || !l_values || !dinv || !tableau || !b || !bh || !q || !dt || !weights || !res || !explicit_ || !K ||
+        !state || !stage || !iters || !nlfail || !newton_its || !work || !dq || !stats || !start_d || !dtin_d ||
+        !host_state || !host_stage || !host_stats || !host_nlfail || !host_q)
+    {
+      set_error("gb_flamelet_async_tick_batch: null array");
+      return GB_ERR_ARG;
+    }
+    if (F == 0)
+      return 0;
+    const int ns = m->h.dm.ns, nzi = prm->nzi, ndof = ns * nzi;
+    double *dx = work, *xn = dx + (size_t)F * ndof, *fn = xn + (size_t)F * ndof;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host_start)
+    {
+      bool any = false;
+      for (int k = 0; k < F; ++k)
+        any = any || host_start[k] != 0;
+      if (any)
+      {
+        if (!host_dt)
+        {
+          set_error("gb_flamelet_async_tick_batch: host_start needs host_dt");
+          return GB_ERR_ARG;
+        }
+        CK(cudaMemcpyAsync(start_d, host_start, sizeof(int) * F, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dtin_d, host_dt, sizeof(double) * F, cudaMemcpyHostToDevice, st));
+        RC(gb_async_round_kernels(F, ndof, nstages, tableau, 0, 2, reinterpret_cast<const double *>(start_d), nullptr,
+                                  dtin_d, q, dt, gamma, weights, tolerance, x, f, res, explicit_, K, state, stage, iters,
+                                  nlfail, newton_its, stream));
+      }
+    }
+    int rounds = 0;
+    bool any_complete = false;
+    while (rounds < max_rounds)
+    {
+      RC(gb_btddod_full_solve_inv_batch(F, d_factors, l_values, dinv, res, nzi, ns, dx, nullptr, stream));
+      RC(gb_async_round_kernels(F, ndof, nstages, tableau, max_iterations, 0, fn, xn, dx, q, dt, gamma, weights, tolerance, x,
+                                f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
+      RC(gb_flamelet_rhs_batch(m, F, xn, prm, fn, stream));
+      RC(gb_async_round_kernels(F, ndof, nstages, tableau, max_iterations, 1, fn, xn, dx, q, dt, gamma, weights, tolerance, x,
+                                f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
+      CK(cudaMemcpyAsync(host_state, state, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(host_stage, stage, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      ++rounds;
+      bool any_active = false;
+      for (int k = 0; k < F; ++k)
+      {
+        any_active = any_active || host_state[k] != 0;
+        any_complete = any_complete || (host_state[k] == 0 && host_stage[k] == nstages);
+      }
+      if (any_complete || !any_active)
+        break;
+    }
+    if (any_complete)
+    {
+      const double *kp[6];
+      for (int j = 0; j < nstages; ++j)
+        kp[j] = K + (size_t)j * F * ndof;
+      RC(gb_esdirk_finish_batch(F, ndof, nstages, kp, b, bh, dt, weights, dq, stats, stream));
+      RC(gb_async_round_kernels(F, ndof, nstages, tableau, clip_negative, 3, dq, nullptr, stats, q, dt, gamma, weights,
+                                tolerance, x, f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
+      CK(cudaMemcpyAsync(host_stats, stats, sizeof(double) * 3 * F, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(host_nlfail, nlfail, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+      for (int k = 0; k < F; ++k)
+        if (host_state[k] == 0 && host_stage[k] == nstages)
+          CK(cudaMemcpyAsync(host_q + (size_t)k * ndof, q + (size_t)k * ndof, sizeof(double) * ndof,
+                             cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    return rounds;
+  }
+
   int gb_flamelet_jacobian_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm,
                                  int compute_eigenvalues, double diffterm, int scale_and_offset, double prefactor,
                                  int rates_sensitivity_option, int sensitivity_transform_option, double *out_expeig,

@@ -213,6 +213,145 @@ __global__ void __launch_bounds__(NT) k_newton_tail_staged(int n, int ndof, int 
   }
 }
 
+// ---- members that advance independently of each other ACROSS steps (time/batched.py: integrate_batch_async) ----------
+// state[m]: 0 = not taking part in this round (waiting for host control / factors, or finished), 1 = BEGIN (the round's
+// right-hand side is f(q): it becomes K[0] and the member enters its first implicit stage), 2 = inside the stages.
+__global__ void __launch_bounds__(NT) k_async_update(int ndof, const double *__restrict__ x, const double *__restrict__ dx,
+                                                     const double *__restrict__ q, const int *__restrict__ state,
+                                                     double *__restrict__ xn)
+{
+  const int m = blockIdx.x, st = state[m];
+  if (st == 0)
+    return; // (xn keeps a finite, stale value: the round's right-hand side of this member is not used)
+  const size_t base = (size_t)m * ndof;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+    xn[base + i] = st == 1 ? q[base + i] : x[base + i] - dx[base + i];
+}
+
+__global__ void __launch_bounds__(NT) k_async_tail(int n, int ndof, int nstages, StageCoef sc, int max_iter,
+                                                   const double *__restrict__ fn, const double *__restrict__ xn,
+                                                   const double *__restrict__ q, const double *__restrict__ dt,
+                                                   double gamma, const double *__restrict__ w, double tol,
+                                                   double *__restrict__ x, double *__restrict__ f, double *__restrict__ res,
+                                                   double *__restrict__ expl, double *__restrict__ K, int *__restrict__ state,
+                                                   int *__restrict__ stage, int *__restrict__ iters,
+                                                   int *__restrict__ nlfail, int *__restrict__ newton_its)
+{
+  const int m = blockIdx.x, st = state[m];
+  if (st == 0)
+    return;
+  const size_t base = (size_t)m * ndof, kstride = (size_t)n * ndof;
+  const double h = dt[m];
+  if (st == 1)
+  { // first stage of a new step: K[0] = f(q), (x, f) = (q, K[0]), explicit part and residual of stage 1
+    for (int i = threadIdx.x; i < ndof; i += NT)
+    {
+      const double fi = fn[base + i], qi = q[base + i];
+      K[base + i] = fi;
+      x[base + i] = qi;
+      f[base + i] = fi;
+      const double e = sc.a[1][0] * fi;
+      expl[base + i] = e;
+      res[base + i] = h * (gamma * fi + e) - (qi - qi);
+    }
+    if (threadIdx.x == 0)
+    {
+      state[m] = 2;
+      stage[m] = 1;
+      iters[m] = 0;
+      nlfail[m] = 0;
+    }
+    return;
+  }
+  double nrm = 0.;
+  int bad = 0;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    const double fi = fn[base + i], xi = xn[base + i];
+    const double r = h * (gamma * fi + expl[base + i]) - (xi - q[base + i]);
+    x[base + i] = xi;
+    f[base + i] = fi;
+    res[base + i] = r;
+    const double a = fabs(r * w[base + i]);
+    bad |= (a != a);
+    nrm = fmax(nrm, a);
+  }
+  block_max_nan(nrm, bad);
+  const bool ok = !bad && nrm < tol;
+  const int it = iters[m] + 1, s = stage[m];
+  const bool stage_end = ok || it >= max_iter;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    newton_its[m] += 1;
+  if (!stage_end)
+  {
+    if (threadIdx.x == 0)
+      iters[m] = it;
+    return;
+  }
+  const int s1 = s + 1;
+  for (int i = threadIdx.x; i < ndof; i += NT)
+  {
+    const double fi = f[base + i];
+    K[(size_t)s * kstride + base + i] = fi;
+    if (s1 < nstages)
+    {
+      double e = sc.a[s1][s1 - 1] * fi;
+      for (int j = s1 - 2; j >= 0; --j)
+        e = e + sc.a[s1][j] * K[(size_t)j * kstride + base + i];
+      expl[base + i] = e;
+      res[base + i] = h * (gamma * fi + e) - (x[base + i] - q[base + i]);
+    }
+  }
+  if (threadIdx.x == 0)
+  {
+    if (!ok)
+      nlfail[m] = 1;
+    iters[m] = 0;
+    stage[m] = s1;
+    if (s1 >= nstages)
+      state[m] = 0; // the step's stages are complete: the host takes over (stage[m] == nstages tells it so)
+  }
+}
+
+// members the host sends into a new step: state 1 (BEGIN), stage 0, their step size
+__global__ void k_async_start(int n, const int *__restrict__ start, const double *__restrict__ dt_in, int *__restrict__ state,
+                              int *__restrict__ stage, double *__restrict__ dt)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n && start[m])
+  {
+    state[m] = 1;
+    stage[m] = 0;
+    dt[m] = dt_in[m];
+  }
+}
+
+// members that have completed the stages of a step (state 0, stage == nstages) and whose update is finite (stats[2]):
+// q <- q + dq, clipped at zero if asked (the accepted step of integrate_batch); stage is reset so that the completion
+// is reported once
+__global__ void __launch_bounds__(NT) k_async_accept(int n, int ndof, int nstages, const double *__restrict__ dq,
+                                                     const double *__restrict__ stats, int clip, const int *__restrict__ state,
+                                                     int *__restrict__ stage, double *__restrict__ q)
+{
+  const int m = blockIdx.x;
+  if (state[m] != 0 || stage[m] != nstages)
+    return;
+  const bool ok = stats[2 * n + m] > 0.5;
+  const size_t base = (size_t)m * ndof;
+  if (ok)
+    for (int i = threadIdx.x; i < ndof; i += NT)
+    {
+      double v = q[base + i] + dq[base + i];
+      if (clip && v < 0.)
+        v = 0.;
+      q[base + i] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    stage[m] = 0;
+}
+
 // dq = dt*(b0*k0 + b1*k1 + ... ), dqh likewise with bh (left to right, methods.py:598-610); stats[0][m] = max|(dq-dqh)*w|
 // (the error estimate of the PI controller), stats[1][m] = max|dq*w|, stats[2][m] = 1 if every dq is finite else 0
 __global__ void __launch_bounds__(NT) k_esdirk_finish(int ndof, int n, int nk, KPtrs kp, const double *__restrict__ dt,
@@ -471,6 +610,50 @@ extern "C"
         return cuda_rc("gb_newton_tail_staged_batch: count read-back");
     }
     return GB_OK;
+  }
+
+  int gb_async_round_kernels(int n, int ndof, int nstages, const double *tableau, int max_iterations, int phase,
+                             const double *fn, double *xn, const double *dx, const double *q, const double *dt,
+                             double gamma, const double *weights, double tolerance, double *x, double *f, double *res,
+                             double *explicit_, double *K, int *state, int *stage, int *iters, int *nlfail,
+                             int *newton_its, void *stream)
+  { // phase 0: the update kernel (before the right-hand side), phase 1: the tail kernel (after it)
+    int rc = check_n(n, ndof);
+    if (rc != GB_OK || n == 0)
+      return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0)
+    {
+      k_async_update<<<n, NT, 0, st>>>(ndof, x, dx, q, state, xn);
+      ++g_btddod_launches;
+      return cuda_rc("k_async_update");
+    }
+    if (phase == 2)
+    { // start: fn = start flags (int, device), dx = step sizes (device); dt is written
+      k_async_start<<<(n + 127) / 128, 128, 0, st>>>(n, reinterpret_cast<const int *>(fn), dx, state, stage,
+                                                     const_cast<double *>(dt));
+      ++g_btddod_launches;
+      return cuda_rc("k_async_start");
+    }
+    if (phase == 3)
+    { // accept: fn = dq, dx = stats [3][n], max_iterations = clip flag; q is written
+      k_async_accept<<<n, NT, 0, st>>>(n, ndof, nstages, fn, dx, max_iterations, state, stage, const_cast<double *>(q));
+      ++g_btddod_launches;
+      return cuda_rc("k_async_accept");
+    }
+    if (nstages < 2 || nstages > MAXK || !tableau)
+    {
+      set_error("gb_async_round_kernels: 2 <= nstages <= 6 and a tableau required");
+      return GB_ERR_ARG;
+    }
+    StageCoef sc{};
+    for (int a = 0; a < nstages; ++a)
+      for (int b = 0; b < nstages; ++b)
+        sc.a[a][b] = tableau[a * nstages + b];
+    k_async_tail<<<n, NT, 0, st>>>(n, ndof, nstages, sc, max_iterations, fn, xn, q, dt, gamma, weights, tolerance, x, f, res,
+                                   explicit_, K, state, stage, iters, nlfail, newton_its);
+    ++g_btddod_launches;
+    return cuda_rc("k_async_tail");
   }
 
   int gb_esdirk_finish_batch(int n, int ndof, int nk, const double *const *k, const double *b, const double *bh,

@@ -138,6 +138,7 @@ class _BatchOps(object):
         f0 = flamelets[0]
         self.F = len(flamelets)
         self.g = f0._griffon
+        self._mechanism_of_members = f0._mechanism
         self.ns, self.nzi = f0._n_equations, f0._nz_interior
         self.ndof = self.ns * self.nzi
         self.nelem = f0._jac_nelements_griffon
@@ -373,6 +374,38 @@ class _BatchOps(object):
                                                   weights, tolerance, max_iterations, x, f, res, explicit, K, stage, iters,
                                                   nlfail, done, work, counter)
         del keep
+        return out
+
+    def second_griffon(self, k=0):
+        """the k-th extra Griffon handle of the same mechanism (its own work arrays), for kernels that run on another
+        stream while this object's handle is busy -- a handle serves one stream at a time (griffon_b200.h)"""
+        extra = self.__dict__.setdefault('_extra_mechs', dict())
+        if k not in extra:
+            from spitfire_b200.mechanism import ChemicalMechanismSpec
+            m = self._mechanism_of_members
+            extra[k] = ChemicalMechanismSpec(mech_data=m.mech_data, griffon_factory=m._griffon_factory)
+        return extra[k].griffon
+
+    def member_params(self, m):
+        """C-ABI parameter block of the single member m, addressing its rows of the batch's arrays in place (cached)"""
+        cache = self.__dict__.setdefault('_member_prm', dict())
+        if m not in cache:
+            heat = [None] * 4 if self.adiabatic else [h[m:m + 1] for h in self.heat]
+            nz = self.chi.shape[1]
+            tens = (self.cmaj[m:m + 1], self.csub[m:m + 1], self.csup[m:m + 1], self.mc[m:m + 1], self.nc[m:m + 1],
+                    self.chi[m:m + 1])
+            prm = self.g._flamelet_params(self.pressure, self.oxy, self.fuel, self.adiabatic, heat[0], heat[1], heat[2],
+                                          heat[3], self.nzi, *tens, *self.flags,
+                                          strides=(0 if self.adiabatic else self.nzi, self.ndof, self.nzi, nz))
+            cache[m] = (prm, tens, heat)
+        return cache[m][0]
+
+    def jac_rows_on(self, g, q, members, out):
+        """BTDDOD Jacobians of the listed members of q [F, ndof] into the rows of out [len(members), nelem], one launch
+        per member through the Griffon handle g (see second_griffon) -- no gathers of states or coefficient arrays"""
+        for k, m in enumerate(members):
+            g.flamelet_jacobian_batch(1, q[m:m + 1], self.member_params(m), out[k:k + 1], scale_and_offset=False,
+                                      prefactor=1., rates_sens_option=self.rsopt, sens_transform_option=self.stopt)
         return out
 
     def nonfinite_rows(self, a, b):
@@ -644,8 +677,11 @@ class FlameletBatch(object):
         """`Flamelet.integrate_for_heat_loss` (flamelet.py:1263-1286) for every member at once: ESDIRK64 with each
         member's own adaptive step until its temperature profile is nearly linear or it is steady
         (spitfire_b200.time.batched). Returns (libraries over (time, mixture fraction), failed flags)."""
-        from spitfire_b200.time.batched import integrate_batch
+        from spitfire_b200.time import batched
         ops = self.ops
+        # (members advancing independently of each other where the device path offers it: time/batched.py)
+        integrate_batch = batched.integrate_batch_async if batched.can_integrate_async(ops, len(self.flamelets)) else \
+            batched.integrate_batch
         T_bc_max = max(self.flamelets[0]._oxy_stream.T, self.flamelets[0]._fuel_stream.T)
 
         def stop(t, q, residual, nsteps):

@@ -109,6 +109,8 @@ def load_library():
     sig('gb_count_nonfinite_members_batch', I, [I, L, V, L, V, V, V])
     sig('gb_newton_tail_staged_batch', I, [I, I, I, dp, I, V, V, V, V, D, V, D, V, V, V, V, V, V, V, V, V, V, ip, V])
     sig('gb_flamelet_esdirk_stages_batch', I, [P, I, FP, V, V, V, V, I, dp, V, V, D, V, D, I, V, V, V, V, V, V, V, V, V, V, V, ip, V])
+    sig('gb_flamelet_async_tick_batch', I, [P, I, FP, V, V, V, I, dp, dp, dp, V, V, D, V, D, I, I] + [V] * 15 +
+        [I, V, V, V, V, V, V, V, V])
     sig('gb_flamelet_newton_stage_batch', I, [P, I, FP, V, V, V, V, V, V, V, D, V, D, I, V, V, V, V, V, V, ip, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
@@ -172,7 +174,12 @@ def _on_device(*xs):
 
 
 def _stream():
+    """raw handle of torch's current CUDA stream (the direct binding: building a torch.cuda.Stream object per call costs
+    ~20 us, more than the launch it parameterises)"""
     import torch
+    raw = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -431,6 +438,19 @@ class PyCombustionKernels(MechanismSetters):
             _addr(K), i32(stage), i32(iters), i32(nlfail), i32(done), _addr(work), i32(n_left), C.byref(rounds),
             _stream()), 'flamelet_esdirk_stages_batch')
         return left, rounds.value
+
+    def flamelet_async_tick_batch(self, n_flamelets, prm, dev, host, tableau_c, b_c, bh_c, nstages, gamma, tolerance,
+                                  max_iterations, clip_negative, max_rounds, with_start):
+        """one tick of the asynchronous batch integrator (griffon_b200.h: gb_flamelet_async_tick_batch). dev: dict of
+        raw device addresses (ints) keyed like the C arguments, host: dict of raw host addresses; returns the rounds."""
+        d, h = dev, host
+        return check(self._lib.gb_flamelet_async_tick_batch(
+            self._h, int(n_flamelets), C.byref(prm), d['J'], d['L'], d['Dinv'], int(nstages), tableau_c, b_c, bh_c,
+            d['q'], d['dt'], float(gamma), d['w'], float(tolerance), int(max_iterations), int(bool(clip_negative)),
+            d['x'], d['f'], d['res'], d['expl'], d['K'], d['state'], d['stage'], d['iters'], d['nlfail'], d['nits'],
+            d['work'], d['dq'], d['stats'], d['start'], d['dtin'], int(max_rounds),
+            h['start'] if with_start else None, h['dt'], h['state'], h['stage'], h['stats'], h['nlfail'], h['q'],
+            _stream()), 'flamelet_async_tick_batch')
 
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------
     def flamelet_stencils(self, dz, nzi, chi, inv_lewis, out_cmajor, out_csub, out_csup, out_mcoeff, out_ncoeff):

@@ -304,3 +304,207 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
             t_hist[f_].append(float(t[f_]))
             q_hist[f_].append(qf[f_].copy())
     return [np.array(th) for th in t_hist], [np.array(qh) for qh in q_hist], failed
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Members that advance independently of each other across steps.
+#
+# In integrate_batch every Newton iteration of a step is a round of latency-bound kernels that serves all members, and a
+# step takes as many rounds as its SLOWEST member needs -- a different member at different times (measured on BASELINE
+# config 5: 15.8 k rounds for 56 members against 6.4 k Newton iterations of the longest trajectory on its own). Here a
+# round still serves all members, but every member is wherever its own trajectory is: its own step, its own stage, its
+# own Newton iteration (device state machine, csrc/gb_newton.cu: k_async_update / k_async_tail). When a member
+# completes the stages of a step the host does for it exactly what integrate_batch does for everybody at once -- error
+# estimate, acceptance, PI controller, Jacobian-refresh policy, stopping test -- and sends it into its next step; a
+# Jacobian refresh (Jacobian, scaling, Gauss-Jordan elimination: ~3.5 ms, seven rounds' worth) runs on a second stream
+# with a second Griffon handle while the other members keep iterating. Every member's arithmetic is the sequence
+# integrate_batch performs for it, so the trajectories are identical bit for bit (tests/test_gpu_newton.py).
+ASYNC_MEMBERS = _os.environ.get('GB_ASYNC_MEMBERS', '1') != '0'
+
+
+LAST_ASYNC_STATS = dict()
+
+
+def can_integrate_async(ops, F, explicit_inverse_solves=True):
+    return bool(ASYNC_MEMBERS and getattr(ops, 'on_device', False) and explicit_inverse_solves and F > 1 and
+                hasattr(ops, 'second_griffon') and hasattr(ops.g, 'flamelet_async_tick_batch'))
+
+
+def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, minimum_time_step_count=40,
+                          transient_tolerance=1.e-10, maximum_steps_per_jacobian=10, nonlinear_solve_tolerance=1.e-12,
+                          max_nonlinear_iter=20, max_ramp=1.1, ki=0.1333333333, maximum_steps=100000,
+                          fail_factor=0.8, slow_factor=0.8, grow_limit=1.05, shrink_limit=0.9, clip_negative=True,
+                          save_each_step=True, stop_ignores_minimum=False, stop_at_time=None, stats_out=None):
+    """integrate_batch with the members advancing independently of each other (device path, inverse-based solves).
+    Same arguments, same results. stats_out (dict, optional) receives the number of rounds and refresh launches."""
+    import ctypes as C
+    torch, dev, gm = ops.torch, ops.device, ops.gmod
+    F, ndof = q0.shape
+    nst = 6
+    w = (1. / ops.scales).contiguous()
+    q = q0.clone()
+    t = np.zeros(F)
+    dt = np.full(F, float(first_time_step))
+    nsteps = np.zeros(F, dtype=np.int64)
+    setup_count = np.zeros(F, dtype=np.int64)
+    refresh = np.ones(F, dtype=bool)
+    attempts = np.zeros(F, dtype=np.int64)
+    residual_full = np.full(F, np.inf)
+    NEED, WAIT, RUN, FIN = 0, 1, 2, 3
+    phase = np.full(F, NEED)
+    f64 = dict(dtype=torch.float64, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    J = torch.zeros((F, ops.nelem), **f64)
+    L = torch.zeros((F, ops.nzi * ops.ns * ops.ns), **f64)
+    Dinv = torch.zeros_like(L)
+    K = torch.zeros((nst, F, ndof), **f64)
+    x, f, res, expl = q.clone(), torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(q)
+    work = torch.zeros((3, F, ndof), **f64)
+    work[1].copy_(q)  # (the kernels' x - dx buffer starts from a finite state for members that are not active yet)
+    dt_d, dtin_d = torch.zeros(F, **f64), torch.zeros(F, **f64)
+    state_d, stage_d, iters_d, nlfail_d, nits_d, start_d = (torch.zeros(F, **i32) for _ in range(6))
+    dq = torch.zeros_like(q)
+    stats = torch.zeros((3, F), **f64)
+    ones = torch.ones((F, ndof), **f64)
+    # host side of a tick (pinned): what the host sends (start flags, step sizes) and what comes back
+    pin = lambda shape, dtype: torch.zeros(shape, dtype=dtype).pin_memory()
+    hp = dict(start=pin((F,), torch.int32), dt=pin((F,), torch.float64), state=pin((F,), torch.int32),
+              stage=pin((F,), torch.int32), stats=pin((3, F), torch.float64), nlfail=pin((F,), torch.int32),
+              q=pin((F, ndof), torch.float64))
+    hv = {k_: v.numpy() for k_, v in hp.items()}
+    addr = lambda ten: C.c_void_p(ten.data_ptr())
+    host = {k_: addr(v) for k_, v in hp.items()}
+    devp = dict(J=addr(J), L=addr(L), Dinv=addr(Dinv), q=addr(q), dt=addr(dt_d), w=addr(w), x=addr(x), f=addr(f),
+                res=addr(res), expl=addr(expl), K=addr(K), state=addr(state_d), stage=addr(stage_d), iters=addr(iters_d),
+                nlfail=addr(nlfail_d), nits=addr(nits_d), work=addr(work), dq=addr(dq), stats=addr(stats),
+                start=addr(start_d), dtin=addr(dtin_d))
+    tab = (C.c_double * (nst * nst))(*[float(_A[a][b]) for a in range(nst) for b in range(nst)])
+    b_c, bh_c = (C.c_double * nst)(*_B), (C.c_double * nst)(*_BH)
+    prm_all, keep_all = ops._params(ops._all(), tuple(range(F)))
+    # Jacobian refreshes run on a few side streams, round robin, each with its own Griffon handle (a handle serves one
+    # stream at a time): a refresh is ~3.5 ms on one SM per member and there are several thousand of them, so one side
+    # stream would serialise more work than the whole integration takes
+    n_side = 6
+    sides = [(torch.cuda.Stream(), ops.second_griffon(k)) for k in range(n_side)]
+    main = torch.cuda.current_stream()
+    pending = []  # (event, member ids) of the Jacobian refreshes in flight
+    t_hist = [[0.] for _ in range(F)]
+    q0_h = q0.cpu().numpy()
+    q_hist = [[q0_h[m].copy()] for m in range(F)]
+    n_rounds = n_refresh = 0
+    pack_d = torch.zeros((3, F), **f64)  # t, residual, step count of every member, for the stopping test
+
+    while np.any(phase != FIN):
+        # ---- members at the start of a step: shorten the step to the final time, refresh the projector if flagged -----
+        need = np.nonzero(phase == NEED)[0]
+        start = []
+        if need.size:
+            if stop_at_time is not None:
+                dt[need] = np.where(t[need] + dt[need] > stop_at_time, stop_at_time - t[need], dt[need])
+            rf = need[refresh[need]]
+            if rf.size:
+                side, g2 = sides[n_refresh % n_side]
+                side.wait_stream(main)  # the members' states are final on the main stream
+                with torch.cuda.stream(side):
+                    # (everything the side stream reads is allocated on it, or lives as long as this function)
+                    Jn = torch.empty((rf.size, ops.nelem), **f64)
+                    ops.jac_rows_on(g2, q, rf.tolist(), Jn)
+                    # (no host-to-device copies here: a synchronous copy would wait for the refresh queued before it)
+                    for k_, m in enumerate(rf.tolist()):
+                        Jn[k_].mul_(float(dt[m] * _G))
+                    ops.add_to_block_diagonal(Jn, 1., ones[:rf.size], -1.)
+                    fact = ops.factorize(Jn, with_inverse=True)
+                    for k_, m in enumerate(rf.tolist()):
+                        J[m].copy_(fact[0][k_]), L[m].copy_(fact[1][k_]), Dinv[m].copy_(fact[3][k_])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                pending.append((ev, rf))
+                phase[rf] = WAIT
+                n_refresh += 1
+            start.extend(need[~refresh[need]].tolist())
+            setup_count[need] += 1
+        # ---- refreshes that have completed ---------------------------------------------------------------------------------
+        if pending:
+            idle = not start and not np.any(phase == RUN)
+            still = []
+            for ev, rf in pending:
+                if idle and not start:
+                    ev.synchronize()
+                if ev.query():
+                    start.extend(rf.tolist())
+                else:
+                    still.append((ev, rf))
+            pending = still
+        hv['start'][:] = 0
+        if start:
+            sid = np.array(start, dtype=np.int64)
+            hv['start'][sid] = 1
+            hv['dt'][sid] = dt[sid]
+            phase[sid] = RUN
+            refresh[sid] = False  # (set again by the policy below at the end of the step)
+        if not np.any(phase == RUN):
+            continue
+        # ---- one tick: start those members, rounds of kernels until a member completes its stages, its step end -----------
+        n_rounds += ops.g.flamelet_async_tick_batch(F, prm_all, devp, host, tab, b_c, bh_c, nst, _G,
+                                                    nonlinear_solve_tolerance, max_nonlinear_iter, clip_negative,
+                                                    1 if pending else 64, bool(start))
+        fin = np.nonzero((phase == RUN) & (hv['state'] == 0) & (hv['stage'] == nst))[0]
+        if fin.size == 0:
+            continue
+        # ---- end of the step for these members: what integrate_batch does for everybody at once ------------------------------
+        st_h = hv['stats'][:, fin]
+        nl_ok = hv['nlfail'][fin] == 0
+        d_all = dt[fin]
+        err, ok = st_h[0], st_h[2] > 0.5
+        with np.errstate(all='ignore'):
+            residual = st_h[1] / d_all
+        acc = fin[ok]
+        if acc.size:
+            d = d_all[ok]
+            t[acc] = t[acc] + d
+            nsteps[acc] += 1
+            e = err[ok]
+            with np.errstate(all='ignore'):
+                ratio = (transient_tolerance / e) ** ki
+            dnew = np.minimum(d * np.minimum(max_ramp, ratio), max_time_step)
+            dnew = np.where(e < 1.e-16, np.minimum(d * max_ramp, max_time_step), dnew)
+            cnt = setup_count[acc]
+            okn = nl_ok[ok]
+            by_count = cnt == maximum_steps_per_jacobian
+            by_slow = ~by_count & ~okn
+            by_size = ~by_count & okn & ((dnew > d * grow_limit) | (dnew < d * shrink_limit))
+            dnew = np.where(by_slow, dnew * slow_factor, dnew)
+            refresh[acc] = by_count | by_slow | by_size
+            setup_count[acc] = np.where(by_count, 0, cnt)
+            dt[acc] = dnew
+            if save_each_step:
+                for m in acc.tolist():
+                    t_hist[m].append(float(t[m]))
+                    q_hist[m].append(hv['q'][m].copy())
+        rej = fin[~ok]
+        if rej.size:
+            dt[rej] = dt[rej] * fail_factor
+            refresh[rej] = True
+        attempts[fin] += 1
+        residual_full[fin] = np.where(np.isfinite(residual), residual, np.inf)
+        pack_d.copy_(torch.from_numpy(np.stack([t, residual_full, nsteps.astype(np.float64)])))
+        done = stop(pack_d[0], q, pack_d[1], pack_d[2].to(torch.int64)).cpu().numpy()
+        if not stop_ignores_minimum:
+            done = done & (nsteps >= minimum_time_step_count)
+        if stop_at_time is not None:
+            done = done | (t >= stop_at_time)
+        done = done | (attempts > maximum_steps)
+        phase[fin] = np.where(done[fin], FIN, NEED)
+    del keep_all
+    for side, _ in sides:
+        main.wait_stream(side)
+    failed = attempts > maximum_steps
+    if not save_each_step:
+        qf = q.cpu().numpy()
+        for m in range(F):
+            t_hist[m].append(float(t[m]))
+            q_hist[m].append(qf[m].copy())
+    LAST_ASYNC_STATS.update(rounds=n_rounds, refresh_launches=n_refresh, members=F)
+    if stats_out is not None:
+        stats_out.update(rounds=n_rounds, refresh_launches=n_refresh, newton_iterations=nits_d.cpu().numpy().tolist())
+    return [np.array(th) for th in t_hist], [np.array(qh) for qh in q_hist], failed

@@ -96,15 +96,18 @@ def test_fused_stage_loop_reproduces_the_eager_one():
     out = []
     # eager tensor loop / device kernels driven from Python / one C-ABI call per stage / one call per step with the
     # members walking through the stages independently of each other
-    for fused, stage, asyn in ((False, False, False), (True, False, False), (True, True, False), (True, True, True)):
+    # ... / the members advancing independently of each other across steps (integrate_batch_async)
+    for fused, stage, asyn, members in ((False, False, False, False), (True, False, False, False),
+                                        (True, True, False, False), (True, True, True, False),
+                                        (True, True, False, True)):
         fls = [Flamelet(tab._transient_heat_loss_specs(specs, table, c)) for c in table.keys()]
         args = tab._transient_integration_args({'transient_tolerance': 1e-10}, False)
-        saved = tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES
-        tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES = fused, stage, asyn
+        saved = tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES, tb.ASYNC_MEMBERS
+        tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES, tb.ASYNC_MEMBERS = fused, stage, asyn, members
         try:
             libs, failed = FlameletBatch(fls).integrate_for_heat_loss(**args)
         finally:
-            tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES = saved
+            tb.FUSED_NEWTON, tb.STAGE_CALL, tb.ASYNC_STAGES, tb.ASYNC_MEMBERS = saved
         assert not any(failed)
         out.append(libs)
     for other in out[1:]:

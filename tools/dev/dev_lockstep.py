@@ -8,6 +8,7 @@ from common import build_mech
 from spitfire_b200 import tabulation as tab
 from spitfire_b200 import flamelet as fl
 from spitfire_b200.flamelet import Flamelet, FlameletBatch, FlameletSpec
+from spitfire_b200.time import batched as _tb
 
 m = build_mech('methane-gri30', 'gpu')
 air = m.stream(stp_air=True); fuel = m.stream('TPX', (300., 101325., 'CH4:1'))
@@ -35,7 +36,10 @@ def run(sel):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     FlameletBatch(fls).integrate_for_heat_loss(**args)
     torch.cuda.synchronize()
+    if _tb.LAST_ASYNC_STATS:
+        print('   async stats:', dict(_tb.LAST_ASYNC_STATS)); _tb.LAST_ASYNC_STATS.clear()
     return time.perf_counter() - t0, count['stages'], count['its']
+print('async members:', _tb.ASYNC_MEMBERS)
 print('all %d members: %.2f s, %d stages, %d iterations' % ((len(keys),) + run(list(range(len(keys))))), flush=True)
 for i in [0, len(keys) - 1]:
     print('member %2d (chi_st %.3g): %.2f s, %d stages, %d iterations' % ((i, keys[i]) + run([i])), flush=True)
