@@ -366,14 +366,15 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
     dq = torch.zeros_like(q)
     stats = torch.zeros((3, F), **f64)
     ones = torch.ones((F, ndof), **f64)
-    # host side of a tick (pinned): what the host sends (start flags, step sizes) and what comes back
+    # host side of a tick (pinned): what the host sends (start flags, step sizes) and what comes back. Two sets: the
+    # host processes the results of tick k (and prepares tick k+2) while tick k+1 runs
     pin = lambda shape, dtype: torch.zeros(shape, dtype=dtype).pin_memory()
-    hp = dict(start=pin((F,), torch.int32), dt=pin((F,), torch.float64), state=pin((F,), torch.int32),
-              stage=pin((F,), torch.int32), stats=pin((3, F), torch.float64), nlfail=pin((F,), torch.int32),
-              q=pin((F, ndof), torch.float64))
-    hv = {k_: v.numpy() for k_, v in hp.items()}
     addr = lambda ten: C.c_void_p(ten.data_ptr())
-    host = {k_: addr(v) for k_, v in hp.items()}
+    hps = [dict(start=pin((F,), torch.int32), dt=pin((F,), torch.float64), state=pin((F,), torch.int32),
+                stage=pin((F,), torch.int32), stats=pin((3, F), torch.float64), nlfail=pin((F,), torch.int32),
+                q=pin((F, ndof), torch.float64)) for _ in range(2)]
+    hvs = [{k_: v.numpy() for k_, v in hp.items()} for hp in hps]
+    hosts = [{k_: addr(v) for k_, v in hp.items()} for hp in hps]
     devp = dict(J=addr(J), L=addr(L), Dinv=addr(Dinv), q=addr(q), dt=addr(dt_d), w=addr(w), x=addr(x), f=addr(f),
                 res=addr(res), expl=addr(expl), K=addr(K), state=addr(state_d), stage=addr(stage_d), iters=addr(iters_d),
                 nlfail=addr(nlfail_d), nits=addr(nits_d), work=addr(work), dq=addr(dq), stats=addr(stats),
@@ -386,72 +387,32 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
     # stream would serialise more work than the whole integration takes
     n_side = 6
     sides = [(torch.cuda.Stream(), ops.second_griffon(k)) for k in range(n_side)]
-    main = torch.cuda.current_stream()
+    ctrl = torch.cuda.Stream()  # the stopping test runs here: it must not queue behind the rounds in flight
+    device = torch.cuda.current_device()
     pending = []  # (event, member ids) of the Jacobian refreshes in flight
     t_hist = [[0.] for _ in range(F)]
     q0_h = q0.cpu().numpy()
     q_hist = [[q0_h[m].copy()] for m in range(F)]
     n_rounds = n_refresh = 0
     pack_d = torch.zeros((3, F), **f64)  # t, residual, step count of every member, for the stopping test
+    torch.cuda.synchronize()
 
-    while np.any(phase != FIN):
-        # ---- members at the start of a step: shorten the step to the final time, refresh the projector if flagged -----
-        need = np.nonzero(phase == NEED)[0]
-        start = []
-        if need.size:
-            if stop_at_time is not None:
-                dt[need] = np.where(t[need] + dt[need] > stop_at_time, stop_at_time - t[need], dt[need])
-            rf = need[refresh[need]]
-            if rf.size:
-                side, g2 = sides[n_refresh % n_side]
-                side.wait_stream(main)  # the members' states are final on the main stream
-                with torch.cuda.stream(side):
-                    # (everything the side stream reads is allocated on it, or lives as long as this function)
-                    Jn = torch.empty((rf.size, ops.nelem), **f64)
-                    ops.jac_rows_on(g2, q, rf.tolist(), Jn)
-                    # (no host-to-device copies here: a synchronous copy would wait for the refresh queued before it)
-                    for k_, m in enumerate(rf.tolist()):
-                        Jn[k_].mul_(float(dt[m] * _G))
-                    ops.add_to_block_diagonal(Jn, 1., ones[:rf.size], -1.)
-                    fact = ops.factorize(Jn, with_inverse=True)
-                    for k_, m in enumerate(rf.tolist()):
-                        J[m].copy_(fact[0][k_]), L[m].copy_(fact[1][k_]), Dinv[m].copy_(fact[3][k_])
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                pending.append((ev, rf))
-                phase[rf] = WAIT
-                n_refresh += 1
-            start.extend(need[~refresh[need]].tolist())
-            setup_count[need] += 1
-        # ---- refreshes that have completed ---------------------------------------------------------------------------------
-        if pending:
-            idle = not start and not np.any(phase == RUN)
-            still = []
-            for ev, rf in pending:
-                if idle and not start:
-                    ev.synchronize()
-                if ev.query():
-                    start.extend(rf.tolist())
-                else:
-                    still.append((ev, rf))
-            pending = still
-        hv['start'][:] = 0
-        if start:
-            sid = np.array(start, dtype=np.int64)
-            hv['start'][sid] = 1
-            hv['dt'][sid] = dt[sid]
-            phase[sid] = RUN
-            refresh[sid] = False  # (set again by the policy below at the end of the step)
-        if not np.any(phase == RUN):
-            continue
-        # ---- one tick: start those members, rounds of kernels until a member completes its stages, its step end -----------
-        n_rounds += ops.g.flamelet_async_tick_batch(F, prm_all, devp, host, tab, b_c, bh_c, nst, _G,
-                                                    nonlinear_solve_tolerance, max_nonlinear_iter, clip_negative,
-                                                    1 if pending else 64, bool(start))
+    # The ticks run on a worker thread (the C call releases the interpreter lock): while tick k+1 iterates on the device
+    # the host does the step-end control of the members that completed in tick k and launches their Jacobian refreshes.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(1)
+
+    def run_tick(bi, with_start, max_rounds):
+        torch.cuda.set_device(device)
+        return ops.g.flamelet_async_tick_batch(F, prm_all, devp, hosts[bi], tab, b_c, bh_c, nst, _G,
+                                               nonlinear_solve_tolerance, max_nonlinear_iter, clip_negative, max_rounds,
+                                               with_start)
+
+    def step_end(hv):
+        """what integrate_batch does for everybody at once, for the members that completed a step in this tick"""
         fin = np.nonzero((phase == RUN) & (hv['state'] == 0) & (hv['stage'] == nst))[0]
         if fin.size == 0:
-            continue
-        # ---- end of the step for these members: what integrate_batch does for everybody at once ------------------------------
+            return
         st_h = hv['stats'][:, fin]
         nl_ok = hv['nlfail'][fin] == 0
         d_all = dt[fin]
@@ -487,14 +448,83 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
             refresh[rej] = True
         attempts[fin] += 1
         residual_full[fin] = np.where(np.isfinite(residual), residual, np.inf)
-        pack_d.copy_(torch.from_numpy(np.stack([t, residual_full, nsteps.astype(np.float64)])))
-        done = stop(pack_d[0], q, pack_d[1], pack_d[2].to(torch.int64)).cpu().numpy()
+        with torch.cuda.stream(ctrl):  # (the rows of these members are final: their tick has been synchronised)
+            pack_d.copy_(torch.from_numpy(np.stack([t, residual_full, nsteps.astype(np.float64)])))
+            done = stop(pack_d[0], q, pack_d[1], pack_d[2].to(torch.int64)).cpu().numpy()
         if not stop_ignores_minimum:
             done = done & (nsteps >= minimum_time_step_count)
         if stop_at_time is not None:
             done = done | (t >= stop_at_time)
         done = done | (attempts > maximum_steps)
         phase[fin] = np.where(done[fin], FIN, NEED)
+
+    inflight, bi = None, 0
+    try:
+        while True:
+            # ---- members at the start of a step: shorten it to the final time, refresh the projector if flagged --------
+            need = np.nonzero(phase == NEED)[0]
+            start = []
+            if need.size:
+                if stop_at_time is not None:
+                    dt[need] = np.where(t[need] + dt[need] > stop_at_time, stop_at_time - t[need], dt[need])
+                rf = need[refresh[need]]
+                if rf.size:
+                    side, g2 = sides[n_refresh % n_side]
+                    with torch.cuda.stream(side):
+                        # (the members' states are final: the tick that accepted them has been synchronised. Nothing is
+                        # copied from the host here: a synchronous copy would wait for the refresh queued before it)
+                        Jn = torch.empty((rf.size, ops.nelem), **f64)
+                        ops.jac_rows_on(g2, q, rf.tolist(), Jn)
+                        for k_, m in enumerate(rf.tolist()):
+                            Jn[k_].mul_(float(dt[m] * _G))
+                        ops.add_to_block_diagonal(Jn, 1., ones[:rf.size], -1.)
+                        fact = ops.factorize(Jn, with_inverse=True)
+                        for k_, m in enumerate(rf.tolist()):
+                            J[m].copy_(fact[0][k_]), L[m].copy_(fact[1][k_]), Dinv[m].copy_(fact[3][k_])
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    pending.append((ev, rf))
+                    phase[rf] = WAIT
+                    n_refresh += 1
+                start.extend(need[~refresh[need]].tolist())
+                setup_count[need] += 1
+            # ---- refreshes that have completed -----------------------------------------------------------------------------
+            if pending:
+                idle = not start and inflight is None and not np.any(phase == RUN)
+                still = []
+                for ev, rf in pending:
+                    if idle and not start:
+                        ev.synchronize()
+                    if ev.query():
+                        start.extend(rf.tolist())
+                    else:
+                        still.append((ev, rf))
+                pending = still
+            # ---- next tick: start those members, rounds of kernels until a member completes its stages --------------------
+            hv = hvs[bi]
+            hv['start'][:] = 0
+            if start:
+                sid = np.array(start, dtype=np.int64)
+                hv['start'][sid] = 1
+                hv['dt'][sid] = dt[sid]
+                phase[sid] = RUN
+                refresh[sid] = False  # (set again by the policy at the end of the step)
+            nxt = None
+            if np.any(phase == RUN):
+                nxt = (pool.submit(run_tick, bi, bool(start), 1 if (pending or inflight is not None) else 16), bi)
+                bi ^= 1
+            # ---- meanwhile: the step ends of the tick that has just finished ------------------------------------------------
+            if inflight is not None:
+                n_rounds += inflight[0].result()
+                step_end(hvs[inflight[1]])
+            inflight = nxt
+            if inflight is None and not pending and not np.any(phase == NEED):
+                if np.all(phase == FIN):
+                    break
+    finally:
+        pool.shutdown(wait=True)
+    main = torch.cuda.current_stream()
+    main.wait_stream(ctrl)
     del keep_all
     for side, _ in sides:
         main.wait_stream(side)
