@@ -255,6 +255,17 @@ int gb_btddod_full_solve_inv_batch(int n_systems, const double *d_factors, const
  * shorter latency chain per system than factorize_inv (one barrier and bs, not ~3 bs, dependent steps per block). */
 int gb_btddod_full_invert_batch(int n_systems, const double *matrix, int num_blocks, int block_size,
                                 double *out_l_values, double *out_dinv, void *stream);
+/* Extension: the TWISTED ("burn at both ends") form of the elimination above, for the same consumers. Two CTAs of a
+ * thread-block cluster share a system: one eliminates downwards from block 0 (L_i, D'_i as above), the other upwards
+ * from block nb-1 (U_i = diag(sup_i) D''_{i+1}^{-1}, D''_i = D_i - U_i diag(sub_i)); they meet at block m = (nb-1)/2,
+ * D*_m = D_m - L_m diag(sup_{m-1}) - U_m diag(sub_m). out_l_values holds L_i in slot i <= m and U_{i-1} in slot i > m,
+ * out_dinv the inverses of D'_i (i < m), D*_m, D''_i (i > m); block 0 of out_l_values (never read as a multiplier)
+ * carries the tag {m, magic} by which gb_btddod_full_solve_inv_batch recognises the format and sweeps from both ends
+ * at once (two CTAs, two cluster barriers): the dependent chain of the elimination AND of every solve is halved.
+ * Same solution as the one-sided elimination up to rounding (a different, equally stable elimination order). Falls
+ * back to the one-sided form for num_blocks < 4 or when GB_BT_TWIST=0 is set in the environment. */
+int gb_btddod_full_invert_twisted_batch(int n_systems, const double *matrix, int num_blocks, int block_size,
+                                        double *out_l_values, double *out_dinv, void *stream);
 int gb_btddod_full_factorize_host(int n_systems, double *d_factors, int num_blocks, int block_size,
                                   double *out_l_values, int *out_d_pivots);
 int gb_btddod_full_solve_host(int n_systems, const double *d_factors, const double *l_values, const int *d_pivots,

@@ -13,9 +13,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/griffon_b200.h"
+#include "gb_kernels.cuh"
 #include "gb_mech.h"
 
 namespace gb
@@ -785,8 +787,13 @@ __device__ __forceinline__ void cp_async_wait_group()
 
 __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const double *d_factors, const double *l_values,
                                                                  const double *dinv, const double *rhs, int nb, int bs,
-                                                                 double *solution, int staged, const int *rows)
+                                                                 double *solution, int staged, const int *rows, int pairs)
 {
+  // pairs != 0: launched as clusters of two CTAs per system. Factors from the TWISTED elimination (gb_btinv.cu: the
+  // tag in block 0 of l_values) are then applied from both ends at once -- CTA 0 sweeps the blocks 0..m downwards and
+  // back, CTA 1 the blocks nb-1..m+1 upwards and back, the two meeting at block m through two cluster barriers -- which
+  // halves the dependent chain of a solve. Plain factors: CTA 0 alone runs the one-sided sweep (m = nb-1).
+  const unsigned int crank = pairs ? cluster_ctarank() : 0u;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb2 = bs * bs;
@@ -820,17 +827,31 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     }
   }
 
-  for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
+  for (int sys = pairs ? (int)clusterid_x() : blockIdx.x; sys < nsys; sys += pairs ? (int)nclusterid_x() : gridDim.x)
   {
     const int fsys = rows ? rows[sys] : sys; // where this system's factors live (right-hand sides are compact)
     const double *D = d_factors + (size_t)fsys * mat_stride;
     const double *Lv = l_values + (size_t)fsys * nb * nb2;
     const double *Di = dinv + (size_t)fsys * nb * nb2;
-    const double *sup = D + (size_t)nb * nb2 + (size_t)(nb - 1) * bs;
     const double *b = rhs + (size_t)sys * nb * bs;
     double *x = solution + (size_t)sys * nb * bs;
-    const int nstream = 2 * nb - 1;
-    auto src_of = [&](int s) { return s < nb - 1 ? Lv + (size_t)(s + 1) * nb2 : Di + (size_t)(nstream - 1 - s) * nb2; };
+    // meeting block m of the sweep(s): nb-1 for plain factors
+    const bool twisted = pairs && nb >= 4 && bs >= 2 && __ldg(Lv + 1) == BT_TWIST_MAGIC;
+    const int m = twisted ? (int)__ldg(Lv) : nb - 1;
+    if (crank != 0 && !twisted)
+      continue;
+    const bool top = crank == 0;
+    // this CTA: nf forward steps (block i, multiplier slot i for the top sweep / i+1 for the bottom one), then nbk
+    // back steps
+    const int nf = top ? m : nb - 1 - m, nbk = top ? m + 1 : nb - 1 - m;
+    // off-diagonal that couples a solved block to the next one of the back sweep: sup_{i-1} going up, sub_i going down
+    const double *offd = D + (size_t)nb * nb2 + (top ? (size_t)(nb - 1) * bs : (size_t)0);
+    const int nstream = nf + nbk;
+    auto blk_of = [&](int s) { return s < nf ? (top ? s + 1 : nb - 2 - s) : (top ? m - (s - nf) : m + 1 + (s - nf)); };
+    auto src_of = [&](int s) {
+      const int i = blk_of(s);
+      return s < nf ? Lv + (size_t)(top ? i : i + 1) * nb2 : Di + (size_t)i * nb2;
+    };
     // Block s lands at ring[(gs0+s) % STAGES] + (1 if its source address is an odd multiple of 8 bytes): one TMA bulk
     // copy of the 16-byte aligned span that lies inside the block's neighbourhood (a single SM cannot keep enough
     // LDGSTS requests in flight to stream 22 KB per step), plus the odd last element, if any, by an 8-byte cp.async.
@@ -838,8 +859,9 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     const unsigned int parL = (unsigned int)(reinterpret_cast<size_t>(Lv) >> 3) & 1u;
     const unsigned int parD = (unsigned int)(reinterpret_cast<size_t>(Di) >> 3) & 1u;
     auto par_of = [&](int s) {
-      return s < nb - 1 ? (parL + (unsigned int)(s + 1) * (unsigned int)nb2) & 1u
-                        : (parD + (unsigned int)(nstream - 1 - s) * (unsigned int)nb2) & 1u;
+      const int i = blk_of(s);
+      return s < nf ? (parL + (unsigned int)(top ? i : i + 1) * (unsigned int)nb2) & 1u
+                    : (parD + (unsigned int)i * (unsigned int)nb2) & 1u;
     };
     auto fetch = [&](int s) {
       if (s < nstream && warp == SI_THREADS / 32 - 1)
@@ -864,26 +886,46 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     auto buf_of = [&](int s) { return ring + (unsigned int)((gs0 + s) % SI_STAGES) * (unsigned int)bufsz + par_of(s); };
     __syncthreads(); // the previous system is done with the shared arrays
     if (staged)
-      for (int e = tid; e < nb * bs; e += SI_THREADS)
+    { // (the blocks this CTA's sweep touches)
+      const int e0 = top ? 0 : (m + 1) * bs, e1 = top ? (m + 1) * bs : nb * bs;
+      for (int e = e0 + tid; e < e1; e += SI_THREADS)
         yv[e] = b[e];
+    }
     for (int s = 0; s < SI_STAGES - 1; ++s)
       fetch(s);
     for (int j = tid; j < 2 * bsp; j += SI_THREADS)
       if (j % bsp >= bs)
         v0[j] = 0.; // the padding of both vectors stays zero for the whole sweep
-    for (int j = tid; j < bs; j += SI_THREADS)
     {
-      v0[j] = b[j];
-      x[j] = b[j];
+      const size_t first = top ? (size_t)0 : (size_t)(nb - 1) * bs;
+      for (int j = tid; j < bs; j += SI_THREADS)
+      {
+        v0[j] = b[first + j];
+        x[first + j] = b[first + j];
+      }
     }
     for (int s = 0; s < nstream; ++s)
     {
-      const bool fwd = s < nb - 1;
-      const int i = fwd ? s + 1 : nstream - 1 - s;
+      const bool fwd = s < nf;
+      const int i = blk_of(s);
+      // back steps: is there a next block, which one, and the off-diagonal entry that couples it
+      const bool has_next = top ? i > 0 : i < nb - 1;
+      const int inext = top ? i - 1 : i + 1, ioff = top ? i - 1 : i;
+      // bottom sweep, last forward step: only t = U_m z_{m+1} is wanted (handed to the top sweep through x_m's slot)
+      const bool hand_t = twisted && !top && fwd && s == nf - 1;
+      if (twisted && !top && s == nf)
+      { // the top sweep has published x_m: right-hand side of the first downward step
+        __syncthreads();
+        cluster_sync_all();
+        double *vfirst = v0 + (s & 1) * bsp;
+        for (int j = tid; j < bs; j += SI_THREADS)
+          vfirst[j] = (staged ? yv[(size_t)(m + 1) * bs + j] : b[(size_t)(m + 1) * bs + j]) -
+                      __ldg(offd + (size_t)m * bs + j) * __ldcg(x + (size_t)m * bs + j);
+      }
       // operand of the epilogue that does not depend on this sweep: issued before the wait (first 64 rows)
       double sup0 = 0.;
-      if (!fwd && i > 0 && part == 0 && warp * 8 + sub < bs)
-        sup0 = __ldg(sup + (size_t)(i - 1) * bs + warp * 8 + sub);
+      if (!fwd && has_next && part == 0 && warp * 8 + sub < bs)
+        sup0 = __ldg(offd + (size_t)ioff * bs + warp * 8 + sub);
 #ifdef GB_JAC_TIMELINE
       long long c0 = clock64();
 #endif
@@ -915,12 +957,12 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
         if (part == 0 && live)
         {
           if (fwd)
-            e0 = staged ? yv[(size_t)i * bs + row] : b[(size_t)i * bs + row];
-          else if (i > 0)
+            e0 = hand_t ? 0. : (staged ? yv[(size_t)i * bs + row] : b[(size_t)i * bs + row]);
+          else if (has_next)
           {
-            e0 = staged ? yv[(size_t)(i - 1) * bs + row] : x[(size_t)(i - 1) * bs + row];
+            e0 = staged ? yv[(size_t)inext * bs + row] : x[(size_t)inext * bs + row];
             if (row0 > 0)
-              e1 = __ldg(sup + (size_t)(i - 1) * bs + row);
+              e1 = __ldg(offd + (size_t)ioff * bs + row);
           }
         }
         // part p takes the columns 16 j + 8 (p & 1) + 4 (p >> 1) + t, t < 4: the two parts of a half-warp are eight
@@ -999,7 +1041,7 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
           if (fwd)
           { // y_i = b_i - L_i y_{i-1}
             const double y = e0 - acc;
-            if (staged)
+            if (staged && !hand_t)
               yv[(size_t)i * bs + row] = y;
             else
               x[(size_t)i * bs + row] = y;
@@ -1008,9 +1050,23 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
           else
           { // x_i = Dinv_i v; the next right-hand side is y_{i-1} - sup_{i-1} o x_i
             x[(size_t)i * bs + row] = acc;
-            if (i > 0)
+            if (has_next)
               vout[row] = e0 - e1 * acc;
           }
+        }
+      }
+      if (twisted)
+      {
+        if (top && s == nf - 1)
+        { // y_m is complete; the bottom sweep hands over -U_m z_{m+1}: the first back step solves for x_m
+          cluster_sync_all();
+          for (int j = tid; j < bs; j += SI_THREADS)
+            vout[j] += __ldcg(x + (size_t)m * bs + j);
+        }
+        else if (top ? s == nf : s == nf - 1)
+        { // publish x_m (top) / -t (bottom) to the other CTA
+          __threadfence();
+          cluster_sync_all();
         }
       }
 #ifdef GB_JAC_TIMELINE
@@ -1103,6 +1159,23 @@ int bt_check(int n, int nb, int bs)
   }
   return GB_OK;
 }
+} // namespace
+bool gb::bt_twist_ok(int nb, int bs)
+{
+  static int enabled = -1;
+  if (enabled < 0)
+  {
+    const char *e = getenv("GB_BT_TWIST");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled || nb < 4 || bs < 2)
+    return false;
+  // (k_btddod_solve_inv with the right-hand side staged in shared memory, see gb_btddod_full_solve_inv_batch)
+  const size_t base = sizeof(double) * ((size_t)SI_STAGES * (((size_t)bs * bs + 3) & ~(size_t)1) + 2 * (((size_t)bs + 63) & ~(size_t)63)) + 64 + 16;
+  return base + sizeof(double) * (size_t)nb * bs <= (size_t)227 * 1024;
+}
+namespace
+{
 int sm_count_bt()
 {
   int dev = 0, n = 1;
@@ -1163,8 +1236,21 @@ extern "C"
     const int staged = with_rhs <= (size_t)227 * 1024 ? 1 : 0; // the right-hand side too, when it fits
     const size_t smem = staged ? with_rhs : base;
     BCK(cudaFuncSetAttribute(k_btddod_solve_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_btddod_solve_inv<<<n, SI_THREADS, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution,
-                                                                      staged, system_rows);
+    if (bt_twist_ok(nb, bs))
+    { // clusters of two CTAs per system: factors of the twisted elimination are applied from both ends at once
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (unsigned int)n), cfg.blockDim = dim3(SI_THREADS);
+      cfg.dynamicSmemBytes = smem, cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+      cfg.attrs = at, cfg.numAttrs = 1;
+      BCK(cudaLaunchKernelEx(&cfg, k_btddod_solve_inv, n, d_factors, l_values, dinv, rhs, nb, bs, solution, staged,
+                             system_rows, 1));
+    }
+    else
+      k_btddod_solve_inv<<<n, SI_THREADS, smem, (cudaStream_t)stream>>>(n, d_factors, l_values, dinv, rhs, nb, bs, solution,
+                                                                        staged, system_rows, 0);
     ++g_btddod_launches;
     BCK(cudaGetLastError());
     return GB_OK;

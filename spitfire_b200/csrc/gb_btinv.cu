@@ -71,8 +71,19 @@ __device__ __forceinline__ double fast_rcp(double x)
 // IW warps per CTA (a power of two), R rows per lane (bs <= 32 R), C column slots per warp (bs <= IW C)
 template <int R, int C, int IW>
 __global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const double *__restrict__ mats, int nb, int bs,
-                                                        double *__restrict__ l_values, double *__restrict__ dinv)
+                                                        double *__restrict__ l_values, double *__restrict__ dinv, int twist)
 {
+  // twist != 0 (launched as clusters of two CTAs per system): TWISTED elimination. CTA 0 eliminates downwards from
+  // block 0, CTA 1 upwards from block nb-1 with the roles of the two off-diagonals exchanged,
+  //     D''_{nb-1} = D_{nb-1},   U_i = diag(sup_i) D''_{i+1}^{-1},   D''_i = D_i - U_i diag(sub_i),
+  // and the two meet at block m = (nb-1)/2:   D*_m = D_m - L_m diag(sup_{m-1}) - U_m diag(sub_m).
+  // Slot i of l_values holds L_i for i <= m and U_{i-1} for i > m; dinv holds the inverses of D'_i, D*_m, D''_i; block
+  // 0 of l_values carries the tag {m, BT_TWIST_MAGIC} by which k_btddod_solve_inv recognises the format. The dependent
+  // chain of a system is halved.
+  const unsigned int crank = twist ? cluster_ctarank() : 0u;
+  const bool top = crank == 0;
+  const int m = twist ? (nb - 1) / 2 : nb - 1;
+  const int nblk = top ? m + 1 : nb - 1 - m;
   constexpr int INT_ = IW * 32;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,15 +97,20 @@ __global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const doubl
   int *sinvp = sperm + 32 * R;              // [bs] step at which row r was the pivot
   const size_t mat_stride = (size_t)bs * ((size_t)nb * bs + 2 * (nb - 1));
 
-  for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x)
+  for (int sys = twist ? (int)clusterid_x() : blockIdx.x; sys < nsys; sys += twist ? (int)nclusterid_x() : gridDim.x)
   {
     const double *M = mats + (size_t)sys * mat_stride;
     const double *subd = M + (size_t)nb * nb2, *supd = subd + (size_t)(nb - 1) * bs;
+    // row / column scaling of the previous inverse for the j-th block of this CTA's sweep (block i = blk_of(j)):
+    // downwards sub_{i-1} by row and sup_{i-1} by column, upwards sup_i by row and sub_i by column
+    const double *rowd = top ? subd : supd, *cold = top ? supd : subd;
+    auto blk_of = [&](int j) { return top ? j : nb - 1 - j; };
     double *Lv = l_values + (size_t)sys * nb * nb2;
     double *Di = dinv + (size_t)sys * nb * nb2;
     double S[R][C], Dn[R][C], subn[R], supn[C];
     // block i into registers, with the off-diagonal entries that turn it into D'_i (sub_{i-1} by row, sup_{i-1} by column)
-    auto load_block = [&](int i) {
+    auto load_block = [&](int j) {
+      const int i = blk_of(j), io = top ? i - 1 : i;
       const double *D = M + (size_t)i * nb2;
 #pragma unroll
       for (int b = 0; b < C; ++b)
@@ -106,16 +122,21 @@ __global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const doubl
           const int row = lane + 32 * a;
           Dn[a][b] = (row < bs && col < bs) ? __ldg(D + (size_t)col * bs + row) : 0.;
         }
-        supn[b] = (i > 0 && col < bs) ? __ldg(supd + (size_t)(i - 1) * bs + col) : 0.;
+        supn[b] = (j > 0 && col < bs) ? __ldg(cold + (size_t)io * bs + col) : 0.;
       }
 #pragma unroll
       for (int a = 0; a < R; ++a)
-        subn[a] = (i > 0 && lane + 32 * a < bs) ? __ldg(subd + (size_t)(i - 1) * bs + lane + 32 * a) : 0.;
+        subn[a] = (j > 0 && lane + 32 * a < bs) ? __ldg(rowd + (size_t)io * bs + lane + 32 * a) : 0.;
     };
     load_block(0);
     __syncthreads(); // the previous system is done with the shared arrays
-    for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nblk; ++j)
     {
+      const int i = blk_of(j);
+      const size_t slot = top ? (size_t)i : (size_t)i + 1; // where this block's multiplier goes
+      const bool meet = twist && top && j == m;           // the block where the two sweeps meet
+      if (meet)
+        cluster_sync_all(); // U_m (slot m+1) has been written by the other CTA
       // ---- D'_i: the first block as it is; then D_i - (sub o Dinv_{i-1}) o sup, L_i on the way (:48-75) --------------
 #pragma unroll
       for (int b = 0; b < C; ++b)
@@ -126,19 +147,21 @@ __global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const doubl
         {
           const int row = lane + 32 * a;
           double v = Dn[a][b];
-          if (i > 0 && row < bs && col < bs)
+          if (j > 0 && row < bs && col < bs)
           {
             const double l = subn[a] * sInv[(size_t)col * bs + row];
-            Lv[(size_t)i * nb2 + (size_t)col * bs + row] = l;
+            Lv[slot * nb2 + (size_t)col * bs + row] = l;
             v = v - l * supn[b];
           }
-          else if (i == 0 && row < bs && col < bs)
-            Lv[(size_t)col * bs + row] = 0.; // (block 0 of l_values is never read; defined for reproducibility)
+          if (top && j == 0 && row < bs && col < bs) // block 0 of l_values is never read as a multiplier: zero, or the tag
+            Lv[(size_t)col * bs + row] = (twist && col == 0 && row < 2) ? (row == 0 ? (double)m : BT_TWIST_MAGIC) : 0.;
+          if (meet && row < bs && col < bs)
+            v = v - __ldcg(Lv + (size_t)(m + 1) * nb2 + (size_t)col * bs + row) * __ldg(subd + (size_t)m * bs + col);
           S[a][b] = v;
         }
       }
-      if (i + 1 < nb)
-        load_block(i + 1); // lands during the elimination
+      if (j + 1 < nblk)
+        load_block(j + 1); // lands during the elimination
       // ---- Gauss-Jordan with implicit partial pivoting ---------------------------------------------------------------
       // Step k: the warp that owns column k ("owner") finds the pivot and publishes {pivot row, 1/pivot, column k};
       // every warp then updates its columns. The owner of step k+1 runs ahead: as soon as step k's data is there it
@@ -298,6 +321,13 @@ __global__ void __launch_bounds__(IW * 32) k_btddod_invert(int nsys, const doubl
       for (int e = tid; e < nb2; e += INT_)
         Di[(size_t)i * nb2 + e] = sInv[e];
     }
+    if (twist && !top)
+    { // hand U_m = diag(sup_m) D''_{m+1}^{-1} to the CTA that eliminates the meeting block
+      for (int e = tid; e < nb2; e += INT_)
+        Lv[(size_t)(m + 1) * nb2 + e] = __ldg(supd + (size_t)m * bs + e % bs) * sInv[e];
+      __threadfence();
+      cluster_sync_all();
+    }
   }
 }
 
@@ -309,7 +339,7 @@ int inv_fail(cudaError_t e, const char *what)
 }
 
 template <int R, int C, int IW>
-int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, double *dinv, cudaStream_t st)
+int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, double *dinv, cudaStream_t st, bool twist)
 {
   const size_t nb2 = (size_t)bs * bs;
   const size_t smem = sizeof(double) * (nb2 + (nb2 & 1) + 2 * 32 * R + 2) + sizeof(int) * (2 + 2 * 32 * R) + 16;
@@ -320,8 +350,21 @@ int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, d
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / smem));
+  if (twist)
+  { // one cluster of two CTAs per system
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned int)std::min(n, std::max(1, sms * per_sm / 2))), cfg.blockDim = dim3(IW * 32);
+    cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, k_btddod_invert<R, C, IW>, n, mats, nb, bs, l_values, dinv, 1);
+    ++g_btddod_launches;
+    return e == cudaSuccess ? GB_OK : inv_fail(e, "k_btddod_invert (clusters)");
+  }
   const int grid = std::min(n, sms * per_sm);
-  k_btddod_invert<R, C, IW><<<grid, IW * 32, smem, st>>>(n, mats, nb, bs, l_values, dinv);
+  k_btddod_invert<R, C, IW><<<grid, IW * 32, smem, st>>>(n, mats, nb, bs, l_values, dinv, 0);
   ++g_btddod_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? GB_OK : inv_fail(e, "k_btddod_invert");
@@ -331,8 +374,8 @@ int launch_invert(int n, const double *mats, int nb, int bs, double *l_values, d
 
 using namespace gb;
 
-extern "C" int gb_btddod_full_invert_batch(int n, const double *matrix, int nb, int bs, double *out_l_values,
-                                           double *out_dinv, void *stream)
+static int invert_impl(int n, const double *matrix, int nb, int bs, double *out_l_values, double *out_dinv, void *stream,
+                       bool tw)
 {
   if (n < 0 || nb < 1 || bs < 1 || (n > 0 && (!matrix || !out_l_values || !out_dinv)))
   {
@@ -352,20 +395,32 @@ extern "C" int gb_btddod_full_invert_batch(int n, const double *matrix, int nb, 
     w16 = (e && atoi(e) == 16) ? 1 : 0;
   }
   if (bs <= 16)
-    return launch_invert<1, 2, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<1, 2, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   if (bs <= 32)
-    return w16 ? launch_invert<1, 2, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
-               : launch_invert<1, 4, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<1, 2, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw)
+               : launch_invert<1, 4, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   if (bs <= 56)
-    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
-               : launch_invert<2, 7, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw)
+               : launch_invert<2, 7, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   if (bs <= 64)
-    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st)
-               : launch_invert<2, 8, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return w16 ? launch_invert<2, 4, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw)
+               : launch_invert<2, 8, 8>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   if (bs <= 96)
-    return launch_invert<3, 6, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<3, 6, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   if (bs <= 128)
-    return launch_invert<4, 8, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st);
+    return launch_invert<4, 8, 16>(n, matrix, nb, bs, out_l_values, out_dinv, st, tw);
   set_error("gb_btddod_full_invert_batch: block size above 128 is not supported");
   return GB_ERR_UNSUPPORTED;
+}
+
+extern "C" int gb_btddod_full_invert_batch(int n, const double *matrix, int nb, int bs, double *out_l_values,
+                                           double *out_dinv, void *stream)
+{
+  return invert_impl(n, matrix, nb, bs, out_l_values, out_dinv, stream, false);
+}
+
+extern "C" int gb_btddod_full_invert_twisted_batch(int n, const double *matrix, int nb, int bs, double *out_l_values,
+                                                   double *out_dinv, void *stream)
+{
+  return invert_impl(n, matrix, nb, bs, out_l_values, out_dinv, stream, bt_twist_ok(nb, bs));
 }

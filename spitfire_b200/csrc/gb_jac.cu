@@ -134,6 +134,8 @@ __device__ __forceinline__ void gather_step(unsigned int u, const double *sR, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int JAC_SLOTS = 8; // start-time slots of the persistent CTAs (see `stagger`)
+
 template <int G>
 __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 {
@@ -238,6 +240,19 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
   };
   fetch_T(blockIdx.x);
   finish_T();
+  // De-phasing: all CTAs of the persistent grid start together and take the same time per tile, so without a start
+  // offset every SM reaches its store-bound output phase at the same moment and the chip-wide write path, not the
+  // SM's own, sets the length of that phase. CTA b waits (b mod JAC_SLOTS) * stagger cycles once.
+  if (a.stagger > 0)
+  {
+    if (tid == 0)
+    {
+      const long long t0 = clock64(), d = (long long)(blockIdx.x % JAC_SLOTS) * a.stagger;
+      while (clock64() - t0 < d)
+        __nanosleep(256);
+    }
+    __syncthreads();
+  }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
     const int tile0 = tile * G;
@@ -767,7 +782,13 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 #pragma unroll
           for (int sl = 0; sl < G; ++sl)
             if (sl < gcount)
+            {
+#ifdef GB_JAC_STCS
+              __stcs(ob[sl] + off, v[sl]);
+#else
               ob[sl][off] = v[sl];
+#endif
+            }
         }
       }
     }
@@ -806,8 +827,14 @@ static cudaError_t launch_jac_g(const ChemArgs &a, size_t smem, cudaStream_t s)
   per_sm = std::min(per_sm, 8);
   if (const char *e = getenv("GB_JAC_CTAS"))
     per_sm = std::max(1, atoi(e));
-  const int grid = std::max(1, std::min(ntiles, jac_sm_count() * per_sm));
-  k_jac<G><<<grid, threads, smem, s>>>(a);
+  int grid = std::max(1, std::min(ntiles, jac_sm_count() * per_sm));
+  if (const char *e = getenv("GB_JAC_GRID"))
+    grid = std::max(1, std::min(grid, atoi(e)));
+  ChemArgs b = a;
+  b.stagger = 0;
+  if (const char *e = getenv("GB_JAC_STAGGER"))
+    b.stagger = std::max(0, atoi(e));
+  k_jac<G><<<grid, threads, smem, s>>>(b);
   ++g_jac_launches;
   return cudaGetLastError();
 }

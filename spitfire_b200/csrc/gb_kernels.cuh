@@ -58,6 +58,7 @@ struct ChemArgs
   FlameletDev fl;
   int G;           // states per CTA tile
   int GS;          // smem stride per index (G padded to odd)
+  int stagger;     // k_jac: start delay (cycles) per CTA phase slot, see launch_jac_g
 };
 
 // launches; return cudaError_t of the launch
@@ -77,6 +78,39 @@ cudaError_t launch_block_max_real_eig(int nblocks, const double *base, long stri
                                       cudaStream_t s);
 // out[b * n + q] = max(maxre[b] - diffterm, 0)
 cudaError_t launch_expand_expeig(int nblocks, int n, const double *maxre, double diffterm, double *out, cudaStream_t s);
+// ---- twisted ("burn at both ends") block-Thomas elimination (gb_btinv.cu, k_btddod_solve_inv) ----------------------
+// Factors made by the twisted elimination carry a tag in block 0 of l_values (never read otherwise): element 0 = the
+// meeting block m, element 1 = BT_TWIST_MAGIC. bt_twist_ok: the one rule both kernels' launchers follow (nb >= 4,
+// bs >= 2, right-hand side staged in shared memory, not disabled by GB_BT_TWIST=0).
+constexpr double BT_TWIST_MAGIC = 2.718281828459045e-300;
+bool bt_twist_ok(int nb, int bs);
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int cluster_ctarank()
+{
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int clusterid_x()
+{
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int nclusterid_x()
+{
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+// all threads of both CTAs; orders global and shared-memory accesses across the barrier at cluster scope
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::
+                   : "memory");
+}
+#endif
 long kernel_launch_count();
 void count_launch();
 #ifdef GB_JAC_TIMELINE

@@ -279,6 +279,7 @@ class _BatchOps(object):
     # 3-4x shorter than the pivoted triangular solves (griffon_b200.h, gb_btddod_full_*_inv_batch).
     explicit_inverse_solves = True
     gauss_jordan_inverses = True  # k_btddod_invert instead of LU + dgetrs-on-identity (gb_btinv.cu)
+    twisted_elimination = True    # ... eliminating from both ends at once (two CTAs of a cluster per flamelet)
     _rows32 = (None, None)  # last (int64 rows, int32 copy) pair handed to the solve kernel
 
     def factor_store(self, F):
@@ -309,7 +310,8 @@ class _BatchOps(object):
             Dinv = torch.empty((n, self.nzi * self.ns * self.ns), dtype=torch.float64, device=self.device)
             if getattr(self, 'gauss_jordan_inverses', True):
                 # the solvers only ever apply these factors through solve_inv: inverses alone, by the short-chain kernel
-                self.gmod.btddod_full_invert(J, self.nzi, self.ns, L, Dinv, n_systems=n)
+                self.gmod.btddod_full_invert(J, self.nzi, self.ns, L, Dinv, n_systems=n,
+                                             twisted=getattr(self, 'twisted_elimination', True))
             else:
                 self.gmod.btddod_full_factorize_inv(J, self.nzi, self.ns, L, piv, Dinv, n_systems=n)
             return J, L, piv, Dinv

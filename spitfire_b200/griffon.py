@@ -97,6 +97,7 @@ def load_library():
     sig('gb_btddod_full_factorize_inv_batch', I, [I, V, I, I, V, V, V, V])
     sig('gb_btddod_full_solve_inv_batch', I, [I, V, V, V, V, I, I, V, V, V])
     sig('gb_btddod_full_invert_batch', I, [I, V, I, I, V, V, V])
+    sig('gb_btddod_full_invert_twisted_batch', I, [I, V, I, I, V, V, V])
     sig('gb_max_real_eigenvalue_batch', I, [I, I, V, V, V])
     sig('gb_btddod_full_matvec_batch', I, [I, V, V, I, I, V, V])
     sig('gb_btddod_scale_and_add_diagonal_batch', I, [I, V, D, V, D, I, I, V])
@@ -571,12 +572,15 @@ def max_real_eigenvalue(blocks, n, out, n_blocks):
           'gb_max_real_eigenvalue_batch')
 
 
-def btddod_full_invert(matrix, num_blocks, block_size, out_l_values, out_dinv, n_systems=1):
+def btddod_full_invert(matrix, num_blocks, block_size, out_l_values, out_dinv, n_systems=1, twisted=False):
     """extension (device arrays only): block-Thomas elimination by Gauss-Jordan inverses; `matrix` is left intact and
-    serves as the d_factors argument of btddod_full_solve_inv"""
-    check(load_library().gb_btddod_full_invert_batch(int(n_systems), _addr(matrix), int(num_blocks), int(block_size),
-                                                     _addr(out_l_values), _addr(out_dinv), _stream()),
-          'gb_btddod_full_invert_batch')
+    serves as the d_factors argument of btddod_full_solve_inv. twisted: the two-sided elimination (two CTAs of a
+    cluster per system meeting in the middle block; btddod_full_solve_inv recognises the format by its tag)"""
+    lib = load_library()
+    fn = lib.gb_btddod_full_invert_twisted_batch if twisted else lib.gb_btddod_full_invert_batch
+    check(fn(int(n_systems), _addr(matrix), int(num_blocks), int(block_size), _addr(out_l_values), _addr(out_dinv),
+             _stream()),
+          'gb_btddod_full_invert_twisted_batch' if twisted else 'gb_btddod_full_invert_batch')
 
 
 def btddod_full_solve_inv(d_factors, l_values, dinv, rhs, num_blocks, block_size, out_solution, n_systems=1,

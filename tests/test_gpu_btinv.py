@@ -82,3 +82,69 @@ def test_invert_pivots_on_a_permuted_block():
     gm.btddod_full_solve_inv(dA, L, Di, torch.from_numpy(b).cuda(), nb, bs, x, n_systems=1)
     ref = np.linalg.solve(assemble_dense(A[0], nb, bs), b[0])
     assert np.max(np.abs(x.cpu().numpy()[0] - ref)) <= 1e-9 * np.max(np.abs(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nb,bs', [(4, 2), (4, 5), (5, 11), (7, 32), (8, 33), (126, 53), (127, 53), (9, 64), (6, 65), (3, 7)])
+def test_twisted_elimination_solves_like_the_dense_matrix(nb, bs):
+    """gb_btddod_full_invert_twisted_batch + gb_btddod_full_solve_inv_batch (two CTAs of a cluster per system, meeting
+    in the middle block) against the dense solve and against the one-sided elimination; (3, 7): below four blocks the
+    twisted entry point falls back to the one-sided form"""
+    import torch
+    from spitfire_b200 import griffon as gm
+    n = 5
+    A = _systems(n, nb, bs, seed=nb * 77 + bs, dominance=2. * np.sqrt(bs))
+    dA = torch.from_numpy(A).cuda()
+    keep = dA.clone()
+    L = torch.zeros((n, nb * bs * bs), dtype=torch.float64, device='cuda')
+    Di = torch.zeros_like(L)
+    gm.btddod_full_invert(dA, nb, bs, L, Di, n_systems=n, twisted=True)
+    assert torch.equal(dA, keep)
+    m = (nb - 1) // 2
+    if nb >= 4 and bs <= 64:
+        # the format tag, the untouched top half (same arithmetic as the one-sided elimination) and a different bottom
+        assert float(L[0, 0]) == float(m) and float(L[0, 1]) == 2.718281828459045e-300
+        L1, D1 = torch.zeros_like(L), torch.zeros_like(L)
+        gm.btddod_full_invert(dA, nb, bs, L1, D1, n_systems=n)
+        assert torch.equal(Di[:, :m * bs * bs], D1[:, :m * bs * bs])
+        assert torch.equal(L[:, bs * bs:(m + 1) * bs * bs], L1[:, bs * bs:(m + 1) * bs * bs])
+        assert not torch.equal(Di[:, (m + 1) * bs * bs:], D1[:, (m + 1) * bs * bs:])
+    rng = np.random.default_rng(11)
+    b = rng.standard_normal((n, nb * bs))
+    db = torch.from_numpy(b).cuda()
+    x = torch.zeros_like(db)
+    gm.btddod_full_solve_inv(dA, L, Di, db, nb, bs, x, n_systems=n)
+    xh = x.cpu().numpy()
+    for s in range(n):
+        ref = np.linalg.solve(assemble_dense(A[s], nb, bs), b[s])
+        assert np.max(np.abs(xh[s] - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # a subset of the systems addressed in place, right-hand sides compact
+    rows = torch.tensor([3, 0, 4], dtype=torch.int32, device='cuda')
+    sub = torch.zeros((3, nb * bs), dtype=torch.float64, device='cuda')
+    gm.btddod_full_solve_inv(dA, L, Di, db[rows.long()].contiguous(), nb, bs, sub, n_systems=3, system_rows=rows)
+    assert torch.equal(sub, x[rows.long()])
+    # repeatable bit for bit
+    x2 = torch.zeros_like(db)
+    gm.btddod_full_solve_inv(dA, L, Di, db, nb, bs, x2, n_systems=n)
+    assert torch.equal(x, x2)
+
+
+@pytest.mark.gpu
+def test_twisted_elimination_large_batch():
+    """more systems than cluster slots: the persistent loops of both kernels"""
+    import torch
+    from spitfire_b200 import griffon as gm
+    n, nb, bs = 200, 6, 11
+    A = _systems(n, nb, bs, seed=5, dominance=2. * np.sqrt(bs))
+    dA = torch.from_numpy(A).cuda()
+    L = torch.zeros((n, nb * bs * bs), dtype=torch.float64, device='cuda')
+    Di = torch.zeros_like(L)
+    gm.btddod_full_invert(dA, nb, bs, L, Di, n_systems=n, twisted=True)
+    b = np.random.default_rng(2).standard_normal((n, nb * bs))
+    db = torch.from_numpy(b).cuda()
+    x = torch.zeros_like(db)
+    gm.btddod_full_solve_inv(dA, L, Di, db, nb, bs, x, n_systems=n)
+    xh = x.cpu().numpy()
+    for s in (0, 73, 148, 199):
+        ref = np.linalg.solve(assemble_dense(A[s], nb, bs), b[s])
+        assert np.max(np.abs(xh[s] - ref)) <= 1e-10 * np.max(np.abs(ref))
