@@ -348,7 +348,9 @@ int gb_flamelet_esdirk_stages_batch(gb_mech *m, int F, const gb_flamelet_params 
  * members completed, the embedded error estimate (b, bh: HOST arrays; dq, stats: device), q <- q + dq (clipped at zero
  * if clip_negative) for the completed members whose update is finite, and host_stats [3][F], host_nlfail [F] and the
  * rows of the completed members in host_q [F][ndof] are filled. Returns the rounds taken or a negative error code.
- * newton_its[m] accumulates the member's Newton iterations; start_d / dtin_d: device work arrays of F ints / doubles. */
+ * newton_its[m] accumulates the member's Newton iterations; start_d / dtin_d: device work arrays of F ints / doubles.
+ * host_members (may be NULL) / n_members: a superset of the members that are inside a step during this tick; the
+ * flamelet right-hand side of a round is evaluated for those only (at most 64; otherwise, or if NULL, for all F). */
 int gb_async_round_kernels(int n, int ndof, int nstages, const double *tableau, int max_iterations, int phase,
                            const double *fn, double *xn, const double *dx, const double *q, const double *dt,
                            double gamma, const double *weights, double tolerance, double *x, double *f, double *res,
@@ -362,7 +364,7 @@ int gb_flamelet_async_tick_batch(gb_mech *m, int F, const gb_flamelet_params *pr
                                  int *nlfail, int *newton_its, double *work, double *dq, double *stats, int *start_d,
                                  double *dtin_d, int max_rounds, const int *host_start, const double *host_dt,
                                  int *host_state, int *host_stage, double *host_stats, int *host_nlfail, double *host_q,
-                                 void *stream);
+                                 const int *host_members, int n_members, void *stream);
 /* Status "> 0 = number of members with non-finite output" (SURVEY 8(b)): flags_out[m] (device, may be NULL) = 1 if row m of
  * a [n][len_a] -- or of b [n][len_b], if given -- holds an Inf or NaN. Synchronises the stream and returns the number of
  * such members (>= 0) or a negative error code. The asynchronous *_batch entry points cannot report it themselves; the

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -127,6 +128,19 @@ extern "C"
 {
 
   long gb_kernel_launch_count(void) { return kernel_launch_count(); }
+  // host-clock accounting of gb_flamelet_async_tick_batch (one integrator at a time): {ticks, rounds, seconds inside
+  // the calls, seconds inside the round loops, seconds from launch to synchronised end of the solves (GB_TICK_PROFILE=1
+  // only: adds a synchronisation per round)}
+  static double g_tick_stats[8] = {0};
+  void gb_debug_tick_stats(double *out, int reset)
+  {
+    for (int k = 0; k < 8; ++k)
+    {
+      out[k] = g_tick_stats[k];
+      if (reset)
+        g_tick_stats[k] = 0.;
+    }
+  }
 #ifdef GB_JAC_TIMELINE
   int gb_debug_jac_timeline(long long *out /* [16*32] */) { return gb::debug_jac_timeline(out); }
   int gb_debug_bt_timeline(long long *out /* [8] */) { return gb::debug_bt_timeline(out); }
@@ -795,8 +809,10 @@ extern "C"
     return GB_OK;
   }
 
-  int gb_flamelet_rhs_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm, double *out_rhs,
-                            void *stream)
+  // members (host, may be NULL): evaluate only the flamelets members[0..n_members) of the batch (rows of the others
+  // are left untouched); at most 64 of them, else everything is evaluated
+  static int flamelet_rhs_members(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm, double *out_rhs,
+                                  const int *members, int n_members, void *stream)
   {
     RC(ready(m));
     RC(check_flamelet(F, state, prm, out_rhs));
@@ -810,8 +826,28 @@ extern "C"
     a.p = prm->pressure;
     a.out0 = out_rhs;
     RC(flamelet_dev(m, F, state, prm, &a.fl, (cudaStream_t)stream));
+    if (members && n_members > 0 && n_members < F && n_members <= 64 && F <= 256)
+    {
+      a.fl.nmembers = n_members;
+      for (int k = 0; k < n_members; ++k)
+      {
+        if (members[k] < 0 || members[k] >= F)
+        {
+          set_error("flamelet right-hand side: member index out of range");
+          return GB_ERR_ARG;
+        }
+        a.fl.members[k] = (unsigned char)members[k];
+      }
+      a.n = n_members * prm->nzi;
+    }
     CK(launch_rates(a, (cudaStream_t)stream));
     return GB_OK;
+  }
+
+  int gb_flamelet_rhs_batch(gb_mech *m, int F, const double *state, const gb_flamelet_params *prm, double *out_rhs,
+                            void *stream)
+  {
+    return flamelet_rhs_members(m, F, state, prm, out_rhs, nullptr, 0, stream);
   }
 
   // The Newton loop of one implicit stage for F flamelets, entirely behind the C-ABI: per iteration the inverse-based
@@ -908,7 +944,8 @@ extern "C"
                                    int *iters, int *nlfail, int *newton_its, double *work, double *dq, double *stats,
                                    int *start_d, double *dtin_d, int max_rounds, const int *host_start,
                                    const double *host_dt, int *host_state, int *host_stage, double *host_stats,
-                                   int *host_nlfail, double *host_q, void *stream)
+                                   int *host_nlfail, double *host_q, const int *host_members, int n_members,
+                                   void *stream)
   {
     RC(ready(m));
     RC(check_flamelet(F, x, prm, f));
@@ -924,6 +961,10 @@ extern "C"
     const int ns = m->h.dm.ns, nzi = prm->nzi, ndof = ns * nzi;
     double *dx = work, *xn = dx + (size_t)F * ndof, *fn = xn + (size_t)F * ndof;
     cudaStream_t st = (cudaStream_t)stream;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    static const bool tick_profile = getenv("GB_TICK_PROFILE") != nullptr;
+    const clk::time_point tick_t0 = clk::now();
     if (host_start)
     {
       bool any = false;
@@ -945,12 +986,25 @@ extern "C"
     }
     int rounds = 0;
     bool any_complete = false;
+    const clk::time_point loop_t0 = clk::now();
     while (rounds < max_rounds)
     {
+      const clk::time_point r0 = clk::now();
       RC(gb_btddod_full_solve_inv_batch(F, d_factors, l_values, dinv, res, nzi, ns, dx, nullptr, stream));
+      if (tick_profile)
+      {
+        CK(cudaStreamSynchronize(st));
+        g_tick_stats[4] += secs(r0, clk::now());
+      }
       RC(gb_async_round_kernels(F, ndof, nstages, tableau, max_iterations, 0, fn, xn, dx, q, dt, gamma, weights, tolerance, x,
                                 f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
-      RC(gb_flamelet_rhs_batch(m, F, xn, prm, fn, stream));
+      const clk::time_point r1 = clk::now();
+      RC(flamelet_rhs_members(m, F, xn, prm, fn, host_members, n_members, stream));
+      if (tick_profile)
+      {
+        CK(cudaStreamSynchronize(st));
+        g_tick_stats[5] += secs(r1, clk::now());
+      }
       RC(gb_async_round_kernels(F, ndof, nstages, tableau, max_iterations, 1, fn, xn, dx, q, dt, gamma, weights, tolerance, x,
                                 f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
       CK(cudaMemcpyAsync(host_state, state, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
@@ -966,6 +1020,17 @@ extern "C"
       if (any_complete || !any_active)
         break;
     }
+    g_tick_stats[3] += secs(loop_t0, clk::now());
+    g_tick_stats[1] += rounds;
+    struct TickEnd
+    {
+      clk::time_point t0;
+      ~TickEnd()
+      {
+        g_tick_stats[0] += 1.;
+        g_tick_stats[2] += std::chrono::duration<double>(clk::now() - t0).count();
+      }
+    } tick_end{tick_t0};
     if (any_complete)
     {
       const double *kp[6];

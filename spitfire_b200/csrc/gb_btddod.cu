@@ -813,6 +813,7 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
   }
   __syncthreads();
   int gs0 = 0; // blocks streamed by this CTA before the current system (ring slot and barrier phase follow from it)
+  int pair_iter = 0; // systems this pair of CTAs has looked at (selects one of two decision words)
   // byte offsets, inside a block, of the sixteen matrix entries this thread multiplies in the fast path (bs <= 64):
   // the same for every step, kept in registers so that a step's loads are plain 32-bit shared addresses
   unsigned int mofs[16];
@@ -835,9 +836,27 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     const double *Di = dinv + (size_t)fsys * nb * nb2;
     const double *b = rhs + (size_t)sys * nb * bs;
     double *x = solution + (size_t)sys * nb * bs;
-    // meeting block m of the sweep(s): nb-1 for plain factors
-    const bool twisted = pairs && nb >= 4 && bs >= 2 && __ldg(Lv + 1) == BT_TWIST_MAGIC;
-    const int m = twisted ? (int)__ldg(Lv) : nb - 1;
+    // meeting block m of the sweep(s): nb-1 for plain factors. CTA 0 reads the tag and the pair agrees on ITS reading
+    // through distributed shared memory (a caller that refreshes factors on another stream while a solve of the whole
+    // batch is in flight -- the asynchronous integrator does, for members that are not inside a step -- must not be able
+    // to split the pair over a half-written tag: one CTA would wait for the other at a cluster barrier for ever)
+    int mdec = -1;
+    if (pairs)
+    {
+      int *sdec = reinterpret_cast<int *>(sm + 4) + (pair_iter & 1);
+      if (crank == 0 && tid == 0)
+      {
+        const int mt = (nb >= 4 && bs >= 2 && __ldg(Lv + 1) == BT_TWIST_MAGIC) ? (int)__ldg(Lv) : -1;
+        *sdec = (mt >= 1 && mt <= nb - 2) ? mt : -1;
+      }
+      cluster_sync_all();
+      unsigned int remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(sdec)), "r"(0));
+      asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(mdec) : "r"(remote) : "memory");
+      ++pair_iter;
+    }
+    const bool twisted = mdec >= 0;
+    const int m = twisted ? mdec : nb - 1;
     if (crank != 0 && !twisted)
       continue;
     const bool top = crank == 0;

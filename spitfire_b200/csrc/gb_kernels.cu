@@ -106,7 +106,8 @@ __device__ __forceinline__ void load_tile(const ChemArgs &a, int tile0, int gcou
     for (int item = threadIdx.x; item < gcount * ns; item += blockDim.x)
     {
       const int g = item / ns, j = item - g * ns;
-      const double v = a.in_state[(size_t)(tile0 + g) * ns + j];
+      const int sidx = a.mode == MODE_FLAMELET_RHS ? flamelet_state_index(a.fl, tile0 + g) : tile0 + g;
+      const double v = a.in_state[(size_t)sidx * ns + j];
       if (j == 0)
         SM(sc, Tile::S_T, g) = v;
       else
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(512, 1) k_rates(const ChemArgs a)
         if (threadIdx.x < gcount)
         {
           const int g = threadIdx.x;
-          const int sidx = tile0 + g, F = sidx / nzi, i = sidx - F * nzi;
+          const int sidx = flamelet_state_index(fl, tile0 + g), F = sidx / nzi, i = sidx - F * nzi;
           const double rho = SM(sc, Tile::S_RHO, g), cp = SM(sc, Tile::S_CP, g), T = SM(sc, Tile::S_T, g);
           double rhs0 = SM(sc, Tile::S_AUX0, g);
           if (!fl.adiabatic)
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(512, 1) k_rates(const ChemArgs a)
         for (int item = threadIdx.x; item < gcount * ns; item += blockDim.x)
         {
           const int g = item / ns, j = item - g * ns;
-          const int sidx = tile0 + g, F = sidx / nzi, i = sidx - F * nzi;
+          const int sidx = flamelet_state_index(fl, tile0 + g), F = sidx / nzi, i = sidx - F * nzi;
           double v;
           if (j == 0)
             v = SM(sc, Tile::S_AUX0, g);
@@ -693,7 +694,13 @@ cudaError_t launch_rates(const ChemArgs &a_in, cudaStream_t s)
   // smaller tiles, whose latency is lower (GRI, 1008 states: 72 us with 7-state tiles against 115 us with 31)
   int G = env_int("GB_RATES_G", 0);
   if (G <= 0)
-    G = std::min(31, std::max(7, (a.n + sm_count() - 1) / sm_count()));
+  {
+    // ... and batches of a few waves get equal tiles: 7168 states (56 flamelets of 128 points) are 2 x 148 tiles of 25
+    // states rather than 148 + 84 tiles of 31 (the second wave costs as much as the first)
+    const int sms = sm_count();
+    const int waves = std::max(1, (a.n + 31 * sms - 1) / (31 * sms));
+    G = std::min(31, std::max(7, (a.n + waves * sms - 1) / (waves * sms)));
+  }
   while (G > 1 && rates_smem(a.dm, G | 1) > (size_t)maxsm)
     G -= 2;
   if (rates_smem(a.dm, G | 1) > (size_t)maxsm)

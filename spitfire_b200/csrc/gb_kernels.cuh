@@ -44,7 +44,19 @@ struct FlameletDev
   int scale_and_offset;
   double prefactor;
   int chem_only; // diagonal blocks as they stand at flamelet_kernels.cpp:1327 (before cmajor etc.): the eigenvalue pass
+  // flamelet right-hand side of a SUBSET of the batch (asynchronous integrator: only the members inside a step): the
+  // kernel's n = nmembers * nzi states are the points of the flamelets members[0..nmembers); 0 = all, in order
+  int nmembers;
+  unsigned char members[64];
 };
+// state index in the batch's arrays of the l-th state a flamelet right-hand side launch works on
+__host__ __device__ inline int flamelet_state_index(const FlameletDev &fl, int l)
+{
+  if (fl.nmembers <= 0)
+    return l;
+  const int k = l / fl.nzi;
+  return (int)fl.members[k] * fl.nzi + (l - k * fl.nzi);
+}
 
 struct ChemArgs
 {

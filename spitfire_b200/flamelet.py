@@ -410,6 +410,18 @@ class _BatchOps(object):
                                       prefactor=1., rates_sens_option=self.rsopt, sens_transform_option=self.stopt)
         return out
 
+    def jac_scaled_row_on(self, g, q, m, prefactor, out):
+        """row m of out [F, nelem] <- prefactor * J(q[m]) - I (the scale-and-offset option of the Jacobian kernel,
+        flamelet_kernels.cpp:1395-1408), through the Griffon handle g"""
+        g.flamelet_jacobian_batch(1, q[m:m + 1], self.member_params(m), out[m:m + 1], scale_and_offset=True,
+                                  prefactor=prefactor, rates_sens_option=self.rsopt, sens_transform_option=self.stopt)
+
+    def invert_row(self, J, L, Dinv, m):
+        """block elimination by inverses of system m of J [F, nelem] into row m of L and Dinv (what `factorize` with
+        with_inverse does for a batch, in place in the caller's arrays)"""
+        self.gmod.btddod_full_invert(J[m:m + 1], self.nzi, self.ns, L[m:m + 1], Dinv[m:m + 1], n_systems=1,
+                                     twisted=getattr(self, 'twisted_elimination', True))
+
     def nonfinite_rows(self, a, b):
         """bool [n]: the member's row of a or of b holds an Inf or NaN. On the device one kernel writes the flags
         (gb_count_nonfinite_members_batch), on the host the tensor expressions do."""
@@ -688,6 +700,10 @@ class FlameletBatch(object):
 
         def stop(t, q, residual, nsteps):
             return (q.amax(dim=1) < (1. + temperature_tolerance) * T_bc_max) | (residual < steady_tolerance)
+
+        # the same test on host rows (numpy), for the integrator that has the completed members' states on the host
+        stop.host = lambda t, q, residual, nsteps: \
+            (q.max(axis=1) < (1. + temperature_tolerance) * T_bc_max) | (residual < steady_tolerance)
 
         q0 = ops.torch.as_tensor(np.array([fl._current_state for fl in self.flamelets])).to(ops.device)
         times, states, failed = integrate_batch(ops, q0, stop, first_time_step=first_time_step,

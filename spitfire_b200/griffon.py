@@ -111,7 +111,7 @@ def load_library():
     sig('gb_newton_tail_staged_batch', I, [I, I, I, dp, I, V, V, V, V, D, V, D, V, V, V, V, V, V, V, V, V, V, ip, V])
     sig('gb_flamelet_esdirk_stages_batch', I, [P, I, FP, V, V, V, V, I, dp, V, V, D, V, D, I, V, V, V, V, V, V, V, V, V, V, V, ip, V])
     sig('gb_flamelet_async_tick_batch', I, [P, I, FP, V, V, V, I, dp, dp, dp, V, V, D, V, D, I, I] + [V] * 15 +
-        [I, V, V, V, V, V, V, V, V])
+        [I, V, V, V, V, V, V, V, V, I, V])
     sig('gb_flamelet_newton_stage_batch', I, [P, I, FP, V, V, V, V, V, V, V, D, V, D, I, V, V, V, V, V, V, ip, V])
     sig('gb_btddod_full_factorize_host', I, [I, V, I, I, V, V])
     sig('gb_btddod_full_solve_host', I, [I, V, V, V, V, I, I, V])
@@ -441,7 +441,7 @@ class PyCombustionKernels(MechanismSetters):
         return left, rounds.value
 
     def flamelet_async_tick_batch(self, n_flamelets, prm, dev, host, tableau_c, b_c, bh_c, nstages, gamma, tolerance,
-                                  max_iterations, clip_negative, max_rounds, with_start):
+                                  max_iterations, clip_negative, max_rounds, with_start, members=None):
         """one tick of the asynchronous batch integrator (griffon_b200.h: gb_flamelet_async_tick_batch). dev: dict of
         raw device addresses (ints) keyed like the C arguments, host: dict of raw host addresses; returns the rounds."""
         d, h = dev, host
@@ -451,6 +451,7 @@ class PyCombustionKernels(MechanismSetters):
             d['x'], d['f'], d['res'], d['expl'], d['K'], d['state'], d['stage'], d['iters'], d['nlfail'], d['nits'],
             d['work'], d['dq'], d['stats'], d['start'], d['dtin'], int(max_rounds),
             h['start'] if with_start else None, h['dt'], h['state'], h['stage'], h['stats'], h['nlfail'], h['q'],
+            None if members is None else members.ctypes.data, 0 if members is None else int(members.size),
             _stream()), 'flamelet_async_tick_batch')
 
     # ---- flamelet (griffon.pyx:556-679) ---------------------------------------------------------------------------

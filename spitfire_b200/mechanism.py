@@ -359,7 +359,8 @@ class ChemicalMechanismSpec(object):
     def _get_atoms_in_stream(self, stream, atom_names):
         atom_amounts = {atom: 0 for atom in atom_names}
         X = stream.X
-        for i, species in enumerate(self._species_names):
+        # (species in index order as in the reference; absent species add exact zeros and are skipped)
+        for i in np.nonzero(X)[0].tolist():
             for atom in atom_names:
                 atom_amounts[atom] += X[i] * self.n_atoms(i, atom)
         return atom_amounts

@@ -320,6 +320,9 @@ def integrate_batch(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.e-3, m
 # with a second Griffon handle while the other members keep iterating. Every member's arithmetic is the sequence
 # integrate_batch performs for it, so the trajectories are identical bit for bit (tests/test_gpu_newton.py).
 ASYNC_MEMBERS = _os.environ.get('GB_ASYNC_MEMBERS', '1') != '0'
+# Jacobian refreshes of the asynchronous integrator written and eliminated in place in the batch's factor arrays
+# (GB_DIRECT_REFRESH=0: through temporaries and tensor copies, as the lock-step batch does; same numbers)
+DIRECT_REFRESH = _os.environ.get('GB_DIRECT_REFRESH', '1') != '0'
 
 
 LAST_ASYNC_STATS = dict()
@@ -385,8 +388,9 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
     # Jacobian refreshes run on a few side streams, round robin, each with its own Griffon handle (a handle serves one
     # stream at a time): a refresh is ~3.5 ms on one SM per member and there are several thousand of them, so one side
     # stream would serialise more work than the whole integration takes
-    n_side = 6
+    n_side = 8
     sides = [(torch.cuda.Stream(), ops.second_griffon(k)) for k in range(n_side)]
+    direct_refresh = DIRECT_REFRESH and getattr(ops, 'gauss_jordan_inverses', False)
     ctrl = torch.cuda.Stream()  # the stopping test runs here: it must not queue behind the rounds in flight
     device = torch.cuda.current_device()
     pending = []  # (event, member ids) of the Jacobian refreshes in flight
@@ -402,11 +406,11 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(1)
 
-    def run_tick(bi, with_start, max_rounds):
+    def run_tick(bi, with_start, max_rounds, members):
         torch.cuda.set_device(device)
         return ops.g.flamelet_async_tick_batch(F, prm_all, devp, hosts[bi], tab, b_c, bh_c, nst, _G,
                                                nonlinear_solve_tolerance, max_nonlinear_iter, clip_negative, max_rounds,
-                                               with_start)
+                                               with_start, members)
 
     def step_end(hv):
         """what integrate_batch does for everybody at once, for the members that completed a step in this tick"""
@@ -448,9 +452,16 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
             refresh[rej] = True
         attempts[fin] += 1
         residual_full[fin] = np.where(np.isfinite(residual), residual, np.inf)
-        with torch.cuda.stream(ctrl):  # (the rows of these members are final: their tick has been synchronised)
-            pack_d.copy_(torch.from_numpy(np.stack([t, residual_full, nsteps.astype(np.float64)])))
-            done = stop(pack_d[0], q, pack_d[1], pack_d[2].to(torch.int64)).cpu().numpy()
+        stop_host = getattr(stop, 'host', None)
+        if stop_host is not None:
+            # the stopping test on the host copies of the completed members' rows (they came back with the tick): no
+            # device work, no synchronisation
+            done = np.zeros(F, dtype=bool)
+            done[fin] = stop_host(t[fin], hv['q'][fin], residual_full[fin], nsteps[fin])
+        else:
+            with torch.cuda.stream(ctrl):  # (the rows of these members are final: their tick has been synchronised)
+                pack_d.copy_(torch.from_numpy(np.stack([t, residual_full, nsteps.astype(np.float64)])))
+                done = stop(pack_d[0], q, pack_d[1], pack_d[2].to(torch.int64)).cpu().numpy()
         if not stop_ignores_minimum:
             done = done & (nsteps >= minimum_time_step_count)
         if stop_at_time is not None:
@@ -468,19 +479,35 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
                 if stop_at_time is not None:
                     dt[need] = np.where(t[need] + dt[need] > stop_at_time, stop_at_time - t[need], dt[need])
                 rf = need[refresh[need]]
-                if rf.size:
+                if rf.size and direct_refresh:
+                    # dt gamma J - I straight out of the Jacobian kernel into the member's rows of the batch's arrays,
+                    # eliminated in place there: two launches per member, no temporaries, no copies (the rounds in
+                    # flight read these rows for the idle member and discard what they compute). One side stream per
+                    # member, round robin: the members of a refresh do not wait for each other.
+                    for m in rf.tolist():
+                        side, g2 = sides[n_refresh % n_side]
+                        with torch.cuda.stream(side):
+                            ops.jac_scaled_row_on(g2, q, m, float(dt[m] * _G), J)
+                            ops.invert_row(J, L, Dinv, m)
+                            ev = torch.cuda.Event()
+                            ev.record(side)
+                        pending.append((ev, np.array([m])))
+                        n_refresh += 1
+                    phase[rf] = WAIT
+                elif rf.size:
                     side, g2 = sides[n_refresh % n_side]
                     with torch.cuda.stream(side):
                         # (the members' states are final: the tick that accepted them has been synchronised. Nothing is
                         # copied from the host here: a synchronous copy would wait for the refresh queued before it)
-                        Jn = torch.empty((rf.size, ops.nelem), **f64)
-                        ops.jac_rows_on(g2, q, rf.tolist(), Jn)
-                        for k_, m in enumerate(rf.tolist()):
-                            Jn[k_].mul_(float(dt[m] * _G))
-                        ops.add_to_block_diagonal(Jn, 1., ones[:rf.size], -1.)
-                        fact = ops.factorize(Jn, with_inverse=True)
-                        for k_, m in enumerate(rf.tolist()):
-                            J[m].copy_(fact[0][k_]), L[m].copy_(fact[1][k_]), Dinv[m].copy_(fact[3][k_])
+                        if True:
+                            Jn = torch.empty((rf.size, ops.nelem), **f64)
+                            ops.jac_rows_on(g2, q, rf.tolist(), Jn)
+                            for k_, m in enumerate(rf.tolist()):
+                                Jn[k_].mul_(float(dt[m] * _G))
+                            ops.add_to_block_diagonal(Jn, 1., ones[:rf.size], -1.)
+                            fact = ops.factorize(Jn, with_inverse=True)
+                            for k_, m in enumerate(rf.tolist()):
+                                J[m].copy_(fact[0][k_]), L[m].copy_(fact[1][k_]), Dinv[m].copy_(fact[3][k_])
                         ev = torch.cuda.Event()
                         ev.record(side)
                     pending.append((ev, rf))
@@ -511,7 +538,10 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
                 refresh[sid] = False  # (set again by the policy at the end of the step)
             nxt = None
             if np.any(phase == RUN):
-                nxt = (pool.submit(run_tick, bi, bool(start), 1 if (pending or inflight is not None) else 16), bi)
+                # (the members inside a step: a superset of those the device still iterates on -- the ones that completed
+                # in the tick in flight are idle there -- and all the right-hand side kernel of a round needs to visit)
+                running = np.ascontiguousarray(np.nonzero(phase == RUN)[0], dtype=np.int32)
+                nxt = (pool.submit(run_tick, bi, bool(start), 1 if (pending or inflight is not None) else 16, running), bi)
                 bi ^= 1
             # ---- meanwhile: the step ends of the tick that has just finished ------------------------------------------------
             if inflight is not None:
