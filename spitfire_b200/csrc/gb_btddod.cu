@@ -1101,6 +1101,9 @@ __global__ void __launch_bounds__(SI_THREADS) k_btddod_solve_inv(int nsys, const
     cp_async_wait_group<0>();
     gs0 += nstream;
   }
+  // (a CTA's shared memory must outlive the other CTA's reads of it: leave together)
+  if (pairs)
+    cluster_sync_all();
 }
 
 __global__ void k_btddod_matvec(int nsys, const double *matrix, const double *vec, int nb, int bs, double *out)
