@@ -379,6 +379,11 @@ int gb_accept_step_batch(int n, int ndof, const double *dq, const int *accept, i
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long gb_kernel_launch_count(void);
+/* host-clock accounting of gb_flamelet_async_tick_batch since the last reset: out[0] ticks, [1] rounds, [2] seconds
+ * inside the calls, [3] seconds inside the round loops, [4] / [5] seconds until the solve / the right-hand side of a
+ * round had finished (only with GB_TICK_PROFILE set in the environment, which adds two synchronisations per round);
+ * out: 8 doubles. tools/dev/dev_tick_stats.py */
+void gb_debug_tick_stats(double *out, int reset);
 /* name of the build (arch, flags), for logs */
 const char *gb_build_info(void);
 /* FP64 vector peak of the current device, measured with a dependent-free DFMA (kind 0) or DMUL+DADD (kind 1)

@@ -1081,7 +1081,13 @@ class Flamelet(object):
         ne, names = self._n_equations, self._mechanism.species_names
         sl = (lambda a: (slice(None), a)) if lead else (lambda a: a)
         S = states if lead else states.reshape(-1)
-        pick = (lambda off: S[:, off::ne]) if lead else (lambda off: S[off::ne])
+        if lead and S.shape[0] > 8:
+            # (one transposing pass, then every variable is a contiguous [nt, nzi] block: a saved trajectory is a few MB,
+            # which 53 strided sweeps would each pull through the cache again)
+            St = np.ascontiguousarray(S.reshape(S.shape[0], -1, ne).transpose(2, 0, 1))
+            pick = lambda off: St[off]
+        else:
+            pick = (lambda off: S[:, off::ne]) if lead else (lambda off: S[off::ne])
         T = lib.get_empty_dataset()
         T[sl(0)], T[sl(slice(1, -1))], T[sl(-1)] = self._oxy_stream.T, pick(0), self._fuel_stream.T
         lib['temperature'] = T

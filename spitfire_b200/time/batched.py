@@ -40,6 +40,7 @@ STAGE_CALL = True
 # trajectory on its own takes 6,447). Off by default; bit-identical to the stage-by-stage loop (tests/test_gpu_newton.py).
 ASYNC_STAGES = False
 import os as _os
+import time as _time
 if _os.environ.get('GB_NEWTON_MODE') in ('eager', 'fused', 'stage', 'async'):  # (A/B switch for tools/bench_slfm.py)
     FUSED_NEWTON = _os.environ['GB_NEWTON_MODE'] != 'eager'
     STAGE_CALL = _os.environ['GB_NEWTON_MODE'] in ('stage', 'async')
@@ -398,6 +399,8 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
     q0_h = q0.cpu().numpy()
     q_hist = [[q0_h[m].copy()] for m in range(F)]
     n_rounds = n_refresh = 0
+    host_wait = host_ctrl = 0.  # seconds the host waited for a tick / spent on the step-end control
+    _t_begin = _time.perf_counter()
     pack_d = torch.zeros((3, F), **f64)  # t, residual, step count of every member, for the stopping test
     torch.cuda.synchronize()
 
@@ -545,8 +548,12 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
                 bi ^= 1
             # ---- meanwhile: the step ends of the tick that has just finished ------------------------------------------------
             if inflight is not None:
+                _t0 = _time.perf_counter()
                 n_rounds += inflight[0].result()
+                _t1 = _time.perf_counter()
                 step_end(hvs[inflight[1]])
+                host_wait += _t1 - _t0
+                host_ctrl += _time.perf_counter() - _t1
             inflight = nxt
             if inflight is None and not pending and not np.any(phase == NEED):
                 if np.all(phase == FIN):
@@ -564,7 +571,8 @@ def integrate_batch_async(ops, q0, stop, first_time_step=1.e-6, max_time_step=1.
         for m in range(F):
             t_hist[m].append(float(t[m]))
             q_hist[m].append(qf[m].copy())
-    LAST_ASYNC_STATS.update(rounds=n_rounds, refresh_launches=n_refresh, members=F)
+    LAST_ASYNC_STATS.update(rounds=n_rounds, refresh_launches=n_refresh, members=F, host_wait_s=host_wait,
+                            host_step_end_s=host_ctrl, wall_s=_time.perf_counter() - _t_begin)
     if stats_out is not None:
         stats_out.update(rounds=n_rounds, refresh_launches=n_refresh, newton_iterations=nits_d.cpu().numpy().tolist())
     return [np.array(th) for th in t_hist], [np.array(qh) for qh in q_hist], failed

@@ -25,3 +25,5 @@ for rep in range(2):
     s = list(buf)
     print(f'members {len(fls)} wall {wall:.3f} s  ticks {int(s[0])} rounds {int(s[1])}  in ticks {s[2]:.3f} s  in round loops {s[3]:.3f} s'
           f'  per round {s[3] / max(s[1], 1) * 1e3:.3f} ms  solve(sync) {s[4]:.3f} s  update+rhs(sync) {s[5]:.3f} s  steps {sum(l.shape[0] for l in libs)}', flush=True)
+    from spitfire_b200.time import batched
+    print('   ', {k: (round(v, 3) if isinstance(v, float) else v) for k, v in batched.LAST_ASYNC_STATS.items()}, flush=True)
