@@ -986,6 +986,29 @@ extern "C"
     }
     int rounds = 0;
     bool any_complete = false;
+    // Opt-in (GB_TICK_PUBLISH=1), measured not to pay: larger batches complete a member's step in nearly every round, so
+    // the error estimate and the acceptance kernel can run at the end of EVERY round, that kernel writing the round's
+    // outcome (states, stages, and the statistics and new state rows of the completed members) straight into the mapped
+    // pinned host arrays -- one synchronisation per round and no copy operations instead of two synchronisations and
+    // 4 + k copies. 56 GRI-128 trajectories: 0.417 ms per tick against 0.422 ms (the 53 KB rows written over PCIe by
+    // the kernel cost what the second synchronisation did); bit-identical results.
+    static const bool publish_enabled = getenv("GB_TICK_PUBLISH") && atoi(getenv("GB_TICK_PUBLISH")) != 0;
+    int *hd_state = nullptr, *hd_stage = nullptr, *hd_nlfail = nullptr;
+    double *hd_stats = nullptr, *hd_q = nullptr;
+    bool publish = publish_enabled && !tick_profile && F >= 16;
+    if (publish)
+    {
+      publish = cudaHostGetDevicePointer((void **)&hd_state, host_state, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer((void **)&hd_stage, host_stage, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer((void **)&hd_stats, host_stats, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer((void **)&hd_nlfail, host_nlfail, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer((void **)&hd_q, host_q, 0) == cudaSuccess;
+      if (!publish)
+        cudaGetLastError(); // (host arrays that are not mapped pinned memory: the two-step form)
+    }
+    const double *kp_all[6];
+    for (int j = 0; j < nstages && j < 6; ++j)
+      kp_all[j] = K + (size_t)j * F * ndof;
     const clk::time_point loop_t0 = clk::now();
     while (rounds < max_rounds)
     {
@@ -1007,8 +1030,17 @@ extern "C"
       }
       RC(gb_async_round_kernels(F, ndof, nstages, tableau, max_iterations, 1, fn, xn, dx, q, dt, gamma, weights, tolerance, x,
                                 f, res, explicit_, K, state, stage, iters, nlfail, newton_its, stream));
-      CK(cudaMemcpyAsync(host_state, state, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(host_stage, stage, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+      if (publish)
+      {
+        RC(gb_esdirk_finish_batch(F, ndof, nstages, kp_all, b, bh, dt, weights, dq, stats, stream));
+        RC(async_accept_publish(F, ndof, nstages, dq, stats, clip_negative, state, stage, q, nlfail, hd_state, hd_stage,
+                                hd_stats, hd_nlfail, hd_q, st));
+      }
+      else
+      {
+        CK(cudaMemcpyAsync(host_state, state, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(host_stage, stage, sizeof(int) * F, cudaMemcpyDeviceToHost, st));
+      }
       CK(cudaStreamSynchronize(st));
       ++rounds;
       bool any_active = false;
@@ -1031,7 +1063,7 @@ extern "C"
         g_tick_stats[2] += std::chrono::duration<double>(clk::now() - t0).count();
       }
     } tick_end{tick_t0};
-    if (any_complete)
+    if (any_complete && !publish)
     {
       const double *kp[6];
       for (int j = 0; j < nstages; ++j)

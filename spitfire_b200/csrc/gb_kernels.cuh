@@ -123,6 +123,10 @@ __device__ __forceinline__ void cluster_sync_all()
                    : "memory");
 }
 #endif
+// gb_newton.cu: acceptance kernel of the asynchronous integrator that writes the round's outcome into mapped host memory
+int async_accept_publish(int n, int ndof, int nstages, const double *dq, const double *stats, int clip, const int *state,
+                         int *stage, double *q, const int *nlfail, int *h_state, int *h_stage, double *h_stats,
+                         int *h_nlfail, double *h_q, cudaStream_t st);
 long kernel_launch_count();
 void count_launch();
 #ifdef GB_JAC_TIMELINE

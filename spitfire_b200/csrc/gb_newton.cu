@@ -352,6 +352,52 @@ __global__ void __launch_bounds__(NT) k_async_accept(int n, int ndof, int nstage
     stage[m] = 0;
 }
 
+// k_async_accept that also PUBLISHES the outcome of the round to the host: every member's state and stage (as they
+// stood before the reset) and, for the members that completed their step, the statistics, the Newton-failure flag and
+// the new state row -- written straight into mapped pinned host memory, so that a round of the asynchronous integrator
+// ends with one synchronisation and no copy operations (gb_flamelet_async_tick_batch).
+__global__ void __launch_bounds__(NT) k_async_accept_publish(int n, int ndof, int nstages, const double *__restrict__ dq,
+                                                             const double *__restrict__ stats, int clip,
+                                                             const int *__restrict__ state, int *__restrict__ stage,
+                                                             double *__restrict__ q, const int *__restrict__ nlfail,
+                                                             int *__restrict__ h_state, int *__restrict__ h_stage,
+                                                             double *__restrict__ h_stats, int *__restrict__ h_nlfail,
+                                                             double *__restrict__ h_q)
+{
+  const int m = blockIdx.x;
+  const int st = state[m], sg = stage[m];
+  const bool done = st == 0 && sg == nstages;
+  if (done)
+  {
+    const bool ok = stats[2 * n + m] > 0.5;
+    const size_t base = (size_t)m * ndof;
+    for (int i = threadIdx.x; i < ndof; i += NT)
+    {
+      double v = q[base + i];
+      if (ok)
+      {
+        v = v + dq[base + i];
+        if (clip && v < 0.)
+          v = 0.;
+        q[base + i] = v;
+      }
+      h_q[base + i] = v;
+    }
+    if (threadIdx.x < 3)
+      h_stats[threadIdx.x * n + m] = stats[threadIdx.x * n + m];
+    if (threadIdx.x == 3)
+      h_nlfail[m] = nlfail[m];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    h_state[m] = st;
+    h_stage[m] = sg;
+    if (done)
+      stage[m] = 0;
+  }
+}
+
 // dq = dt*(b0*k0 + b1*k1 + ... ), dqh likewise with bh (left to right, methods.py:598-610); stats[0][m] = max|(dq-dqh)*w|
 // (the error estimate of the PI controller), stats[1][m] = max|dq*w|, stats[2][m] = 1 if every dq is finite else 0
 __global__ void __launch_bounds__(NT) k_esdirk_finish(int ndof, int n, int nk, KPtrs kp, const double *__restrict__ dt,
@@ -473,6 +519,17 @@ int cuda_rc(const char *what)
   return GB_OK;
 }
 } // namespace
+
+// see k_async_accept_publish; the h_* pointers are device addresses of mapped pinned host arrays
+int async_accept_publish(int n, int ndof, int nstages, const double *dq, const double *stats, int clip, const int *state,
+                         int *stage, double *q, const int *nlfail, int *h_state, int *h_stage, double *h_stats,
+                         int *h_nlfail, double *h_q, cudaStream_t st)
+{
+  k_async_accept_publish<<<n, NT, 0, st>>>(n, ndof, nstages, dq, stats, clip, state, stage, q, nlfail, h_state, h_stage,
+                                           h_stats, h_nlfail, h_q);
+  ++g_btddod_launches;
+  return cuda_rc("k_async_accept_publish");
+}
 
 // the non-finite member count in three steps, so that a pipelined host entry point can accumulate over its chunks
 int nonfinite_reset(cudaStream_t st)
