@@ -353,6 +353,11 @@ def time_library_builds(args, world, cpu_sample=None):
         _gri_flamelet_specs(m), diss_rate_values=chis, verbose=False, n_defect_st=16, wave=8)
     out['nonadiabatic_defect_slfm_s'] = time.perf_counter() - t0
     out['nonadiabatic_shape'] = list(lib.shape)
+    try:  # this rank's heat-loss trajectories: rounds of the asynchronous integrator, seconds inside it
+        from spitfire_b200.time import batched as _batched
+        out['trajectories'] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in _batched.LAST_ASYNC_STATS.items()}
+    except Exception:
+        pass
     out['T_max'] = float(lib['temperature'].max())
     if cpu_sample is not None:
         sc = cpu_sample['chis']

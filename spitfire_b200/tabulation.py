@@ -287,7 +287,7 @@ def _trajectory_groups(flamelet_specs, n_members):
     import os
     if not _griffon_on_device(flamelet_specs):
         return 1
-    g = TRAJECTORY_GROUPS if TRAJECTORY_GROUPS is not None else os.environ.get('GB_TRAJECTORY_GROUPS')
+    g = os.environ.get('GB_TRAJECTORY_GROUPS', TRAJECTORY_GROUPS)
     g = int(g) if g is not None else min(8, n_members // 2)
     return max(1, min(g, n_members))
 
