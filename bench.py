@@ -356,6 +356,7 @@ def time_library_builds(args, world, cpu_sample=None):
     try:  # this rank's heat-loss trajectories: rounds of the asynchronous integrator, seconds inside it
         from spitfire_b200.time import batched as _batched
         out['trajectories'] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in _batched.LAST_ASYNC_STATS.items()}
+        out['stages_s'] = {k: round(v, 4) for k, v in tab.LAST_BUILD_TIMES.items()}
     except Exception:
         pass
     out['T_max'] = float(lib['temperature'].max())

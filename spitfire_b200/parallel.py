@@ -66,6 +66,56 @@ def gather_dicts(local):
     return merged
 
 
+def gather_profile_dicts(local):
+    """gather_dicts for dictionaries {key: {name: 1-D float64 array}} whose entries all carry the same names and array
+    length (the per-(chi_st, defect) profile sets of the non-adiabatic builders: ~1e5 arrays of one grid line each).
+    Pickling that many small arrays costs seconds; here a rank's profiles travel as ONE array [entry, name, point] next
+    to the key and name lists, and the merged dictionary holds views into the gathered arrays. Falls back to
+    gather_dicts when the entries are not uniform."""
+    import numpy as np
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return dict(local)
+    keys = list(local.keys())
+    names, npts, uniform = [], 0, True
+    if keys:
+        names = list(local[keys[0]].keys())
+        npts = int(np.asarray(local[keys[0]][names[0]]).size) if names else 0
+        for k in keys:
+            e = local[k]
+            if list(e.keys()) != names or any(np.asarray(e[q]).shape != (npts,) for q in names):
+                uniform = False
+                break
+    # one small object per rank (keys, names, sizes), then the numbers as one tensor collective
+    metas = [None] * d.get_world_size()
+    d.all_gather_object(metas, (bool(uniform), keys, names, npts))
+    if not all(m[0] for m in metas):
+        return gather_dicts(local)
+    import torch
+    live = [m for m in metas if m[1]]
+    if not live:
+        return dict()
+    nn, nz = len(live[0][2]), live[0][3]
+    if any(len(m[2]) != nn or m[3] != nz for m in live):
+        return gather_dicts(local)
+    nmax = max(len(m[1]) for m in metas)
+    pack = np.zeros((nmax, nn, nz))
+    for i, k in enumerate(keys):
+        e = local[k]
+        for j, q in enumerate(names):
+            pack[i, j] = e[q]
+    dev = torch.device('cuda', torch.cuda.current_device()) if d.get_backend() == 'nccl' else torch.device('cpu')
+    mine = torch.from_numpy(pack).to(dev)
+    parts = [torch.empty_like(mine) for _ in metas]
+    d.all_gather(parts, mine)
+    merged = dict()
+    for (_, pkeys, pnames, _), part in zip(metas, parts):
+        ppack = part.cpu().numpy()
+        for i, k in enumerate(pkeys):
+            merged[k] = {q: ppack[i, j] for j, q in enumerate(pnames)}
+    return merged
+
+
 def barrier():
     d = _dist()
     if d is not None:

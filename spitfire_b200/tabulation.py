@@ -461,6 +461,8 @@ def _expand_enthalpy_defect_dimension_steady_batch(chi_list, managed_dict, flame
 
 
 _pool_job = None
+# where the last non-adiabatic build of this process spent its time (seconds per stage; bench.py reports it)
+LAST_BUILD_TIMES = dict()
 
 
 def _pool_expand(chi_st):
@@ -488,9 +490,12 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
                                                          integration_args=None, wave=1, batch_expansions=True):
     """adiabatic chain on every rank (it is short and every rank needs all of it), then this rank's share of the
     independent heat-loss expansions, then one gather (tabulation.py:522-591)"""
+    _t0 = perf_counter()
     table_dict, z_values, x_values = build_adiabatic_slfm_library(flamelet_specs, diss_rate_values, diss_rate_ref,
                                                                   verbose, solver_verbose, _return_intermediates=True,
                                                                   wave=wave)
+    LAST_BUILD_TIMES.clear()
+    LAST_BUILD_TIMES['adiabatic_chain_s'] = perf_counter() - _t0
     expand = _expand_enthalpy_defect_dimension_transient if heat_loss_expansion == 'transient' else \
         _expand_enthalpy_defect_dimension_steady
     if verbose and parallel.rank() == 0:
@@ -525,7 +530,13 @@ def _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_lo
         for chi_st in mine:
             expand(chi_st, local, flamelet_specs, table_dict, h_stoich_spacing, verbose, integration_args,
                    solver_verbose)
-    merged = parallel.gather_dicts(local)
+    LAST_BUILD_TIMES['own_expansions_s'] = perf_counter() - cput0
+    _t0 = perf_counter()
+    parallel.barrier()
+    LAST_BUILD_TIMES['wait_for_other_ranks_s'] = perf_counter() - _t0
+    _t0 = perf_counter()
+    merged = parallel.gather_profile_dicts(local)
+    LAST_BUILD_TIMES['gather_s'] = perf_counter() - _t0
     if verbose and parallel.rank() == 0:
         print('-' * 82)
         print('enthalpy defect dimension expanded in {:6.2f} s'.format(perf_counter() - cput0))
@@ -569,10 +580,15 @@ def _interpolate_to_structured_defect_dimension(unstructured_table, n_defect_sto
     structured = dict()
     for chi_st, gs in by_chi.items():
         g_sorted = np.sort(np.array(gs))
-        first = unstructured_table[(chi_st, g_sorted[0])]
-        for q in first.keys():
-            data = np.array([np.asarray(unstructured_table[(chi_st, g)][q], dtype=np.float64) for g in g_sorted])
-            out = _interp_columns(defect_space, g_sorted, data)
+        entries = [unstructured_table[(chi_st, g)] for g in g_sorted]
+        names = list(entries[0].keys())
+        # all properties of this chi_st in one interpolation: [defect, property, z] -> columns (property, z); the
+        # columns are independent, so every value is the one the property-by-property loop computes
+        data_all = np.array([[np.asarray(e[q], dtype=np.float64) for q in names] for e in entries])
+        ng, nq, nz = data_all.shape
+        out_all = _interp_columns(defect_space, g_sorted, data_all.reshape(ng, nq * nz)).reshape(-1, nq, nz)
+        for j, q in enumerate(names):
+            data, out = data_all[:, j], out_all[:, j]
             if extend and q in ('enthalpy', 'enthalpy_defect') and g_sorted.size > 1:
                 lo = defect_space < g_sorted[0]
                 slope = (data[1] - data[0]) / (g_sorted[1] - g_sorted[0])
@@ -582,8 +598,8 @@ def _interpolate_to_structured_defect_dimension(unstructured_table, n_defect_sto
                 out[hi] = data[-1] + (defect_space[hi, None] - g_sorted[-1]) * slope
             if q in ('density', 'temperature') and np.any(out < 1.e-14):
                 raise ValueError(f'{q} < 1.e-14 detected!')
-            for ig, g in enumerate(defect_space):
-                structured.setdefault((chi_st, g), dict())[q] = out[ig]
+        for ig, g in enumerate(defect_space):
+            structured[(chi_st, g)] = {q: out_all[ig, j] for j, q in enumerate(names)}
     if verbose and parallel.rank() == 0:
         print('Structured enthalpy defect dimension built in {:6.2f} s'.format(perf_counter() - cput0), flush=True)
     return structured, np.array(sorted(by_chi.keys())), defect_space[::-1]
@@ -601,8 +617,11 @@ def _build_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion=
     ugt = _build_unstructured_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion, diss_rate_values,
                                                                diss_rate_ref, verbose, solver_verbose, h_stoich_spacing,
                                                                num_procs, integration_args, wave=wave)
+    _t0 = perf_counter()
     table, x_values, g_values = _interpolate_to_structured_defect_dimension(ugt, n_defect_st, verbose=verbose,
                                                                             extend=extend_defect_dim)
+    LAST_BUILD_TIMES['structured_interpolation_s'] = perf_counter() - _t0
+    _t0 = perf_counter()
     key0 = list(table.keys())[0]
     z_values = table[key0][_mixture_fraction_name]
     output_library = Library(Dimension(_mixture_fraction_name, z_values),
@@ -615,6 +634,7 @@ def _build_nonadiabatic_defect_slfm_library(flamelet_specs, heat_loss_expansion=
             for ig, g in enumerate(g_values):
                 values[:, ix, ig] = table[(x, g)][quantity]
         output_library[quantity] = values
+    LAST_BUILD_TIMES['assembly_s'] = perf_counter() - _t0
     _write_library_footer(cput00, verbose)
     return output_library
 
