@@ -693,6 +693,7 @@ cudaError_t launch_rates(const ChemArgs &a_in, cudaStream_t s)
   // tile size: 31 states per CTA for large batches; small batches (a few flamelets) are spread over all SMs with
   // smaller tiles, whose latency is lower (GRI, 1008 states: 72 us with 7-state tiles against 115 us with 31)
   int G = env_int("GB_RATES_G", 0);
+  bool dynamic_tiles = false;
   if (G <= 0)
   {
     // ... and batches of a few waves get equal tiles: 7168 states (56 flamelets of 128 points) are 2 x 148 tiles of 25
@@ -700,6 +701,15 @@ cudaError_t launch_rates(const ChemArgs &a_in, cudaStream_t s)
     const int sms = sm_count();
     const int waves = std::max(1, (a.n + 31 * sms - 1) / (31 * sms));
     G = std::min(31, std::max(7, (a.n + waves * sms - 1) / (waves * sms)));
+    // GB_RATES_TPS = t > 1: batches of up to a few waves are cut into about t tiles per SM, one CTA per tile, so that
+    // the hardware deals the tiles to whatever SMs are free (other streams' kernels may hold some: the Jacobian
+    // refreshes of the asynchronous integrator do) instead of one tile per SM and a second wave for the unlucky ones
+    static const int tps = std::max(1, env_int("GB_RATES_TPS", 1));
+    if (tps > 1 && a.n <= 4 * 31 * sms)
+    {
+      G = std::min(31, std::max(7, (a.n + tps * sms - 1) / (tps * sms)));
+      dynamic_tiles = true;
+    }
   }
   while (G > 1 && rates_smem(a.dm, G | 1) > (size_t)maxsm)
     G -= 2;
@@ -716,7 +726,7 @@ cudaError_t launch_rates(const ChemArgs &a_in, cudaStream_t s)
     attr = true;
   }
   const int ntiles = (a.n + G - 1) / G;
-  const int grid = std::min(ntiles, sm_count());
+  const int grid = dynamic_tiles ? ntiles : std::min(ntiles, sm_count());
   const int threads = env_int("GB_RATES_THREADS", 512);
   k_rates<<<grid, threads, sm, s>>>(a);
   ++g_launches;
