@@ -242,7 +242,11 @@ int gb_btddod_scale_and_add_diagonal_batch(int n_systems, double *matrix, double
  * btddod_matrix_kernels.cpp:48-63), and gb_btddod_full_solve_inv_batch runs the back sweep as matrix-vector
  * products with them (no pivots, no triangular solves). Same result up to rounding; used inside Newton loops.
  * system_rows (device, may be NULL): the factors of the k-th right-hand side are those of system system_rows[k] of the
- * factor arrays, so a solver can address a subset of a batch without gathering 8 MB of factors per member. */
+ * factor arrays, so a solver can address a subset of a batch without gathering 8 MB of factors per member.
+ * The solve is launched as thread-block clusters of two CTAs per system when the sizes allow it (num_blocks >= 4, the
+ * right-hand side fits in shared memory): factors tagged by gb_btddod_full_invert_twisted_batch (below) are then
+ * applied from both ends at once; factors of the two one-sided eliminations are swept by the first CTA alone.
+ * block 0 of l_values is never a multiplier: it is zero (one-sided eliminations) or holds the tag. */
 int gb_btddod_full_factorize_inv_batch(int n_systems, double *d_factors, int num_blocks, int block_size,
                                        double *out_l_values, int *out_d_pivots, double *out_dinv, void *stream);
 int gb_btddod_full_solve_inv_batch(int n_systems, const double *d_factors, const double *l_values, const double *dinv,
