@@ -783,10 +783,12 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
           for (int sl = 0; sl < G; ++sl)
             if (sl < gcount)
             {
-#ifdef GB_JAC_STCS
-              __stcs(ob[sl] + off, v[sl]);
-#else
+              // (streaming store: the Jacobian is written once and never read back by this kernel; measured 1 % on the
+              // whole kernel, 6.88 against 6.95 ms per 262,144 states)
+#ifdef GB_JAC_NO_STCS
               ob[sl][off] = v[sl];
+#else
+              __stcs(ob[sl] + off, v[sl]);
 #endif
             }
         }
