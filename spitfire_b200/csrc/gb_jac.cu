@@ -522,62 +522,113 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     fetch_T(tile + gridDim.x);
     {
       const int ncsp = dm.jp_ncsp, ncs = dm.jp_ncs;
-      // parts first, on whole warps, so that the row jobs start on a warp boundary
-      const int npw = (ncsp + 31) & ~31;
-      for (int job = tid; job < npw + ns * G; job += nt)
+      [[maybe_unused]] const int nw = nt >> 5;
+      // parts first (lane per part), then the row constants on all threads. Measured alternatives (262,144 GRI-3.0
+      // states, whole kernel): parts dealt round-robin to ALL warps (-DGB_JAC_CS_SPREAD: a part is a dependent chain of
+      // shared-memory reads, so sixteen warps with fourteen parts each should beat seven full warps) 6.82 ms against
+      // 6.78 ms; the loop over a part's items software-pipelined by hand (-DGB_JAC_CS_PIPE) spills (128 registers)
+      // and costs 18 %.
+#ifdef GB_JAC_CS_SPREAD
+      for (int job = lane * nw + warp; job < ncsp; job += 32 * nw)
+#else
+      for (int job = tid; job < ncsp; job += nt)
+#endif
       {
-        if (job < npw)
-        {
-          if (job >= ncsp)
-            continue;
-          const int d = t_csparts[3 * job], p0 = t_csparts[3 * job + 1], p1 = t_csparts[3 * job + 2];
-          double acc[G];
+        const int d = t_csparts[3 * job], p0 = t_csparts[3 * job + 1], p1 = t_csparts[3 * job + 2];
+        double acc[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          acc[g] = 0.;
+        // sum over species (ascending) of h_i (cp_i for the last destination) times the row value: the inner
+        // products of isobaric_reactor_kernels.cpp:74-92
+        const double *wsrc = (d == ncs - 1) ? s.scp : s.sh;
+        auto fetch = [&](int p, double (&w)[G], double (&v)[G]) {
+          const unsigned int u = t_csitems[p];
+          Rows<G>::load(wsrc + (size_t)(u >> 16) * G, rot, w);
+          Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
+        };
+        auto mac = [&](const double (&w)[G], const double (&v)[G]) {
 #pragma unroll
           for (int g = 0; g < G; ++g)
-            acc[g] = 0.;
-          // sum over species (ascending) of h_i (cp_i for the last destination) times the row value: the inner
-          // products of isobaric_reactor_kernels.cpp:74-92
-          const double *wsrc = (d == ncs - 1) ? s.scp : s.sh;
-          for (int p = p0; p < p1; ++p)
-          {
-            const unsigned int u = t_csitems[p];
-            double w[G], v[G];
-            Rows<G>::load(wsrc + (size_t)(u >> 16) * G, rot, w);
-            Rows<G>::load_swz(s.sR, (int)(u & 0xffff), rot, v);
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-              acc[g] += w[g] * v[g];
-          }
-          Rows<G>::store(s.sTH + (size_t)job * G, rot, acc);
+            acc[g] += w[g] * v[g];
+        };
+#ifndef GB_JAC_CS_PIPE
+        for (int p = p0; p < p1; ++p)
+        {
+          double w[G], v[G];
+          fetch(p, w, v);
+          mac(w, v);
         }
-        else
-        { // chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343)
-          const int item = job - npw;
-          const int i = item / G, g = item - i * G;
-          const double invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
-          const double w = SJ(rowsrc[i], g), wr = SJ(rowsrc[ns + i], g);
-          const double wT = SJ(rowsrc[2 * ns + i], g);
-          const double nmA = SJ(rowsrc[3 * ns + i], g), nmB = SJ(rowsrc[4 * ns + i], g);
-          const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
-          const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
-          SMG(s.sg, i, g) = invRho;
-          SMG(s.sdb, i, g) = invRho * nmA + nRM * prho;
-          SMG(s.sdcp, i, g) = invRho * nmB;
-          if (i < nsm1)
+#else
+        if (p0 < p1)
+        {
+          double wa[G], va[G], wb[G], vb[G];
+          fetch(p0, wa, va);
+          for (int p = p0;; p += 2)
           {
-            SJ(dm.jp_c0base + i, g) = wT * invRho - roT * prho; // J[1+i, 0]
-            if (reactor && g < gcount)
-            { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
-              double v = w * invRho;
-              if (open)
-                v += (a.rx.y_in[i] - SMG(s.sy, i, g)) * invTau;
-              a.out0[(size_t)(tile0 + g) * ns + 1 + i] = v;
-            }
+            const bool hb = p + 1 < p1;
+            if (hb)
+              fetch(p + 1, wb, vb);
+            mac(wa, va);
+            if (!hb)
+              break;
+            const bool ha = p + 2 < p1;
+            if (ha)
+              fetch(p + 2, wa, va);
+            mac(wb, vb);
+            if (!ha)
+              break;
+          }
+        }
+#endif
+        Rows<G>::store(s.sTH + (size_t)job * G, rot, acc);
+      }
+      // row constants: chem_jac_isobaric rows (:75-98) folded with transform_isobaric_primitive_jacobian (:319-343).
+      // (Dealing them first to the threads of the warps that carry no parts, -DGB_JAC_CS_OFFSET, is 1.4 % slower on the
+      // whole kernel: 6.85 against 6.75 ms, paired runs.)
+#ifdef GB_JAC_CS_OFFSET
+      for (int item = (tid + nt - (((ncsp + 31) & ~31) % nt)) % nt; item < ns * G; item += nt)
+#else
+      for (int item = tid; item < ns * G; item += nt)
+#endif
+      {
+        const int i = item / G, g = item - i * G;
+        const double invRho = SMG(s.sc, J_IRHO, g), rho = SMG(s.sc, J_RHO, g);
+        const double w = SJ(rowsrc[i], g), wr = SJ(rowsrc[ns + i], g);
+        const double wT = SJ(rowsrc[2 * ns + i], g);
+        const double nmA = SJ(rowsrc[3 * ns + i], g), nmB = SJ(rowsrc[4 * ns + i], g);
+        const double prho = invRho * (wr - invRho * w); // P[1+i, rho]
+        const double nRM = -rho * SMG(s.sc, J_MMW, g), roT = rho / SMG(s.sc, J_T, g);
+        SMG(s.sg, i, g) = invRho;
+        SMG(s.sdb, i, g) = invRho * nmA + nRM * prho;
+        SMG(s.sdcp, i, g) = invRho * nmB;
+        if (i < nsm1)
+        {
+          SJ(dm.jp_c0base + i, g) = wT * invRho - roT * prho; // J[1+i, 0]
+          if (reactor && g < gcount)
+          { // right-hand side, chem_rhs_isobaric :19-29 (+ :194-218)
+            double v = w * invRho;
+            if (open)
+              v += (a.rx.y_in[i] - SMG(s.sy, i, g)) * invTau;
+            a.out0[(size_t)(tile0 + g) * ns + 1 + i] = v;
           }
         }
       }
     }
     TL_MARK(8)
+    __syncthreads();
+    // ---- column sums: the parts of a destination added up in part order, once per (destination, state), into the slot
+    // of its first part (every temperature-row entry needs seven of these sums: formed inside that phase they were
+    // seven dependent loops on its critical path, and the six per-state ones were formed by all ns threads of a state)
+    for (int item = tid; item < dm.jp_ncs * G; item += nt)
+    {
+      const int d = item / G, g = item - d * G;
+      const int p0 = t_cspfirst[d], p1 = t_cspfirst[d + 1];
+      double v = SMG(s.sTH, p0, g);
+      for (int p = p0 + 1; p < p1; ++p)
+        v += SMG(s.sTH, p, g);
+      SMG(s.sTH, p0, g) = v;
+    }
     __syncthreads();
     // ---- temperature row (:58-98, 142-168; flamelet_kernels.cpp:1290-1320) ----------------------------------------------------
     finish_T();
@@ -585,13 +636,7 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     {
       const int c = item / G, g = item - c * G;
       const int ncs = dm.jp_ncs;
-      auto colsum = [&](int d) {
-        const int p0 = t_cspfirst[d], p1 = t_cspfirst[d + 1];
-        double v = SMG(s.sTH, p0, g);
-        for (int p = p0 + 1; p < p1; ++p)
-          v += SMG(s.sTH, p, g);
-        return v;
-      };
+      auto colsum = [&](int d) { return SMG(s.sTH, t_cspfirst[d], g); };
       const double rho = SMG(s.sc, J_RHO, g), cp = SMG(s.sc, J_CP, g), T = SMG(s.sc, J_T, g);
       const double cpsensT = SMG(s.sc, J_DCP, g);
       const double invRhoCp = 1. / (rho * cp), invRho = SMG(s.sc, J_IRHO, g), invCp = 1. / cp;
