@@ -520,6 +520,11 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
 
     // ---- column-sum parts (lane per part, G accumulators) and row constants (thread per (species, state)) --------------
     fetch_T(tile + gridDim.x);
+#ifdef GB_JAC_EARLY_PREFETCH
+    // (measured, not adopted: requesting the next tile's state here, two phases before the store-bound output phase,
+    // instead of at its start: 6.80 against 6.73 ms per 262,144 states, paired runs)
+    pre = fetch_state(tile + gridDim.x);
+#endif
     {
       const int ncsp = dm.jp_ncsp, ncs = dm.jp_ncs;
       [[maybe_unused]] const int nw = nt >> 5;
@@ -741,7 +746,9 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     __syncthreads();
 
     // ---- output: column 0, then the columns 1..ns-1 with one row per thread ----------------------------------------------------
+#ifndef GB_JAC_EARLY_PREFETCH
     pre = fetch_state(tile + gridDim.x);
+#endif
     for (int item = tid; item < ns * G; item += nt)
     {
       const int g = item / ns, r = item - g * ns;
