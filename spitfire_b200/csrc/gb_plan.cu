@@ -395,6 +395,10 @@ int build_jac_plan(const HostMech &m, const std::vector<int> &flags, const std::
     std::iota(gorder.begin(), gorder.end(), 0);
     std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return groups[a].cost > groups[b].cost; });
     std::vector<double> load(nwarps, 0.);
+    // (Round 2, measured and NOT adopted: the timeline shows ~450 cycles of loop overhead per group and ~3,800 cycles
+    // for the last warp's chain, which this model leaves out -- warp arrivals at the end of the phase spread from 11.5 k
+    // to 23.5 k cycles. Adding both makes the arrivals even and the kernel 0.9 % SLOWER (6.76 against 6.70 ms, paired
+    // runs): the phase is bound by the issue slots of the schedulers, not by its longest warp.)
     load[nwarps - 1] = 1500.; // the last warp starts with the mixture cp chain (k_jac)
     std::vector<std::vector<int>> per_warp(nwarps);
     for (int gi : gorder)
