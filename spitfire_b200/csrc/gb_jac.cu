@@ -477,6 +477,29 @@ __global__ void __launch_bounds__(512, 1) k_jac(const ChemArgs a)
     // ---- recombine split destinations in part order -------------------------------------------------------------------------------
     if (dm.jp_nfix > 0)
     {
+#ifdef GB_JAC_FIX_VEC2
+      // (measured, not adopted: 6.74-6.77 against 6.61 ms per 262,144 states, paired runs)
+      if (G >= 2)
+      { // two states (one 16-byte chunk of the swizzled rows) per thread: one pass over the block for GRI-3.0
+        constexpr int H = G >= 2 ? G / 2 : 1;
+        for (int item = tid; item < dm.jp_nfix * H; item += nt)
+        {
+          const int fi = item / H, j = item - fi * H;
+          const int dst = t_fix[3 * fi], first = t_fix[3 * fi + 1], np = t_fix[3 * fi + 2];
+          double2 *pd = reinterpret_cast<double2 *>(s.sR + (size_t)dst * G + 2 * Rows<G>::chunk(j, dst));
+          double2 v = *pd;
+          for (int p = 0; p < np; ++p)
+          {
+            const int row = first + p;
+            const double2 x = *reinterpret_cast<const double2 *>(s.sR + (size_t)row * G + 2 * Rows<G>::chunk(j, row));
+            v.x += x.x;
+            v.y += x.y;
+          }
+          *pd = v;
+        }
+      }
+      else
+#endif
       for (int item = tid; item < dm.jp_nfix * G; item += nt)
       {
         const int fi = item / G, g = item - fi * G;
