@@ -68,6 +68,20 @@ def compute_specific_enthalpy(mechanism, output_library):
     return output_library
 
 
+def _enthalpy_of_states(mechanism, T, Y):
+    """specific enthalpy of the states (T [n], Y [n, ns]) -- the arithmetic of compute_specific_enthalpy for a selection"""
+    Tf = np.ascontiguousarray(T, dtype=np.float64).reshape(-1)
+    Yf = np.ascontiguousarray(Y, dtype=np.float64).reshape(Tf.size, -1)
+    g = mechanism.griffon
+    h = np.zeros(Tf.size)
+    if hasattr(g, 'thermo_batch'):
+        g.thermo_batch(5, Tf, Yf, h)  # GB_THERMO_H_MIX
+    else:
+        for i in range(Tf.size):
+            h[i] = g.enthalpy_mix(Tf[i], Yf[i])
+    return h
+
+
 def _copy_specs(flamelet_specs):
     return FlameletSpec(**flamelet_specs) if isinstance(flamelet_specs, dict) else copy.copy(flamelet_specs)
 
@@ -243,11 +257,33 @@ def _transient_integration_args(input_integration_args, solver_verbose):
 def _store_transient_library(managed_dict, chi_st, fnonad, transient_lib, h_stoich_spacing):
     """sub-sample the trajectory in stoichiometric enthalpy and store the kept profiles (tabulation.py:375-400)"""
     z = fnonad.mixfrac_grid
-    z_st = fnonad.mechanism.stoich_mixture_fraction(fnonad.fuel_stream, fnonad.oxy_stream)
-    h_tz = compute_specific_enthalpy(fnonad.mechanism, transient_lib)['enthalpy']
-    indices = _subsample_by_stoich_enthalpy(z, z_st, h_tz, h_stoich_spacing, include_last=True)
+    mech = fnonad.mechanism
+    z_st = mech.stoich_mixture_fraction(fnonad.fuel_stream, fnonad.oxy_stream)
+    names = mech.species_names
+    nt, nz = transient_lib['temperature'].shape
+    if not FAST_TRANSIENT_STORE or nz < 8:
+        h_tz = compute_specific_enthalpy(mech, transient_lib)['enthalpy']
+        indices = _subsample_by_stoich_enthalpy(z, z_st, h_tz, h_stoich_spacing, include_last=True)
+        props = [q for q in transient_lib.props]
+        _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_tz, indices)
+        return
+    # The sub-sampling looks at the enthalpy interpolated to z_st only -- a value np.interp forms from the two grid
+    # points that bracket z_st -- and full profiles are stored for the kept time levels alone. So the enthalpy is
+    # evaluated at a four-point window around z_st for every time level and on the whole grid for the kept ones:
+    # ~5 x fewer states to assemble and evaluate than the whole (time, z) plane, same values (the enthalpy of a state
+    # does not depend on which other states are evaluated with it).
+    j = int(np.clip(np.searchsorted(z, z_st, side='right') - 1, 0, nz - 2))
+    cols = np.arange(max(j - 1, 0), min(j + 3, nz))
+    Tw = transient_lib['temperature'][:, cols]
+    Yw = np.stack([transient_lib['mass fraction ' + sp][:, cols] for sp in names], axis=-1)
+    h_win = _enthalpy_of_states(mech, Tw, Yw).reshape(nt, cols.size)
+    indices = _subsample_by_stoich_enthalpy(z[cols], z_st, h_win, h_stoich_spacing, include_last=True)
+    Tk = transient_lib['temperature'][indices, :]
+    Yk = np.stack([transient_lib['mass fraction ' + sp][indices, :] for sp in names], axis=-1)
+    h_keep = _enthalpy_of_states(mech, Tk, Yk).reshape(len(indices), nz)
+    h_rows = {i: h_keep[k] for k, i in enumerate(indices)}
     props = [q for q in transient_lib.props]
-    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_tz, indices)
+    _store_defect_profiles(managed_dict, chi_st, z, z_st, lambda q, i: transient_lib[q][i, :], props, h_rows, indices)
 
 
 def _expand_enthalpy_defect_dimension_transient(chi_st, managed_dict, flamelet_specs, table_dict, h_stoich_spacing,
@@ -460,6 +496,8 @@ def _expand_enthalpy_defect_dimension_steady_batch(chi_list, managed_dict, flame
             len(chi_list), min(chi_list), max(chi_list), perf_counter() - cput0), flush=True)
 
 
+# heat-loss trajectories stored through the reduced enthalpy evaluation of _store_transient_library (same values)
+FAST_TRANSIENT_STORE = True
 _pool_job = None
 # where the last non-adiabatic build of this process spent its time (seconds per stage; bench.py reports it)
 LAST_BUILD_TIMES = dict()
