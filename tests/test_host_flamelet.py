@@ -65,6 +65,8 @@ def test_two_rank_gloo_sweep_matches_gold(tmp_path):
     g = gold('nonadiabatic_defect_transient_slfm')
     assert int(d['world']) == 2
     assert sorted(d['owned_0'].tolist() + d['owned_1'].tolist()) == [0, 1, 2, 3]
+    # parallel.gather_profile_dicts: packed gather with uneven entry counts, and the fallback for ragged entries
+    assert d['gather_profile_dicts_ok'].tolist() == [True, True]
     for p in ('temperature', 'mass fraction H2O', 'mass fraction OH', 'enthalpy_defect'):
         a, b = d[p], g['prop_' + p]
         assert np.max(np.abs(a - b) / (1e-6 * np.abs(b) + 1e-6)) <= 1., p
