@@ -731,6 +731,7 @@ class Flamelet(object):
     _grid_types = ['uniform', 'clustered']
     _rates_sensitivity_option_dict = {'dense': 0, 'no-TBAF': 1, 'sparse': 2}
     _sensitivity_transform_option_dict = {'exact': 0}
+    _grid_cache = dict()
 
     @classmethod
     def _uniform_grid(cls, grid_points):
@@ -746,13 +747,19 @@ class Flamelet(object):
         if grid_cluster_point < 0. or grid_cluster_point > 1.:
             raise ValueError('z_cluster must be between 0 and 1! Given value: ' + str(grid_cluster_point))
         b, zc = grid_cluster_intensity, grid_cluster_point
-        z = np.linspace(0., 1., grid_points)
-        zo = 1.0 / (2.0 * b) * np.log((1. + (np.exp(b) - 1.) * zc) / (1. + (np.exp(-b) - 1.) * zc))
-        a = np.sinh(b * zo)
-        for i in range(grid_points):
-            z[i] = zc / a * (np.sinh(b * (z[i] - zo)) + a)
-        z[-1] = 1.
-        return z, z[1:] - z[:-1]
+        key = (int(grid_points), float(zc), float(b))
+        hit = cls._grid_cache.get(key)
+        if hit is None:  # (a library build constructs a few hundred flamelets on the same grid)
+            z = np.linspace(0., 1., grid_points)
+            zo = 1.0 / (2.0 * b) * np.log((1. + (np.exp(b) - 1.) * zc) / (1. + (np.exp(-b) - 1.) * zc))
+            a = np.sinh(b * zo)
+            for i in range(grid_points):
+                z[i] = zc / a * (np.sinh(b * (z[i] - zo)) + a)
+            z[-1] = 1.
+            if len(cls._grid_cache) > 64:
+                cls._grid_cache.clear()
+            hit = cls._grid_cache[key] = (z, z[1:] - z[:-1])
+        return hit[0].copy(), hit[1].copy()
 
     @classmethod
     def make_clustered_grid(cls, grid_points, grid_cluster_point, grid_cluster_intensity=6.):
